@@ -1,0 +1,105 @@
+// Shared device helpers for the AIR hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace air {
+
+constexpr int ACT_NONE = 0;
+constexpr int ACT_ELU = 1;
+
+// tf.nn.elu [upstream Eigen functor]: x if x > 0 else exp(x) - 1  (neural.py:20)
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expf(x) - 1.0f; }
+
+// tf.nn.softplus [upstream functor]: threshold = log(eps) + 2; x > -thr -> x; x < thr -> exp(x);
+// else log(exp(x) + 1)   (NormalWithSoftplusScale, cell.py:130, modules.py:17)
+__device__ __forceinline__ float softplus_f(float x) {
+  const float thr = -13.942385f;  // logf(FLT_EPSILON) + 2
+  if (x > -thr) return x;
+  float ex = expf(x);
+  if (x < thr) return ex;
+  return logf(ex + 1.0f);
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) { return act == ACT_ELU ? elu_f(v) : v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; every thread gets the result.  `red` must hold >= 32 floats.  Ends with a barrier.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// Sonnet builds the warp grid with np.linspace(-1, 1, n, dtype=float32): float64 maths, cast at the end.
+__device__ __forceinline__ float linspace_pm1(int i, int n) {
+  if (n <= 1) return -1.0f;
+  double step = 2.0 / (double)(n - 1);
+  return (float)(-1.0 + (double)i * step);
+}
+
+// snt.resampler [upstream C++/CUDA kernel] on one single-channel plane held in (shared or global) memory:
+// bilinear sample at pixel coords (x, y); zero outside (-1, Ws) x (-1, Hs); taps outside the plane read 0.
+__device__ __forceinline__ float resample_plane(const float* __restrict__ D, int Hs, int Ws, float x, float y) {
+  if (!(x > -1.0f && y > -1.0f && x < (float)Ws && y < (float)Hs)) return 0.f;
+  const float fxf = floorf(x), fyf = floorf(y);
+  const int fx = (int)fxf, fy = (int)fyf, cx = fx + 1, cy = fy + 1;
+  const float dx = (fxf + 1.0f) - x, dy = (fyf + 1.0f) - y;
+  const bool fx_ok = fx >= 0 && fx <= Ws - 1, cx_ok = cx >= 0 && cx <= Ws - 1;
+  const bool fy_ok = fy >= 0 && fy <= Hs - 1, cy_ok = cy >= 0 && cy <= Hs - 1;
+  const float v_ff = (fx_ok && fy_ok) ? D[fy * Ws + fx] : 0.f;
+  const float v_cc = (cx_ok && cy_ok) ? D[cy * Ws + cx] : 0.f;
+  const float v_fc = (fx_ok && cy_ok) ? D[cy * Ws + fx] : 0.f;   // (fx, cy)
+  const float v_cf = (cx_ok && fy_ok) ? D[fy * Ws + cx] : 0.f;   // (cx, fy)
+  const float one = 1.0f;
+  // same association as the reference kernel: dx*dy*ff + (1-dx)(1-dy)*cc + dx(1-dy)*fc + (1-dx)dy*cf
+  float r = __fmul_rn(__fmul_rn(dx, dy), v_ff);
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(one - dx, one - dy), v_cc));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(dx, one - dy), v_fc));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(one - dx, dy), v_cf));
+  return r;
+}
+
+// AffineGridWarper(source = img HxW, output = hxw, no_shear_2d): pixel coordinate along one axis,
+//   coord = s * (u * S) + t * S + S,  S = (n_src - 1) / 2,  u = linspace(-1, 1, n_out)[i]
+__device__ __forceinline__ float fwd_coord(float s, float t, int i, int n_out, int n_src) {
+  const float S = ((float)n_src - 1.0f) * 0.5f;
+  const float uS = __fmul_rn(linspace_pm1(i, n_out), S);
+  return __fadd_rn(__fadd_rn(__fmul_rn(s, uS), __fmul_rn(t, S)), S);
+}
+
+// AffineGridWarper.inverse() for the no-shear case (a = sx, d = sy, b = c = 0):
+//   det = sx * sy; a' = sy / det; d' = sx / det; tx' = a' * tx; ty' = d' * ty
+//   x_g = a' * (U * S_w) + (-tx') * S_w + S_w   (U = linspace(-1, 1, W) over canvas columns), y likewise.
+struct InvWarp {
+  float ax, bx;   // x_g = ax * US + bx_term ... kept as the three operands to preserve rounding order
+  float ay, by;
+};
+__device__ __forceinline__ void inv_params(float sx, float tx, float sy, float ty, float& a_inv, float& d_inv,
+                                           float& ntx, float& nty) {
+  const float det = __fmul_rn(sx, sy);
+  a_inv = __fdiv_rn(sy, det);
+  d_inv = __fdiv_rn(sx, det);
+  ntx = -__fmul_rn(a_inv, tx);
+  nty = -__fmul_rn(d_inv, ty);
+}
+__device__ __forceinline__ float inv_coord(float a_inv, float nt, int i, int n_canvas, int n_glimpse) {
+  const float S = ((float)n_glimpse - 1.0f) * 0.5f;
+  const float US = __fmul_rn(linspace_pm1(i, n_canvas), S);
+  return __fadd_rn(__fadd_rn(__fmul_rn(a_inv, US), __fmul_rn(nt, S)), S);
+}
+
+}  // namespace air

@@ -1,0 +1,297 @@
+"""Engine: one air_handle (libair_b200.so) + the caller-owned output buffers of the fused forward pass.
+
+This is the only place where the Python layer talks to the hot-path entry points of the C ABI
+(air_create / air_forward / air_forward_host / air_cell_step / air_destroy).  torch provides device memory and the
+stream; nothing is computed in torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AIR_MAX_HIDDEN, AIR_MAX_STEPS, AIR_N_SCALARS, SCALAR_INDEX, air_config, air_outputs, air_prior
+from ._lib import check, current_stream_ptr, ptr
+
+
+@dataclass
+class CellConfig:
+    """Hyper-parameters of the path; defaults = scripts/multi_mnist.py:24-94 + mnist_model.py:13-44."""
+    H: int = 50
+    W: int = 50
+    h: int = 20
+    w: int = 20
+    na: int = 50
+    nh: int = 256
+    enc_hidden: Sequence[int] = (256, 256)
+    glenc_hidden: Sequence[int] = (256, 256)
+    dec_hidden: Sequence[int] = (256, 256)
+    where_hidden: Sequence[int] = (256, 256)
+    steps_hidden: Sequence[int] = (128, 64)
+    output_std: float = 0.3
+    output_multiplier: float = 0.5
+    explore_eps: Optional[float] = 1e-3
+    scale_bias: float = 0.5
+    step_bias: float = 0.75
+    what_scale_offset: float = 0.5
+    forget_bias: float = 1.0
+    max_crop_size: float = 1.0
+    discrete_steps: bool = True
+    precision: int = _lib.AIR_PREC_FP32
+
+    @property
+    def P(self):
+        return self.H * self.W
+
+    @property
+    def G(self):
+        return self.h * self.w
+
+
+def param_spec(cfg: CellConfig) -> List[Tuple[str, Tuple[int, int]]]:
+    """Canonical flat parameter layout (the Sonnet variables of cell.py:61-69 in creation order); weights [in, out]
+    row-major like snt.Linear.  Must equal the table the C library reports (checked in Engine.__init__)."""
+    spec: List[Tuple[str, Tuple[int, int]]] = []
+
+    def mlp(prefix, n_in, hidden, n_out=None):
+        d = n_in
+        for i, n in enumerate(hidden):
+            spec.append((f"{prefix}.{i}.w", (d, n)))
+            spec.append((f"{prefix}.{i}.b", (1, n)))
+            d = n
+        if n_out is not None:
+            spec.append((f"{prefix}.out.w", (d, n_out)))
+            spec.append((f"{prefix}.out.b", (1, n_out)))
+        return d
+
+    n_enc = mlp("input_encoder", cfg.P, cfg.enc_hidden)
+    spec.append(("lstm.w", (n_enc + cfg.nh, 4 * cfg.nh)))
+    spec.append(("lstm.b", (1, 4 * cfg.nh)))
+    spec.append(("lstm.h0", (1, cfg.nh)))
+    spec.append(("lstm.c0", (1, cfg.nh)))
+    mlp("transform_estimator", cfg.nh, cfg.where_hidden, 8)
+    mlp("steps_predictor", cfg.nh, cfg.steps_hidden, 1)
+    n_gl = mlp("glimpse_encoder", cfg.G, cfg.glenc_hidden)
+    spec.append(("what.w", (n_gl, 2 * cfg.na)))
+    spec.append(("what.b", (1, 2 * cfg.na)))
+    mlp("glimpse_decoder", cfg.na, cfg.dec_hidden, cfg.G)
+    return spec
+
+
+def param_count(cfg: CellConfig) -> int:
+    return sum(r * c for _, (r, c) in param_spec(cfg))
+
+
+def make_views(spec, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+    views, off = {}, 0
+    for name, (r, c) in spec:
+        n = r * c
+        v = flat[off:off + n]
+        views[name] = v.view(c) if (r == 1 and not name.endswith(".w")) else v.view(r, c)
+        off += n
+    assert off == flat.numel()
+    return views
+
+
+def _fill_hidden(dst, src):
+    src = list(src)
+    if not (1 <= len(src) <= AIR_MAX_HIDDEN):
+        raise _lib.AirError(f"an MLP needs 1..{AIR_MAX_HIDDEN} hidden layers, got {len(src)}")
+    for i, v in enumerate(src):
+        dst[i] = int(v)
+    return len(src)
+
+
+def make_prior(what_prior=None, where_scale_prior=None, where_shift_prior=None, steps_success_prob=0.5,
+               steps_prob_is_f64=True, steps_weight=1.0, analytic=True, use_prior=True, use_reinforce=True) -> air_prior:
+    """Pack the AttrDict-style priors of AIRModel.train_step (model.py:261-265) into the C struct."""
+    def get(d, k, default):
+        if d is None:
+            return default
+        if isinstance(d, dict):
+            return d.get(k, default)
+        return getattr(d, k, default)
+
+    p = air_prior()
+    p.what_loc = float(get(what_prior, "loc", 0.0))
+    p.what_scale = float(get(what_prior, "scale", 1.0))
+    p.where_scale_loc = float(get(where_scale_prior, "loc", 0.0))
+    p.where_scale_scale = float(get(where_scale_prior, "scale", 1.0))
+    shift_loc = get(where_shift_prior, "loc", None)
+    p.where_shift_has_loc = int(shift_loc is not None)
+    p.where_shift_loc = float(shift_loc if shift_loc is not None else 0.0)
+    p.where_shift_scale = float(get(where_shift_prior, "scale", 1.0))
+    p.steps_success_prob = float(steps_success_prob)
+    p.steps_prob_is_f64 = int(bool(steps_prob_is_f64))
+    p.steps_weight = float(steps_weight)
+    p.analytic = int(bool(analytic))
+    p.use_prior = int(bool(use_prior))
+    p.use_reinforce = int(bool(use_reinforce))
+    return p
+
+
+class Engine:
+    """Owns an air_handle for (cfg, B, T) on one device and the output tensors of the fused call."""
+
+    CELL_OUTPUTS = "canvas glimpse what what_loc what_scale where where_loc where_scale presence_prob presence".split()
+
+    def __init__(self, cfg: CellConfig, B: int, T: int, device=None, materialise_canvas=True, materialise_viz=True):
+        if not torch.cuda.is_available():
+            raise _lib.AirError("no CUDA device: the AIR hot path has no CPU fallback")
+        self.cfg, self.B, self.T = cfg, int(B), int(T)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = _lib.lib()
+        c = air_config()
+        c.B, c.H, c.W, c.h, c.w, c.T, c.na, c.nh = self.B, cfg.H, cfg.W, cfg.h, cfg.w, self.T, cfg.na, cfg.nh
+        c.n_enc_hidden = _fill_hidden(c.enc_hidden, cfg.enc_hidden)
+        c.n_glenc_hidden = _fill_hidden(c.glenc_hidden, cfg.glenc_hidden)
+        c.n_dec_hidden = _fill_hidden(c.dec_hidden, cfg.dec_hidden)
+        c.n_where_hidden = _fill_hidden(c.where_hidden, cfg.where_hidden)
+        c.n_steps_hidden = _fill_hidden(c.steps_hidden, cfg.steps_hidden)
+        c.output_std = float(cfg.output_std)
+        c.output_multiplier = float(cfg.output_multiplier)
+        c.explore_eps = -1.0 if cfg.explore_eps is None else float(cfg.explore_eps)
+        c.scale_bias = float(cfg.scale_bias)
+        c.step_bias = float(cfg.step_bias)
+        c.what_scale_offset = float(cfg.what_scale_offset)
+        c.forget_bias = float(cfg.forget_bias)
+        c.max_crop_size = float(cfg.max_crop_size)
+        c.discrete_steps = int(bool(cfg.discrete_steps))
+        c.precision = int(cfg.precision)
+        self._c_cfg = c
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.air_create(C.byref(c), C.byref(self._handle)), "air_create")
+        # the C library's parameter table must be the layout the Python side assumes
+        spec = param_spec(cfg)
+        n = self.lib.air_param_entries(self._handle)
+        assert n == len(spec), (n, len(spec))
+        off = 0
+        for i, (name, (r, cc)) in enumerate(spec):
+            nm, o, rr, cl = C.c_char_p(), C.c_int64(), C.c_int32(), C.c_int32()
+            check(self.lib.air_param_entry(self._handle, i, C.byref(nm), C.byref(o), C.byref(rr), C.byref(cl)))
+            assert (nm.value.decode(), o.value, rr.value, cl.value) == (name, off, r, cc), (nm.value, name)
+            off += r * cc
+        self.n_params = int(self.lib.air_param_count(self._handle))
+        assert self.n_params == off
+        self._alloc_outputs(materialise_canvas, materialise_viz)
+
+    # ------------------------------------------------------------------------------------------
+    def _alloc_outputs(self, canvas: bool, viz: bool):
+        T, B, cfg, dev = self.T, self.B, self.cfg, self.device
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        o = {
+            "canvas": f(T, B, cfg.P) if canvas else None,
+            "glimpse": f(T, B, cfg.G),
+            "glimpse_viz": f(T, B, cfg.G) if viz else None,
+            "what": f(T, B, cfg.na), "what_loc": f(T, B, cfg.na), "what_scale": f(T, B, cfg.na),
+            "where": f(T, B, 4), "where_loc": f(T, B, 4), "where_scale": f(T, B, 4),
+            "presence_prob": f(T, B, 1), "presence": f(T, B, 1),
+            "final_h": f(B, cfg.nh), "final_c": f(B, cfg.nh),
+            "num_steps_posterior": f(B, T + 1), "num_step_per_sample": f(B), "prior_step_weight": f(T, B),
+            "rec_loss_per_sample": f(B), "kl_num_steps_per_sample": f(B), "kl_what_per_sample": f(B),
+            "kl_where_per_sample": f(B), "loss_per_sample": f(B), "num_steps_log_prob": f(B),
+            "scalars": torch.zeros(AIR_N_SCALARS, device=dev, dtype=torch.float32),
+        }
+        self.out = o
+        s = air_outputs()
+        for name in _lib.OUTPUT_FIELDS:
+            t = o[name]
+            setattr(s, name, None if t is None else t.data_ptr())
+        self._c_out = s
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.air_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.air_workspace_bytes(self._handle))
+
+    # ------------------------------------------------------------------------------------------
+    def _chk(self, t, shape, name):
+        if t is None:
+            return None
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.AirError(f"{name} must be a contiguous CUDA float32 tensor")
+        if int(np.prod(t.shape)) != int(np.prod(shape)):
+            raise _lib.AirError(f"{name} has {tuple(t.shape)}, expected {tuple(shape)}")
+        return t
+
+    def forward(self, params, img, eps_where, eps_what, u_pres, prior: Optional[air_prior] = None, baseline=None):
+        """T unrolled steps + ELBO terms: one air_forward enqueue on torch's current stream.  Returns self.out."""
+        T, B, cfg = self.T, self.B, self.cfg
+        self._chk(params, (self.n_params,), "params")
+        self._chk(img, (B, cfg.H, cfg.W), "img")
+        self._chk(eps_where, (T, B, 4), "eps_where")
+        self._chk(eps_what, (T, B, cfg.na), "eps_what")
+        self._chk(u_pres, (T, B, 1), "u_pres")
+        self._chk(baseline, (B,), "baseline")
+        with torch.cuda.device(self.device):
+            check(self.lib.air_forward(self._handle, ptr(params), ptr(img), ptr(eps_where), ptr(eps_what), ptr(u_pres),
+                                       ptr(baseline), C.byref(prior) if prior is not None else None,
+                                       C.byref(self._c_out), current_stream_ptr()), "air_forward")
+        return self.out
+
+    def forward_host(self, params, img_host, eps_where_host, eps_what_host, u_pres_host, prior: air_prior,
+                     scalars_host, loss_per_sample_host):
+        """End-to-end call with HOST inputs/outputs (H2D + forward + D2H + stream sync inside the C call)."""
+        for t in (img_host, eps_where_host, eps_what_host, u_pres_host, scalars_host, loss_per_sample_host):
+            assert t is not None and not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.air_forward_host(self._handle, ptr(params), ptr(img_host), ptr(eps_where_host),
+                                            ptr(eps_what_host), ptr(u_pres_host), C.byref(prior),
+                                            C.byref(self._c_out), ptr(scalars_host), ptr(loss_per_sample_host),
+                                            current_stream_ptr()), "air_forward_host")
+        return scalars_host, loss_per_sample_host
+
+    def elbo_scalars(self, baseline, prior: air_prior):
+        """Re-form the batch means with a baseline [B] (model.py:224-230,247-248)."""
+        self._chk(baseline, (self.B,), "baseline")
+        with torch.cuda.device(self.device):
+            check(self.lib.air_elbo_scalars(self._handle, ptr(baseline.contiguous()), C.byref(prior),
+                                            C.byref(self._c_out), current_stream_ptr()), "air_elbo_scalars")
+        return self.out["scalars"]
+
+    def cell_step(self, params, img, canvas, h, c, presence, eps_where, eps_what, u_pres):
+        """One AIRCell step (cell.py:116-171); canvas / h / c / presence are updated IN PLACE.  Returns the per-step
+        outputs glimpse, what, what_loc, what_scale, where, where_loc, where_scale, presence_prob."""
+        B, cfg, dev = self.B, self.cfg, self.device
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        o = dict(glimpse=f(B, cfg.G), what=f(B, cfg.na), what_loc=f(B, cfg.na), what_scale=f(B, cfg.na),
+                 where=f(B, 4), where_loc=f(B, 4), where_scale=f(B, 4), presence_prob=f(B, 1))
+        with torch.cuda.device(dev):
+            check(self.lib.air_cell_step(self._handle, ptr(params), ptr(img), ptr(canvas), ptr(h), ptr(c),
+                                         ptr(presence), ptr(eps_where), ptr(eps_what), ptr(u_pres),
+                                         ptr(o["glimpse"]), ptr(o["what"]), ptr(o["what_loc"]), ptr(o["what_scale"]),
+                                         ptr(o["where"]), ptr(o["where_loc"]), ptr(o["where_scale"]),
+                                         ptr(o["presence_prob"]), current_stream_ptr()), "air_cell_step")
+        return o
+
+    # -- instrumentation -------------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.air_launch_count(self._handle))
+
+    def profile(self, on: bool):
+        check(self.lib.air_profile_enable(self._handle, int(on)), "air_profile_enable")
+
+    def stage_times_ms(self) -> Dict[str, float]:
+        """Device time of each stage of the last forward (CUDA events on the launching stream)."""
+        buf = (C.c_float * _lib.AIR_N_STAGES)()
+        check(self.lib.air_profile_read(self._handle, buf, _lib.AIR_N_STAGES), "air_profile_read")
+        return {self.lib.air_stage_name(i).decode(): float(buf[i]) for i in range(_lib.AIR_N_STAGES)}
+
+    def scalar(self, name: str) -> torch.Tensor:
+        return self.out["scalars"][SCALAR_INDEX[name]]

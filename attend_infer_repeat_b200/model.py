@@ -1,0 +1,221 @@
+"""AIRModel -- mirror of the reference's model.py (model.py:15-376) over the fused CUDA path.
+
+The reference builds a TF graph once and evaluates it with sess.run; here the "graph" is one fused C-ABI enqueue
+(Engine.forward) whose caller-owned output buffers are exposed under the same attribute names
+(canvas, glimpse, what, ..., rec_loss, kl_what, loss, ...).  ``forward()`` plays the role of sess.run: it re-evaluates
+every attribute in place for a new batch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from . import functional as F
+from .cell import AIRCell
+from .engine import make_prior
+from .ops import Loss
+from .prior import NumStepsDistribution, geometric_prior
+
+
+class _Normal:
+    """Stand-in for tf.contrib.distributions.Normal(loc, scale) exposed as ``output_distrib`` (model.py:97)."""
+
+    def __init__(self, loc, scale):
+        self.loc, self.scale = loc, scale
+
+
+def _get(d, k, default=None):
+    if d is None:
+        return default
+    if isinstance(d, dict):
+        return d.get(k, default)
+    return getattr(d, k, default)
+
+
+class AIRModel:
+    """Generic AIR model"""
+
+    def __init__(self, obs, nums, max_steps, glimpse_size,
+                 n_appearance, transition, input_encoder, glimpse_encoder, glimpse_decoder, transform_estimator,
+                 steps_predictor,
+                 output_std=1., discrete_steps=True, output_multiplier=1.,
+                 explore_eps=None, debug=False, **kwargs):
+        """Arguments as in the reference (model.py:18-22).  ``obs`` [B,H,W] and ``nums`` [n_max+1,B,1] are CUDA tensors;
+        **kwargs go to AIRCell (here: precision=, device=, seed=, materialise_canvas=)."""
+        if not obs.is_cuda:
+            raise _lib.AirError("obs must live on a CUDA device (there is no CPU path)")
+        self.obs = obs.to(torch.float32).contiguous()
+        self.nums = nums
+        self.max_steps = int(max_steps)
+        self.glimpse_size = tuple(glimpse_size)
+        self.n_appearance = n_appearance
+        self.output_std = output_std
+        self.discrete_steps = discrete_steps
+        self.explore_eps = explore_eps
+        self.debug = debug
+        self.output_multiplier = output_multiplier
+        shape = list(self.obs.shape)
+        self.batch_size = shape[0]
+        self.img_size = shape[1:]
+        self._materialise_canvas = bool(kwargs.pop("materialise_canvas", True))
+        self._prior_struct = None
+        self._train_cfg = None
+        self.global_step = 0
+        self._build(transition, input_encoder, glimpse_encoder, glimpse_decoder, transform_estimator,
+                    steps_predictor, kwargs)
+
+    def _build(self, transition, input_encoder, glimpse_encoder, glimpse_decoder, transform_estimator,
+               steps_predictor, kwargs):
+        kwargs.setdefault("device", self.obs.device)
+        self.cell = AIRCell(self.img_size, self.glimpse_size, self.n_appearance, transition,
+                            input_encoder, glimpse_encoder, glimpse_decoder, transform_estimator, steps_predictor,
+                            canvas_init=None,
+                            discrete_steps=self.discrete_steps,
+                            explore_eps=self.explore_eps,
+                            debug=self.debug,
+                            output_std=self.output_std, output_multiplier=self.output_multiplier,
+                            **kwargs)
+        self.engine = self.cell.engine(self.batch_size, self.max_steps, materialise_canvas=self._materialise_canvas,
+                                       materialise_viz=self._materialise_canvas)
+        self.forward()
+
+    @property
+    def params(self):
+        return self.cell.params
+
+    # ------------------------------------------------------------------------------------------------------
+    def _current_prior(self):
+        tc = self._train_cfg
+        if tc is None:
+            return make_prior(steps_success_prob=0.5, steps_prob_is_f64=False)
+        nsp = tc["num_steps_prior"]
+        if _get(nsp, "anneal") is not None:
+            s = F.anneal_weight(_get(nsp, "init"), _get(nsp, "final"), _get(nsp, "anneal"), self.global_step,
+                                _get(nsp, "steps"), _get(nsp, "hold_init", 0.), _get(nsp, "steps_div", 1.))
+            is64 = True
+        else:
+            s, is64 = float(_get(nsp, "init")), False
+        self.steps_prior_success_prob = s
+        return make_prior(tc["what_prior"], tc["where_scale_prior"], tc["where_shift_prior"], s, is64,
+                          _get(nsp, "weight", 1.), _get(nsp, "analytic", True), bool(self.use_prior),
+                          tc["use_reinforce"])
+
+    def forward(self, obs=None, nums=None, noise=None):
+        """Re-evaluate the model on a batch (the sess.run of the reference): T fused cell steps + ELBO terms.
+        ``noise`` = (eps_where[T,B,4], eps_what[T,B,na], u_pres[T,B,1]); drawn on the device when omitted."""
+        if obs is not None:
+            assert tuple(obs.shape) == tuple(self.obs.shape)
+            self.obs = obs.to(torch.float32).contiguous()
+        if nums is not None:
+            self.nums = nums
+        T, B = self.max_steps, self.batch_size
+        if noise is None:
+            noise = self.cell.draw_noise(B, T)
+        eps_where, eps_what, u_pres = (n.contiguous() for n in noise)
+        self._prior_struct = self._current_prior()
+        o = self.engine.forward(self.cell.params, self.obs, eps_where, eps_what, u_pres, self._prior_struct)
+
+        # attributes named by AIRCell.output_names (model.py:86-87) and the post-processing of model.py:89-104
+        for name in self.cell.output_names:
+            setattr(self, name, o[name])
+        self.decoded_glimpse = o["glimpse"]
+        self.final_state = (o["final_h"], o["final_c"])
+        if o["glimpse_viz"] is not None:
+            self.glimpse = o["glimpse_viz"].view(T, B, *self.glimpse_size)
+        if o["canvas"] is not None:
+            self.canvas = o["canvas"].view(T, B, *self.img_size)
+            self.final_canvas = self.canvas[-1]
+            self.output_distrib = _Normal(self.final_canvas, self.output_std)
+        self.num_steps_distrib = NumStepsDistribution(o["presence_prob"].view(T, B).t(), joint=o["num_steps_posterior"])
+        self.num_step_per_sample = o["num_step_per_sample"]
+        self.num_step = self.engine.scalar("num_step")
+        if self.nums is not None:
+            self.gt_num_steps = self.nums.sum(0).reshape(-1)
+        if self._train_cfg is not None:
+            self._expose_losses(o)
+        return o
+
+    # ------------------------------------------------------------------------------------------------------
+    def _expose_losses(self, o):
+        """Attributes created by train_step / _prior_loss / _reinforce in the reference (model.py:143-372)."""
+        eng = self.engine
+        self.rec_loss_per_sample = o["rec_loss_per_sample"]
+        self.rec_loss = eng.scalar("rec_loss")
+        self.kl_num_steps_per_sample = o["kl_num_steps_per_sample"]
+        self.kl_num_steps = eng.scalar("kl_num_steps")
+        self.kl_what = eng.scalar("kl_what")
+        self.kl_where = eng.scalar("kl_where")
+        self.prior_step_weight = o["prior_step_weight"]
+        tc = self._train_cfg
+        sw = float(_get(tc["num_steps_prior"], "weight", 1.))
+        self.prior_loss = Loss()
+        self.prior_loss.add(self.kl_num_steps, self.kl_num_steps_per_sample, weight=sw)
+        self.prior_loss.add(self.kl_what, o["kl_what_per_sample"])
+        self.prior_loss.add(self.kl_where, o["kl_where_per_sample"])
+        self.prior_weight = float(bool(self.use_prior))
+        loss = Loss()
+        loss._value, loss._per_sample = eng.scalar("loss"), o["loss_per_sample"]
+        self.loss = loss
+        self.reinforce_imp_weight = self.rec_loss_per_sample
+        if tc["use_reinforce"]:
+            if not _get(tc["num_steps_prior"], "analytic", True):
+                self.reinforce_imp_weight = self.rec_loss_per_sample + self.prior_loss.per_sample
+            if self.baseline_module is not None:
+                b = self.baseline_module(self.obs, self.what, self.where, self.presence, self.final_state)
+                self.baseline = b                                                 # [B,1]
+                eng.elbo_scalars(b.reshape(-1), self._prior_struct)               # REINFORCE with the baseline mean
+                # [B] - [B,1] broadcasts to [B,B] in the reference; exposed as written, lazily
+                self.importance_weight = self.reinforce_imp_weight - b
+                self.baseline_loss = .5 * ((self.reinforce_imp_weight - b) ** 2).mean()
+            else:
+                self.importance_weight = self.reinforce_imp_weight
+            self.reinforce_loss = eng.scalar("reinforce_loss")
+        self.opt_loss = eng.scalar("opt_loss")
+        if self.nums is not None:
+            self.num_step_accuracy = (self.gt_num_steps == self.num_step_per_sample).to(torch.float32).mean()
+
+    def train_step(self, learning_rate, l2_weight=0., what_prior=None, where_scale_prior=None,
+                   where_shift_prior=None,
+                   num_steps_prior=None, use_prior=True,
+                   use_reinforce=True, baseline=None, decay_rate=None,
+                   optimizer=None, opt_kwargs=dict(momentum=.9, centered=True)):
+        """Creates the train step and the global_step (model.py:261-376).
+
+        Built so far: the whole loss side (rec / KL / REINFORCE terms, Loss bookkeeping, annealed step prior).  The
+        gradient + centered-RMSProp update is SURVEY 8(f) row 1 ("next") and is not built yet, so the returned
+        ``train_op`` evaluates forward + ELBO on a fresh batch and advances ``global_step`` (which drives the prior
+        annealing) but leaves the parameters untouched."""
+        if decay_rate is not None:
+            raise NotImplementedError("NVIL moving-average normalisation (decay_rate) is not built")
+        if l2_weight:
+            raise NotImplementedError("l2_weight > 0 only affects the optimiser, which is not built")
+        if num_steps_prior is None:
+            raise ValueError("num_steps_prior is required (model.py:292 dereferences it)")
+        self.l2_weight = l2_weight
+        self.what_prior, self.where_scale_prior = what_prior, where_scale_prior
+        self.where_shift_prior, self.num_steps_prior = where_shift_prior, num_steps_prior
+        if not hasattr(self, 'baseline'):
+            self.baseline = baseline
+        if getattr(self, "baseline_module", None) is None:
+            self.baseline_module = self.baseline if callable(self.baseline) else None
+        self.use_prior = use_prior
+        self.use_reinforce = use_reinforce
+        self.learning_rate = learning_rate
+        self._train_cfg = dict(what_prior=what_prior, where_scale_prior=where_scale_prior,
+                               where_shift_prior=where_shift_prior, num_steps_prior=num_steps_prior,
+                               use_reinforce=use_reinforce)
+        self.forward()
+
+        def train_op(obs=None, nums=None, noise=None):
+            out = self.forward(obs, nums, noise)
+            self.global_step += 1
+            return out
+
+        self._train_step = train_op
+        return self._train_step, lambda: self.global_step
+
+    def toggle_prior(self):
+        """use_prior.assign(not use_prior) (model.py:306-308)."""
+        self.use_prior = not self.use_prior

@@ -1,0 +1,250 @@
+/*
+ * air_b200.h -- C ABI of the B200-native AIR (Attend-Infer-Repeat) hot path.
+ *
+ * The reference (akosiorek/attend_infer_repeat) has no FFI of its own: its boundary is a Python
+ * class surface (AIRCell / AIRModel / NumStepsDistribution) on top of Sonnet's custom-op library
+ * (snt.resampler) and the TensorFlow kernels.  Every entry point below names the reference
+ * interface (file:line under /root/reference) that it replaces.  The Python mirror of the reference
+ * classes (attend_infer_repeat_b200/*.py) binds these symbols with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless the
+ *     parameter name ends in `_host`;
+ *   - all tensors are dense row-major float32 unless stated, time-major [T,B,...] like
+ *     tf.nn.dynamic_rnn(time_major=True) (model.py:83-84);
+ *   - every call enqueues on the caller's stream (`stream` is a cudaStream_t passed as void*) and
+ *     returns without synchronising unless the name ends in `_host`;
+ *   - return value: 0 = ok, negative = air_status; air_last_error() gives the message of the last
+ *     failure on the calling thread;
+ *   - the library never allocates persistent device memory except the workspace owned by an
+ *     air_handle (air_create .. air_destroy).
+ */
+#ifndef AIR_B200_H_
+#define AIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIR_ABI_VERSION 1
+#define AIR_MAX_HIDDEN 4   /* hidden layers per MLP (reference script uses 2) */
+#define AIR_MAX_STEPS 8    /* max_steps (reference script uses 3)            */
+
+typedef enum air_status {
+  AIR_OK = 0,
+  AIR_ERR_ARG = -1,       /* bad shape / null pointer / unsupported configuration */
+  AIR_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed          */
+  AIR_ERR_ARCH = -3,      /* device is not sm_100 (no other target is built)      */
+  AIR_ERR_NOMEM = -4,
+  AIR_ERR_RANGE = -5      /* tensor-core split path saw a value outside fp16 range */
+} air_status;
+
+typedef enum air_precision {
+  AIR_PREC_FP32 = 0,      /* fp32 FMA on CUDA cores: bit-faithful to an fp32 reference up to summation order */
+  AIR_PREC_TC_SPLIT = 1   /* tcgen05 fp16x2-split (3 MMAs / product), fp32-class accuracy on tensor cores    */
+} air_precision;
+
+/* Hyper-parameters of the path: AIRCell.__init__ (cell.py:15-69), AIRModel.__init__ (model.py:18-64),
+ * AIRonMNIST.__init__ (mnist_model.py:13-44), values in scripts/multi_mnist.py:24-94. */
+typedef struct air_config {
+  int32_t B;                 /* batch size (model.py:60)                                */
+  int32_t H, W;              /* image size (cell.py:38)                                 */
+  int32_t h, w;              /* glimpse / crop size (cell.py:40)                        */
+  int32_t T;                 /* max_steps (model.py:83)                                 */
+  int32_t na;                /* n_appearance (cell.py:41)                               */
+  int32_t nh;                /* LSTM units, snt.LSTM(256) (mnist_model.py:35)           */
+  int32_t n_enc_hidden;   int32_t enc_hidden[AIR_MAX_HIDDEN];    /* Encoder (input),  modules.py:66-76  */
+  int32_t n_glenc_hidden; int32_t glenc_hidden[AIR_MAX_HIDDEN];  /* Encoder (glimpse)                   */
+  int32_t n_dec_hidden;   int32_t dec_hidden[AIR_MAX_HIDDEN];    /* Decoder, modules.py:79-91           */
+  int32_t n_where_hidden; int32_t where_hidden[AIR_MAX_HIDDEN];  /* StochasticTransformParam, :53-63    */
+  int32_t n_steps_hidden; int32_t steps_hidden[AIR_MAX_HIDDEN];  /* StepsPredictor, :112-122            */
+  float output_std;          /* model.py:97 (mnist_model.py:42 -> .3)                   */
+  float output_multiplier;   /* model.py:58,93                                          */
+  float explore_eps;         /* cell.py:140-141; < 0 means None                         */
+  float scale_bias;          /* transform_var_bias, modules.py:54,63                    */
+  float step_bias;           /* modules.py:121                                          */
+  float what_scale_offset;   /* cell.py:66 (0.5)                                        */
+  float forget_bias;         /* snt.LSTM default 1.0                                    */
+  float max_crop_size;       /* modules.py:29                                           */
+  int32_t discrete_steps;    /* cell.py:143-151                                         */
+  int32_t precision;         /* air_precision                                           */
+} air_config;
+
+/* Priors and loss switches: AIRModel.train_step arguments (model.py:261-265) and the AttrDicts of
+ * scripts/multi_mnist.py:38-51.  The annealed success probability (model.py:106-124,133-142) is a
+ * scalar schedule: compute it with air_anneal_weight() and pass it in. */
+typedef struct air_prior {
+  float what_loc, what_scale;                 /* what_prior                               */
+  float where_scale_loc, where_scale_scale;   /* where_scale_prior                        */
+  float where_shift_loc, where_shift_scale;   /* where_shift_prior                        */
+  int32_t where_shift_has_loc;                /* 'loc' in where_shift_prior (model.py:202) */
+  double steps_success_prob;                  /* model.py:133-142                         */
+  int32_t steps_prob_is_f64;                  /* 1: annealed (float64 island); 0: python float -> float32 (prior.py:28) */
+  float steps_weight;                         /* num_steps_prior.weight (model.py:154)    */
+  int32_t analytic;                           /* num_steps_prior.analytic (model.py:157)  */
+  int32_t use_prior;                          /* prior_weight = float(use_prior), model.py:331 */
+  int32_t use_reinforce;                      /* model.py:335                             */
+} air_prior;
+
+/* Caller-owned output buffers of one unrolled forward pass (+ ELBO terms).  A NULL pointer means
+ * "do not materialise" for the optional ones (marked opt).
+ * Names follow AIRCell.output_names (cell.py:97-99) and the AIRModel attributes (model.py:86-104,
+ * 143-372). */
+typedef struct air_outputs {
+  /* AIRCell outputs stacked time-major by dynamic_rnn (model.py:84-87) */
+  float* canvas;            /* opt [T,B,H*W]  canvas * output_multiplier (model.py:92-93)          */
+  float* glimpse;           /*     [T,B,h*w]  raw decoder output (cell output "glimpse")            */
+  float* glimpse_viz;       /* opt [T,B,h*w]  presence * sigmoid(glimpse) (model.py:90)             */
+  float* what;              /*     [T,B,na]                                                         */
+  float* what_loc;          /*     [T,B,na]                                                         */
+  float* what_scale;        /*     [T,B,na]                                                         */
+  float* where;             /*     [T,B,4]   (sx,tx,sy,ty), modules.py:42                           */
+  float* where_loc;         /*     [T,B,4]                                                          */
+  float* where_scale;       /*     [T,B,4]                                                          */
+  float* presence_prob;     /*     [T,B,1]                                                          */
+  float* presence;          /*     [T,B,1]                                                          */
+  float* final_h;           /*     [B,nh]    final_state (model.py:89)                              */
+  float* final_c;           /*     [B,nh]                                                           */
+  /* NumStepsDistribution + ELBO terms (prior.py:119-151, model.py:126-251,319-343) */
+  float* num_steps_posterior;     /* [B,T+1] num_steps_distrib.prob()                               */
+  float* num_step_per_sample;     /* [B]     model.py:102                                           */
+  float* prior_step_weight;       /* [T,B]   model.py:157-165                                       */
+  float* rec_loss_per_sample;     /* [B]     model.py:320-321                                       */
+  float* kl_num_steps_per_sample; /* [B]     model.py:149                                           */
+  float* kl_what_per_sample;      /* [B]     model.py:181-182                                       */
+  float* kl_where_per_sample;     /* [B]     model.py:209-210                                       */
+  float* loss_per_sample;         /* [B]     loss.per_sample (ops.py:12-29)                         */
+  float* num_steps_log_prob;      /* [B]     num_steps_distrib.log_prob(num_step_per_sample)        */
+  float* scalars;                 /* [AIR_N_SCALARS] batch SUMS /B, see air_scalar                  */
+} air_outputs;
+
+typedef enum air_scalar {
+  AIR_S_REC_LOSS = 0,        /* model.py:322                                   */
+  AIR_S_KL_NUM_STEPS = 1,    /* model.py:151                                   */
+  AIR_S_KL_WHAT = 2,         /* model.py:184                                   */
+  AIR_S_KL_WHERE = 3,        /* model.py:212                                   */
+  AIR_S_PRIOR_LOSS = 4,      /* prior_loss.value                               */
+  AIR_S_LOSS = 5,            /* loss.value ; ELBO = -loss.value                */
+  AIR_S_REINFORCE = 6,       /* model.py:247-248 (0 if !use_reinforce)         */
+  AIR_S_OPT_LOSS = 7,        /* model.py:335-343 (without L2)                  */
+  AIR_S_NUM_STEP = 8,        /* model.py:103                                   */
+  AIR_S_MEAN_REC_LOGQ = 9,   /* mean_j rec_j * log q(n_j)   (REINFORCE pieces) */
+  AIR_S_MEAN_LOGQ = 10,      /* mean_j log q(n_j)                              */
+  AIR_S_MEAN_BASELINE = 11,  /* mean_i baseline_i                              */
+  AIR_N_SCALARS = 16
+} air_scalar;
+
+typedef struct air_handle air_handle;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int32_t air_abi_version(void);
+const char* air_last_error(void);
+
+/* ---- handle: replaces graph construction in AIRCell.__init__ / AIRModel._build (cell.py:15-69,
+ *      model.py:66-104).  Allocates the activation workspace for cfg->B samples on the current device. */
+int32_t air_create(const air_config* cfg, air_handle** out);
+int32_t air_destroy(air_handle* h);
+/* number of float32 parameters and the canonical flat layout (name, offset, rows, cols) -- the
+ * variables Sonnet would create for the modules of cell.py:61-69. */
+int64_t air_param_count(const air_handle* h);
+int32_t air_param_entries(const air_handle* h);
+int32_t air_param_entry(const air_handle* h, int32_t i, const char** name, int64_t* offset,
+                        int32_t* rows, int32_t* cols);
+int64_t air_workspace_bytes(const air_handle* h);
+
+/* ---- instrumentation (bench.py): kernels launched so far through this handle, and per-stage device
+ *      time of the LAST air_forward measured with CUDA events on the caller's stream. */
+typedef enum air_stage {
+  AIR_ST_ENCODER = 0,     /* input Encoder GEMMs (cell.py:125)                       */
+  AIR_ST_LSTM = 1,        /* gx GEMM + T x (recurrent GEMM + gate math) (cell.py:126) */
+  AIR_ST_WHERE_MLP = 2,   /* transform-estimator GEMMs (cell.py:129)                 */
+  AIR_ST_STEPS = 3,       /* steps-predictor GEMMs + presence scan (cell.py:137-151) */
+  AIR_ST_READ = 4,        /* where sampling + STN glimpse read (cell.py:130-135)     */
+  AIR_ST_GLIMPSE_ENC = 5, /* glimpse Encoder + what head (cell.py:153-156)           */
+  AIR_ST_DECODER = 6,     /* Decoder GEMMs (cell.py:158)                             */
+  AIR_ST_PAINT_ELBO = 7,  /* inverse STN paint + ELBO terms + batch means            */
+  AIR_N_STAGES = 8
+} air_stage;
+int64_t air_launch_count(const air_handle* h);
+int32_t air_profile_enable(air_handle* h, int32_t on);
+int32_t air_profile_read(air_handle* h, float* ms_per_stage, int32_t n);
+const char* air_stage_name(int32_t i);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+/* T unrolled AIRCell steps + post-processing + ELBO terms in one enqueue:
+ * tf.nn.dynamic_rnn over AIRCell._build (model.py:81-104, cell.py:116-171) followed by the loss
+ * assembly of AIRModel.train_step (model.py:319-343), _prior_loss (126-216), _reinforce (218-251).
+ *   params     [air_param_count]   flat float32 parameters
+ *   img        [B,H,W]             obs
+ *   eps_where  [T,B,4]             N(0,1) draws of where_distrib.sample()    (cell.py:133)
+ *   eps_what   [T,B,na]            N(0,1) draws of what_distrib.sample()     (cell.py:156)
+ *   u_pres     [T,B,1]             U[0,1) draws of presence_distrib.sample() (cell.py:147)
+ *   baseline   [B] or NULL         BaselineMLP output (model.py:224-230)
+ *   prior      NULL -> only the cell outputs are produced (no ELBO terms) */
+int32_t air_forward(air_handle* h, const float* params, const float* img, const float* eps_where,
+                    const float* eps_what, const float* u_pres, const float* baseline,
+                    const air_prior* prior, const air_outputs* outs, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies img and the noise host->device, runs
+ * air_forward, copies `scalars` and the [B] ELBO vectors back and synchronises the stream.  `outs`
+ * still points at DEVICE buffers; the *_host arguments receive the copies (may be NULL).
+ * This is the end-to-end call a sess.run([loss...]) of the reference maps to (multi_mnist.py:136). */
+int32_t air_forward_host(air_handle* h, const float* params, const float* img_host,
+                         const float* eps_where_host, const float* eps_what_host,
+                         const float* u_pres_host, const air_prior* prior, const air_outputs* outs,
+                         float* scalars_host, float* loss_per_sample_host, void* stream);
+
+/* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
+ * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be
+ * known after the forward pass): AIRModel._reinforce, model.py:218-251. */
+int32_t air_elbo_scalars(air_handle* h, const float* baseline, const air_prior* prior,
+                         const air_outputs* outs, void* stream);
+
+/* One AIRCell step with explicit state, the RNNCore contract of cell.py:116-171:
+ * state = [img, canvas, what, where, (h, c), presence]; `canvas`, `h`, `c`, `presence` are updated
+ * in place; outputs (10 tensors of cell.py:167-168) are written as [B,.] (canvas NOT multiplied). */
+int32_t air_cell_step(air_handle* h, const float* params, const float* img, float* canvas,
+                      float* hstate, float* cstate, float* presence, const float* eps_where,
+                      const float* eps_what, const float* u_pres, float* out_glimpse, float* out_what,
+                      float* out_what_loc, float* out_what_scale, float* out_where,
+                      float* out_where_loc, float* out_where_scale, float* out_presence_prob,
+                      void* stream);
+
+/* ---- building blocks (stand-alone, for unit parity) -------------------------------------------- */
+/* snt.Linear + transfer (neural.py:42-60): out[M,N] = act(A[M,K] @ Wt[K,N] + bias[N]); act 0 none, 1 ELU */
+int32_t air_linear(const float* A, const float* Wt, const float* bias, float* out, int32_t M, int32_t N,
+                   int32_t K, int32_t act, int32_t precision, void* stream);
+/* snt.LSTM step (mnist_model.py:35): gates = [x,h] @ W[nx+nh,4nh] + b, order i,j,f,o; h,c updated in place */
+int32_t air_lstm_step(const float* x, float* hstate, float* cstate, const float* W, const float* b,
+                      int32_t B, int32_t nx, int32_t nh, float forget_bias, void* stream);
+/* SpatialTransformer (modules.py:94-109; cell.py:58,135): crop[B,h,w] from img[B,H,W], where[B,4] */
+int32_t air_stn_read(const float* img, const float* where, float* crop, int32_t B, int32_t H, int32_t W,
+                     int32_t h, int32_t w, void* stream);
+/* inverse SpatialTransformer (modules.py:100-102; cell.py:59,159): out[B,H,W] gathered from glimpse[B,h,w] */
+int32_t air_stn_paint(const float* glimpse, const float* where, float* out, int32_t B, int32_t H,
+                      int32_t W, int32_t h, int32_t w, void* stream);
+/* prior.py:62-68: probs[n,T] -> pmf[n,T+1] (float64 island inside) */
+int32_t air_bernoulli_to_modified_geometric(const float* probs, float* pmf, int64_t n, int32_t T,
+                                            void* stream);
+/* prior.py:26-32: prior[T+1]; is_f64 selects float64 (out is double*) or float32 (out is float*) maths */
+int32_t air_geometric_prior(double success_prob, int32_t n_steps, int32_t is_f64, void* out, void* stream);
+/* prior.py:71-90: kl[n,m] = float32(p * log(p / q)) where p > zero_prob_value else 0; q is [m] float64 */
+int32_t air_tabular_kl(const float* p, const double* q, float* kl, int64_t n, int32_t m,
+                       double zero_prob_value, void* stream);
+/* prior.py:103-116 sample_from_tensor: out[i] = pmf[i, int32(samples[i])] (flat gather; index clamped to [0, m-1]) */
+int32_t air_sample_from_tensor(const float* pmf, const float* samples, float* out, int64_t n, int32_t m,
+                               void* stream);
+/* prior.py:141-151: out[n] = log(max(pmf[i, int(samples[i])], 1e-32)) */
+int32_t air_num_steps_log_prob(const float* pmf, const float* samples, float* out, int64_t n, int32_t m,
+                               void* stream);
+/* model.py:106-124 (host scalar, float64): anneal_type 0 = 'exp', 1 = 'linear' */
+double air_anneal_weight(double init_val, double final_val, int32_t anneal_type, double global_step,
+                         double anneal_steps, double hold_for, double steps_div);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIR_B200_H_ */

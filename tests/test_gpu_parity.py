@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA library (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): absolute 1e-4 on O(1) outputs, relative 1e-4 on the ELBO sums, exact on
+presence / step counts / gather indices (with the near-tie rule of tests/util.py:presence_mismatches).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import attend_infer_repeat_b200 as air
+from attend_infer_repeat_b200 import functional as AF
+from oracle import air_oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _where(B, g, lo=0.2, hi=1.1):
+    sx = torch.rand(B, 1, generator=g) * (hi - lo) + lo
+    sy = torch.rand(B, 1, generator=g) * (hi - lo) + lo
+    tx = torch.rand(B, 1, generator=g) * 1.6 - 0.8
+    ty = torch.rand(B, 1, generator=g) * 1.6 - 0.8
+    return torch.cat([sx, tx, sy, ty], 1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,h,w", [(50, 50, 20, 20), (100, 100, 28, 28), (3, 3, 2, 2), (17, 31, 5, 9)])
+def test_stn_read(H, W, h, w):
+    g = torch.Generator().manual_seed(0)
+    B = 33
+    img = torch.rand(B, H, W, generator=g)
+    where = _where(B, g)
+    where[0] = torch.tensor([1., 0., 1., 0.])            # identity-sized crop
+    where[1] = torch.tensor([-0.7, 0.3, 0.5, -0.2])      # negative scale (mirrored), unconstrained after sampling
+    where[2] = torch.tensor([2.5, 0.9, 2.5, -0.9])       # mostly outside the image -> zero padding
+    where[3] = torch.tensor([1e-4, 0., 1e-4, 0.])        # degenerate: all samples in one cell
+    ref = O.stn_read(img, where, (h, w))
+    out = AF.stn_read(img.to(DEV), where.to(DEV), (h, w)).cpu()
+    U.assert_close(out, ref, atol=2e-6, rtol=1e-6, name="stn_read")
+
+
+@pytest.mark.parametrize("H,W,h,w", [(50, 50, 20, 20), (100, 100, 28, 28), (3, 3, 2, 2), (17, 31, 5, 9)])
+def test_stn_paint(H, W, h, w):
+    g = torch.Generator().manual_seed(1)
+    B = 33
+    gl = torch.randn(B, h, w, generator=g)
+    where = _where(B, g)
+    where[0] = torch.tensor([1., 0., 1., 0.])
+    where[1] = torch.tensor([-0.7, 0.3, 0.5, -0.2])
+    where[2] = torch.tensor([0.05, 0.9, 0.05, -0.9])     # tiny object near the border
+    where[3] = torch.tensor([0.0, 0.1, 0.5, 0.1])        # sx = 0 -> det = 0 -> inf/nan coords -> zeros (App. C5)
+    ref = O.stn_paint(gl, where, (H, W))
+    out = AF.stn_paint(gl.to(DEV), where.to(DEV), (H, W)).cpu()
+    assert torch.isfinite(out).all()
+    U.assert_close(out, ref, atol=1e-5, rtol=1e-5, name="stn_paint")
+
+
+def test_stn_identity_roundtrip():
+    img = torch.rand(5, 20, 20)
+    where = torch.tensor([[1., 0., 1., 0.]]).repeat(5, 1)
+    assert torch.allclose(AF.stn_read(img.to(DEV), where.to(DEV), (20, 20)).cpu(), img, atol=1e-5)
+    assert torch.allclose(AF.stn_paint(img.to(DEV), where.to(DEV), (20, 20)).cpu(), img, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,K,N,act", [(64, 2500, 256, 1), (192, 256, 8, 0), (130, 50, 256, 1), (7, 17, 1, 0),
+                                       (257, 400, 100, 0), (1, 3, 5, 1), (300, 256, 1024, 0)])
+def test_linear(M, K, N, act):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    ref = x @ w + b
+    if act:
+        ref = O.elu(ref)
+    out = AF.linear(x.to(DEV), w.to(DEV), b.to(DEV), act).cpu()
+    U.assert_close(out, ref, atol=2e-5, rtol=2e-5, name="linear")
+
+
+def test_lstm_step():
+    g = torch.Generator().manual_seed(3)
+    B, nx, nh = 37, 256, 256
+    x, h, c = torch.randn(B, nx, generator=g), torch.randn(B, nh, generator=g), torch.randn(B, nh, generator=g)
+    w = torch.randn(nx + nh, 4 * nh, generator=g) / math.sqrt(nx + nh)
+    b = 0.1 * torch.randn(4 * nh, generator=g)
+    h_ref, c_ref = O.lstm_step(x, h, c, w, b, 1.0)
+    h_out, c_out = AF.lstm_step(x.to(DEV), h.to(DEV), c.to(DEV), w.to(DEV), b.to(DEV), 1.0)
+    U.assert_close(h_out.cpu(), h_ref, atol=1e-5, name="lstm h")
+    U.assert_close(c_out.cpu(), c_ref, atol=1e-5, name="lstm c")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the unrolled forward pass + ELBO
+# ----------------------------------------------------------------------------------------------------------
+CELL_KEYS = ["glimpse", "what", "what_loc", "what_scale", "where", "where_loc", "where_scale", "presence_prob"]
+
+
+def _check_forward(ocfg, B, pc, seed=0, global_step=0, baseline=None, precision=air.AIR_PREC_FP32, atol=1e-4,
+                   weight_gain=1.0):
+    params, img, nums, noise = U.make_problem(ocfg, B, seed, weight_gain)
+    ref = O.forward(ocfg, pc, params, img, *noise, global_step=global_step, baseline=baseline)
+    out = U.run_cuda(ocfg, params, img, noise, pc, global_step, baseline, precision)
+    T = ocfg.T
+    for k in CELL_KEYS:
+        U.assert_close(out[k], ref["outs"][k], atol=atol, rtol=1e-4, name=k)
+    if ocfg.discrete_steps:
+        bad, unsafe = U.presence_mismatches(out["presence"], ref["outs"]["presence_prob"].reshape(T, B),
+                                            noise[2].reshape(T, B))
+        assert bad == 0, f"{bad} presence mismatches away from ties"
+        assert unsafe <= max(1, B * T // 1000)
+        same = (out["presence"].reshape(T, B) == ref["outs"]["presence"].reshape(T, B)).all(0)
+    else:
+        U.assert_close(out["presence"], ref["outs"]["presence"], atol=atol, name="presence")
+        same = torch.ones(B, dtype=torch.bool)
+    # canvas / losses only compared on samples whose discrete path agrees (all of them unless a near-tie flipped)
+    assert same.float().mean() > 0.995
+    canvas_ref = ref["canvas"].reshape(T, B, -1)
+    U.assert_close(out["canvas"][:, same], canvas_ref[:, same], atol=atol, rtol=1e-4, name="canvas")
+    U.assert_close(out["glimpse_viz"][:, same], ref["glimpse"].reshape(T, B, -1)[:, same], atol=atol, name="glimpse_viz")
+    U.assert_close(out["final_h"], ref["final_h"], atol=atol, name="final_h")
+    U.assert_close(out["final_c"], ref["final_c"], atol=atol, name="final_c")
+    U.assert_close(out["num_steps_posterior"], ref["num_steps_posterior"], atol=1e-5, rtol=1e-4, name="q(n)")
+    if ocfg.discrete_steps:
+        assert torch.equal(out["num_step_per_sample"][same], ref["num_step_per_sample"][same])
+    else:
+        U.assert_close(out["num_step_per_sample"], ref["num_step_per_sample"], atol=1e-5, name="num_step_per_sample")
+    U.assert_close(out["prior_step_weight"], ref["prior_step_weight"], atol=1e-5, rtol=1e-4, name="step weight")
+    for k_c, k_o in [("rec_loss_per_sample", "rec_loss_per_sample"), ("kl_num_steps_per_sample", "kl_num_steps_per_sample"),
+                     ("kl_what_per_sample", "kl_what_per_sample"), ("kl_where_per_sample", "kl_where_per_sample"),
+                     ("loss_per_sample", "loss_per_sample"), ("num_steps_log_prob", "num_steps_log_prob")]:
+        U.assert_close(out[k_c][same], ref[k_o][same], atol=1e-4, rtol=1e-4, name=k_c)
+    if bool(same.all()):
+        s = out["scalars"]
+        idx = air._lib.SCALAR_INDEX
+        for name, key in [("rec_loss", "rec_loss"), ("kl_num_steps", "kl_num_steps"), ("kl_what", "kl_what"),
+                          ("kl_where", "kl_where"), ("prior_loss", "prior_loss"), ("loss", "loss"),
+                          ("opt_loss", "opt_loss"), ("num_step", "num_step")]:
+            U.assert_close(s[idx[name]], ref[key].float(), atol=1e-4, rtol=1e-4, name="scalar " + name)
+        if pc.use_reinforce:
+            U.assert_close(s[idx["reinforce_loss"]], ref["reinforce_loss"].float(), atol=2e-4, rtol=2e-4,
+                           name="reinforce")
+        U.assert_close(-s[idx["loss"]], ref["elbo"].float(), atol=0, rtol=1e-4, name="ELBO")
+    return out, ref
+
+
+def test_forward_script_config_b64():
+    """BASELINE.json configs[0]: 50x50, T=3, B=64 -- annealed float64 step prior at a mid-anneal global step."""
+    _check_forward(U.oracle_cfg(**U.SCRIPT), 64, O.PriorConfig(), seed=0, global_step=20000)
+
+
+def test_forward_step0_prior_edge():
+    """global_step 0: success prob 1 - 1e-15 (not representable in fp32) -> float64 island matters."""
+    _check_forward(U.oracle_cfg(**U.SCRIPT), 32, O.PriorConfig(), seed=1, global_step=0)
+
+
+def test_forward_tiny_odd_shapes():
+    """Widths of test/cell_test.py (5/7/11/13/17 hidden units, 3x3 image, 2x2 crop): unaligned everything."""
+    _check_forward(U.oracle_cfg(**U.TINY), 10, O.PriorConfig(), seed=2, global_step=5000, weight_gain=2.0)
+
+
+def test_forward_config_d_small_batch():
+    """BASELINE.json configs[3] shapes (100x100 canvas, 28x28 glimpse, T=5) at a small batch."""
+    _check_forward(U.oracle_cfg(**U.CONFIG_D), 12, O.PriorConfig(), seed=3, global_step=30000)
+
+
+def test_forward_variants():
+    base = dict(U.SCRIPT)
+    # no explore eps, continuous steps, non-analytic weights, fixed float32 prior, shift prior without loc, no prior
+    _check_forward(U.oracle_cfg(explore_eps=None, **base), 16,
+                   O.PriorConfig(steps_anneal=None, steps_init=0.3, where_shift_loc=None), seed=4)
+    _check_forward(U.oracle_cfg(discrete_steps=False, **base), 16, O.PriorConfig(analytic=False, steps_weight=0.5),
+                   seed=5, global_step=50000)
+    _check_forward(U.oracle_cfg(**base), 16, O.PriorConfig(use_prior=False, use_reinforce=False,
+                                                             what_scale=2.0, where_scale_loc=0.5, where_shift_scale=0.7),
+                   seed=6, global_step=90000)
+
+
+def test_forward_with_baseline_bb_broadcast():
+    """REINFORCE with a [B,1] baseline: the reference's [B]-[B,1] -> [B,B] broadcast."""
+    B = 24
+    baseline = 50.0 * torch.randn(B, 1, generator=torch.Generator().manual_seed(9))
+    _check_forward(U.oracle_cfg(**U.SCRIPT), B, O.PriorConfig(), seed=7, global_step=15000, baseline=baseline)
+
+
+def test_forward_ragged_batch_sizes():
+    for B in (2, 3, 129):
+        _check_forward(U.oracle_cfg(**U.SCRIPT), B, O.PriorConfig(), seed=10 + B, global_step=12000)
+
+
+def test_forward_trained_like_weights():
+    """Larger weights push activations, softplus and the STN through their non-linear ranges."""
+    _check_forward(U.oracle_cfg(**U.SCRIPT), 48, O.PriorConfig(), seed=8, global_step=60000, weight_gain=2.5,
+                   atol=3e-4)
+
+
+def test_cell_step_chain_equals_unroll():
+    """AIRCell.__call__ T times (the RNNCore contract, cell.py:116-171) == the fused unroll == the oracle."""
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    B = 20
+    params, img, nums, noise = U.make_problem(ocfg, B, seed=11)
+    ref, _ = O.unroll(ocfg, params, img, *noise)
+    cell = air.AIRCell((ocfg.H, ocfg.W), (ocfg.h, ocfg.w), ocfg.na, air.LSTM(ocfg.nh),
+                       lambda: air.Encoder(ocfg.enc_hidden), lambda: air.Encoder(ocfg.glenc_hidden),
+                       lambda s: air.Decoder(ocfg.dec_hidden, s),
+                       lambda n: air.StochasticTransformParam(ocfg.where_hidden, n, scale_bias=ocfg.scale_bias),
+                       lambda: air.StepsPredictor(ocfg.steps_hidden, ocfg.step_bias),
+                       explore_eps=ocfg.explore_eps, device=DEV)
+    cell.params.copy_(O.flatten_params(ocfg, params).to(DEV))
+    state = cell.initial_state(img.to(DEV))
+    assert [tuple(s.shape) if torch.is_tensor(s) else tuple(tuple(x.shape) for x in s) for s in state] == \
+        [(B, 2500), (B, 2500), (B, 50), (B, 4), ((B, 256), (B, 256)), (B, 1)]
+    for t in range(ocfg.T):
+        outs, state = cell(None, state, noise=tuple(n[t].to(DEV) for n in noise))
+        assert len(outs) == 10 and len(state) == 6
+        for name, o in zip(cell.output_names, outs):
+            U.assert_close(o.cpu(), ref[name][t], atol=1e-4, name=f"step {t} {name}")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]: B = 4096)
+# ----------------------------------------------------------------------------------------------------------
+def test_full_size_batch_split_invariance_and_oracle_sample():
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    B = 4096
+    pc = O.PriorConfig()
+    params, img, nums, noise = U.make_problem(ocfg, B, seed=21)
+    full = U.run_cuda(ocfg, params, img, noise, pc, 20000)
+    # (1) samples are independent: the two halves run separately give bit-identical per-sample results
+    half = B // 2
+    for lo in (0, half):
+        part = U.run_cuda(ocfg, params, img[lo:lo + half], tuple(n[:, lo:lo + half].contiguous() for n in noise), pc, 20000)
+        for k in ("loss_per_sample", "rec_loss_per_sample", "num_step_per_sample", "kl_what_per_sample"):
+            assert torch.equal(part[k], full[k][lo:lo + half]), k
+        assert torch.equal(part["what"], full["what"][:, lo:lo + half])
+        assert torch.equal(part["canvas"], full["canvas"][:, lo:lo + half])
+    # (2) batch mean == mean of the per-sample vector
+    s = full["scalars"]
+    idx = air._lib.SCALAR_INDEX
+    assert abs(float(s[idx["loss"]]) - float(full["loss_per_sample"].double().mean())) < 1e-4 * abs(float(s[idx["loss"]]))
+    # (3) q(n) is a pmf; presence is monotone non-increasing in t and in {0,1}
+    assert torch.allclose(full["num_steps_posterior"].sum(1), torch.ones(B), atol=1e-6)
+    pres = full["presence"].reshape(ocfg.T, B)
+    assert ((pres == 0) | (pres == 1)).all() and (pres[1:] <= pres[:-1]).all()
+    assert torch.equal(full["num_step_per_sample"], pres.sum(0))
+    # (4) a strided sample of 64 canvases against the oracle
+    sel = torch.arange(0, B, 64)
+    ref = O.forward(ocfg, pc, params, img[sel], *(n[:, sel] for n in noise), global_step=20000)
+    U.assert_close(full["loss_per_sample"][sel], ref["loss_per_sample"], atol=0, rtol=1e-4, name="loss sample")
+    U.assert_close(full["what"][:, sel], ref["outs"]["what"], atol=1e-4, name="what sample")
+    assert torch.equal(full["num_step_per_sample"][sel], ref["num_step_per_sample"])
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the Python class surface (model.py / mnist_model.py / scripts/multi_mnist.py:82-100)
+# ----------------------------------------------------------------------------------------------------------
+def test_air_on_mnist_surface():
+    B, T = 32, 3
+    img, nums = O.synthetic_multi_mnist(B, 50, 50, seed=5)
+    x, y = img.to(DEV), nums.to(DEV)
+    n_hiddens = [256, 256]
+    model = air.AIRonMNIST(x, y, max_steps=T, explore_eps=1e-3, inpt_encoder_hidden=n_hiddens,
+                           glimpse_encoder_hidden=n_hiddens, glimpse_decoder_hidden=n_hiddens,
+                           transform_estimator_hidden=n_hiddens, steps_pred_hidden=[128, 64],
+                           baseline_hidden=[256, 128], transform_var_bias=.5, step_bias=.75, output_multiplier=.5)
+    assert model.params.numel() == 1782525
+    for name, shape in [("canvas", (T, B, 50, 50)), ("glimpse", (T, B, 20, 20)), ("what", (T, B, 50)),
+                        ("what_loc", (T, B, 50)), ("what_scale", (T, B, 50)), ("where", (T, B, 4)),
+                        ("where_loc", (T, B, 4)), ("where_scale", (T, B, 4)), ("presence_prob", (T, B, 1)),
+                        ("presence", (T, B, 1)), ("final_canvas", (B, 50, 50)), ("num_step_per_sample", (B,)),
+                        ("gt_num_steps", (B,))]:
+        assert tuple(getattr(model, name).shape) == shape, name
+    assert tuple(model.num_steps_distrib.prob().shape) == (B, T + 1)
+    num_steps_prior = dict(anneal='exp', init=1. - 1e-15, final=1e-7, steps_div=1e4, steps=1e5, hold_init=1e3)
+    pr = dict(loc=0., scale=1.)
+    train_op, global_step = model.train_step(1e-4, 0., pr, pr, pr, num_steps_prior)
+    noise = model.cell.draw_noise(B, T, generator=torch.Generator(device=DEV).manual_seed(3))
+    train_op(noise=noise)
+    assert global_step() == 1
+    # cross-check every exposed loss attribute against the oracle, with the model's own weights and its baseline
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    params = O.unflatten_params(ocfg, model.params.detach().cpu())
+    bl = model.baseline.detach().cpu()
+    ref = O.forward(ocfg, O.PriorConfig(), params, img, *(n.cpu() for n in noise), global_step=0, baseline=bl)
+    bview = {k.replace("baseline.", "baseline."): v.detach().cpu() for k, v in model.baseline_module.views.items()}
+    bl_ref = O.baseline_mlp(bview, 2, img, ref["outs"]["what"], ref["outs"]["where"], ref["outs"]["presence"],
+                            ref["final_h"], ref["final_c"])
+    U.assert_close(bl, bl_ref, atol=2e-4, rtol=1e-4, name="baseline")
+    for attr, key in [("rec_loss", "rec_loss"), ("kl_num_steps", "kl_num_steps"), ("kl_what", "kl_what"),
+                      ("kl_where", "kl_where"), ("reinforce_loss", "reinforce_loss"), ("opt_loss", "opt_loss")]:
+        U.assert_close(getattr(model, attr).cpu(), ref[key].float(), atol=2e-4, rtol=2e-4, name=attr)
+    U.assert_close(model.loss.value.cpu(), ref["loss"].float(), rtol=1e-4, name="loss.value")
+    U.assert_close(model.loss.per_sample.cpu(), ref["loss_per_sample"], rtol=1e-4, name="loss.per_sample")
+    U.assert_close(model.prior_loss.value.cpu(), ref["prior_loss"].float(), rtol=1e-4, name="prior_loss.value")
+    assert tuple(model.importance_weight.shape) == (B, B)
+    U.assert_close(model.importance_weight.cpu(), ref["importance_weight"], atol=1e-2, rtol=1e-4, name="imp weight")
+    assert 0.0 <= float(model.num_step_accuracy) <= 1.0
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(air.AirError):
+        AF.stn_read(torch.rand(1, 4, 4), torch.rand(1, 4), (2, 2))
+    with pytest.raises(air.AirError):
+        air.AIRonMNIST(torch.rand(2, 50, 50), None, max_steps=3)
+
+
+def test_bad_config_is_an_error():
+    with pytest.raises(air.AirError):
+        air.Engine(air.CellConfig(), 4, air._lib.AIR_MAX_STEPS + 1)
+    with pytest.raises(air.AirError):
+        air.Engine(air.CellConfig(output_std=0.0), 4, 3)

@@ -1,0 +1,119 @@
+"""CPU-side tests (no GPU needed): the C-ABI library builds, loads and exports every symbol include/air_b200.h
+declares; the Python mirror of the reference's class surface lowers to the configuration / parameter layout the oracle
+uses; host-only helpers (Loss, clip_preserve, anneal schedule, prior packing)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import attend_infer_repeat_b200 as air
+from attend_infer_repeat_b200 import _lib
+from oracle import air_oracle as O
+from tests import util as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    path = _lib.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "air_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(air_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    handle = ctypes.CDLL(path)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in air_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert _lib.lib().air_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # air_config: 8 ints + 5 * (1 + AIR_MAX_HIDDEN) ints + 8 floats + 2 ints ; all 4-byte fields -> no padding
+    assert ctypes.sizeof(_lib.air_config) == 4 * (8 + 5 * (1 + _lib.AIR_MAX_HIDDEN) + 8 + 2)
+    assert ctypes.sizeof(_lib.air_outputs) == 8 * len(_lib.OUTPUT_FIELDS)
+    # air_prior: 6 floats, int, (pad), double, int, float, 3 ints (+ tail pad) with 8-byte alignment
+    assert ctypes.sizeof(_lib.air_prior) == 64
+    assert _lib.air_prior.steps_success_prob.offset == 32
+
+
+def test_anneal_weight_matches_oracle():
+    for step in (0, 500, 1000, 1500, 20000, 101000, 500000):
+        a = air.functional.anneal_weight(1 - 1e-15, 1e-7, "exp", step, 1e5, 1e3, 1e4)
+        b = float(O.anneal_weight(1 - 1e-15, 1e-7, "exp", step, 1e5, 1e3, 1e4))
+        assert abs(a - b) <= 1e-15 * max(1.0, abs(b)) or abs(a - b) / abs(b) < 1e-12, (step, a, b)
+        a = air.functional.anneal_weight(0.9, 0.1, "linear", step, 1e5, 1e3, 1.0)
+        b = float(O.anneal_weight(0.9, 0.1, "linear", step, 1e5, 1e3, 1.0))
+        assert abs(a - b) < 1e-14
+    with pytest.raises(NotImplementedError):
+        air.functional.anneal_weight(1, 0, "cosine", 0, 1)
+
+
+def test_param_layout_matches_oracle():
+    for kw in (U.SCRIPT, U.CONFIG_D, U.TINY):
+        ocfg = U.oracle_cfg(**kw)
+        ccfg = U.cell_cfg(ocfg)
+        a = [(n, int(r * c)) for n, (r, c) in air.param_spec(ccfg)]
+        b = [(n, int(torch.tensor(s).prod())) for n, s in O.param_spec(ocfg)]
+        assert a == b
+    assert air.param_count(air.CellConfig()) == 1782525
+    assert air.param_count(U.cell_cfg(U.oracle_cfg(**U.CONFIG_D))) == 3899517
+
+
+def test_module_descriptors_lower_to_script_config():
+    """The factories of mnist_model.py:32-41 / multi_mnist.py:82-94 produce the configuration the fused path expects."""
+    from functools import partial
+    te = partial(air.StochasticTransformParam, [256, 256], scale_bias=.5)(4)
+    assert te._n_param == 8 and te._scale_bias == .5 and te._n_hidden == [256, 256]
+    assert air.Encoder(5)._n_hidden == [5]                         # test/cell_test.py passes ints
+    d = air.Decoder([256, 256], (20, 20))
+    assert d.mlp.output_size == 400
+    lstm = air.LSTM(256)
+    assert lstm.output_size[0] == 256 and lstm.state_size == (256, 256)
+    with pytest.raises(RuntimeError):
+        air.MLP([4])(torch.zeros(1, 4))                           # unbound module: no silent fallback
+
+
+def test_make_prior_packing():
+    p = air.make_prior(dict(loc=0.1, scale=2.0), dict(loc=0.2, scale=3.0), dict(scale=4.0), 0.25, True, 0.5, False,
+                       True, False)
+    assert (round(p.what_loc, 6), p.what_scale, p.where_shift_has_loc, p.where_shift_scale) == (0.1, 2.0, 0, 4.0)
+    assert (p.steps_success_prob, p.steps_prob_is_f64, p.steps_weight, p.analytic, p.use_prior, p.use_reinforce) == \
+        (0.25, 1, 0.5, 0, 1, 0)
+    p = air.make_prior(where_shift_prior=dict(loc=0.0, scale=1.0))
+    assert p.where_shift_has_loc == 1
+
+
+def test_loss_accumulator_and_clip_preserve():
+    l = air.Loss()
+    assert float(l.value) == 0.0
+    l.add(torch.tensor(2.0), torch.tensor([1.0, 3.0]))
+    inner = air.Loss()
+    inner.add(torch.tensor(1.0), torch.tensor([0.5, 1.5]), weight=2.0)
+    l.add(inner, weight=0.5)
+    assert float(l.value) == 3.0 and l.per_sample.tolist() == [1.5, 4.5]
+    with pytest.raises(AssertionError):
+        l.add(torch.tensor(1.0), torch.tensor([1.0, 2.0, 3.0]))    # ops.py:26 shape assert
+    x = torch.tensor([1e-40, 0.5], requires_grad=True)
+    y = air.clip_preserve(x, 1e-32, 1.0)
+    y.sum().backward()
+    assert y[0].item() == pytest.approx(1e-32) and x.grad.tolist() == [1.0, 1.0]
+
+
+def test_no_cuda_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(air.AirError):
+        air.Engine(air.CellConfig(), 4, 3)
+    with pytest.raises(air.AirError):
+        air.functional.stn_read(torch.rand(1, 4, 4), torch.rand(1, 4), (2, 2))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "attend_infer_repeat_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
