@@ -90,6 +90,7 @@ SYMBOLS = {
     "air_profile_enable": (C.c_int32, [_P, C.c_int32]),
     "air_profile_read": (C.c_int32, [_P, _P, C.c_int32]),
     "air_stage_name": (C.c_char_p, [C.c_int32]),
+    "air_check_range": (C.c_int32, [_P, _P]),
     "air_forward": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_forward_host": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P, _P,
                                      _P]),

@@ -11,18 +11,25 @@
 //   * the canvas accumulates in registers over t inside the paint kernel, which also produces every
 //     per-sample ELBO term; a last tiny kernel forms the batch means.
 // Every row's arithmetic is unchanged; only the batching differs.
+//
+// Two dense-layer engines share that data flow (air_config.precision):
+//   AIR_PREC_FP32     linear_simt.cuh  fp32 FMA, activations cross HBM as fp32 rows
+//   AIR_PREC_TC_SPLIT linear_tc.cuh    tcgen05 fp16x2-split MMAs, activations cross HBM as "hl" fp16 planes
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/air_b200.h"
 #include "cell_kernels.cuh"
 #include "common.cuh"
 #include "linear_simt.cuh"
+#include "linear_tc.cuh"
 
 namespace {
 
@@ -40,9 +47,12 @@ int32_t fail(air_status st, const std::string& msg) {
       return fail(AIR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
   } while (0)
 
+using air::tc::round_up;
+
 struct Layer {
-  int64_t w_off = 0, b_off = 0;
+  int64_t w_off = 0, b_off = -1;   // float offsets into the flat parameter buffer (b_off < 0: no bias)
   int K = 0, N = 0;
+  int tc = -1;                     // index into air_handle::tcw (prepared tensor-core weight) or -1
 };
 struct Mlp {
   std::vector<Layer> layers;   // hidden layers (ELU) followed by the optional linear output layer
@@ -54,6 +64,25 @@ struct ParamEntry {
   int rows, cols;
 };
 
+// One activation matrix in the representation(s) the active engine needs.
+struct Buf {
+  float* f32 = nullptr;   // fp32 rows (SIMT engine operands; final outputs of either engine)
+  int ld = 0;
+  __half* hl = nullptr;   // "hl" fp16 planes (tensor-core engine operands), see linear_tc.cuh
+  int rows_alloc = 0;     // rows per plane
+  int kpad = 0;           // row pitch in halves = round_up(width, 64)
+  size_t plane() const { return (size_t)rows_alloc * kpad; }
+  air::HlOut hl_out() const { return air::HlOut{hl, plane(), kpad}; }
+};
+
+// A weight matrix prepared for the tensor-core engine: W^T, fp16 split of (w * 2^8), [2][N_alloc][Kpad].
+struct TcWeight {
+  int64_t src_off = 0;
+  int K = 0, N = 0, Kpad = 0, N_alloc = 0, BN = 0;
+  int64_t arena_off = 0;   // halves
+  CUtensorMap tm;
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -61,21 +90,29 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct air_handle {
   air_config cfg;
   int P = 0, G = 0, n_enc = 0;
+  bool use_tc = false;
   std::vector<ParamEntry> entries;
   int64_t n_params = 0;
   Mlp enc, where_mlp, steps_mlp, glenc, dec;
-  Layer what_lin;
+  Layer what_lin, lstm_x, lstm_h;
   int64_t lstm_w = 0, lstm_b = 0, lstm_h0 = 0, lstm_c0 = 0;
   int max_width = 0;
   // workspace (one cudaMalloc)
   char* ws = nullptr;
   size_t ws_bytes = 0;
-  float *buf_a = nullptr, *buf_b = nullptr;   // ping-pong activations [T*B, max_width]
-  float *e = nullptr, *gx = nullptr, *gates = nullptr, *h_init = nullptr, *cbuf = nullptr, *hs = nullptr;
-  float *m = nullptr, *logit = nullptr, *crop = nullptr, *r = nullptr;
-  // staging for air_forward_host
-  float *st_img = nullptr, *st_eps_where = nullptr, *st_eps_what = nullptr, *st_u = nullptr;
-  float *st_pres_in = nullptr;
+  // activations
+  Buf ping, pong;                                  // hidden activations of the MLP chains [T*B, max_width]
+  Buf x, e, h_init, hs, crop, what_in;             // GEMM A operands produced by non-GEMM kernels (+ e)
+  float *gx = nullptr, *gates = nullptr, *cbuf = nullptr, *m = nullptr, *logit = nullptr, *r = nullptr;
+  // staging for air_forward_host / air_cell_step
+  float *st_img = nullptr, *st_eps_where = nullptr, *st_eps_what = nullptr, *st_u = nullptr, *st_pres_in = nullptr;
+  // tensor-core engine state
+  std::vector<TcWeight> tcw;
+  __half* arena = nullptr;
+  air::tc::PrepEntry* prep_table = nullptr;
+  int prep_tiles = 0;
+  int* range_flag = nullptr;
+  std::map<std::pair<const void*, int>, CUtensorMap> tmap_cache;
   // instrumentation: kernel-launch counter and optional per-stage CUDA-event timing (air_profile_*)
   uint64_t launches = 0;
   bool profile = false;
@@ -123,41 +160,100 @@ bool valid_hidden(const int32_t* v, int n) {
   return true;
 }
 
-// one dense layer; every GEMM of the path goes through here (engine selection + launch accounting)
-cudaError_t gemm(air_handle* h, const float* A, int lda, const float* Wt, int ldw, const float* bias,
-                 const float* addend, int ldadd, float* C, int ldc, int M, int N, int K, int act, cudaStream_t st) {
-  ++h->launches;
-  return air::launch_linear_simt(A, lda, Wt, ldw, bias, addend, ldadd, C, ldc, M, N, K, act, st);
-}
-
-cudaError_t linear(air_handle* h, const float* A, int lda, const float* params, const Layer& l,
-                   const float* addend, int ldadd, float* C, int ldc, int M, int act, cudaStream_t st) {
-  return gemm(h, A, lda, params + l.w_off, l.N, params + l.b_off, addend, ldadd, C, ldc, M, l.N, l.K, act, st);
-}
-
 inline void mark(air_handle* h, int stage, cudaStream_t st) {
   if (h->profile) cudaEventRecord(h->ev[stage], st);
 }
 
-// neural.MLP (neural.py:63-102): ELU hidden layers, linear output layer.  Intermediate activations ping-pong
-// between the two workspace buffers; the last layer writes `out`.
-cudaError_t run_mlp(air_handle* h, const float* params, const Mlp& mlp, const float* in, int ld_in, int M,
-                    float* out, int ld_out, cudaStream_t st) {
-  const float* cur = in;
-  int ld = ld_in;
+void register_tc_weight(air_handle* h, Layer& l, bool feeds_gemm) {
+  TcWeight w;
+  w.src_off = l.w_off;
+  w.K = l.K;
+  w.N = l.N;
+  w.Kpad = round_up(l.K, air::tc::BK);
+  w.BN = (l.N <= 32 && !feeds_gemm) ? 32 : 64;   // hl outputs (operands of a following GEMM) need the 64-wide tile
+  w.N_alloc = round_up(l.N, w.BN);
+  l.tc = (int)h->tcw.size();
+  h->tcw.push_back(w);
+}
+
+int32_t get_tmap_a(air_handle* h, const Buf& b, const CUtensorMap** out) {
+  const auto key = std::make_pair((const void*)b.hl, b.kpad);
+  auto it = h->tmap_cache.find(key);
+  if (it == h->tmap_cache.end()) {
+    CUtensorMap tm;
+    if (!air::tc::make_tmap(&tm, b.hl, b.kpad, 2 * (int64_t)b.rows_alloc, air::tc::BM))
+      return fail(AIR_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation buffer");
+    it = h->tmap_cache.emplace(key, tm).first;
+  }
+  *out = &it->second;
+  return AIR_OK;
+}
+
+// One dense layer: out = act(in[row0 : row0 + M] @ W + bias (+ addend)).  `want_f32` / `want_hl` select which
+// representation(s) of the result are materialised; every GEMM of the path goes through here.
+int32_t dense(air_handle* h, const float* params, const Buf& in, int row0, const Layer& l, bool use_bias,
+              const float* addend, int ldadd, const Buf& out, bool want_f32, bool want_hl, int M, int act,
+              cudaStream_t st) {
+  ++h->launches;
+  const float* bias = (use_bias && l.b_off >= 0) ? params + l.b_off : nullptr;
+  if (!h->use_tc) {
+    AIR_CUDA(air::launch_linear_simt(in.f32 + (size_t)row0 * in.ld, in.ld, params + l.w_off, l.N, bias, addend, ldadd,
+                                     out.f32, out.ld, M, l.N, l.K, act, st));
+    return AIR_OK;
+  }
+  const TcWeight& w = h->tcw[l.tc];
+  if (in.kpad != w.Kpad) return fail(AIR_ERR_ARG, "internal: operand pitch does not match the prepared weight");
+  const CUtensorMap* tm_a = nullptr;
+  const int32_t rc = get_tmap_a(h, in, &tm_a);
+  if (rc != AIR_OK) return rc;
+  air::tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.addend = addend;
+  p.ldadd = ldadd;
+  p.out_f32 = want_f32 ? out.f32 : nullptr;
+  p.ldc = out.ld;
+  p.out_hl = want_hl ? out.hl : nullptr;
+  p.hl_plane = out.plane();
+  p.ld_hl = out.kpad;
+  p.M = M;
+  p.N = l.N;
+  p.num_k_blocks = w.Kpad / air::tc::BK;
+  p.a_lo_row = in.rows_alloc;
+  p.a_row0 = row0;
+  p.b_lo_row = w.N_alloc;
+  p.act = act;
+  p.range_flag = h->range_flag;
+  if (want_hl && w.BN != 64) return fail(AIR_ERR_ARG, "internal: hl output needs a 64-wide tile");
+  AIR_CUDA(air::tc::launch_gemm(w.BN, *tm_a, w.tm, p, w.N_alloc, st));
+  return AIR_OK;
+}
+
+// neural.MLP (neural.py:63-102): ELU hidden layers, linear output layer.  Hidden activations ping-pong between the two
+// workspace buffers (fp32 rows or hl planes depending on the engine); the last layer writes `out`.
+int32_t run_mlp(air_handle* h, const float* params, const Mlp& mlp, const Buf& in, int M, const Buf& out,
+                bool out_f32, bool out_hl, cudaStream_t st) {
+  const Buf* cur = &in;
   const int nl = (int)mlp.layers.size();
   for (int i = 0; i < nl; ++i) {
     const Layer& l = mlp.layers[i];
     const bool last = (i == nl - 1);
-    float* dst = last ? out : ((cur == h->buf_a) ? h->buf_b : h->buf_a);
-    const int ldd = last ? ld_out : l.N;
+    Buf dst = last ? out : ((cur == &h->ping) ? h->pong : h->ping);
+    if (!last) {
+      dst.ld = l.N;
+      dst.kpad = round_up(l.N, air::tc::BK);
+    }
     const int act = (i < mlp.n_hidden) ? air::ACT_ELU : air::ACT_NONE;
-    cudaError_t e = linear(h, cur, ld, params, l, nullptr, 0, dst, ldd, M, act, st);
-    if (e != cudaSuccess) return e;
-    cur = dst;
-    ld = ldd;
+    const int32_t rc = dense(h, params, *cur, 0, l, true, nullptr, 0, dst, last ? out_f32 : !h->use_tc,
+                             last ? out_hl : h->use_tc, M, act, st);
+    if (rc != AIR_OK) return rc;
+    if (!last) {
+      Buf* slot = (cur == &h->ping) ? &h->pong : &h->ping;
+      *slot = dst;
+      cur = slot;
+    }
   }
-  return cudaSuccess;
+  return AIR_OK;
 }
 
 int32_t check_outs(const air_outputs* o, bool need_elbo) {
@@ -182,47 +278,89 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   const int B = c.B, nh = c.nh, P = h->P, G = h->G, na = c.na;
   const int TB = T_run * B;
   const int thr = 256;
+  const bool tc = h->use_tc;
+  const air::HlOut no_hl{nullptr, 0, 0};
+  int32_t rc;
+
+  // 0. tensor-core engine: (re)build the fp16-split W^T arena from the current parameters and split the images
+  mark(h, AIR_ST_ENCODER, st);
+  Buf x = h->x;
+  x.f32 = const_cast<float*>(img);
+  x.ld = P;
+  if (tc) {
+    air::tc::prep_weights_kernel<<<h->prep_tiles, 256, 0, st>>>(params, h->arena, h->prep_table, (int)h->tcw.size(),
+                                                                h->range_flag);
+    AIR_CUDA(cudaGetLastError());
+    const size_t n4 = (size_t)B * ((P + 3) / 4);
+    air::tc::split_rows_kernel<<<(unsigned)((n4 + thr - 1) / thr), thr, 0, st>>>(img, P, x.hl, x.plane(), x.kpad, B, P,
+                                                                                h->range_flag);
+    AIR_CUDA(cudaGetLastError());
+    h->launches += 2;
+  }
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
-  mark(h, AIR_ST_ENCODER, st);
-  AIR_CUDA(run_mlp(h, params, h->enc, img, P, B, h->e, h->n_enc, st));
+  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc, tc, st)) != AIR_OK) return rc;
   mark(h, AIR_ST_LSTM, st);
 
   // 2. gx = e @ W[:n_enc] + b   (input half of snt.LSTM's [x,h] @ W + b)
-  AIR_CUDA(gemm(h, h->e, h->n_enc, params + h->lstm_w, 4 * nh, params + h->lstm_b, nullptr, 0, h->gx, 4 * nh, B, 4 * nh,
-                h->n_enc, air::ACT_NONE, st));
+  Buf gx;
+  gx.f32 = h->gx;
+  gx.ld = 4 * nh;
+  if ((rc = dense(h, params, h->e, 0, h->lstm_x, true, nullptr, 0, gx, true, false, B, air::ACT_NONE, st)) != AIR_OK)
+    return rc;
 
   // 3. recurrence: gates = gx + h_{t-1} @ W[n_enc:]; (c, h_t) pointwise
   if (h_in) {
-    AIR_CUDA(cudaMemcpyAsync(h->h_init, h_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
+    AIR_CUDA(cudaMemcpyAsync(h->h_init.f32, h_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
     AIR_CUDA(cudaMemcpyAsync(h->cbuf, c_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
+    if (tc) {
+      air::split_state_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(h_in, B, nh, h->h_init.hl_out());
+      AIR_CUDA(cudaGetLastError());
+      ++h->launches;
+    }
   } else {
-    air::lstm_init_state_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(params + h->lstm_h0, params + h->lstm_c0,
-                                                                         h->h_init, h->cbuf, B, nh);
+    air::lstm_init_state_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(
+        params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, h->cbuf, B, nh, tc ? h->h_init.hl_out() : no_hl);
     AIR_CUDA(cudaGetLastError());
     ++h->launches;
   }
+  Buf gates;
+  gates.f32 = h->gates;
+  gates.ld = 4 * nh;
   for (int t = 0; t < T_run; ++t) {
-    const float* h_prev = (t == 0) ? h->h_init : h->hs + (size_t)(t - 1) * B * nh;
-    AIR_CUDA(gemm(h, h_prev, nh, params + h->lstm_w + (int64_t)h->n_enc * 4 * nh, 4 * nh, nullptr, h->gx, 4 * nh,
-                  h->gates, 4 * nh, B, 4 * nh, nh, air::ACT_NONE, st));
+    const Buf& h_prev = (t == 0) ? h->h_init : h->hs;
+    const int row0 = (t == 0) ? 0 : (t - 1) * B;
+    if ((rc = dense(h, params, h_prev, row0, h->lstm_h, false, h->gx, 4 * nh, gates, true, false, B, air::ACT_NONE,
+                    st)) != AIR_OK)
+      return rc;
+    air::HlOut hs_hl = no_hl;
+    if (tc) {
+      hs_hl = h->hs.hl_out();
+      hs_hl.p += (size_t)t * B * h->hs.kpad;
+    }
     air::lstm_pointwise_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(h->gates, h->cbuf,
-                                                                        h->hs + (size_t)t * B * nh, B, nh,
-                                                                        c.forget_bias);
+                                                                        h->hs.f32 + (size_t)t * B * nh, B, nh,
+                                                                        c.forget_bias, hs_hl);
     AIR_CUDA(cudaGetLastError());
     ++h->launches;
   }
   if (o->final_h)
-    AIR_CUDA(cudaMemcpyAsync(o->final_h, h->hs + (size_t)(T_run - 1) * B * nh, sizeof(float) * B * nh,
+    AIR_CUDA(cudaMemcpyAsync(o->final_h, h->hs.f32 + (size_t)(T_run - 1) * B * nh, sizeof(float) * B * nh,
                              cudaMemcpyDeviceToDevice, st));
   if (o->final_c)
     AIR_CUDA(cudaMemcpyAsync(o->final_c, h->cbuf, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
 
   // 4. heads over all T*B hidden states at once
   mark(h, AIR_ST_WHERE_MLP, st);
-  AIR_CUDA(run_mlp(h, params, h->where_mlp, h->hs, nh, TB, h->m, 8, st));          // modules.py:58-63
+  Buf m;
+  m.f32 = h->m;
+  m.ld = 8;
+  if ((rc = run_mlp(h, params, h->where_mlp, h->hs, TB, m, true, false, st)) != AIR_OK) return rc;   // modules.py:58-63
   mark(h, AIR_ST_STEPS, st);
-  AIR_CUDA(run_mlp(h, params, h->steps_mlp, h->hs, nh, TB, h->logit, 1, st));      // modules.py:119-122
+  Buf logit;
+  logit.f32 = h->logit;
+  logit.ld = 1;
+  if ((rc = run_mlp(h, params, h->steps_mlp, h->hs, TB, logit, true, false, st)) != AIR_OK) return rc;   // :119-122
   air::presence_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->logit, u_pres, presence_in, o->presence_prob, o->presence,
                                                         T_run, B, c.step_bias, c.explore_eps, c.discrete_steps);
   AIR_CUDA(cudaGetLastError());
@@ -230,33 +368,46 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   mark(h, AIR_ST_READ, st);
 
   // 5. where sampling + glimpse read   (cell.py:129-135)
-  air::where_read_kernel<<<B, 256, sizeof(float) * P, st>>>(h->m, eps_where, img, o->where, o->where_loc,
-                                                            o->where_scale, h->crop, T_run, B, c.H, c.W, c.h, c.w,
-                                                            c.max_crop_size, c.scale_bias);
+  air::where_read_kernel<<<B, 256, air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st>>>(h->m, eps_where, img, o->where, o->where_loc,
+                                                            o->where_scale, tc ? nullptr : h->crop.f32,
+                                                            tc ? h->crop.hl_out() : no_hl, T_run, B, c.H, c.W, c.h,
+                                                            c.w, c.max_crop_size, c.scale_bias);
   AIR_CUDA(cudaGetLastError());
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
   // 6. glimpse encoder -> what   (cell.py:153-156)
-  AIR_CUDA(run_mlp(h, params, h->glenc, h->crop, G, TB, (h->glenc.layers.size() & 1) ? h->buf_a : h->buf_b,
-                   h->glenc.layers.back().N, st));
   {
-    const float* q = (h->glenc.layers.size() & 1) ? h->buf_a : h->buf_b;
-    AIR_CUDA(linear(h, q, h->glenc.layers.back().N, params, h->what_lin, nullptr, 0, h->r, 2 * na, TB, air::ACT_NONE,
-                    st));
-  }
-  {
+    const Layer& last = h->glenc.layers.back();
+    Buf q = (h->glenc.layers.size() & 1) ? h->ping : h->pong;   // where the chain's last layer may land
+    q.ld = last.N;
+    q.kpad = round_up(last.N, air::tc::BK);
+    if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc, tc, st)) != AIR_OK) return rc;
+    Buf r;
+    r.f32 = h->r;
+    r.ld = 2 * na;
+    if ((rc = dense(h, params, q, 0, h->what_lin, true, nullptr, 0, r, true, false, TB, air::ACT_NONE, st)) != AIR_OK)
+      return rc;
     const size_t n = (size_t)TB * na;
     air::what_kernel<<<(unsigned)((n + thr - 1) / thr), thr, 0, st>>>(h->r, eps_what, o->what, o->what_loc,
                                                                       o->what_scale, (size_t)TB, na,
-                                                                      c.what_scale_offset);
+                                                                      c.what_scale_offset,
+                                                                      tc ? h->what_in.hl_out() : no_hl);
     AIR_CUDA(cudaGetLastError());
     ++h->launches;
   }
   mark(h, AIR_ST_DECODER, st);
 
   // 7. decoder   (cell.py:158)
-  AIR_CUDA(run_mlp(h, params, h->dec, o->what, na, TB, o->glimpse, G, st));
+  {
+    Buf what = h->what_in;
+    what.f32 = o->what;
+    what.ld = na;
+    Buf glimpse;
+    glimpse.f32 = o->glimpse;
+    glimpse.ld = G;
+    if ((rc = run_mlp(h, params, h->dec, what, TB, glimpse, true, false, st)) != AIR_OK) return rc;
+  }
   mark(h, AIR_ST_PAINT_ELBO, st);
 
   // 8. paint + ELBO   (cell.py:159-165, model.py:89-104,126-251,319-343)
@@ -287,10 +438,15 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   a.output_std = c.output_std;
   a.output_multiplier = mult;
   a.do_elbo = prior ? 1 : 0;
-  if (prior) a.prior = *prior;
-  const size_t smem = sizeof(float) * ((size_t)T_run * G + (size_t)T_run * (c.W + c.H));
-  air::paint_elbo_kernel<<<B, 256, smem, st>>>(a);
-  AIR_CUDA(cudaGetLastError());
+  if (prior) {
+    a.prior = *prior;
+    // geometric_prior(success_prob, T) (prior.py:26-32): one table for the whole batch, float64 or float32 island
+    for (int k = 0; k <= T_run; ++k)
+      a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
+                                                  : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
+  }
+  a.lp_const = (float)(0.5 * 1.8378770664093453 /* log(2 pi) */ + std::log((double)c.output_std));
+  AIR_CUDA(air::launch_paint_elbo(a, st));
   ++h->launches;
 
   if (prior) {
@@ -306,6 +462,74 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
 
 const char* const kStageNames[AIR_N_STAGES] = {"input_encoder", "lstm",        "where_mlp", "steps_presence",
                                                "where_read",    "glimpse_enc", "decoder",   "paint_elbo"};
+
+// carve a buffer out of the workspace (two passes: sizing with base == nullptr, then assignment)
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(char* b) : base(b) {}
+  template <class T>
+  T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(n * sizeof(T), 1024);
+    return p;
+  }
+};
+
+void carve_workspace(air_handle* h, Carver& cv) {
+  const air_config& c = h->cfg;
+  const size_t TB = (size_t)c.T * c.B, B = c.B;
+  const bool tc = h->use_tc;
+  const int B_alloc = round_up(c.B, air::tc::BM), TB_alloc = round_up((int)TB, air::tc::BM);
+  auto f32 = [&](Buf& b, size_t rows, int width) {
+    b.f32 = cv.take<float>(rows * width);
+    b.ld = width;
+  };
+  auto hl = [&](Buf& b, int rows_alloc, int width) {
+    b.rows_alloc = rows_alloc;
+    b.kpad = round_up(width, air::tc::BK);
+    b.hl = cv.take<__half>(2 * (size_t)rows_alloc * b.kpad);
+  };
+  // fp32 side
+  if (!tc) {
+    f32(h->ping, TB, h->max_width);
+    f32(h->pong, TB, h->max_width);
+    f32(h->e, B, h->n_enc);
+    f32(h->crop, TB, h->G);
+  }
+  f32(h->h_init, B, c.nh);
+  f32(h->hs, TB, c.nh);
+  h->gx = cv.take<float>(B * 4 * c.nh);
+  h->gates = cv.take<float>(B * 4 * c.nh);
+  h->cbuf = cv.take<float>(B * c.nh);
+  h->m = cv.take<float>(TB * 8);
+  h->logit = cv.take<float>(TB);
+  h->r = cv.take<float>(TB * 2 * c.na);
+  h->st_img = cv.take<float>(B * h->P);
+  h->st_eps_where = cv.take<float>(TB * 4);
+  h->st_eps_what = cv.take<float>(TB * c.na);
+  h->st_u = cv.take<float>(TB);
+  h->st_pres_in = cv.take<float>(B);
+  // tensor-core side
+  if (tc) {
+    hl(h->ping, TB_alloc, h->max_width);
+    hl(h->pong, TB_alloc, h->max_width);
+    hl(h->x, B_alloc, h->P);
+    hl(h->e, B_alloc, h->n_enc);
+    hl(h->h_init, B_alloc, c.nh);
+    hl(h->hs, TB_alloc, c.nh);
+    hl(h->crop, TB_alloc, h->G);
+    hl(h->what_in, TB_alloc, c.na);
+    size_t halves = 0;
+    for (TcWeight& w : h->tcw) {
+      w.arena_off = (int64_t)halves;
+      halves += align_up(2 * (size_t)w.N_alloc * w.Kpad, 512);
+    }
+    h->arena = cv.take<__half>(halves);
+    h->prep_table = cv.take<air::tc::PrepEntry>(h->tcw.size());
+    h->range_flag = cv.take<int>(1);
+  }
+}
 
 }  // namespace
 
@@ -342,12 +566,20 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
   h->cfg = c;
   h->P = c.H * c.W;
   h->G = c.h * c.w;
+  h->use_tc = c.precision == AIR_PREC_TC_SPLIT;
   // canonical flat parameter order == the Sonnet variables of cell.py:61-69 in creation order
   h->n_enc = build_mlp(h, h->enc, "input_encoder", h->P, c.enc_hidden, c.n_enc_hidden, 0);
   h->lstm_w = add_entry(h, "lstm.w", h->n_enc + c.nh, 4 * c.nh);
   h->lstm_b = add_entry(h, "lstm.b", 1, 4 * c.nh);
   h->lstm_h0 = add_entry(h, "lstm.h0", 1, c.nh);
   h->lstm_c0 = add_entry(h, "lstm.c0", 1, c.nh);
+  h->lstm_x.w_off = h->lstm_w;                                  // rows [0, n_enc) of lstm.w: the input half
+  h->lstm_x.b_off = h->lstm_b;
+  h->lstm_x.K = h->n_enc;
+  h->lstm_x.N = 4 * c.nh;
+  h->lstm_h.w_off = h->lstm_w + (int64_t)h->n_enc * 4 * c.nh;   // rows [n_enc, n_enc + nh): the recurrent half
+  h->lstm_h.K = c.nh;
+  h->lstm_h.N = 4 * c.nh;
   build_mlp(h, h->where_mlp, "transform_estimator", c.nh, c.where_hidden, c.n_where_hidden, 8);
   build_mlp(h, h->steps_mlp, "steps_predictor", c.nh, c.steps_hidden, c.n_steps_hidden, 1);
   const int n_gl = build_mlp(h, h->glenc, "glimpse_encoder", h->G, c.glenc_hidden, c.n_glenc_hidden, 0);
@@ -357,9 +589,24 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
   h->what_lin.b_off = add_entry(h, "what.b", 1, 2 * c.na);
   build_mlp(h, h->dec, "glimpse_decoder", c.na, c.dec_hidden, c.n_dec_hidden, h->G);
 
+  if (h->use_tc) {
+    if (!air::tc::get_encode_fn()) {
+      delete h;
+      return fail(AIR_ERR_CUDA, "air_create: cuTensorMapEncodeTiled is not available from the driver");
+    }
+    for (Mlp* mlp : {&h->enc, &h->where_mlp, &h->steps_mlp, &h->glenc, &h->dec}) {
+      const bool chain_feeds_gemm = (mlp == &h->enc || mlp == &h->glenc);   // their last layer is another GEMM's input
+      for (size_t i = 0; i < mlp->layers.size(); ++i)
+        register_tc_weight(h, mlp->layers[i], chain_feeds_gemm || i + 1 < mlp->layers.size());
+    }
+    register_tc_weight(h, h->lstm_x, false);
+    register_tc_weight(h, h->lstm_h, false);
+    register_tc_weight(h, h->what_lin, false);
+  }
+
   // shared-memory budgets of the per-canvas kernels
-  const size_t smem_read = sizeof(float) * h->P;
-  const size_t smem_paint = sizeof(float) * ((size_t)c.T * h->G + (size_t)c.T * (c.W + c.H));
+  const size_t smem_read = air::where_read_smem(c.T, c.H, c.W, c.h, c.w);
+  const size_t smem_paint = air::paint_smem(c.T, c.H, c.W, c.h, c.w);
   if (smem_read > 200 * 1024 || smem_paint > 200 * 1024) {
     delete h;
     return fail(AIR_ERR_ARG, "air_create: image / glimpse tile does not fit in shared memory");
@@ -368,32 +615,47 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
     cudaFuncSetAttribute(air::where_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
     cudaFuncSetAttribute(air::stn_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
   }
-  if (smem_paint > 48 * 1024)
-    cudaFuncSetAttribute(air::paint_elbo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_paint);
 
-  // workspace carve-up
-  const size_t TB = (size_t)c.T * c.B, B = c.B;
-  struct Slot { float** p; size_t n; };
-  const Slot slots[] = {
-      {&h->buf_a, TB * h->max_width}, {&h->buf_b, TB * h->max_width}, {&h->e, B * h->n_enc},
-      {&h->gx, B * 4 * c.nh},         {&h->gates, B * 4 * c.nh},      {&h->h_init, B * c.nh},
-      {&h->cbuf, B * c.nh},           {&h->hs, TB * c.nh},            {&h->m, TB * 8},
-      {&h->logit, TB},                {&h->crop, TB * h->G},          {&h->r, TB * 2 * c.na},
-      {&h->st_img, B * h->P},         {&h->st_eps_where, TB * 4},     {&h->st_eps_what, TB * c.na},
-      {&h->st_u, TB},                 {&h->st_pres_in, B},
-  };
-  size_t total = 0;
-  for (const Slot& s : slots) total += align_up(s.n * sizeof(float), 256);
-  cudaError_t e = cudaMalloc(&h->ws, total);
+  // workspace: size it, allocate once, carve it
+  Carver sizing(nullptr);
+  carve_workspace(h, sizing);
+  cudaError_t e = cudaMalloc(&h->ws, sizing.off);
   if (e != cudaSuccess) {
     delete h;
     return fail(AIR_ERR_NOMEM, std::string("air_create: cudaMalloc workspace: ") + cudaGetErrorString(e));
   }
-  h->ws_bytes = total;
-  size_t off = 0;
-  for (const Slot& s : slots) {
-    *s.p = reinterpret_cast<float*>(h->ws + off);
-    off += align_up(s.n * sizeof(float), 256);
+  h->ws_bytes = sizing.off;
+  Carver real(h->ws);
+  carve_workspace(h, real);
+  if (h->use_tc) {
+    // zero once: the K padding of every hl operand and the N padding of the weight arena must stay zero
+    e = cudaMemset(h->ws, 0, h->ws_bytes);
+    std::vector<air::tc::PrepEntry> table;
+    int tiles = 0;
+    bool ok = e == cudaSuccess;
+    for (TcWeight& w : h->tcw) {
+      air::tc::PrepEntry pe;
+      pe.src_off = w.src_off;
+      pe.dst_off = w.arena_off;
+      pe.plane = (int64_t)w.N_alloc * w.Kpad;
+      pe.K = w.K;
+      pe.N = w.N;
+      pe.Kpad = w.Kpad;
+      pe.tile_begin = tiles;
+      pe.tiles_n = (w.N + 31) / 32;
+      tiles += pe.tiles_n * ((w.K + 31) / 32);
+      table.push_back(pe);
+      ok = ok && air::tc::make_tmap(&w.tm, h->arena + w.arena_off, w.Kpad, 2 * (int64_t)w.N_alloc, w.BN);
+    }
+    h->prep_tiles = tiles;
+    if (ok)
+      ok = cudaMemcpy(h->prep_table, table.data(), sizeof(air::tc::PrepEntry) * table.size(),
+                      cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+      cudaFree(h->ws);
+      delete h;
+      return fail(AIR_ERR_CUDA, "air_create: tensor-core engine set-up failed (memset / tensor maps / table upload)");
+    }
   }
   *out = h;
   return AIR_OK;
@@ -441,6 +703,20 @@ int32_t air_profile_read(air_handle* h, float* ms_per_stage, int32_t n) {
 }
 
 const char* air_stage_name(int32_t i) { return (i >= 0 && i < AIR_N_STAGES) ? kStageNames[i] : ""; }
+
+int32_t air_check_range(air_handle* h, void* stream) {
+  if (!h) return fail(AIR_ERR_ARG, "air_check_range: NULL handle");
+  if (!h->use_tc) return AIR_OK;
+  int flag = 0;
+  AIR_CUDA(cudaMemcpyAsync(&flag, h->range_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  AIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag) {
+    AIR_CUDA(cudaMemsetAsync(h->range_flag, 0, sizeof(int), (cudaStream_t)stream));
+    return fail(AIR_ERR_RANGE, "a weight*2^8 or an activation exceeded the fp16 range (65504) in the tensor-core "
+                               "split engine; use AIR_PREC_FP32 for this model");
+  }
+  return AIR_OK;
+}
 
 int32_t air_forward(air_handle* h, const float* params, const float* img, const float* eps_where,
                     const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
@@ -522,9 +798,63 @@ int32_t air_cell_step(air_handle* h, const float* params, const float* img, floa
 
 int32_t air_linear(const float* A, const float* Wt, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
                    int32_t act, int32_t precision, void* stream) {
-  if (!A || !Wt || !out || M < 0 || N < 1 || K < 1) return fail(AIR_ERR_ARG, "air_linear: bad argument");
-  if (precision != AIR_PREC_FP32) return fail(AIR_ERR_ARG, "air_linear: only AIR_PREC_FP32 stand-alone");
-  AIR_CUDA(air::launch_linear_simt(A, K, Wt, N, bias, nullptr, 0, out, N, M, N, K, act, (cudaStream_t)stream));
+  if (!A || !Wt || !out || M < 1 || N < 1 || K < 1) return fail(AIR_ERR_ARG, "air_linear: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == AIR_PREC_FP32) {
+    AIR_CUDA(air::launch_linear_simt(A, K, Wt, N, bias, nullptr, 0, out, N, M, N, K, act, st));
+    return AIR_OK;
+  }
+  if (precision != AIR_PREC_TC_SPLIT) return fail(AIR_ERR_ARG, "air_linear: unknown precision");
+  // stand-alone tensor-core layer: build the hl operands in a temporary arena, run one GEMM, free
+  namespace tc = air::tc;
+  if (!tc::get_encode_fn()) return fail(AIR_ERR_CUDA, "air_linear: cuTensorMapEncodeTiled is not available");
+  const int Kpad = round_up(K, tc::BK), BN = N <= 32 ? 32 : 64, N_alloc = round_up(N, BN), M_alloc = round_up(M, tc::BM);
+  const size_t a_halves = 2 * (size_t)M_alloc * Kpad, w_halves = 2 * (size_t)N_alloc * Kpad;
+  const size_t bytes = align_up(a_halves * 2, 1024) + align_up(w_halves * 2, 1024) + 1024;
+  char* tmp = nullptr;
+  AIR_CUDA(cudaMallocAsync(&tmp, bytes, st));
+  AIR_CUDA(cudaMemsetAsync(tmp, 0, bytes, st));
+  __half* a_hl = reinterpret_cast<__half*>(tmp);
+  __half* w_hl = reinterpret_cast<__half*>(tmp + align_up(a_halves * 2, 1024));
+  tc::PrepEntry* table = reinterpret_cast<tc::PrepEntry*>(tmp + align_up(a_halves * 2, 1024) + align_up(w_halves * 2, 1024));
+  int* flag = reinterpret_cast<int*>(table + 1);
+  tc::PrepEntry pe;
+  pe.src_off = 0;
+  pe.dst_off = 0;
+  pe.plane = (int64_t)N_alloc * Kpad;
+  pe.K = K;
+  pe.N = N;
+  pe.Kpad = Kpad;
+  pe.tile_begin = 0;
+  pe.tiles_n = (N + 31) / 32;
+  AIR_CUDA(cudaMemcpyAsync(table, &pe, sizeof(pe), cudaMemcpyHostToDevice, st));
+  tc::prep_weights_kernel<<<pe.tiles_n * ((K + 31) / 32), 256, 0, st>>>(Wt, w_hl, table, 1, flag);
+  AIR_CUDA(cudaGetLastError());
+  const size_t n4 = (size_t)M * ((K + 3) / 4);
+  tc::split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(A, K, a_hl, (size_t)M_alloc * Kpad, Kpad, M, K, flag);
+  AIR_CUDA(cudaGetLastError());
+  CUtensorMap tm_a, tm_b;
+  if (!tc::make_tmap(&tm_a, a_hl, Kpad, 2 * (int64_t)M_alloc, tc::BM) ||
+      !tc::make_tmap(&tm_b, w_hl, Kpad, 2 * (int64_t)N_alloc, BN))
+    return fail(AIR_ERR_CUDA, "air_linear: cuTensorMapEncodeTiled failed");
+  tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.out_f32 = out;
+  p.ldc = N;
+  p.M = M;
+  p.N = N;
+  p.num_k_blocks = Kpad / tc::BK;
+  p.a_lo_row = M_alloc;
+  p.b_lo_row = N_alloc;
+  p.act = act;
+  p.range_flag = flag;
+  AIR_CUDA(tc::launch_gemm(BN, tm_a, tm_b, p, N_alloc, st));
+  int host_flag = 0;
+  AIR_CUDA(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  AIR_CUDA(cudaStreamSynchronize(st));
+  AIR_CUDA(cudaFreeAsync(tmp, st));
+  if (host_flag) return fail(AIR_ERR_RANGE, "air_linear: operand outside the fp16 range of the split engine");
   return AIR_OK;
 }
 
@@ -539,7 +869,8 @@ int32_t air_lstm_step(const float* x, float* hstate, float* cstate, const float*
   AIR_CUDA(air::launch_linear_simt(x, nx, W, 4 * nh, b, nullptr, 0, gx, 4 * nh, B, 4 * nh, nx, air::ACT_NONE, st));
   AIR_CUDA(air::launch_linear_simt(hstate, nh, W + (size_t)nx * 4 * nh, 4 * nh, nullptr, gx, 4 * nh, gates, 4 * nh, B,
                                    4 * nh, nh, air::ACT_NONE, st));
-  air::lstm_pointwise_kernel<<<(B * nh + 255) / 256, 256, 0, st>>>(gates, cstate, hstate, B, nh, forget_bias);
+  air::lstm_pointwise_kernel<<<(B * nh + 255) / 256, 256, 0, st>>>(gates, cstate, hstate, B, nh, forget_bias,
+                                                                  air::HlOut{nullptr, 0, 0});
   AIR_CUDA(cudaGetLastError());
   AIR_CUDA(cudaFreeAsync(gates, st));
   return AIR_OK;
@@ -549,7 +880,7 @@ int32_t air_stn_read(const float* img, const float* where, float* crop, int32_t 
                      int32_t w, void* stream) {
   if (!img || !where || !crop || B < 1 || H < 1 || W < 1 || h < 1 || w < 1)
     return fail(AIR_ERR_ARG, "air_stn_read: bad argument");
-  const size_t smem = sizeof(float) * (size_t)H * W;
+  const size_t smem = air::where_read_smem(1, H, W, h, w);
   if (smem > 200 * 1024) return fail(AIR_ERR_ARG, "air_stn_read: image does not fit in shared memory");
   if (smem > 48 * 1024)
     AIR_CUDA(cudaFuncSetAttribute(air::stn_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -562,7 +893,7 @@ int32_t air_stn_paint(const float* glimpse, const float* where, float* out, int3
                       int32_t w, void* stream) {
   if (!glimpse || !where || !out || B < 1 || H < 1 || W < 1 || h < 1 || w < 1)
     return fail(AIR_ERR_ARG, "air_stn_paint: bad argument");
-  const size_t smem = sizeof(float) * (size_t)h * w;
+  const size_t smem = air::paint_smem(1, H, W, h, w);
   if (smem > 200 * 1024) return fail(AIR_ERR_ARG, "air_stn_paint: glimpse does not fit in shared memory");
   if (smem > 48 * 1024)
     AIR_CUDA(cudaFuncSetAttribute(air::stn_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -2,6 +2,11 @@
 // spatial-transformer glimpse read and the inverse-transformer canvas paint fused with the ELBO terms.
 // All HBM-bound byte work: one CTA per canvas, the image / glimpse tile staged once in shared memory
 // (cp.async.bulk where the tile is 16-byte sized), coalesced output rows, warp-shuffle reductions.
+//
+// Both transformer directions are axis-aligned (no shear), so the bilinear footprint of an output pixel is the outer
+// product of a per-column and a per-row tap pair.  Each CTA first builds small shared-memory tables of those taps
+// (index pair + weight pair per output column / row, coordinates computed exactly as Sonnet does), then every output
+// pixel costs four shared-memory loads and the reference kernel's arithmetic, in the reference's association order.
 #pragma once
 #include "common.cuh"
 #include "../../include/air_b200.h"
@@ -38,23 +43,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ bool bulk_ok(const void* src, int n_floats) {
+  return ((n_floats & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+}
 
-// Stage `n` floats from global into shared: TMA bulk copy when the tile is 16-byte aligned/sized, plain
-// coalesced loads otherwise (tiny test shapes such as the 3x3 images of test/cell_test.py).  Ends with a barrier.
-__device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__ src, int n, uint64_t* bar,
-                                           uint32_t& parity) {
-  const bool bulk_ok = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  if (bulk_ok) {
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, (uint32_t)n * 4u);
-      bulk_g2s(dst, src, (uint32_t)n * 4u, bar);
-    }
-    mbar_wait(bar, parity);
-    parity ^= 1u;
-  } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
+// ---------------------------------------------------------------------------------------------------
+// bilinear taps along one axis (snt.resampler semantics: zero outside (-1, n); taps outside [0, n-1] read 0)
+// ---------------------------------------------------------------------------------------------------
+struct __align__(16) Tap {
+  float wf, wc;   // weight of the floor tap (= ceil - coord) and of the ceil tap (= 1 - that); 0 where the tap reads 0
+  int i_f, i_c;   // clamped indices of the two taps
+};
+__device__ __forceinline__ Tap make_tap(float coord, int n) {
+  Tap t;
+  const bool inside = coord > -1.0f && coord < (float)n;
+  const float f = floorf(coord);
+  const int fi = (int)f, ci = fi + 1;
+  const float d = (f + 1.0f) - coord;
+  t.wf = (inside && fi >= 0 && fi <= n - 1) ? d : 0.f;
+  t.wc = (inside && ci >= 0 && ci <= n - 1) ? 1.0f - d : 0.f;
+  t.i_f = min(max(fi, 0), n - 1);
+  t.i_c = min(max(ci, 0), n - 1);
+  return t;
+}
+// same association as the reference kernel: dx*dy*D(fx,fy) + (1-dx)(1-dy)*D(cx,cy) + dx(1-dy)*D(fx,cy) + (1-dx)dy*D(cx,fy)
+__device__ __forceinline__ float bilinear(const float* __restrict__ D, int Ws, const Tap& x, const Tap& y) {
+  const float* rf = D + y.i_f * Ws;
+  const float* rc = D + y.i_c * Ws;
+  float r = __fmul_rn(__fmul_rn(x.wf, y.wf), rf[x.i_f]);
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wc), rc[x.i_c]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wf, y.wc), rc[x.i_f]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wf), rf[x.i_c]));
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -62,18 +82,25 @@ __device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // trainable initial state (h0, c0) [nh] tiled to the batch (cell.py:103)
 __global__ void lstm_init_state_kernel(const float* __restrict__ h0, const float* __restrict__ c0,
-                                       float* __restrict__ h, float* __restrict__ c, int B, int nh) {
+                                       float* __restrict__ h, float* __restrict__ c, int B, int nh, HlOut h_hl) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * nh) return;
   const int u = (int)(i % nh);
   h[i] = h0[u];
   c[i] = c0[u];
+  if (h_hl.p) hl_store(h_hl, i / nh, u, h0[u]);
+}
+// explicit incoming hidden state (air_cell_step) -> hl operand of the recurrent GEMM
+__global__ void split_state_kernel(const float* __restrict__ h, int B, int nh, HlOut h_hl) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * nh) return;
+  hl_store(h_hl, i / nh, (int)(i % nh), h[i]);
 }
 
 // gates[B,4nh] (order i, j, f, o) already hold [x,h] @ W + b.  c <- sig(f + fb) * c + sig(i) * tanh(j);
 // h <- tanh(c) * sig(o).
 __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ c,
-                                      float* __restrict__ h_out, int B, int nh, float forget_bias) {
+                                      float* __restrict__ h_out, int B, int nh, float forget_bias, HlOut h_hl) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * nh) return;
   const size_t b = idx / nh;
@@ -82,7 +109,9 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __
   const float gi = g[u], gj = g[nh + u], gf = g[2 * nh + u], go = g[3 * nh + u];
   const float c_new = __fadd_rn(__fmul_rn(sigmoid_f(gf + forget_bias), c[idx]), __fmul_rn(sigmoid_f(gi), tanhf(gj)));
   c[idx] = c_new;
-  h_out[idx] = __fmul_rn(tanhf(c_new), sigmoid_f(go));
+  const float h_new = __fmul_rn(tanhf(c_new), sigmoid_f(go));
+  h_out[idx] = h_new;
+  if (h_hl.p) hl_store(h_hl, b, u, h_new);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -117,71 +146,106 @@ __global__ void presence_kernel(const float* __restrict__ logit /*[T,B]*/, const
 //   m[T,B,8] = transform-estimator MLP output; loc = (sig, tanh, sig, tanh)(m[0:4]) * (max_crop,1,max_crop,1);
 //   scale = softplus(m[4:8] + scale_bias); where = eps * scale + loc       (modules.py:41-63, cell.py:129-133)
 //   crop[t,b] = resampler(img[b], AffineGridWarper(where))                  (modules.py:104-109, cell.py:135)
-// dynamic smem: H*W floats.
+// dynamic smem: H*W floats (image) + T*(w+h) taps.
 // ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t where_read_smem(int T, int H, int W, int h, int w) {
+  return sizeof(float) * ((size_t)H * W + 4) / 16 * 16 + 16 + sizeof(Tap) * (size_t)T * (w + h);
+}
+
 __global__ void __launch_bounds__(256)
 where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_where, const float* __restrict__ img,
                   float* __restrict__ where, float* __restrict__ where_loc, float* __restrict__ where_scale,
-                  float* __restrict__ crop, int T, int B, int H, int W, int h, int w, float max_crop,
+                  float* __restrict__ crop, HlOut crop_hl, int T, int B, int H, int W, int h, int w, float max_crop,
                   float scale_bias) {
-  extern __shared__ __align__(16) float s_img[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
-  __shared__ float s_where[4];
+  __shared__ float s_where[AIR_MAX_STEPS][4];
   const int b = blockIdx.x;
   const int P = H * W, G = h * w;
-  if (threadIdx.x == 0) {
+  float* s_img = reinterpret_cast<float*>(smem_raw);
+  Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * ((size_t)P + 4) / 16 * 16 + 16));   // [T][w]
+  Tap* s_ty = s_tx + (size_t)T * w;                                                                 // [T][h]
+  const float* src = img + (size_t)b * P;
+  const bool bulk = bulk_ok(src, P);
+  if (threadIdx.x == 0 && bulk) {
     mbar_init(&bar, 1);
     fence_mbar_init();
+    mbar_expect_tx(&bar, (uint32_t)P * 4u);
+    bulk_g2s(s_img, src, (uint32_t)P * 4u, &bar);
+  }
+  // the T where codes of this canvas (4 components each) while the image is in flight
+  if (threadIdx.x < 4 * T) {
+    const int t = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const size_t row = (size_t)t * B + b;
+    const float mk = m[row * 8 + k];
+    const float loc = (k & 1) ? tanhf(mk) : __fmul_rn(max_crop, sigmoid_f(mk));
+    const float sc = softplus_f(m[row * 8 + 4 + k] + scale_bias);
+    const float wv = __fadd_rn(__fmul_rn(eps_where[row * 4 + k], sc), loc);
+    where_loc[row * 4 + k] = loc;
+    where_scale[row * 4 + k] = sc;
+    where[row * 4 + k] = wv;
+    s_where[t][k] = wv;
+  }
+  if (!bulk)
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_img[i] = src[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * (w + h); i += blockDim.x) {
+    const int t = i / (w + h), j = i - t * (w + h);
+    if (j < w) s_tx[t * w + j] = make_tap(fwd_coord(s_where[t][0], s_where[t][1], j, w, W), W);
+    else       s_ty[t * h + (j - w)] = make_tap(fwd_coord(s_where[t][2], s_where[t][3], j - w, h, H), H);
   }
   __syncthreads();
-  uint32_t parity = 0;
-  stage_tile(s_img, img + (size_t)b * P, P, &bar, parity);
-
+  if (bulk) mbar_wait(&bar, 0);
+  const int NT = blockDim.x;
+  const int dr = NT / w, dc = NT - dr * w;
   for (int t = 0; t < T; ++t) {
     const size_t row = (size_t)t * B + b;
-    if (threadIdx.x < 4) {
-      const int k = threadIdx.x;
-      const float mk = m[row * 8 + k];
-      const float loc = (k & 1) ? tanhf(mk) : __fmul_rn(max_crop, sigmoid_f(mk));
-      const float sc = softplus_f(m[row * 8 + 4 + k] + scale_bias);
-      const float wv = __fadd_rn(__fmul_rn(eps_where[row * 4 + k], sc), loc);
-      where_loc[row * 4 + k] = loc;
-      where_scale[row * 4 + k] = sc;
-      where[row * 4 + k] = wv;
-      s_where[k] = wv;
+    float* cf = crop ? crop + row * (size_t)G : nullptr;
+    __half* ch = crop_hl.p ? crop_hl.p + row * (size_t)crop_hl.ld : nullptr;
+    const Tap* txs = s_tx + t * w;
+    const Tap* tys = s_ty + t * h;
+    int r = (int)threadIdx.x / w, c = (int)threadIdx.x - r * w;
+    for (int g = threadIdx.x; g < G; g += NT) {
+      const Tap tx = txs[c], ty = tys[r];
+      float v = 0.f;
+      if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear(s_img, W, tx, ty);
+      if (cf) cf[g] = v;
+      if (ch) {
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        ch[g] = hi;
+        ch[crop_hl.plane + g] = lo;
+      }
+      c += dc;
+      r += dr;
+      if (c >= w) {
+        c -= w;
+        ++r;
+      }
     }
-    __syncthreads();
-    const float sx = s_where[0], tx = s_where[1], sy = s_where[2], ty = s_where[3];
-    float* out = crop + row * (size_t)G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      const int r = g / w, c = g - r * w;
-      const float x = fwd_coord(sx, tx, c, w, W);
-      const float y = fwd_coord(sy, ty, r, h, H);
-      out[g] = resample_plane(s_img, H, W, x, y);
-    }
-    __syncthreads();
   }
 }
 
-// stand-alone forward STN with explicit where codes (air_stn_read)
+// stand-alone forward STN with explicit where codes (air_stn_read); dynamic smem: H*W floats + (w+h) taps
 __global__ void __launch_bounds__(256)
 stn_read_kernel(const float* __restrict__ img, const float* __restrict__ where, float* __restrict__ crop, int H,
                 int W, int h, int w) {
-  extern __shared__ __align__(16) float s_img[];
-  __shared__ uint64_t bar;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int b = blockIdx.x;
   const int P = H * W, G = h * w;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
+  float* s_img = reinterpret_cast<float*>(smem_raw);
+  Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * ((size_t)P + 4) / 16 * 16 + 16));
+  Tap* s_ty = s_tx + w;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s_img[i] = img[(size_t)b * P + i];
+  const float sx = where[b * 4 + 0], tx = where[b * 4 + 1], sy = where[b * 4 + 2], ty = where[b * 4 + 3];
+  for (int j = threadIdx.x; j < w + h; j += blockDim.x) {
+    if (j < w) s_tx[j] = make_tap(fwd_coord(sx, tx, j, w, W), W);
+    else       s_ty[j - w] = make_tap(fwd_coord(sy, ty, j - w, h, H), H);
   }
   __syncthreads();
-  uint32_t parity = 0;
-  stage_tile(s_img, img + (size_t)b * P, P, &bar, parity);
-  const float sx = where[b * 4 + 0], tx = where[b * 4 + 1], sy = where[b * 4 + 2], ty = where[b * 4 + 3];
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     const int r = g / w, c = g - r * w;
-    crop[(size_t)b * G + g] = resample_plane(s_img, H, W, fwd_coord(sx, tx, c, w, W), fwd_coord(sy, ty, r, h, H));
+    crop[(size_t)b * G + g] = bilinear(s_img, W, s_tx[c], s_ty[r]);
   }
 }
 
@@ -191,7 +255,7 @@ stn_read_kernel(const float* __restrict__ img, const float* __restrict__ where, 
 // ---------------------------------------------------------------------------------------------------
 __global__ void what_kernel(const float* __restrict__ r, const float* __restrict__ eps, float* __restrict__ what,
                             float* __restrict__ what_loc, float* __restrict__ what_scale, size_t rows, int na,
-                            float offset) {
+                            float offset, HlOut what_hl) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * (size_t)na) return;
   const size_t row = idx / na;
@@ -200,7 +264,9 @@ __global__ void what_kernel(const float* __restrict__ r, const float* __restrict
   const float sc = softplus_f(r[row * 2 * na + na + j] + offset);
   what_loc[idx] = loc;
   what_scale[idx] = sc;
-  what[idx] = __fadd_rn(__fmul_rn(eps[idx], sc), loc);
+  const float wv = __fadd_rn(__fmul_rn(eps[idx], sc), loc);
+  what[idx] = wv;
+  if (what_hl.p) hl_store(what_hl, row, j, wv);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -242,18 +308,21 @@ struct ElboArgs {
   float* num_steps_log_prob;
   int T, B, H, W, h, w, na;
   float output_std, output_multiplier;
+  float lp_const;              // 0.5 log(2 pi) + log(output_std), the constant of Normal.log_prob (host, float64)
   int do_elbo;
   air_prior prior;
+  double steps_prior[AIR_MAX_STEPS + 1];   // geometric_prior(success_prob, T) (prior.py:26-32): the same table for
+                                           // every canvas, computed once on the host (air_api.cu:steps_prior_table)
 };
 
 // prior.py:26-32 geometric_prior in float64 [upstream Geometric(probs=1-s).prob(k) = exp(k*log1p(-probs) + log(probs))]
-__device__ __forceinline__ double geom_prior_f64(double s, int k) {
+__host__ __device__ inline double geom_prior_f64(double s, int k) {
   s = fmin(fmax(s, 1e-7), 1.0 - 1e-15);
   const double probs = 1.0 - s;
   return exp((double)k * log1p(-probs) + log(probs));
 }
 // same in float32 (python-float success probability -> tf.float32 graph constants)
-__device__ __forceinline__ float geom_prior_f32(float s, int k) {
+__host__ __device__ inline float geom_prior_f32(float s, int k) {
   s = fminf(fmaxf(s, 1e-7f), (float)(1.0 - 1e-15));
   const float probs = 1.0f - s;
   return expf((float)k * log1pf(-probs) + logf(probs));
@@ -291,53 +360,112 @@ __device__ __forceinline__ float tabular_kl_entry(float p, double q, double zero
 //   rec[b]   = sum_px 0.5 ((x - mu)/sigma)^2 + log sigma + 0.5 log 2 pi, mu = multiplier * canvas_T (model.py:319-321)
 //   KL terms per sample (model.py:126-216), q(n) (prior.py:62-68), log q(n_b) (prior.py:148-151)
 // The canvas is never read back from HBM: it accumulates in a register per pixel across the T steps and is
-// written once per step (coalesced rows).  dynamic smem: T*G (glimpses) + T*(W+H) (inverse-grid tables) floats.
+// written once per step (coalesced rows).  dynamic smem: T*G floats (glimpses) + T*(W+H) taps.
 // ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) {
+  return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H);
+}
+
+template <int T>
 __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
-  __shared__ float s_pres[AIR_MAX_STEPS], s_w[AIR_MAX_STEPS], s_red[32];
+  __shared__ float s_pres[AIR_MAX_STEPS], s_w[AIR_MAX_STEPS], s_klw[AIR_MAX_STEPS], s_red[32];
   __shared__ float s_q[AIR_MAX_STEPS + 1];
-  const int T = a.T, B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
+  __shared__ float s_kln;
+  const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
   const int P = H * W, G = h * w;
   const int b = blockIdx.x;
-  float* s_gl = smem;                 // [T][G]
-  float* s_x = s_gl + (size_t)T * G;  // [T][W] glimpse-space x of every canvas column
-  float* s_y = s_x + (size_t)T * W;   // [T][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
+  Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);         // [T][W]
+  Tap* s_ty = s_tx + (size_t)T * W;                                                                      // [T][H]
 
-  if (threadIdx.x == 0) {
+  // stage the T decoded glimpses of this canvas (TMA bulk copies, one mbarrier)
+  const bool bulk = bulk_ok(a.glimpse, G);
+  if (threadIdx.x == 0 && bulk) {
     mbar_init(&bar, 1);
     fence_mbar_init();
+    mbar_expect_tx(&bar, (uint32_t)(T * G) * 4u);
+    for (int t = 0; t < T; ++t)
+      bulk_g2s(s_gl + (size_t)t * G, a.glimpse + ((size_t)t * B + b) * G, (uint32_t)G * 4u, &bar);
+  }
+  if (!bulk)
+    for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
+      const int t = i / G, g = i - t * G;
+      s_gl[i] = a.glimpse[((size_t)t * B + b) * G + g];
+    }
+  // inverse-warp tap tables while the copy is in flight: glimpse-space taps of every canvas column / row
+  for (int i = threadIdx.x; i < T * (W + H); i += blockDim.x) {
+    const int t = i / (W + H), j = i - t * (W + H);
+    const float* wh = a.where + ((size_t)t * B + b) * 4;
+    float a_inv, d_inv, ntx, nty;
+    inv_params(wh[0], wh[1], wh[2], wh[3], a_inv, d_inv, ntx, nty);
+    if (j < W) s_tx[t * W + j] = make_tap(inv_coord(a_inv, ntx, j, W, w), w);
+    else       s_ty[t * H + (j - W)] = make_tap(inv_coord(d_inv, nty, j - W, H, h), h);
+  }
+  if (threadIdx.x < T) s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
+
+  const air_prior& pr = a.prior;
+  if (a.do_elbo) {
+    if (warp == 0) {
+      // step-count posterior q(n), KL(q(n) || prior) and the per-step weights: lane k owns n = k (float64 island)
+      const int k = lane;
+      double pi = 0.0;
+      if (k <= T) {
+        double cum = 1.0;
+        for (int j = 0; j < k && j < T; ++j) cum *= (double)a.presence_prob[(size_t)j * B + b];
+        pi = (k < T) ? (1.0 - (double)a.presence_prob[(size_t)k * B + b]) * cum : cum;
+      }
+      double sum = pi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      float q = 0.f, kl = 0.f;
+      if (k <= T) {
+        q = (float)(pi / sum);
+        kl = tabular_kl_entry(q, a.steps_prior[k], 0.0);
+        s_q[k] = q;
+        a.num_steps_posterior[(size_t)b * (T + 1) + k] = q;
+      }
+      float kl_n = 0.f;   // fp32 sum over n in index order (model.py:149)
+      for (int j = 0; j <= T; ++j) {
+        const float v = __shfl_sync(0xffffffffu, kl, j);
+        kl_n = (j == 0) ? v : __fadd_rn(kl_n, v);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_kln = kl_n;
+        a.kl_num_steps_per_sample[b] = kl_n;
+        float n = 0.f;
+        for (int t = 0; t < T; ++t) n += a.presence[(size_t)t * B + b];
+        a.num_step_per_sample[b] = n;
+        int idx = (int)n;
+        idx = idx < 0 ? 0 : (idx > T ? T : idx);
+        a.num_steps_log_prob[b] = logf(fmaxf(s_q[idx], 1e-32f));
+        if (pr.analytic) {   // reverse cumsum of q(n)[1:]   (model.py:157-161)
+          float cs = 0.f;
+          for (int t = T - 1; t >= 0; --t) {
+            cs = (t == T - 1) ? s_q[t + 1] : __fadd_rn(cs, s_q[t + 1]);
+            s_w[t] = cs;
+          }
+        } else {
+          for (int t = 0; t < T; ++t) s_w[t] = a.presence[(size_t)t * B + b];
+        }
+        for (int t = 0; t < T; ++t) a.prior_step_weight[(size_t)t * B + b] = s_w[t];
+      }
+    }
+    // KL(what) per step: one warp per step (model.py:174-186)
+    for (int t = warp; t < T; t += (blockDim.x >> 5)) {
+      float v = 0.f;
+      const size_t base = ((size_t)t * B + b) * a.na;
+      for (int i = lane; i < a.na; i += 32)
+        v += normal_kl(a.what_loc[base + i], a.what_scale[base + i], pr.what_loc, pr.what_scale);
+      v = warp_sum(v);
+      if (lane == 0) s_klw[t] = v;
+    }
   }
   __syncthreads();
-  // stage the T decoded glimpses of this canvas
-  {
-    const bool bulk_ok = ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.glimpse) & 15) == 0);
-    if (bulk_ok) {
-      if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (uint32_t)(T * G) * 4u);
-        for (int t = 0; t < T; ++t)
-          bulk_g2s(s_gl + (size_t)t * G, a.glimpse + ((size_t)t * B + b) * G, (uint32_t)G * 4u, &bar);
-      }
-    } else {
-      for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
-        const int t = i / G, g = i - t * G;
-        s_gl[i] = a.glimpse[((size_t)t * B + b) * G + g];
-      }
-    }
-    // inverse-grid tables while the copy is in flight
-    for (int i = threadIdx.x; i < T * (W + H); i += blockDim.x) {
-      const int t = i / (W + H), j = i - t * (W + H);
-      const float* wh = a.where + ((size_t)t * B + b) * 4;
-      float a_inv, d_inv, ntx, nty;
-      inv_params(wh[0], wh[1], wh[2], wh[3], a_inv, d_inv, ntx, nty);
-      if (j < W) s_x[t * W + j] = inv_coord(a_inv, ntx, j, W, w);
-      else       s_y[t * H + (j - W)] = inv_coord(d_inv, nty, j - W, H, h);
-    }
-    if (threadIdx.x < T) s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
-    if (bulk_ok) mbar_wait(&bar, 0);
-    __syncthreads();
-  }
+  if (bulk) mbar_wait(&bar, 0);
 
   // optional visualisation output: presence * sigmoid(glimpse)   (model.py:90)
   if (a.glimpse_viz) {
@@ -347,69 +475,59 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
     }
   }
 
-  const float mult = a.output_multiplier, sigma = a.output_std;
-  const float lp_const = (float)(0.5 * 1.8378770664093453 /*log(2 pi)*/ + log((double)sigma));
+  // ---- paint: per-thread pixels p = tid, tid + 256, ...; (row, col) tracked incrementally; the T-step loop is unrolled
+  // at compile time so every base pointer and presence value sits in a register.  A step whose presence is 0
+  // (block-uniform) or whose inverse-warp footprint misses the pixel (both taps of an axis weightless: the
+  // reference's "outside" case) contributes exactly 0 and is skipped.
+  const float mult = a.output_multiplier, sigma = a.output_std, lp_const = a.lp_const;
+  const int NT = blockDim.x;
+  const int dr = NT / W, dc = NT - dr * W;
+  int r = (int)threadIdx.x / W, c = (int)threadIdx.x - r * W;
+  float pres[T];
+  float* cdst[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    pres[t] = s_pres[t];
+    cdst[t] = a.canvas ? a.canvas + ((size_t)t * B + b) * P : nullptr;
+  }
+  const float* cin = a.canvas_in ? a.canvas_in + (size_t)b * P : nullptr;
+  const float* obs = a.img + (size_t)b * P;
   float rec = 0.f;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    const int r = p / W, c = p - r * W;
-    float acc = a.canvas_in ? a.canvas_in[(size_t)b * P + p] : 0.f;
+  for (int p = threadIdx.x; p < P; p += NT) {
+    float acc = cin ? cin[p] : 0.f;
+    const float x_obs = a.do_elbo ? obs[p] : 0.f;
+#pragma unroll
     for (int t = 0; t < T; ++t) {
-      const float v = resample_plane(s_gl + (size_t)t * G, h, w, s_x[t * W + c], s_y[t * H + r]);
-      acc = __fadd_rn(acc, __fmul_rn(s_pres[t], v));
-      if (a.canvas) a.canvas[((size_t)t * B + b) * P + p] = __fmul_rn(acc, mult);
+      if (pres[t] != 0.f) {
+        const Tap tx = s_tx[t * W + c], ty = s_ty[t * H + r];
+        if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) {
+          const float v = bilinear(s_gl + t * G, w, tx, ty);
+          acc = __fadd_rn(acc, __fmul_rn(pres[t], v));
+        }
+      }
+      if (cdst[t]) cdst[t][p] = __fmul_rn(acc, mult);
     }
     if (a.do_elbo) {
       const float mu = __fmul_rn(acc, mult);
-      const float z = __fdiv_rn(a.img[(size_t)b * P + p] - mu, sigma);
+      const float z = __fdiv_rn(x_obs - mu, sigma);
       rec += __fadd_rn(__fmul_rn(__fmul_rn(0.5f, z), z), lp_const);
+    }
+    c += dc;
+    r += dr;
+    if (c >= W) {
+      c -= W;
+      ++r;
     }
   }
   if (!a.do_elbo) return;
   rec = block_sum(rec, s_red);
 
-  // step-count posterior, its KL and the per-step weights: tiny float64 island, one thread
-  const air_prior& pr = a.prior;
   if (threadIdx.x == 0) {
-    modified_geometric_row(a.presence_prob + b, B, T, s_q);
-    float kl_n = 0.f;
-    for (int k = 0; k <= T; ++k) {
-      const double prior_k = pr.steps_prob_is_f64 ? geom_prior_f64(pr.steps_success_prob, k)
-                                                  : (double)geom_prior_f32((float)pr.steps_success_prob, k);
-      kl_n += tabular_kl_entry(s_q[k], prior_k, 0.0);
-      a.num_steps_posterior[(size_t)b * (T + 1) + k] = s_q[k];
+    float kl_what = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float v = __fmul_rn(s_klw[t], s_w[t]);
+      kl_what = (t == 0) ? v : __fadd_rn(kl_what, v);
     }
-    a.kl_num_steps_per_sample[b] = kl_n;
-    float n = 0.f;
-    for (int t = 0; t < T; ++t) n += s_pres[t];
-    a.num_step_per_sample[b] = n;
-    int idx = (int)n;
-    idx = idx < 0 ? 0 : (idx > T ? T : idx);
-    a.num_steps_log_prob[b] = logf(fmaxf(s_q[idx], 1e-32f));
-    if (pr.analytic) {   // reverse cumsum of q(n)[1:]   (model.py:157-161)
-      float cs = 0.f;
-      for (int t = T - 1; t >= 0; --t) {
-        cs = (t == T - 1) ? s_q[t + 1] : __fadd_rn(cs, s_q[t + 1]);
-        s_w[t] = cs;
-      }
-    } else {
-      for (int t = 0; t < T; ++t) s_w[t] = s_pres[t];
-    }
-    for (int t = 0; t < T; ++t) a.prior_step_weight[(size_t)t * B + b] = s_w[t];
-  }
-  __syncthreads();
-
-  // KL(what)   (model.py:174-186)
-  float kl_what = 0.f;
-  for (int t = 0; t < T; ++t) {
-    float v = 0.f;
-    const size_t base = ((size_t)t * B + b) * a.na;
-    for (int i = threadIdx.x; i < a.na; i += blockDim.x)
-      v += normal_kl(a.what_loc[base + i], a.what_scale[base + i], pr.what_loc, pr.what_scale);
-    v = block_sum(v, s_red);
-    kl_what = (t == 0) ? __fmul_rn(v, s_w[t]) : __fadd_rn(kl_what, __fmul_rn(v, s_w[t]));
-  }
-
-  if (threadIdx.x == 0) {
     // KL(where)   (model.py:188-214): (sx, sy) vs scale prior, (tx, ty) vs shift prior
     float kl_where = 0.f;
     for (int t = 0; t < T; ++t) {
@@ -423,7 +541,7 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
       const float ws_t = __fmul_rn(s, s_w[t]);
       kl_where = (t == 0) ? ws_t : __fadd_rn(kl_where, ws_t);
     }
-    const float kl_n = a.kl_num_steps_per_sample[b];
+    const float kl_n = s_kln;
     a.rec_loss_per_sample[b] = rec;
     a.kl_what_per_sample[b] = kl_what;
     a.kl_where_per_sample[b] = kl_where;
@@ -433,20 +551,54 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
   }
 }
 
+template <int T>
+inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStream_t st) {
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(paint_elbo_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  paint_elbo_kernel<T><<<a.B, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_paint_elbo(const ElboArgs& a, cudaStream_t st) {
+  const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);
+  switch (a.T) {
+    case 1: return launch_paint_elbo_t<1>(a, smem, st);
+    case 2: return launch_paint_elbo_t<2>(a, smem, st);
+    case 3: return launch_paint_elbo_t<3>(a, smem, st);
+    case 4: return launch_paint_elbo_t<4>(a, smem, st);
+    case 5: return launch_paint_elbo_t<5>(a, smem, st);
+    case 6: return launch_paint_elbo_t<6>(a, smem, st);
+    case 7: return launch_paint_elbo_t<7>(a, smem, st);
+    case 8: return launch_paint_elbo_t<8>(a, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // stand-alone inverse STN (air_stn_paint): out[b] = resampler(glimpse[b], inverse warp(where[b]))
+// dynamic smem: h*w floats + (W+H) taps
 __global__ void __launch_bounds__(256)
 stn_paint_kernel(const float* __restrict__ glimpse, const float* __restrict__ where, float* __restrict__ out, int H,
                  int W, int h, int w) {
-  extern __shared__ __align__(16) float s_gl[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int b = blockIdx.x;
   const int P = H * W, G = h * w;
+  float* s_gl = reinterpret_cast<float*>(smem_raw);
+  Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)G + 15) / 16 * 16);
+  Tap* s_ty = s_tx + W;
   for (int i = threadIdx.x; i < G; i += blockDim.x) s_gl[i] = glimpse[(size_t)b * G + i];
-  __syncthreads();
   float a_inv, d_inv, ntx, nty;
   inv_params(where[b * 4 + 0], where[b * 4 + 1], where[b * 4 + 2], where[b * 4 + 3], a_inv, d_inv, ntx, nty);
+  for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
+    if (j < W) s_tx[j] = make_tap(inv_coord(a_inv, ntx, j, W, w), w);
+    else       s_ty[j - W] = make_tap(inv_coord(d_inv, nty, j - W, H, h), h);
+  }
+  __syncthreads();
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const int r = p / W, c = p - r * W;
-    out[(size_t)b * P + p] = resample_plane(s_gl, h, w, inv_coord(a_inv, ntx, c, W, w), inv_coord(d_inv, nty, r, H, h));
+    out[(size_t)b * P + p] = bilinear(s_gl, w, s_tx[c], s_ty[r]);
   }
 }
 

@@ -1,5 +1,6 @@
 // Shared device helpers for the AIR hot path (sm_100a).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -25,6 +26,26 @@ __device__ __forceinline__ float softplus_f(float x) {
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == ACT_ELU ? elu_f(v) : v; }
+
+// fp16x2 split operand format of the tensor-core engine (linear_tc.cuh): x = hi + lo, hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+// Optional second output of a producer kernel: the consumer GEMM's A operand in "hl" format
+// (fp16 [2][rows_alloc][ld]: hi plane, then lo plane; see linear_tc.cuh).  p == nullptr -> not written.
+struct HlOut {
+  __half* p;
+  size_t plane;
+  int ld;
+};
+__device__ __forceinline__ void hl_store(const HlOut& o, size_t row, int col, float x) {
+  __half hi, lo;
+  split_f16(x, hi, lo);
+  __half* d = o.p + row * (size_t)o.ld + col;
+  d[0] = hi;
+  d[o.plane] = lo;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -84,10 +105,6 @@ __device__ __forceinline__ float fwd_coord(float s, float t, int i, int n_out, i
 // AffineGridWarper.inverse() for the no-shear case (a = sx, d = sy, b = c = 0):
 //   det = sx * sy; a' = sy / det; d' = sx / det; tx' = a' * tx; ty' = d' * ty
 //   x_g = a' * (U * S_w) + (-tx') * S_w + S_w   (U = linspace(-1, 1, W) over canvas columns), y likewise.
-struct InvWarp {
-  float ax, bx;   // x_g = ax * US + bx_term ... kept as the three operands to preserve rounding order
-  float ay, by;
-};
 __device__ __forceinline__ void inv_params(float sx, float tx, float sy, float ty, float& a_inv, float& d_inv,
                                            float& ntx, float& nty) {
   const float det = __fmul_rn(sx, sy);

@@ -279,6 +279,11 @@ class Engine:
                                          ptr(o["presence_prob"]), current_stream_ptr()), "air_cell_step")
         return o
 
+    def check_range(self):
+        """Raise if the tensor-core split engine saw an operand outside the fp16 range (synchronises)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.air_check_range(self._handle, current_stream_ptr()), "air_check_range")
+
     # -- instrumentation -------------------------------------------------------------------------
     @property
     def launch_count(self) -> int:

@@ -173,6 +173,11 @@ int32_t air_profile_enable(air_handle* h, int32_t on);
 int32_t air_profile_read(air_handle* h, float* ms_per_stage, int32_t n);
 const char* air_stage_name(int32_t i);
 
+/* AIR_PREC_TC_SPLIT carries operands as fp16 hi/lo pairs: a weight * 2^8 or an activation beyond +-65504
+ * cannot be represented.  The kernels raise a device flag instead of producing silent infinities; this call
+ * reads it (synchronises the stream), clears it and returns AIR_ERR_RANGE if it was set. */
+int32_t air_check_range(air_handle* h, void* stream);
+
 /* ---- the hot path ----------------------------------------------------------------------------- */
 /* T unrolled AIRCell steps + post-processing + ELBO terms in one enqueue:
  * tf.nn.dynamic_rnn over AIRCell._build (model.py:81-104, cell.py:116-171) followed by the loss

@@ -32,7 +32,10 @@ def make_problem(ocfg, B, seed=0, weight_gain=1.0, random_bias=True):
             v.mul_(weight_gain)
         elif random_bias:
             v.copy_(0.1 * torch.randn(v.shape, generator=g))
-    img, nums = O.synthetic_multi_mnist(B, ocfg.H, ocfg.W, seed=seed)
+    if min(ocfg.H, ocfg.W) >= 8:
+        img, nums = O.synthetic_multi_mnist(B, ocfg.H, ocfg.W, seed=seed)
+    else:   # the 3x3 images of test/cell_test.py:25,55 are np.random.rand
+        img, nums = torch.rand(B, ocfg.H, ocfg.W, generator=g), torch.zeros(3, B, 1)
     noise = O.make_noise(ocfg, B, seed)
     return params, img, nums, noise
 
@@ -58,6 +61,7 @@ def run_cuda(ocfg, params, img, noise, pc=None, global_step=0, baseline=None, pr
     bl = None if baseline is None else baseline.reshape(-1).to(device).contiguous()
     out = eng.forward(flat, img.to(device).contiguous(), ew, ea, u, pr, bl)
     torch.cuda.synchronize()
+    eng.check_range()
     res = {k: (None if v is None else v.detach().cpu().clone()) for k, v in out.items()}
     eng.close()
     return res
