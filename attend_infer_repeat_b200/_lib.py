@@ -94,6 +94,8 @@ SYMBOLS = {
     "air_forward": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_forward_host": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P, _P,
                                      _P]),
+    "air_forward_host_u8": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P, _P,
+                                        _P]),
     "air_elbo_scalars": (C.c_int32, [_P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_cell_step": (C.c_int32, [_P] * 19),
     "air_linear": (C.c_int32, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

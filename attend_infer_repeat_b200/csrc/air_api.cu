@@ -105,6 +105,7 @@ struct air_handle {
   Buf x, e, h_init, hs, crop, what_in;             // GEMM A operands produced by non-GEMM kernels (+ e)
   float *gx = nullptr, *gates = nullptr, *cbuf = nullptr, *m = nullptr, *logit = nullptr, *r = nullptr;
   // staging for air_forward_host / air_cell_step
+  uint8_t* st_img_u8 = nullptr;
   float *st_img = nullptr, *st_eps_where = nullptr, *st_eps_what = nullptr, *st_u = nullptr, *st_pres_in = nullptr;
   // tensor-core engine state
   std::vector<TcWeight> tcw;
@@ -273,7 +274,8 @@ int32_t check_outs(const air_outputs* o, bool need_elbo) {
 int32_t forward_impl(air_handle* h, const float* params, const float* img, const float* eps_where,
                      const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
                      const air_outputs* o, int T_run, const float* h_in, const float* c_in, const float* presence_in,
-                     const float* canvas_in, float* canvas_step_out, float mult, cudaStream_t st) {
+                     const float* canvas_in, float* canvas_step_out, float mult, cudaStream_t st,
+                     bool x_hl_ready = false) {
   const air_config& c = h->cfg;
   const int B = c.B, nh = c.nh, P = h->P, G = h->G, na = c.na;
   const int TB = T_run * B;
@@ -288,14 +290,15 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   x.f32 = const_cast<float*>(img);
   x.ld = P;
   if (tc) {
-    air::tc::prep_weights_kernel<<<h->prep_tiles, 256, 0, st>>>(params, h->arena, h->prep_table, (int)h->tcw.size(),
-                                                                h->range_flag);
-    AIR_CUDA(cudaGetLastError());
-    const size_t n4 = (size_t)B * ((P + 3) / 4);
-    air::tc::split_rows_kernel<<<(unsigned)((n4 + thr - 1) / thr), thr, 0, st>>>(img, P, x.hl, x.plane(), x.kpad, B, P,
-                                                                                h->range_flag);
-    AIR_CUDA(cudaGetLastError());
-    h->launches += 2;
+    AIR_CUDA(air::launch_k(air::tc::prep_weights_kernel, dim3(h->prep_tiles), dim3(256), 0, st, params, h->arena,
+                           h->prep_table, (int)h->tcw.size(), h->range_flag));
+    ++h->launches;
+    if (!x_hl_ready) {
+      const size_t n4 = (size_t)B * ((P + 3) / 4);
+      AIR_CUDA(air::launch_k(air::tc::split_rows_kernel, dim3((unsigned)((n4 + thr - 1) / thr)), dim3(thr), 0, st, img,
+                             P, x.hl, x.plane(), x.kpad, B, P, h->range_flag));
+      ++h->launches;
+    }
   }
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
@@ -314,14 +317,14 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     AIR_CUDA(cudaMemcpyAsync(h->h_init.f32, h_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
     AIR_CUDA(cudaMemcpyAsync(h->cbuf, c_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
     if (tc) {
-      air::split_state_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(h_in, B, nh, h->h_init.hl_out());
-      AIR_CUDA(cudaGetLastError());
+      AIR_CUDA(air::launch_k(air::split_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st, h_in, B, nh,
+                             h->h_init.hl_out()));
       ++h->launches;
     }
   } else {
-    air::lstm_init_state_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(
-        params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, h->cbuf, B, nh, tc ? h->h_init.hl_out() : no_hl);
-    AIR_CUDA(cudaGetLastError());
+    AIR_CUDA(air::launch_k(air::lstm_init_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
+                           params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, h->cbuf, B, nh,
+                           tc ? h->h_init.hl_out() : no_hl));
     ++h->launches;
   }
   Buf gates;
@@ -338,10 +341,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
       hs_hl = h->hs.hl_out();
       hs_hl.p += (size_t)t * B * h->hs.kpad;
     }
-    air::lstm_pointwise_kernel<<<(B * nh + thr - 1) / thr, thr, 0, st>>>(h->gates, h->cbuf,
-                                                                        h->hs.f32 + (size_t)t * B * nh, B, nh,
-                                                                        c.forget_bias, hs_hl);
-    AIR_CUDA(cudaGetLastError());
+    AIR_CUDA(air::launch_k(air::lstm_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st, h->gates,
+                           h->cbuf, h->hs.f32 + (size_t)t * B * nh, B, nh, c.forget_bias, hs_hl));
     ++h->launches;
   }
   if (o->final_h)
@@ -361,18 +362,15 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   logit.f32 = h->logit;
   logit.ld = 1;
   if ((rc = run_mlp(h, params, h->steps_mlp, h->hs, TB, logit, true, false, st)) != AIR_OK) return rc;   // :119-122
-  air::presence_kernel<<<(B + 127) / 128, 128, 0, st>>>(h->logit, u_pres, presence_in, o->presence_prob, o->presence,
-                                                        T_run, B, c.step_bias, c.explore_eps, c.discrete_steps);
-  AIR_CUDA(cudaGetLastError());
+  AIR_CUDA(air::launch_k(air::presence_kernel, dim3((B + 127) / 128), dim3(128), 0, st, h->logit, u_pres, presence_in,
+                         o->presence_prob, o->presence, T_run, B, c.step_bias, c.explore_eps, c.discrete_steps));
   ++h->launches;
   mark(h, AIR_ST_READ, st);
 
   // 5. where sampling + glimpse read   (cell.py:129-135)
-  air::where_read_kernel<<<B, 256, air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st>>>(h->m, eps_where, img, o->where, o->where_loc,
-                                                            o->where_scale, tc ? nullptr : h->crop.f32,
-                                                            tc ? h->crop.hl_out() : no_hl, T_run, B, c.H, c.W, c.h,
-                                                            c.w, c.max_crop_size, c.scale_bias);
-  AIR_CUDA(cudaGetLastError());
+  AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(256), air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
+                         h->m, eps_where, img, o->where, o->where_loc, o->where_scale, tc ? nullptr : h->crop.f32,
+                         tc ? h->crop.hl_out() : no_hl, T_run, B, c.H, c.W, c.h, c.w, c.max_crop_size, c.scale_bias));
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
@@ -389,11 +387,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     if ((rc = dense(h, params, q, 0, h->what_lin, true, nullptr, 0, r, true, false, TB, air::ACT_NONE, st)) != AIR_OK)
       return rc;
     const size_t n = (size_t)TB * na;
-    air::what_kernel<<<(unsigned)((n + thr - 1) / thr), thr, 0, st>>>(h->r, eps_what, o->what, o->what_loc,
-                                                                      o->what_scale, (size_t)TB, na,
-                                                                      c.what_scale_offset,
-                                                                      tc ? h->what_in.hl_out() : no_hl);
-    AIR_CUDA(cudaGetLastError());
+    AIR_CUDA(air::launch_k(air::what_kernel, dim3((unsigned)((n + thr - 1) / thr)), dim3(thr), 0, st, h->r, eps_what,
+                           o->what, o->what_loc, o->what_scale, (size_t)TB, na, c.what_scale_offset,
+                           tc ? h->what_in.hl_out() : no_hl));
     ++h->launches;
   }
   mark(h, AIR_ST_DECODER, st);
@@ -450,10 +446,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   ++h->launches;
 
   if (prior) {
-    air::elbo_scalars_kernel<<<1, 1024, 0, st>>>(o->rec_loss_per_sample, o->kl_num_steps_per_sample,
-                                                 o->kl_what_per_sample, o->kl_where_per_sample, o->num_step_per_sample,
-                                                 o->num_steps_log_prob, baseline, o->scalars, B, *prior);
-    AIR_CUDA(cudaGetLastError());
+    AIR_CUDA(air::launch_k(air::elbo_scalars_kernel, dim3(1), dim3(1024), 0, st, o->rec_loss_per_sample,
+                           o->kl_num_steps_per_sample, o->kl_what_per_sample, o->kl_where_per_sample,
+                           o->num_step_per_sample, o->num_steps_log_prob, baseline, o->scalars, B, *prior));
     ++h->launches;
   }
   mark(h, AIR_N_STAGES, st);
@@ -506,6 +501,7 @@ void carve_workspace(air_handle* h, Carver& cv) {
   h->logit = cv.take<float>(TB);
   h->r = cv.take<float>(TB * 2 * c.na);
   h->st_img = cv.take<float>(B * h->P);
+  h->st_img_u8 = cv.take<uint8_t>(B * h->P);
   h->st_eps_where = cv.take<float>(TB * 4);
   h->st_eps_what = cv.take<float>(TB * c.na);
   h->st_u = cv.take<float>(TB);
@@ -743,6 +739,39 @@ int32_t air_forward_host(air_handle* h, const float* params, const float* img_ho
   AIR_CUDA(cudaMemcpyAsync(h->st_u, u_pres_host, sizeof(float) * TB, cudaMemcpyHostToDevice, st));
   const int32_t rc = air_forward(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs,
                                  stream);
+  if (rc != AIR_OK) return rc;
+  if (prior && scalars_host)
+    AIR_CUDA(cudaMemcpyAsync(scalars_host, outs->scalars, sizeof(float) * AIR_N_SCALARS, cudaMemcpyDeviceToHost, st));
+  if (prior && loss_per_sample_host)
+    AIR_CUDA(cudaMemcpyAsync(loss_per_sample_host, outs->loss_per_sample, sizeof(float) * c.B, cudaMemcpyDeviceToHost,
+                             st));
+  AIR_CUDA(cudaStreamSynchronize(st));
+  return AIR_OK;
+}
+
+int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* img_u8_host,
+                            const float* eps_where_host, const float* eps_what_host, const float* u_pres_host,
+                            const air_prior* prior, const air_outputs* outs, float* scalars_host,
+                            float* loss_per_sample_host, void* stream) {
+  if (!h || !params || !img_u8_host || !eps_where_host || !eps_what_host || !u_pres_host)
+    return fail(AIR_ERR_ARG, "air_forward_host_u8: NULL argument");
+  int32_t rc = check_outs(outs, prior != nullptr);
+  if (rc != AIR_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const air_config& c = h->cfg;
+  const size_t TB = (size_t)c.T * c.B;
+  AIR_CUDA(cudaMemcpyAsync(h->st_img_u8, img_u8_host, (size_t)c.B * h->P, cudaMemcpyHostToDevice, st));
+  AIR_CUDA(cudaMemcpyAsync(h->st_eps_where, eps_where_host, sizeof(float) * TB * 4, cudaMemcpyHostToDevice, st));
+  AIR_CUDA(cudaMemcpyAsync(h->st_eps_what, eps_what_host, sizeof(float) * TB * c.na, cudaMemcpyHostToDevice, st));
+  AIR_CUDA(cudaMemcpyAsync(h->st_u, u_pres_host, sizeof(float) * TB, cudaMemcpyHostToDevice, st));
+  // uint8 -> float32 / 255 (data.py:116) on the device, fused with the first layer's operand split
+  const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
+  AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
+                         (const uint8_t*)h->st_img_u8, h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(),
+                         h->x.kpad, c.B, h->P));
+  ++h->launches;
+  rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
+                    nullptr, nullptr, nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
   if (rc != AIR_OK) return rc;
   if (prior && scalars_host)
     AIR_CUDA(cudaMemcpyAsync(scalars_host, outs->scalars, sizeof(float) * AIR_N_SCALARS, cudaMemcpyDeviceToHost, st));

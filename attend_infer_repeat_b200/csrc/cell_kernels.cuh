@@ -83,6 +83,8 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ D, int Ws, c
 // trainable initial state (h0, c0) [nh] tiled to the batch (cell.py:103)
 __global__ void lstm_init_state_kernel(const float* __restrict__ h0, const float* __restrict__ c0,
                                        float* __restrict__ h, float* __restrict__ c, int B, int nh, HlOut h_hl) {
+  griddep_launch();
+  griddep_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * nh) return;
   const int u = (int)(i % nh);
@@ -92,6 +94,8 @@ __global__ void lstm_init_state_kernel(const float* __restrict__ h0, const float
 }
 // explicit incoming hidden state (air_cell_step) -> hl operand of the recurrent GEMM
 __global__ void split_state_kernel(const float* __restrict__ h, int B, int nh, HlOut h_hl) {
+  griddep_launch();
+  griddep_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * nh) return;
   hl_store(h_hl, i / nh, (int)(i % nh), h[i]);
@@ -101,6 +105,8 @@ __global__ void split_state_kernel(const float* __restrict__ h, int B, int nh, H
 // h <- tanh(c) * sig(o).
 __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ c,
                                       float* __restrict__ h_out, int B, int nh, float forget_bias, HlOut h_hl) {
+  griddep_launch();
+  griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)B * nh) return;
   const size_t b = idx / nh;
@@ -122,6 +128,8 @@ __global__ void presence_kernel(const float* __restrict__ logit /*[T,B]*/, const
                                 const float* __restrict__ presence_in /*[B] or null (=1)*/,
                                 float* __restrict__ presence_prob /*[T,B]*/, float* __restrict__ presence /*[T,B]*/,
                                 int T, int B, float step_bias, float explore_eps, int discrete) {
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float pres = presence_in ? presence_in[b] : 1.0f;
@@ -173,6 +181,8 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
     mbar_expect_tx(&bar, (uint32_t)P * 4u);
     bulk_g2s(s_img, src, (uint32_t)P * 4u, &bar);
   }
+  griddep_launch();
+  griddep_wait();   // the image is an external input; m / eps come from earlier kernels of the chain
   // the T where codes of this canvas (4 components each) while the image is in flight
   if (threadIdx.x < 4 * T) {
     const int t = threadIdx.x >> 2, k = threadIdx.x & 3;
@@ -256,6 +266,8 @@ stn_read_kernel(const float* __restrict__ img, const float* __restrict__ where, 
 __global__ void what_kernel(const float* __restrict__ r, const float* __restrict__ eps, float* __restrict__ what,
                             float* __restrict__ what_loc, float* __restrict__ what_scale, size_t rows, int na,
                             float offset, HlOut what_hl) {
+  griddep_launch();
+  griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * (size_t)na) return;
   const size_t row = idx / na;
@@ -381,6 +393,8 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
   Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);         // [T][W]
   Tap* s_ty = s_tx + (size_t)T * W;                                                                      // [T][H]
 
+  griddep_launch();
+  griddep_wait();
   // stage the T decoded glimpses of this canvas (TMA bulk copies, one mbarrier)
   const bool bulk = bulk_ok(a.glimpse, G);
   if (threadIdx.x == 0 && bulk) {
@@ -559,8 +573,7 @@ inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStrea
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  paint_elbo_kernel<T><<<a.B, 256, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(paint_elbo_kernel<T>, dim3(a.B), dim3(256), smem, st, a);
 }
 inline cudaError_t launch_paint_elbo(const ElboArgs& a, cudaStream_t st) {
   const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);
@@ -612,6 +625,8 @@ elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_
                     const float* __restrict__ logq, const float* __restrict__ baseline, float* __restrict__ scalars,
                     int B, air_prior pr) {
   __shared__ float s_red[32];
+  griddep_launch();
+  griddep_wait();
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const float r = rec[b], lq = logq[b];

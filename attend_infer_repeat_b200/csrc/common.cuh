@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace air {
 
@@ -46,6 +47,45 @@ __device__ __forceinline__ void hl_store(const HlOut& o, size_t row, int col, fl
   d[0] = hi;
   d[o.plane] = lo;
 }
+
+// NaN-propagating max (fmaxf drops NaNs)
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// Programmatic dependent launch (PDL).  Every kernel of the forward chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may start while the previous kernel drains, run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, index setup) and then block in griddep_wait() until the
+// previous grid has completed and its writes are visible.  griddep_launch() lets the NEXT kernel do the same with us.
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = getenv("AIR_NO_PDL") == nullptr;
+  return on;
+}
+
+#ifdef __CUDACC__
+// <<<>>> replacement that sets the PDL attribute (or not)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -20,6 +20,8 @@ linear_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Ws[2][BK][BN];
 
+  griddep_launch();
+  griddep_wait();
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -160,16 +162,15 @@ inline cudaError_t launch_linear_simt(const float* A, int lda, const float* Wt, 
   if (N > 32) {
     constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    linear_simt_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(
-        A, lda, Wt, ldw, bias, addend, ldadd, C, ldc, M, N, K, act);
+    return launch_k(linear_simt_kernel<BM, BN, BK, TM, TN>, grid, dim3((BM / TM) * (BN / TN)), 0, st, A, lda, Wt, ldw,
+                    bias, addend, ldadd, C, ldc, M, N, K, act);
   } else {
     // skinny heads (N = 8 where-head, N = 1 presence logit): tall tiles, little wasted width
     constexpr int BM = 128, BN = 16, BK = 16, TM = 4, TN = 4;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    linear_simt_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(
-        A, lda, Wt, ldw, bias, addend, ldadd, C, ldc, M, N, K, act);
+    return launch_k(linear_simt_kernel<BM, BN, BK, TM, TN>, grid, dim3((BM / TM) * (BN / TN)), 0, st, A, lda, Wt, ldw,
+                    bias, addend, ldadd, C, ldc, M, N, K, act);
   }
-  return cudaGetLastError();
 }
 
 }  // namespace air

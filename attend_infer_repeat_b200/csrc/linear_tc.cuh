@@ -196,6 +196,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) TC_TRACE(1);
+  // PDL: everything above overlapped the previous kernel's tail; operands below come from earlier kernels
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -279,7 +282,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (threadIdx.x == 64) TC_TRACE(7);
     tc_fence_after();
     const bool f32_vec = p.out_f32 && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
-    bool overflow = false;
+    float amax = 0.f;   // NaN-propagating running max |x| of what is written as fp16 hi halves
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -288,14 +291,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tmem_ld_32x16(tmem_base + t_lane + (uint32_t)c0, v);
       tmem_ld_32x16(tmem_base + t_lane + (uint32_t)(BN + c0), vx);
       tmem_ld_wait();
+      if (threadIdx.x == 64) TC_TRACE(10 + 3 * hf);
       if (row_ok) {
+        // warp-uniform variants keep the per-element instruction count down (the epilogue is issue-bound)
+        if (p.act == ACT_ELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          float x = (v[j] + vx[j]) * W_UNSCALE + s_bias[c0 + j] + addf[hf * 16 + j];
-          x = apply_act(x, p.act);
-          v[j] = (n < p.N) ? x : 0.f;
+          for (int j = 0; j < 16; ++j) {
+            const float x = (v[j] + vx[j]) * W_UNSCALE + s_bias[c0 + j] + addf[hf * 16 + j];
+            v[j] = x > 0.f ? x : __expf(x) - 1.0f;   // ex2.approx path: <= 2.4e-7 absolute on (-1, 0]
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (v[j] + vx[j]) * W_UNSCALE + s_bias[c0 + j] + addf[hf * 16 + j];
         }
+        if (n0 + c0 + 16 > p.N) {   // only the last, partial column tile
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j >= p.N) v[j] = 0.f;
+        }
+        if (threadIdx.x == 64) TC_TRACE(11 + 3 * hf);
         if (p.out_f32) {
           float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c0;
           if (f32_vec && n0 + c0 + 16 <= p.N) {
@@ -313,7 +327,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             split_f16(v[j], hi[j], lo[j]);
-            overflow |= __hisinf(hi[j]) || __hisnan(hi[j]);
+            amax = fmax_nan(amax, fabsf(v[j]));
           }
           __half* dh = p.out_hl + (size_t)row * p.ld_hl + n0 + c0;
           __half* dl = dh + p.hl_plane;
@@ -325,7 +339,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
-    if (overflow && p.range_flag) atomicOr(p.range_flag, 1);
+    if (!(amax <= 65504.f) && p.range_flag) atomicOr(p.range_flag, 1);
     if (threadIdx.x == 64) TC_TRACE(8);
   }
 
@@ -342,6 +356,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // fp32 rows -> hl buffer (hi plane, lo plane), zero-padded K is left untouched (buffers are zeroed at creation).
 __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __half* __restrict__ dst, size_t plane,
                                   int ld_dst, int M, int K, int* range_flag) {
+  griddep_launch();
+  griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 elements
   const int kq = (K + 3) / 4;
   if (idx >= (size_t)M * kq) return;
@@ -375,6 +391,50 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __h
   if (overflow && range_flag) atomicOr(range_flag, 1);
 }
 
+// uint8 pixels (the reference's dataset format, data.py:35-107) -> float32 / 255 (load_data, data.py:116) written both
+// as fp32 rows (read by the glimpse-read and paint kernels) and, for the tensor-core engine, as the hl operand of the
+// first encoder layer.  One pass over the image batch.
+__global__ void u8_to_f32_hl_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, __half* __restrict__ hl,
+                                    size_t plane, int ld_hl, int M, int K) {
+  griddep_launch();
+  griddep_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 pixels
+  const int kq = (K + 3) / 4;
+  if (idx >= (size_t)M * kq) return;
+  const int row = (int)(idx / kq), k = (int)(idx % kq) * 4;
+  const uint8_t* s = src + (size_t)row * K + k;
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec = (k + 3 < K) && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  if (vec) {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(s);
+    f[0] = __fdiv_rn((float)u.x, 255.0f);
+    f[1] = __fdiv_rn((float)u.y, 255.0f);
+    f[2] = __fdiv_rn((float)u.z, 255.0f);
+    f[3] = __fdiv_rn((float)u.w, 255.0f);
+    *reinterpret_cast<float4*>(dst + (size_t)row * K + k) = make_float4(f[0], f[1], f[2], f[3]);
+  } else {
+    for (int j = 0; j < 4 && k + j < K; ++j) {
+      f[j] = __fdiv_rn((float)s[j], 255.0f);
+      dst[(size_t)row * K + k + j] = f[j];
+    }
+  }
+  if (hl) {
+    __half* dh = hl + (size_t)row * ld_hl + k;
+    __align__(8) __half hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_f16(f[j], hi[j], lo[j]);
+    if (k + 3 < K) {
+      *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(dh + plane) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+      for (int j = 0; j < 4 && k + j < K; ++j) {
+        dh[j] = hi[j];
+        dh[plane + j] = lo[j];
+      }
+    }
+  }
+}
+
 // One launch converts every weight matrix of the model: W[K,N] fp32 (row-major, ld = N) -> W^T hl [2][N_alloc][Kpad]
 // fp16 split of (w * 2^8).  Each CTA transposes one 32x32 tile through shared memory.
 struct PrepEntry {
@@ -389,6 +449,8 @@ __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena, const PrepEntry* __restrict__ table,
                     int n_entries, int* range_flag) {
   __shared__ float tile[32][33];
+  griddep_launch();
+  griddep_wait();
   int e = 0;
   while (e + 1 < n_entries && (int)blockIdx.x >= table[e + 1].tile_begin) ++e;
   const PrepEntry t = table[e];
@@ -460,8 +522,7 @@ inline cudaError_t launch_gemm_cfg(const CUtensorMap& tm_a, const CUtensorMap& t
     configured = true;
   }
   dim3 grid(n_alloc / BN, (p.M + BM - 1) / BM);
-  linear_tc_kernel<BN, STAGES><<<grid, num_threads(BN), L::TOTAL, st>>>(tm_a, tm_b, p);
-  return cudaGetLastError();
+  return launch_k(linear_tc_kernel<BN, STAGES>, grid, dim3(num_threads(BN)), L::TOTAL, st, tm_a, tm_b, p);
 }
 
 // Tile width `bn` (32 or 64) is fixed by how the weight was prepared.  Short K loops use a 2-stage ring (<= 100 KB of

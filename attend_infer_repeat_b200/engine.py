@@ -264,6 +264,19 @@ class Engine:
                                             C.byref(self._c_out), current_stream_ptr()), "air_elbo_scalars")
         return self.out["scalars"]
 
+    def forward_host_u8(self, params, img_u8_host, eps_where_host, eps_what_host, u_pres_host, prior: air_prior,
+                        scalars_host, loss_per_sample_host):
+        """forward_host with the images in the reference's dataset format (uint8 [B,H,W]); /255 runs on the device."""
+        assert img_u8_host.dtype == torch.uint8 and not img_u8_host.is_cuda and img_u8_host.is_contiguous()
+        for t in (eps_where_host, eps_what_host, u_pres_host, scalars_host, loss_per_sample_host):
+            assert t is not None and not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.air_forward_host_u8(self._handle, ptr(params), ptr(img_u8_host), ptr(eps_where_host),
+                                               ptr(eps_what_host), ptr(u_pres_host), C.byref(prior),
+                                               C.byref(self._c_out), ptr(scalars_host), ptr(loss_per_sample_host),
+                                               current_stream_ptr()), "air_forward_host_u8")
+        return scalars_host, loss_per_sample_host
+
     def cell_step(self, params, img, canvas, h, c, presence, eps_where, eps_what, u_pres):
         """One AIRCell step (cell.py:116-171); canvas / h / c / presence are updated IN PLACE.  Returns the per-step
         outputs glimpse, what, what_loc, what_scale, where, where_loc, where_scale, presence_prob."""

@@ -178,7 +178,7 @@ def cpu_baseline(args):
 # ------------------------------------------------------------------------------------------------------------
 def run_native(args, rank, local_rank, world):
     import attend_infer_repeat_b200 as air
-    from attend_infer_repeat_b200.data import synthetic_multi_mnist
+    from attend_infer_repeat_b200.data import synthetic_multi_mnist_u8
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -200,13 +200,15 @@ def run_native(args, rank, local_rank, world):
 
     # synthetic multi-MNIST-shaped inputs: several distinct resident sets so successive steps never re-read L2-hot data
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    base_img, _ = synthetic_multi_mnist(256, 50, 50, seed=rank)
-    sets = []
+    base_u8 = torch.from_numpy(synthetic_multi_mnist_u8(256, 50, 50, seed=rank)[0])      # dataset format: uint8
+    sets, host_u8 = [], []
     for s in range(args.input_sets):
-        idx = torch.randint(0, base_img.shape[0], (B,), generator=torch.Generator().manual_seed(s))
-        img = base_img[idx].to(dev).contiguous()
+        idx = torch.randint(0, base_u8.shape[0], (B,), generator=torch.Generator().manual_seed(s))
+        u8 = base_u8[idx].contiguous()
+        img = (u8.to(torch.float32) / 255.0).to(dev).contiguous()                          # load_data, data.py:116
         sets.append((img, torch.randn(T, B, 4, device=dev, generator=g), torch.randn(T, B, cfg.na, device=dev, generator=g),
                      torch.rand(T, B, 1, device=dev, generator=g)))
+        host_u8.append(u8.pin_memory())
     # pinned host copies for the end-to-end arm
     host = [tuple(t.cpu().pin_memory() for t in s) for s in sets[:2]]
     scal_h = torch.empty(air._lib.AIR_N_SCALARS).pin_memory()
@@ -251,27 +253,41 @@ def run_native(args, rank, local_rank, world):
     value = world * B * T * args.steps / (ms * 1e-3)
 
     # ---- end-to-end through the C ABI with HOST buffers (H2D of images + noise, D2H of the loss) -------------
-    def e2e_step(i):
+    # Headline: images in the reference's dataset format (uint8 [B,50,50], data.py:35-107), /255 on the device.
+    # Also reported: the same call fed float32 images (what load_data hands to the TF graph, data.py:116).
+    def e2e_step_u8(i):
+        _, ew, ea, u = host[i % len(host)]
+        eng.forward_host_u8(params, host_u8[i % len(host)], ew, ea, u, prior, scal_h, lps_h)
+
+    def e2e_step_f32(i):
         img, ew, ea, u = host[i % len(host)]
         eng.forward_host(params, img, ew, ea, u, prior, scal_h, lps_h)
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    h2d = sum(t.numel() * 4 for t in host[0])
+    def time_e2e(fn):
+        for i in range(3):
+            fn(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            fn(i)
+        torch.cuda.synchronize()
+        ms_ = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_
+
+    e2e_ms = time_e2e(e2e_step_u8)
+    e2e_f32_ms = time_e2e(e2e_step_f32)
+    noise_bytes = sum(t.numel() * 4 for t in host[0][1:])
     d2h = (scal_h.numel() + lps_h.numel()) * 4
-    e2e = {"value": world * B * T * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-           "api": "air_forward_host (pinned host images + noise in, loss scalars + per-sample loss out)"}
+    e2e = {"value": world * B * T * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": host_u8[0].numel() + noise_bytes, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms / args.steps,
+           "api": "air_forward_host_u8 (pinned host uint8 images + float32 noise in, loss scalars + per-sample loss out)",
+           "f32_images": {"value": world * B * T * args.steps / (e2e_f32_ms * 1e-3), "ms_per_step": e2e_f32_ms / args.steps,
+                          "h2d_bytes_per_step": host[0][0].numel() * 4 + noise_bytes, "api": "air_forward_host"}}
 
     # ---- per-stage device time of the hot path (CUDA events on the launching stream, separate pass) ----------
     eng.profile(True)

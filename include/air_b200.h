@@ -202,6 +202,14 @@ int32_t air_forward_host(air_handle* h, const float* params, const float* img_ho
                          const float* u_pres_host, const air_prior* prior, const air_outputs* outs,
                          float* scalars_host, float* loss_per_sample_host, void* stream);
 
+/* Same with the images in the reference's DATASET format: uint8 [B,H,W] (data.py:35-107; load_data divides by 255 on
+ * the host, data.py:116).  The division runs on the device, fused with the first layer's operand preparation, so the
+ * host->device copy is 4x smaller. */
+int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* img_u8_host,
+                            const float* eps_where_host, const float* eps_what_host,
+                            const float* u_pres_host, const air_prior* prior, const air_outputs* outs,
+                            float* scalars_host, float* loss_per_sample_host, void* stream);
+
 /* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
  * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be
  * known after the forward pass): AIRModel._reinforce, model.py:218-251. */

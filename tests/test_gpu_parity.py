@@ -424,3 +424,35 @@ def test_forward_tc_full_size_sample_and_engine_agreement():
     ok = same[sel]
     U.assert_close(b["loss_per_sample"][sel][ok], ref["loss_per_sample"][ok], atol=1e-4 * scale, rtol=1e-4,
                    name="loss sample")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# end-to-end entry points with host buffers (what bench.py's e2e arm calls)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, TC])
+def test_forward_host_entry_points_match_device_call(precision):
+    from attend_infer_repeat_b200.data import synthetic_multi_mnist_u8
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    B = 96
+    pc = O.PriorConfig()
+    params, _, _, noise = U.make_problem(ocfg, B, seed=41)
+    u8 = torch.from_numpy(synthetic_multi_mnist_u8(B, 50, 50, seed=41)[0]).contiguous()
+    img = u8.to(torch.float32) / 255.0                       # load_data (data.py:116)
+    ref = O.forward(ocfg, pc, params, img, *noise, global_step=20000)
+    eng = air.Engine(U.cell_cfg(ocfg, precision), B, ocfg.T, device=DEV)
+    flat = O.flatten_params(ocfg, params).to(DEV)
+    pr = U.prior_struct(pc, 20000)
+    dev_out = eng.forward(flat, img.to(DEV), *(n.to(DEV).contiguous() for n in noise), pr)
+    dev_loss = dev_out["loss_per_sample"].cpu().clone()
+    dev_scal = dev_out["scalars"].cpu().clone()
+    scal, lps = torch.empty(air._lib.AIR_N_SCALARS).pin_memory(), torch.empty(B).pin_memory()
+    pinned = [n.contiguous().pin_memory() for n in noise]
+    eng.forward_host(flat, img.contiguous().pin_memory(), *pinned, pr, scal, lps)
+    assert torch.equal(lps, dev_loss) and torch.equal(scal, dev_scal)
+    scal2, lps2 = torch.empty_like(scal).pin_memory(), torch.empty_like(lps).pin_memory()
+    eng.forward_host_u8(flat, u8.pin_memory(), *pinned, pr, scal2, lps2)        # /255 on the device
+    assert torch.equal(lps2, dev_loss) and torch.equal(scal2, dev_scal)
+    eng.check_range()
+    scale = float(ref["loss_per_sample"].abs().mean())
+    U.assert_close(lps2, ref["loss_per_sample"], atol=1e-4 * scale, rtol=1e-4, name="e2e loss vs oracle")
+    eng.close()
