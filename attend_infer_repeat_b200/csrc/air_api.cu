@@ -270,6 +270,13 @@ int32_t check_outs(const air_outputs* o, bool need_elbo) {
   return AIR_OK;
 }
 
+int32_t check_outs_elbo_only(const air_outputs* o) {
+  if (!o || !o->num_step_per_sample || !o->rec_loss_per_sample || !o->kl_num_steps_per_sample ||
+      !o->kl_what_per_sample || !o->kl_where_per_sample || !o->num_steps_log_prob || !o->scalars)
+    return fail(AIR_ERR_ARG, "air_outputs: per-sample ELBO buffers and `scalars` are mandatory");
+  return AIR_OK;
+}
+
 // The shared body of air_forward / air_cell_step: T_run steps starting from explicit or initial state.
 int32_t forward_impl(air_handle* h, const float* params, const float* img, const float* eps_where,
                      const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
@@ -794,6 +801,68 @@ int32_t air_elbo_scalars(air_handle* h, const float* baseline, const air_prior* 
   return AIR_OK;
 }
 
+int32_t air_elbo_scalars_raw(int32_t B, const float* baseline, const air_prior* prior, const air_outputs* outs,
+                             void* stream) {
+  if (B < 1 || !prior) return fail(AIR_ERR_ARG, "air_elbo_scalars_raw: bad argument");
+  const int32_t rc = check_outs_elbo_only(outs);
+  if (rc != AIR_OK) return rc;
+  AIR_CUDA(air::launch_k(air::elbo_scalars_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream,
+                         outs->rec_loss_per_sample, outs->kl_num_steps_per_sample, outs->kl_what_per_sample,
+                         outs->kl_where_per_sample, outs->num_step_per_sample, outs->num_steps_log_prob, baseline,
+                         outs->scalars, B, *prior));
+  return AIR_OK;
+}
+
+int32_t air_prior_terms(int32_t B, int32_t T, int32_t na, const float* what_loc, const float* what_scale,
+                        const float* where_loc, const float* where_scale, const float* presence_prob,
+                        const float* presence, const air_prior* prior, const air_outputs* outs, void* stream) {
+  if (B < 1 || T < 1 || T > AIR_MAX_STEPS || na < 1 || !what_loc || !what_scale || !where_loc || !where_scale ||
+      !presence_prob || !presence || !prior || !outs)
+    return fail(AIR_ERR_ARG, "air_prior_terms: bad argument");
+  if (!outs->num_steps_posterior || !outs->num_step_per_sample || !outs->prior_step_weight ||
+      !outs->rec_loss_per_sample || !outs->kl_num_steps_per_sample || !outs->kl_what_per_sample ||
+      !outs->kl_where_per_sample || !outs->loss_per_sample || !outs->num_steps_log_prob)
+    return fail(AIR_ERR_ARG, "air_prior_terms: ELBO output buffers are mandatory");
+  cudaStream_t st = (cudaStream_t)stream;
+  // a 1x1 all-zero canvas / glimpse and identity where-codes: the paint part of the fused kernel contributes nothing
+  const size_t TB = (size_t)T * B;
+  float* tmp = nullptr;
+  AIR_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (B + TB + 4 * TB), st));
+  AIR_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * (B + TB + 4 * TB), st));
+  air::ElboArgs a;
+  memset(&a, 0, sizeof(a));
+  a.img = tmp;
+  a.glimpse = tmp + B;
+  a.where = tmp + B + TB;          // zeros: sx = sy = 0 -> the inverse warp is "outside" everywhere -> canvas stays 0
+  a.where_loc = where_loc;
+  a.where_scale = where_scale;
+  a.what_loc = what_loc;
+  a.what_scale = what_scale;
+  a.presence = presence;
+  a.presence_prob = presence_prob;
+  a.num_steps_posterior = outs->num_steps_posterior;
+  a.num_step_per_sample = outs->num_step_per_sample;
+  a.prior_step_weight = outs->prior_step_weight;
+  a.rec_loss_per_sample = outs->rec_loss_per_sample;
+  a.kl_num_steps_per_sample = outs->kl_num_steps_per_sample;
+  a.kl_what_per_sample = outs->kl_what_per_sample;
+  a.kl_where_per_sample = outs->kl_where_per_sample;
+  a.loss_per_sample = outs->loss_per_sample;
+  a.num_steps_log_prob = outs->num_steps_log_prob;
+  a.T = T; a.B = B; a.H = 1; a.W = 1; a.h = 1; a.w = 1; a.na = na;
+  a.output_std = 1.0f;
+  a.output_multiplier = 1.0f;
+  a.lp_const = 0.0f;               // with x = mu = 0 the reconstruction term is exactly 0
+  a.do_elbo = 1;
+  a.prior = *prior;
+  for (int k = 0; k <= T; ++k)
+    a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
+                                                : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
+  AIR_CUDA(air::launch_paint_elbo(a, st));
+  AIR_CUDA(cudaFreeAsync(tmp, st));
+  return AIR_OK;
+}
+
 int32_t air_cell_step(air_handle* h, const float* params, const float* img, float* canvas, float* hstate,
                       float* cstate, float* presence, const float* eps_where, const float* eps_what,
                       const float* u_pres, float* out_glimpse, float* out_what, float* out_what_loc,
@@ -980,6 +1049,13 @@ int32_t air_sample_from_tensor(const float* pmf, const float* samples, float* ou
 
 double air_anneal_weight(double init_val, double final_val, int32_t anneal_type, double global_step,
                          double anneal_steps, double hold_for, double steps_div) {
+  // tf.cast(python_float, tf.float64) first makes a float32 constant (ops.convert_to_tensor), then widens it: the
+  // schedule constants of multi_mnist.py:40-47 enter the float64 island rounded to float32 (1 - 1e-15 -> 1.0).
+  init_val = (double)(float)init_val;
+  final_val = (double)(float)final_val;
+  anneal_steps = (double)(float)anneal_steps;
+  hold_for = (double)(float)hold_for;
+  steps_div = (double)(float)steps_div;
   double step = global_step - hold_for;
   if (step < 0.0) step = 0.0;
   double val = init_val;

@@ -216,6 +216,19 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
 int32_t air_elbo_scalars(air_handle* h, const float* baseline, const air_prior* prior,
                          const air_outputs* outs, void* stream);
 
+/* air_elbo_scalars without a handle (batch size given explicitly); used with air_prior_terms. */
+int32_t air_elbo_scalars_raw(int32_t B, const float* baseline, const air_prior* prior, const air_outputs* outs,
+                             void* stream);
+
+/* The KL / step-count part of the loss on explicit posterior tensors (no images): AIRModel._prior_loss
+ * (model.py:126-216) + NumStepsDistribution (prior.py:119-151).  Inputs are [T,B,.] device tensors; fills the
+ * num_steps_posterior, prior_step_weight, kl_*_per_sample, num_step_per_sample and num_steps_log_prob members of
+ * `outs` (rec_loss_per_sample is set to 0, loss_per_sample to the weighted prior terms).  Follow with
+ * air_elbo_scalars() for the batch means / REINFORCE term.  Runs the same fused kernel as air_forward. */
+int32_t air_prior_terms(int32_t B, int32_t T, int32_t na, const float* what_loc, const float* what_scale,
+                        const float* where_loc, const float* where_scale, const float* presence_prob,
+                        const float* presence, const air_prior* prior, const air_outputs* outs, void* stream);
+
 /* One AIRCell step with explicit state, the RNNCore contract of cell.py:116-171:
  * state = [img, canvas, what, where, (h, c), presence]; `canvas`, `h`, `c`, `presence` are updated
  * in place; outputs (10 tensors of cell.py:167-168) are written as [B,.] (canvas NOT multiplied). */

@@ -533,8 +533,12 @@ class PriorConfig:
 def anneal_weight(init_val, final_val, anneal_type, global_step, anneal_steps, hold_for=0.0, steps_div=1.0):
     """model.py:106-124, float64.  'exp' uses tf.train.exponential_decay(val, step, steps_div, rate) =
     val * rate ** (step / steps_div) [upstream, staircase=False]."""
-    val, final, step, hold_for, anneal_steps, steps_div = (
-        torch.tensor(float(v), dtype=F64) for v in (init_val, final_val, global_step, hold_for, anneal_steps, steps_div))
+    # tf.cast(python_float, tf.float64) goes through a float32 constant first (ops.convert_to_tensor) [upstream]:
+    # the schedule constants enter the float64 island rounded to float32 (1 - 1e-15 -> 1.0); global_step is an int64
+    # variable and is exact.  Confirmed by running the reference's own _anneal_weight (tools/make_golden.py).
+    val, final, hold_for, anneal_steps, steps_div = (
+        torch.tensor(float(v), dtype=F32).to(F64) for v in (init_val, final_val, hold_for, anneal_steps, steps_div))
+    step = torch.tensor(float(global_step), dtype=F64)
     step = torch.clamp(step - hold_for, min=0.0)
     if anneal_type == "exp":
         decay_rate = torch.pow(final / val, steps_div / anneal_steps)

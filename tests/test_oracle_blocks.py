@@ -100,12 +100,19 @@ def test_softplus_elu_match_torch():
 
 
 def test_anneal_weight_closed_form():
+    # the python-float constants enter the float64 island through float32 (tf.cast -> convert_to_tensor), see
+    # tests/golden/reference_loss.npz: init 1 - 1e-15 -> 1.0, final 1e-7 -> float32(1e-7)
+    import numpy as np
+    final = float(np.float32(1e-7))
     pc = O.PriorConfig()
-    assert float(O.steps_prior_success_prob(pc, 0)) == 1.0 - 1e-15
-    assert float(O.steps_prior_success_prob(pc, 1000)) == 1.0 - 1e-15          # hold_init
+    assert float(O.steps_prior_success_prob(pc, 0)) == 1.0
+    assert float(O.steps_prior_success_prob(pc, 1000)) == 1.0                  # hold_init
     s = float(O.steps_prior_success_prob(pc, 51000))
-    assert abs(s - (1 - 1e-15) * (1e-7 / (1 - 1e-15)) ** 0.5) < 1e-12
-    assert float(O.steps_prior_success_prob(pc, 10 ** 6)) == 1e-7               # floor at final
+    assert abs(s - final ** 0.5) < 1e-12
+    assert float(O.steps_prior_success_prob(pc, 10 ** 6)) == final              # floor at final
+    # geometric_prior still clips to 1 - 1e-15 in float64 (prior.py:28), so the step-0 prior is finite
+    p0 = O.geometric_prior(O.steps_prior_success_prob(pc, 0), 3)
+    assert p0.dtype == torch.float64 and torch.isfinite(torch.log(p0)).all() and float(p0[0]) > 0
 
 
 def test_reinforce_broadcast_identity():

@@ -1,0 +1,98 @@
+"""The oracle against golden vectors produced by the REFERENCE'S OWN prior.py / ops.py / model.py source, executed in
+this container over a torch-backed stand-in for the TF primitives (tools/make_golden.py, tools/tf_stub.py).
+This pins the step-count algebra, the anneal schedule, _prior_loss (all KL terms, analytic and sampled weights,
+shift prior with / without loc, prior weights) and _reinforce (with the [B]-[B,1] -> [B,B] broadcast)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import air_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+P = np.load(os.path.join(GOLD, "reference_prior.npz"))
+L = np.load(os.path.join(GOLD, "reference_loss.npz"))
+T32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32)
+
+
+def test_geometric_prior():
+    assert np.allclose(O.geometric_prior(.75, 10).numpy(), P["geom_075_10"], rtol=1e-6, atol=0)
+    assert np.allclose(O.geometric_prior(.005, 3).numpy(), P["geom_0005_3"], rtol=1e-6, atol=0)
+    assert np.allclose(P["geom_075_10"], .25 * .75 ** np.arange(11), atol=1e-6)      # test/prior_test.py:15-24
+
+
+def test_bernoulli_to_modified_geometric_bitwise():
+    assert np.array_equal(O.bernoulli_to_modified_geometric(T32(P["b2mg_in"])).numpy(), P["b2mg_out"])
+    assert np.array_equal(O.bernoulli_to_modified_geometric(T32(P["b2mg5_in"])).numpy(), P["b2mg5_out"])
+    assert np.array_equal(P["b2mg_out"][0], [1, 0, 0, 0]) and np.array_equal(P["b2mg_out"][1], [0, 0, 0, 1])
+
+
+def test_tabular_kl():
+    out = O.tabular_kl(T32(P["tkl_p"]), T32(P["tkl_q"])).numpy()
+    assert np.allclose(out, P["tkl_out"], rtol=1e-6, atol=1e-9)
+    assert out[0, 0] == 0.0 and P["tkl_out"][0, 0] == 0.0
+
+
+def test_num_steps_distribution():
+    joint = O.bernoulli_to_modified_geometric(T32(P["b2mg_in"]))
+    assert np.array_equal(joint.numpy(), P["nsd_joint"])
+    n = T32(P["nsd_samples"])
+    assert np.array_equal(O.num_steps_prob(joint, n).numpy(), P["nsd_prob"])
+    assert np.allclose(O.num_steps_log_prob(joint, n).numpy(), P["nsd_log_prob"], rtol=1e-6, atol=1e-7)
+
+
+def test_clip_preserve():
+    x = T32([1e-40, 0.5, 2.0]).requires_grad_(True)
+    y = O.clip_preserve(x, 1e-32, 1.0)
+    y.sum().backward()
+    assert np.array_equal(y.detach().numpy(), P["clip_out"]) and np.array_equal(x.grad.numpy(), P["clip_grad"])
+
+
+def test_anneal_weight():
+    for i, s in enumerate(L["anneal_steps"]):
+        a = float(O.anneal_weight(1. - 1e-15, 1e-7, "exp", int(s), 1e5, 1e3, 1e4))
+        assert a == pytest.approx(float(L["anneal_exp"][i]), rel=1e-13), (s, a)
+        b = float(O.anneal_weight(.9, .1, "linear", int(s), 1e5, 1e3, 1.))
+        assert b == pytest.approx(float(L["anneal_linear"][i]), rel=1e-13)
+
+
+def _case(i):
+    k = f"c{i}_"
+    cfg = L[k + "cfg"]
+    analytic, has_loc, gstep, anneal, weight = bool(cfg[0]), bool(cfg[1]), int(cfg[2]), bool(cfg[3]), float(cfg[4])
+    pc = O.PriorConfig(what_loc=float(cfg[5]), what_scale=float(cfg[6]), where_scale_loc=float(cfg[7]),
+                       where_scale_scale=float(cfg[8]), where_shift_loc=float(cfg[9]) if has_loc else None,
+                       where_shift_scale=float(cfg[10]), steps_anneal="exp" if anneal else None,
+                       steps_init=float(cfg[11]), steps_weight=weight, analytic=analytic)
+    g = {n[len(k):]: L[n] for n in L.files if n.startswith(k)}
+    return pc, gstep, g
+
+
+@pytest.mark.parametrize("i", range(int(L["n_cases"])))
+def test_prior_loss_and_reinforce(i):
+    pc, gstep, g = _case(i)
+    T, B = g["presence"].shape[:2]
+    cfg = O.AirConfig(T=T)
+    outs = {k: T32(g[k]) for k in ("presence_prob", "presence", "what_loc", "what_scale", "where_loc", "where_scale")}
+    post = dict(num_steps_posterior=O.bernoulli_to_modified_geometric(outs["presence_prob"].reshape(T, B).t()),
+                num_step_per_sample=outs["presence"].sum(0).reshape(B))
+    assert np.array_equal(post["num_steps_posterior"].numpy(), g["posterior"])
+    pl, terms = O.prior_loss(cfg, pc, outs, post, gstep)
+    # annealed: float64 scalar; fixed: the python float itself (it only becomes float32 inside geometric_prior)
+    assert float(terms["steps_prior_success_prob"]) == pytest.approx(
+        float(g["success_prob"]), rel=1e-12 if pc.steps_anneal else 1e-7)
+    close = lambda a, b, rt=2e-6: np.allclose(np.asarray(a), b, rtol=rt, atol=1e-6)
+    assert close(terms["prior_step_weight"].numpy(), g["step_weight"])
+    assert close(terms["kl_num_steps_per_sample"].numpy(), g["kl_num_steps_ps"])
+    assert close(float(terms["kl_num_steps"]), g["kl_num_steps"])
+    assert close(float(terms["kl_what"]), g["kl_what"]) and close(float(terms["kl_where"]), g["kl_where"])
+    assert close(float(pl.value), g["prior_value"]) and close(pl.per_sample.numpy(), g["prior_per_sample"])
+    rec = T32(g["rec"])
+    iw = rec if pc.analytic else rec + pl.per_sample
+    r0, iw0, lp = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, None)
+    assert close(float(r0), g["reinforce_nobaseline"], 1e-5) and close(iw0.numpy(), g["imp_weight_nobaseline"])
+    assert close(lp.numpy(), g["log_prob"])
+    r1, iw1, _ = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, T32(g["baseline"]))
+    assert tuple(iw1.shape) == (B, B) == g["imp_weight_baseline"].shape
+    assert close(iw1.numpy(), g["imp_weight_baseline"]) and close(float(r1), g["reinforce_baseline"], 1e-5)
