@@ -338,15 +338,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="canvases per GPU")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tc"])
+    ap.add_argument("--precision", default="tc", choices=["fp32", "tc"])
     ap.add_argument("--input-sets", type=int, default=4)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20            # ~2 s per 4096-batch step on 8 cores: keep the arm within minutes
         run_reference(args, rank)
         return
     if world == 1 and args.gpus > 1:
