@@ -27,6 +27,7 @@
 
 #include "../../include/air_b200.h"
 #include "cell_kernels.cuh"
+#include "chain_tc.cuh"
 #include "common.cuh"
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
@@ -72,7 +73,12 @@ struct Buf {
   int rows_alloc = 0;     // rows per plane
   int kpad = 0;           // row pitch in halves = round_up(width, 64)
   size_t plane() const { return (size_t)rows_alloc * kpad; }
-  air::HlOut hl_out() const { return air::HlOut{hl, plane(), kpad}; }
+  air::HlOut hl_out() const { return air::HlOut{hl, plane(), kpad, 0}; }
+  // slice-major tiled copy for the fused chains (chain_tc.cuh): [rows_alloc / 128][nsl][128][16] fp16 per plane
+  __half* hlt = nullptr;
+  int nsl = 0;
+  size_t plane_t() const { return (size_t)rows_alloc * nsl * 16; }
+  air::HlOut hlt_out() const { return air::HlOut{hlt, plane_t(), 0, nsl}; }
 };
 
 // A weight matrix prepared for the tensor-core engine: W^T, fp16 split of (w * 2^8), [2][N_alloc][Kpad].
@@ -81,6 +87,11 @@ struct TcWeight {
   int K = 0, N = 0, Kpad = 0, N_alloc = 0, BN = 0;
   int64_t arena_off = 0;   // halves
   CUtensorMap tm;
+  // chain_tc.cuh view of the same prepared weight: n_pass tiles of n_box rows
+  int split_n = 0, split_off = 0;   // what head only: scale half starts at row split_off
+  int n_box = 0, n_pass = 0;
+  CUtensorMap tm_chain;
+  int64_t bias_src = -1, bias_off = 0;   // bias in params; zero-padded copy in the bias arena (floats)
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -95,6 +106,9 @@ struct air_handle {
   int64_t n_params = 0;
   Mlp enc, where_mlp, steps_mlp, glenc, dec;
   Layer what_lin, lstm_x, lstm_h;
+  Layer what_chain;                // what_lin with the loc / scale halves on 16-row boundaries (chain_tc.cuh)
+  bool chain_ok = false;           // the fused-chain kernels cover this configuration
+  int na_off = 0;
   int64_t lstm_w = 0, lstm_b = 0, lstm_h0 = 0, lstm_c0 = 0;
   int max_width = 0;
   // workspace (one cudaMalloc)
@@ -110,6 +124,7 @@ struct air_handle {
   // tensor-core engine state
   std::vector<TcWeight> tcw;
   __half* arena = nullptr;
+  float* bias_arena = nullptr;
   air::tc::PrepEntry* prep_table = nullptr;
   int prep_tiles = 0;
   int* range_flag = nullptr;
@@ -118,6 +133,8 @@ struct air_handle {
   uint64_t launches = 0;
   bool profile = false;
   cudaEvent_t ev[AIR_N_STAGES + 1] = {};
+  long long* trace = nullptr;      // AIR_CHAIN_TRACE=<file prefix>: per-group clock stamps of the chain kernels (debug)
+  int trace_seq = 0;
 };
 
 namespace {
@@ -173,6 +190,7 @@ void register_tc_weight(air_handle* h, Layer& l, bool feeds_gemm) {
   w.Kpad = round_up(l.K, air::tc::BK);
   w.BN = (l.N <= 32 && !feeds_gemm) ? 32 : 64;   // hl outputs (operands of a following GEMM) need the 64-wide tile
   w.N_alloc = round_up(l.N, w.BN);
+  w.bias_src = l.b_off;
   l.tc = (int)h->tcw.size();
   h->tcw.push_back(w);
 }
@@ -277,6 +295,61 @@ int32_t check_outs_elbo_only(const air_outputs* o) {
   return AIR_OK;
 }
 
+// One layer of a fused chain (chain_tc.cuh) from a prepared weight.
+void chain_add(const air_handle* h, air::chain::Params& p, const float* params, const Layer& l, int epi, int a_src,
+               int a_buf, float* out, int ldo) {
+  const TcWeight& w = h->tcw[l.tc];
+  air::chain::Layer& L = p.layer[p.n_layers];
+  p.tm[p.n_layers] = w.tm_chain;
+  L.K = l.K;
+  L.N = w.split_n > 0 ? w.N_alloc : l.N;
+  L.n_box = w.n_box;
+  L.n_pass = w.n_pass;
+  L.lo_row = w.N_alloc;
+  L.epi = epi;
+  L.a_src = a_src;
+  L.a_buf = a_buf;
+  L.bias = h->bias_arena + w.bias_off;
+  L.out = out;
+  L.ldo = ldo;
+  ++p.n_layers;
+}
+// a whole neural.MLP whose first layer reads in[a_buf] and whose last layer writes fp32 rows to `out`
+void chain_add_mlp(const air_handle* h, air::chain::Params& p, const float* params, const Mlp& mlp, int a_buf,
+                   bool first_loads, float* out, int ldo) {
+  const int nl = (int)mlp.layers.size();
+  for (int i = 0; i < nl; ++i) {
+    const bool last = i == nl - 1;
+    chain_add(h, p, params, mlp.layers[i], last && out ? air::chain::EPI_F32 : air::chain::EPI_ELU_A,
+              (i == 0 && first_loads) ? air::chain::A_LOAD : air::chain::A_KEEP, a_buf, last ? out : nullptr, ldo);
+  }
+}
+// debug: AIR_CHAIN_TRACE=<prefix> dumps the per-group SM-clock stamps of every chain launch to <prefix>.<seq>.bin
+int32_t launch_chain_traced(air_handle* h, air::chain::Params& cp, cudaStream_t st) {
+  static const char* prefix = getenv("AIR_CHAIN_TRACE");
+  if (!prefix) {
+    AIR_CUDA(air::chain::launch_chain(cp, st));
+    return AIR_OK;
+  }
+  const int n_cta = (cp.M + air::tc::BM - 1) / air::tc::BM;
+  const size_t n = (size_t)n_cta * air::chain::TRACE_GROUPS * 8;
+  if (!h->trace) AIR_CUDA(cudaMalloc(&h->trace, sizeof(long long) * 4096 * air::chain::TRACE_GROUPS * 8));
+  AIR_CUDA(cudaMemsetAsync(h->trace, 0, sizeof(long long) * n, st));
+  cp.trace = h->trace;
+  AIR_CUDA(air::chain::launch_chain(cp, st));
+  std::vector<long long> host(n);
+  AIR_CUDA(cudaMemcpyAsync(host.data(), h->trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+  AIR_CUDA(cudaStreamSynchronize(st));
+  const std::string path = std::string(prefix) + "." + std::to_string(h->trace_seq++) + ".bin";
+  if (FILE* f = fopen(path.c_str(), "wb")) {
+    fwrite(host.data(), sizeof(long long), n, f);
+    fclose(f);
+  }
+  return AIR_OK;
+}
+
+air::chain::HlIn chain_in(const Buf& b) { return air::chain::HlIn{b.hlt, b.plane_t(), b.nsl}; }
+
 // The shared body of air_forward / air_cell_step: T_run steps starting from explicit or initial state.
 int32_t forward_impl(air_handle* h, const float* params, const float* img, const float* eps_where,
                      const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
@@ -288,7 +361,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   const int TB = T_run * B;
   const int thr = 256;
   const bool tc = h->use_tc;
-  const air::HlOut no_hl{nullptr, 0, 0};
+  const air::HlOut no_hl{nullptr, 0, 0, 0};
   int32_t rc;
 
   // 0. tensor-core engine: (re)build the fp16-split W^T arena from the current parameters and split the images
@@ -298,7 +371,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   x.ld = P;
   if (tc) {
     AIR_CUDA(air::launch_k(air::tc::prep_weights_kernel, dim3(h->prep_tiles), dim3(256), 0, st, params, h->arena,
-                           h->prep_table, (int)h->tcw.size(), h->range_flag));
+                           h->prep_table, (int)h->tcw.size(), h->range_flag, h->bias_arena));
     ++h->launches;
     if (!x_hl_ready) {
       const size_t n4 = (size_t)B * ((P + 3) / 4);
@@ -349,7 +422,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
       hs_hl.p += (size_t)t * B * h->hs.kpad;
     }
     AIR_CUDA(air::launch_k(air::lstm_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st, h->gates,
-                           h->cbuf, h->hs.f32 + (size_t)t * B * nh, B, nh, c.forget_bias, hs_hl));
+                           h->cbuf, h->hs.f32 + (size_t)t * B * nh, B, nh, c.forget_bias, hs_hl,
+                           (tc && h->chain_ok) ? h->hs.hlt_out() : no_hl, (size_t)t * B));
     ++h->launches;
   }
   if (o->final_h)
@@ -363,12 +437,26 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   Buf m;
   m.f32 = h->m;
   m.ld = 8;
-  if ((rc = run_mlp(h, params, h->where_mlp, h->hs, TB, m, true, false, st)) != AIR_OK) return rc;   // modules.py:58-63
-  mark(h, AIR_ST_STEPS, st);
   Buf logit;
   logit.f32 = h->logit;
   logit.ld = 1;
-  if ((rc = run_mlp(h, params, h->steps_mlp, h->hs, TB, logit, true, false, st)) != AIR_OK) return rc;   // :119-122
+  if (tc && h->chain_ok) {
+    // both heads of every (t, canvas) row in ONE launch: hs -> where MLP -> m ; hs -> steps MLP -> logit
+    air::chain::Params cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.M = TB;
+    cp.in[0] = chain_in(h->hs);
+    cp.range_flag = h->range_flag;
+    chain_add_mlp(h, cp, params, h->where_mlp, 0, true, h->m, 8);       // modules.py:58-63
+    chain_add_mlp(h, cp, params, h->steps_mlp, 0, true, h->logit, 1);   // modules.py:119-122
+    if ((rc = launch_chain_traced(h, cp, st)) != AIR_OK) return rc;
+    ++h->launches;
+    mark(h, AIR_ST_STEPS, st);
+  } else {
+    if ((rc = run_mlp(h, params, h->where_mlp, h->hs, TB, m, true, false, st)) != AIR_OK) return rc;   // modules.py:58-63
+    mark(h, AIR_ST_STEPS, st);
+    if ((rc = run_mlp(h, params, h->steps_mlp, h->hs, TB, logit, true, false, st)) != AIR_OK) return rc;   // :119-122
+  }
   AIR_CUDA(air::launch_k(air::presence_kernel, dim3((B + 127) / 128), dim3(128), 0, st, h->logit, u_pres, presence_in,
                          o->presence_prob, o->presence, T_run, B, c.step_bias, c.explore_eps, c.discrete_steps));
   ++h->launches;
@@ -377,39 +465,64 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   // 5. where sampling + glimpse read   (cell.py:129-135)
   AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(256), air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
                          h->m, eps_where, img, o->where, o->where_loc, o->where_scale, tc ? nullptr : h->crop.f32,
-                         tc ? h->crop.hl_out() : no_hl, T_run, B, c.H, c.W, c.h, c.w, c.max_crop_size, c.scale_bias));
+                         tc ? (h->chain_ok ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
+                         c.max_crop_size, c.scale_bias));
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
-  // 6. glimpse encoder -> what   (cell.py:153-156)
-  {
-    const Layer& last = h->glenc.layers.back();
-    Buf q = (h->glenc.layers.size() & 1) ? h->ping : h->pong;   // where the chain's last layer may land
-    q.ld = last.N;
-    q.kpad = round_up(last.N, air::tc::BK);
-    if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc, tc, st)) != AIR_OK) return rc;
-    Buf r;
-    r.f32 = h->r;
-    r.ld = 2 * na;
-    if ((rc = dense(h, params, q, 0, h->what_lin, true, nullptr, 0, r, true, false, TB, air::ACT_NONE, st)) != AIR_OK)
-      return rc;
-    const size_t n = (size_t)TB * na;
-    AIR_CUDA(air::launch_k(air::what_kernel, dim3((unsigned)((n + thr - 1) / thr)), dim3(thr), 0, st, h->r, eps_what,
-                           o->what, o->what_loc, o->what_scale, (size_t)TB, na, c.what_scale_offset,
-                           tc ? h->what_in.hl_out() : no_hl));
+  // 6. glimpse encoder -> what   (cell.py:153-156)   7. decoder   (cell.py:158)
+  if (tc && h->chain_ok) {
+    // crop -> glimpse Encoder -> what head (sample) -> Decoder -> glimpse, one launch, activations resident in TMEM
+    air::chain::Params cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.M = TB;
+    cp.in[0] = chain_in(h->crop);
+    cp.range_flag = h->range_flag;
+    cp.eps_what = eps_what;
+    cp.what = o->what;
+    cp.what_loc = o->what_loc;
+    cp.what_scale = o->what_scale;
+    cp.na = na;
+    cp.na_off = h->na_off;
+    cp.what_offset = c.what_scale_offset;
+    chain_add_mlp(h, cp, params, h->glenc, 0, true, nullptr, 0);
+    chain_add(h, cp, params, h->what_chain, air::chain::EPI_WHAT, air::chain::A_KEEP, 0, nullptr, 0);
+    {
+      Mlp dec = h->dec;
+      dec.layers[0].K = na;
+      chain_add_mlp(h, cp, params, dec, 0, false, o->glimpse, G);
+    }
+    if ((rc = launch_chain_traced(h, cp, st)) != AIR_OK) return rc;
     ++h->launches;
-  }
-  mark(h, AIR_ST_DECODER, st);
-
-  // 7. decoder   (cell.py:158)
-  {
-    Buf what = h->what_in;
-    what.f32 = o->what;
-    what.ld = na;
-    Buf glimpse;
-    glimpse.f32 = o->glimpse;
-    glimpse.ld = G;
-    if ((rc = run_mlp(h, params, h->dec, what, TB, glimpse, true, false, st)) != AIR_OK) return rc;
+    mark(h, AIR_ST_DECODER, st);
+  } else {
+    {
+      const Layer& last = h->glenc.layers.back();
+      Buf q = (h->glenc.layers.size() & 1) ? h->ping : h->pong;   // where the chain's last layer may land
+      q.ld = last.N;
+      q.kpad = round_up(last.N, air::tc::BK);
+      if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc, tc, st)) != AIR_OK) return rc;
+      Buf r;
+      r.f32 = h->r;
+      r.ld = 2 * na;
+      if ((rc = dense(h, params, q, 0, h->what_lin, true, nullptr, 0, r, true, false, TB, air::ACT_NONE, st)) != AIR_OK)
+        return rc;
+      const size_t n = (size_t)TB * na;
+      AIR_CUDA(air::launch_k(air::what_kernel, dim3((unsigned)((n + thr - 1) / thr)), dim3(thr), 0, st, h->r, eps_what,
+                             o->what, o->what_loc, o->what_scale, (size_t)TB, na, c.what_scale_offset,
+                             tc ? h->what_in.hl_out() : no_hl));
+      ++h->launches;
+    }
+    mark(h, AIR_ST_DECODER, st);
+    {
+      Buf what = h->what_in;
+      what.f32 = o->what;
+      what.ld = na;
+      Buf glimpse;
+      glimpse.f32 = o->glimpse;
+      glimpse.ld = G;
+      if ((rc = run_mlp(h, params, h->dec, what, TB, glimpse, true, false, st)) != AIR_OK) return rc;
+    }
   }
   mark(h, AIR_ST_PAINT_ELBO, st);
 
@@ -523,12 +636,21 @@ void carve_workspace(air_handle* h, Carver& cv) {
     hl(h->hs, TB_alloc, c.nh);
     hl(h->crop, TB_alloc, h->G);
     hl(h->what_in, TB_alloc, c.na);
-    size_t halves = 0;
+    auto hlt = [&](Buf& b, int width) {
+      b.nsl = (width + 15) / 16;
+      b.hlt = cv.take<__half>(2 * (size_t)b.rows_alloc * b.nsl * 16);
+    };
+    hlt(h->hs, c.nh);
+    hlt(h->crop, h->G);
+    size_t halves = 0, bias_floats = 0;
     for (TcWeight& w : h->tcw) {
       w.arena_off = (int64_t)halves;
       halves += align_up(2 * (size_t)w.N_alloc * w.Kpad, 512);
+      w.bias_off = (int64_t)bias_floats;
+      bias_floats += (size_t)w.N_alloc;
     }
     h->arena = cv.take<__half>(halves);
+    h->bias_arena = cv.take<float>(bias_floats);
     h->prep_table = cv.take<air::tc::PrepEntry>(h->tcw.size());
     h->range_flag = cv.take<int>(1);
   }
@@ -605,6 +727,27 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
     register_tc_weight(h, h->lstm_x, false);
     register_tc_weight(h, h->lstm_h, false);
     register_tc_weight(h, h->what_lin, false);
+    // fused chains (chain_tc.cuh): every hidden activation must fit the 256-K TMEM operand
+    h->na_off = round_up(c.na, 16);
+    bool ok = getenv("AIR_NO_CHAIN") == nullptr && 2 * h->na_off <= 256;
+    for (const Mlp* mlp : {&h->where_mlp, &h->steps_mlp, &h->glenc, &h->dec})
+      for (int i = 0; i < mlp->n_hidden; ++i) ok = ok && mlp->layers[i].N <= 256;
+    h->chain_ok = ok;
+    if (ok) {
+      h->what_chain = h->what_lin;
+      TcWeight w;
+      w.src_off = h->what_lin.w_off;
+      w.K = h->what_lin.K;
+      w.N = h->what_lin.N;
+      w.Kpad = round_up(w.K, air::tc::BK);
+      w.BN = 64;
+      w.N_alloc = 2 * h->na_off;
+      w.split_n = c.na;
+      w.split_off = h->na_off;
+      w.bias_src = h->what_lin.b_off;
+      h->what_chain.tc = (int)h->tcw.size();
+      h->tcw.push_back(w);
+    }
   }
 
   // shared-memory budgets of the per-canvas kernels
@@ -646,9 +789,21 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
       pe.Kpad = w.Kpad;
       pe.tile_begin = tiles;
       pe.tiles_n = (w.N + 31) / 32;
+      pe.split_n = w.split_n;
+      pe.split_off = w.split_off;
+      pe.bias_src = w.bias_src;
+      pe.bias_dst = w.bias_off;
       tiles += pe.tiles_n * ((w.K + 31) / 32);
       table.push_back(pe);
       ok = ok && air::tc::make_tmap(&w.tm, h->arena + w.arena_off, w.Kpad, 2 * (int64_t)w.N_alloc, w.BN);
+      if (h->chain_ok) {
+        const int n_eff = w.split_n > 0 ? w.N_alloc : w.N;
+        w.n_pass = (n_eff + 255) / 256;
+        w.n_box = round_up((n_eff + w.n_pass - 1) / w.n_pass, 16);
+        if (w.n_pass * w.n_box > w.N_alloc) h->chain_ok = false;
+        else
+          ok = ok && air::chain::make_weight_tmap(&w.tm_chain, h->arena + w.arena_off, w.Kpad, w.N_alloc, w.n_box);
+      }
     }
     h->prep_tiles = tiles;
     if (ok)
@@ -669,6 +824,7 @@ int32_t air_destroy(air_handle* h) {
   for (cudaEvent_t e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
+  if (h->trace) cudaFree(h->trace);
   delete h;
   return AIR_OK;
 }
@@ -925,8 +1081,12 @@ int32_t air_linear(const float* A, const float* Wt, const float* bias, float* ou
   pe.Kpad = Kpad;
   pe.tile_begin = 0;
   pe.tiles_n = (N + 31) / 32;
+  pe.split_n = 0;
+  pe.split_off = 0;
   AIR_CUDA(cudaMemcpyAsync(table, &pe, sizeof(pe), cudaMemcpyHostToDevice, st));
-  tc::prep_weights_kernel<<<pe.tiles_n * ((K + 31) / 32), 256, 0, st>>>(Wt, w_hl, table, 1, flag);
+  pe.bias_src = -1;
+  pe.bias_dst = 0;
+  tc::prep_weights_kernel<<<pe.tiles_n * ((K + 31) / 32), 256, 0, st>>>(Wt, w_hl, table, 1, flag, nullptr);
   AIR_CUDA(cudaGetLastError());
   const size_t n4 = (size_t)M * ((K + 3) / 4);
   tc::split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(A, K, a_hl, (size_t)M_alloc * Kpad, Kpad, M, K, flag);
@@ -968,7 +1128,8 @@ int32_t air_lstm_step(const float* x, float* hstate, float* cstate, const float*
   AIR_CUDA(air::launch_linear_simt(hstate, nh, W + (size_t)nx * 4 * nh, 4 * nh, nullptr, gx, 4 * nh, gates, 4 * nh, B,
                                    4 * nh, nh, air::ACT_NONE, st));
   air::lstm_pointwise_kernel<<<(B * nh + 255) / 256, 256, 0, st>>>(gates, cstate, hstate, B, nh, forget_bias,
-                                                                  air::HlOut{nullptr, 0, 0});
+                                                                  air::HlOut{nullptr, 0, 0, 0},
+                                                                  air::HlOut{nullptr, 0, 0, 0}, 0);
   AIR_CUDA(cudaGetLastError());
   AIR_CUDA(cudaFreeAsync(gates, st));
   return AIR_OK;

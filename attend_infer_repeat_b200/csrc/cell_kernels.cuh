@@ -104,7 +104,8 @@ __global__ void split_state_kernel(const float* __restrict__ h, int B, int nh, H
 // gates[B,4nh] (order i, j, f, o) already hold [x,h] @ W + b.  c <- sig(f + fb) * c + sig(i) * tanh(j);
 // h <- tanh(c) * sig(o).
 __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ c,
-                                      float* __restrict__ h_out, int B, int nh, float forget_bias, HlOut h_hl) {
+                                      float* __restrict__ h_out, int B, int nh, float forget_bias, HlOut h_hl,
+                                      HlOut h_hl2, size_t row0_hl2) {
   griddep_launch();
   griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,6 +119,7 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __
   const float h_new = __fmul_rn(tanhf(c_new), sigmoid_f(go));
   h_out[idx] = h_new;
   if (h_hl.p) hl_store(h_hl, b, u, h_new);
+  if (h_hl2.p) hl_store(h_hl2, row0_hl2 + b, u, h_new);   // second copy in the fused chains' layout, row = t * B + b
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -211,7 +213,6 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   for (int t = 0; t < T; ++t) {
     const size_t row = (size_t)t * B + b;
     float* cf = crop ? crop + row * (size_t)G : nullptr;
-    __half* ch = crop_hl.p ? crop_hl.p + row * (size_t)crop_hl.ld : nullptr;
     const Tap* txs = s_tx + t * w;
     const Tap* tys = s_ty + t * h;
     int r = (int)threadIdx.x / w, c = (int)threadIdx.x - r * w;
@@ -220,12 +221,7 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
       float v = 0.f;
       if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear(s_img, W, tx, ty);
       if (cf) cf[g] = v;
-      if (ch) {
-        __half hi, lo;
-        split_f16(v, hi, lo);
-        ch[g] = hi;
-        ch[crop_hl.plane + g] = lo;
-      }
+      if (crop_hl.p) hl_store(crop_hl, row, g, v);
       c += dc;
       r += dr;
       if (c >= w) {

@@ -35,15 +35,22 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 }
 // Optional second output of a producer kernel: the consumer GEMM's A operand in "hl" format
 // (fp16 [2][rows_alloc][ld]: hi plane, then lo plane; see linear_tc.cuh).  p == nullptr -> not written.
+// nsl > 0 selects the slice-major tiled layout read by the fused chains (chain_tc.cuh):
+// [row tile of 128][K slice of 16][128 rows][16 fp16] per plane, nsl = K slices per row.
 struct HlOut {
   __half* p;
   size_t plane;
   int ld;
+  int nsl;
 };
+__device__ __forceinline__ size_t hl_index(const HlOut& o, size_t row, int col) {
+  if (o.nsl > 0) return (((row >> 7) * (size_t)o.nsl + (size_t)(col >> 4)) * 128 + (row & 127)) * 16 + (col & 15);
+  return row * (size_t)o.ld + col;
+}
 __device__ __forceinline__ void hl_store(const HlOut& o, size_t row, int col, float x) {
   __half hi, lo;
   split_f16(x, hi, lo);
-  __half* d = o.p + row * (size_t)o.ld + col;
+  __half* d = o.p + hl_index(o, row, col);
   d[0] = hi;
   d[o.plane] = lo;
 }

@@ -101,6 +101,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the destination registers of the load so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -444,10 +453,14 @@ struct PrepEntry {
   int K, N, Kpad;
   int tile_begin;      // first tile index of this matrix in the global tile list
   int tiles_n;         // tiles along N
+  int split_n;         // > 0: source columns n >= split_n land at destination row n - split_n + split_off (the what
+  int split_off;       //      head's loc / scale halves, each starting on a 16-row boundary for chain_tc.cuh)
+  int64_t bias_src;    // float offset of the bias in params (< 0: none) and of its zero-padded copy in the bias arena
+  int64_t bias_dst;
 };
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena, const PrepEntry* __restrict__ table,
-                    int n_entries, int* range_flag) {
+                    int n_entries, int* range_flag, float* __restrict__ bias_arena) {
   __shared__ float tile[32][33];
   griddep_launch();
   griddep_wait();
@@ -458,6 +471,13 @@ prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena
   const int tk = local / t.tiles_n, tn = local % t.tiles_n;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const float* W = params + t.src_off;
+  if (tk == 0 && bias_arena && t.bias_src >= 0 && threadIdx.x < 32) {   // padded bias copy (same row remap as W^T)
+    const int n = tn * 32 + threadIdx.x;
+    if (n < t.N) {
+      const int n_dst = (t.split_n > 0 && n >= t.split_n) ? n - t.split_n + t.split_off : n;
+      bias_arena[t.bias_dst + n_dst] = params[t.bias_src + n];
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int k = tk * 32 + ty + i, n = tn * 32 + tx;
@@ -472,7 +492,8 @@ prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena
       __half hi, lo;
       split_f16(tile[tx][ty + i] * W_SCALE, hi, lo);
       overflow |= __hisinf(hi) || __hisnan(hi);
-      __half* d = arena + t.dst_off + (size_t)n * t.Kpad + k;
+      const int n_dst = (t.split_n > 0 && n >= t.split_n) ? n - t.split_n + t.split_off : n;
+      __half* d = arena + t.dst_off + (size_t)n_dst * t.Kpad + k;
       d[0] = hi;
       d[t.plane] = lo;
     }

@@ -300,12 +300,20 @@ def run_native(args, rank, local_rank, world):
     eng.profile(False)
     macs, total_macs = executed_macs_per_sample(cfg, T)
     hbm_peak, tf_peak, peak_kind = measured_peaks()
-    gemm_stages = ["input_encoder", "where_mlp", "decoder"]          # stages that contain ONLY dense-layer launches
+    if prec == air.AIR_PREC_FP32:
+        # stages that contain ONLY dense-layer launches
+        gemm_stages, mac_keys = ["input_encoder", "where_mlp", "decoder"], ["input_encoder", "where_mlp", "decoder"]
+        engine_name = "linear_simt_kernel (fp32 FMA)"
+    else:
+        # the two fused-chain launches (chain_tc.cuh): heads (where + steps MLPs) and glimpse VAE (encoder, what, decoder);
+        # with chains on, the `where_mlp` and `glimpse_enc` stage intervals hold exactly one chain_kernel launch each
+        gemm_stages = ["where_mlp", "glimpse_enc"]
+        mac_keys = ["where_mlp", "steps_presence", "glimpse_enc", "decoder"]
+        engine_name = "chain_kernel (tcgen05 TS-form fp16x2 split, activations resident in TMEM)"
     gemm_ms = sum(acc[s] for s in gemm_stages)
-    gemm_flops = 2.0 * B * sum(macs[s] for s in gemm_stages)
+    gemm_flops = 2.0 * B * sum(macs[s] for s in mac_keys)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     stage_share = {k: round(v / sum(acc.values()), 4) for k, v in acc.items()}
-    engine_name = "linear_simt_kernel (fp32 FMA)" if prec == air.AIR_PREC_FP32 else "linear_tc_kernel (tcgen05 fp16x2 split)"
     roofline = {"bound": "tensor", "kernel": engine_name, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": achieved / tf_peak, "peak_kind": f"bf16 dense sustained, {peak_kind}", "traffic": None,
                 "flops_per_launch_set": gemm_flops, "ms_per_launch_set": gemm_ms,
