@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
+#include "lstm_tc.cuh"
 
 namespace {
 
@@ -92,6 +93,7 @@ struct TcWeight {
   int n_box = 0, n_pass = 0;
   CUtensorMap tm_chain;
   int64_t bias_src = -1, bias_off = 0;   // bias in params; zero-padded copy in the bias arena (floats)
+  int perm_nh = 0;                       // lstm_tc.cuh column regrouping
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -109,6 +111,10 @@ struct air_handle {
   Layer what_chain;                // what_lin with the loc / scale halves on 16-row boundaries (chain_tc.cuh)
   bool chain_ok = false;           // the fused-chain kernels cover this configuration
   int na_off = 0;
+  bool lstm_ok = false;            // the cluster LSTM kernel (lstm_tc.cuh) covers this configuration
+  int lstm_x_perm = -1, lstm_h_perm = -1;   // tcw indices of the regrouped W[:n_enc] / W[n_enc:]
+  float* gx_scr = nullptr;
+  __half* hx = nullptr;
   int64_t lstm_w = 0, lstm_b = 0, lstm_h0 = 0, lstm_c0 = 0;
   int max_width = 0;
   // workspace (one cudaMalloc)
@@ -382,21 +388,23 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   }
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
-  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc, tc, st)) != AIR_OK) return rc;
+  const bool lstm_fused = tc && h->lstm_ok;
+  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused, tc && !lstm_fused, st)) != AIR_OK) return rc;
   mark(h, AIR_ST_LSTM, st);
 
   // 2. gx = e @ W[:n_enc] + b   (input half of snt.LSTM's [x,h] @ W + b)
   Buf gx;
   gx.f32 = h->gx;
   gx.ld = 4 * nh;
-  if ((rc = dense(h, params, h->e, 0, h->lstm_x, true, nullptr, 0, gx, true, false, B, air::ACT_NONE, st)) != AIR_OK)
+  if (!lstm_fused &&
+      (rc = dense(h, params, h->e, 0, h->lstm_x, true, nullptr, 0, gx, true, false, B, air::ACT_NONE, st)) != AIR_OK)
     return rc;
 
   // 3. recurrence: gates = gx + h_{t-1} @ W[n_enc:]; (c, h_t) pointwise
   if (h_in) {
     AIR_CUDA(cudaMemcpyAsync(h->h_init.f32, h_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
     AIR_CUDA(cudaMemcpyAsync(h->cbuf, c_in, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
-    if (tc) {
+    if (tc && !lstm_fused) {
       AIR_CUDA(air::launch_k(air::split_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st, h_in, B, nh,
                              h->h_init.hl_out()));
       ++h->launches;
@@ -404,13 +412,36 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   } else {
     AIR_CUDA(air::launch_k(air::lstm_init_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
                            params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, h->cbuf, B, nh,
-                           tc ? h->h_init.hl_out() : no_hl));
+                           (tc && !lstm_fused) ? h->h_init.hl_out() : no_hl));
     ++h->launches;
   }
   Buf gates;
   gates.f32 = h->gates;
   gates.ld = 4 * nh;
-  for (int t = 0; t < T_run; ++t) {
+  if (lstm_fused) {
+    // gx + all T recurrent steps in one cluster launch (lstm_tc.cuh)
+    air::lstm::Params lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.tm_x = h->tcw[h->lstm_x_perm].tm_chain;
+    lp.tm_h = h->tcw[h->lstm_h_perm].tm_chain;
+    lp.bias = h->bias_arena + h->tcw[h->lstm_x_perm].bias_off;
+    lp.e = h->e.f32;
+    lp.n_enc = h->n_enc;
+    lp.h_init = h->h_init.f32;
+    lp.c = h->cbuf;
+    lp.hs = h->hs.f32;
+    lp.hs_hlt = h->hs.hlt_out();
+    lp.gx_scr = h->gx_scr;
+    lp.hx = h->hx;
+    lp.hx_plane = (size_t)round_up(B, air::tc::BM) * nh;
+    lp.B = B;
+    lp.T = T_run;
+    lp.forget_bias = c.forget_bias;
+    lp.range_flag = h->range_flag;
+    AIR_CUDA(air::lstm::launch_lstm(lp, st));
+    ++h->launches;
+  }
+  for (int t = 0; t < (lstm_fused ? 0 : T_run); ++t) {
     const Buf& h_prev = (t == 0) ? h->h_init : h->hs;
     const int row0 = (t == 0) ? 0 : (t - 1) * B;
     if ((rc = dense(h, params, h_prev, row0, h->lstm_h, false, h->gx, 4 * nh, gates, true, false, B, air::ACT_NONE,
@@ -614,6 +645,7 @@ void carve_workspace(air_handle* h, Carver& cv) {
   }
   f32(h->h_init, B, c.nh);
   f32(h->hs, TB, c.nh);
+  if (tc) f32(h->e, B, h->n_enc);
   h->gx = cv.take<float>(B * 4 * c.nh);
   h->gates = cv.take<float>(B * 4 * c.nh);
   h->cbuf = cv.take<float>(B * c.nh);
@@ -642,6 +674,10 @@ void carve_workspace(air_handle* h, Carver& cv) {
     };
     hlt(h->hs, c.nh);
     hlt(h->crop, h->G);
+    if (h->lstm_ok) {
+      h->gx_scr = cv.take<float>((size_t)B_alloc * 4 * c.nh);
+      h->hx = cv.take<__half>(2 * 2 * (size_t)B_alloc * c.nh);
+    }
     size_t halves = 0, bias_floats = 0;
     for (TcWeight& w : h->tcw) {
       w.arena_off = (int64_t)halves;
@@ -748,6 +784,24 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
       h->what_chain.tc = (int)h->tcw.size();
       h->tcw.push_back(w);
     }
+    // cluster LSTM kernel: snt.LSTM(256) with an encoder output that fits the TMEM operand
+    h->lstm_ok = h->chain_ok && getenv("AIR_NO_LSTM_CLUSTER") == nullptr && c.nh == air::lstm::NH && h->n_enc <= 256;
+    if (h->lstm_ok) {
+      for (int which = 0; which < 2; ++which) {
+        const Layer& l = which == 0 ? h->lstm_x : h->lstm_h;
+        TcWeight w;
+        w.src_off = l.w_off;
+        w.K = l.K;
+        w.N = l.N;
+        w.Kpad = round_up(w.K, air::tc::BK);
+        w.BN = 64;
+        w.N_alloc = l.N;
+        w.perm_nh = c.nh;
+        w.bias_src = which == 0 ? h->lstm_b : -1;
+        (which == 0 ? h->lstm_x_perm : h->lstm_h_perm) = (int)h->tcw.size();
+        h->tcw.push_back(w);
+      }
+    }
   }
 
   // shared-memory budgets of the per-canvas kernels
@@ -793,13 +847,14 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
       pe.split_off = w.split_off;
       pe.bias_src = w.bias_src;
       pe.bias_dst = w.bias_off;
+      pe.perm_nh = w.perm_nh;
       tiles += pe.tiles_n * ((w.K + 31) / 32);
       table.push_back(pe);
       ok = ok && air::tc::make_tmap(&w.tm, h->arena + w.arena_off, w.Kpad, 2 * (int64_t)w.N_alloc, w.BN);
       if (h->chain_ok) {
         const int n_eff = w.split_n > 0 ? w.N_alloc : w.N;
         w.n_pass = (n_eff + 255) / 256;
-        w.n_box = round_up((n_eff + w.n_pass - 1) / w.n_pass, 16);
+        w.n_box = w.perm_nh > 0 ? w.perm_nh : round_up((n_eff + w.n_pass - 1) / w.n_pass, 16);
         if (w.n_pass * w.n_box > w.N_alloc) h->chain_ok = false;
         else
           ok = ok && air::chain::make_weight_tmap(&w.tm_chain, h->arena + w.arena_off, w.Kpad, w.N_alloc, w.n_box);
@@ -1086,6 +1141,7 @@ int32_t air_linear(const float* A, const float* Wt, const float* bias, float* ou
   AIR_CUDA(cudaMemcpyAsync(table, &pe, sizeof(pe), cudaMemcpyHostToDevice, st));
   pe.bias_src = -1;
   pe.bias_dst = 0;
+  pe.perm_nh = 0;
   tc::prep_weights_kernel<<<pe.tiles_n * ((K + 31) / 32), 256, 0, st>>>(Wt, w_hl, table, 1, flag, nullptr);
   AIR_CUDA(cudaGetLastError());
   const size_t n4 = (size_t)M * ((K + 3) / 4);

@@ -457,7 +457,16 @@ struct PrepEntry {
   int split_off;       //      head's loc / scale halves, each starting on a 16-row boundary for chain_tc.cuh)
   int64_t bias_src;    // float offset of the bias in params (< 0: none) and of its zero-padded copy in the bias arena
   int64_t bias_dst;
+  int perm_nh;         // > 0: LSTM gate columns (gate-major, [4][nh]) regrouped per cluster CTA for lstm_tc.cuh:
+                       //      column gate * nh + unit -> row (unit / upc) * nh + gate * upc + unit % upc, upc = nh / 4
 };
+__device__ __forceinline__ int prep_dst_row(const PrepEntry& t, int n) {
+  if (t.perm_nh > 0) {
+    const int upc = t.perm_nh >> 2, gate = n / t.perm_nh, unit = n % t.perm_nh;
+    return (unit / upc) * t.perm_nh + gate * upc + unit % upc;
+  }
+  return (t.split_n > 0 && n >= t.split_n) ? n - t.split_n + t.split_off : n;
+}
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena, const PrepEntry* __restrict__ table,
                     int n_entries, int* range_flag, float* __restrict__ bias_arena) {
@@ -474,8 +483,7 @@ prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena
   if (tk == 0 && bias_arena && t.bias_src >= 0 && threadIdx.x < 32) {   // padded bias copy (same row remap as W^T)
     const int n = tn * 32 + threadIdx.x;
     if (n < t.N) {
-      const int n_dst = (t.split_n > 0 && n >= t.split_n) ? n - t.split_n + t.split_off : n;
-      bias_arena[t.bias_dst + n_dst] = params[t.bias_src + n];
+      bias_arena[t.bias_dst + prep_dst_row(t, n)] = params[t.bias_src + n];
     }
   }
 #pragma unroll
@@ -492,7 +500,7 @@ prep_weights_kernel(const float* __restrict__ params, __half* __restrict__ arena
       __half hi, lo;
       split_f16(tile[tx][ty + i] * W_SCALE, hi, lo);
       overflow |= __hisinf(hi) || __hisnan(hi);
-      const int n_dst = (t.split_n > 0 && n >= t.split_n) ? n - t.split_n + t.split_off : n;
+      const int n_dst = prep_dst_row(t, n);
       __half* d = arena + t.dst_off + (size_t)n_dst * t.Kpad + k;
       d[0] = hi;
       d[t.plane] = lo;

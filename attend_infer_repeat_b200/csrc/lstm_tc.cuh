@@ -1,0 +1,380 @@
+// The whole snt.LSTM recurrence of an unrolled AIR pass in ONE launch (sm_100a): gx = e @ W[:n_enc] + b once, then for
+// t = 1..T: gates = gx + h_{t-1} @ W[n_enc:], (c, h_t) gate math -- mnist_model.py:35 [upstream snt.LSTM], cell.py:126-127.
+//
+// A 128-canvas row tile is owned by a CLUSTER of 4 CTAs.  CTA r computes hidden units [64r, 64r + 64): its weight slab is
+// the 4 x 64 gate columns (i, j, f, o) of those units, so a step is one 128 x 256 x 256 tcgen05 GEMM per CTA (TS form, the
+// A operand h_{t-1} resident in TMEM exactly as in chain_tc.cuh) followed by the gate math of 64 units x 128 rows in the
+// epilogue warps -- i, j, f, o of a unit land in the same thread, c stays in registers for all T steps.  The four h slabs
+// are exchanged through an L2-resident buffer in the chains' slice-major layout (every CTA needs all 256 units of h_t as
+// the next step's operand) and a cluster-scope mbarrier (remote arrive through DSMEM); weights stream from L2 by TMA.
+// 32 row tiles x 4 = 128 CTAs busy instead of the 32 a row-tile-only split would give.
+#pragma once
+#include "chain_tc.cuh"
+
+namespace air {
+namespace lstm {
+
+using namespace air::chain;
+
+constexpr int CLUSTER = 4;
+constexpr int UPC = 64;               // hidden units per CTA
+constexpr int NH = CLUSTER * UPC;     // this kernel is specialised for snt.LSTM(256) (mnist_model.py:35)
+
+struct Params {
+  CUtensorMap tm_x;       // prepared W[:n_enc]^T, rows permuted to [cta][gate][unit] (prep_weights_kernel lstm mode)
+  CUtensorMap tm_h;       // prepared W[n_enc:]^T, same permutation
+  const float* bias;      // lstm.b permuted the same way (bias arena), [4 * NH]
+  const float* e;         // [B, n_enc] fp32: input-encoder output
+  int n_enc;
+  const float* h_init;    // [B, NH] fp32
+  float* c;               // [B, NH] fp32: initial cell state in, final cell state out
+  float* hs;              // [T, B, NH] fp32 out
+  HlOut hs_hlt;           // slice-major tiled hl copy of hs (operand of the heads chain), row = t * B + b
+  float* gx_scr;          // [tiles][4][4][16][128][4] fp32 scratch: gx in the layout of the thread that re-reads it
+  __half* hx;             // [2][2 planes][tiles][16 slices][128][16] fp16: h exchange buffer, double buffered by step parity
+  size_t hx_plane;        // halves per plane = tiles * 16 * 128 * 16
+  int B, T;
+  float forget_bias;
+  int* range_flag;
+};
+
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, float (&v)[4]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait4(float (&a)[4], float (&b)[4], float (&c)[4], float (&d)[4]) {
+  uint32_t* r0 = reinterpret_cast<uint32_t*>(a);
+  uint32_t* r1 = reinterpret_cast<uint32_t*>(b);
+  uint32_t* r2 = reinterpret_cast<uint32_t*>(c);
+  uint32_t* r3 = reinterpret_cast<uint32_t*>(d);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r0[0]), "+r"(r0[1]), "+r"(r0[2]), "+r"(r0[3]), "+r"(r1[0]), "+r"(r1[1]), "+r"(r1[2]), "+r"(r1[3]),
+                 "+r"(r2[0]), "+r"(r2[1]), "+r"(r2[2]), "+r"(r2[3]), "+r"(r3[0]), "+r"(r3[1]), "+r"(r3[2]), "+r"(r3[3])
+               :
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ld_cg_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// c' = sig(f + fb) * c + sig(i) * tanh(j);  h = tanh(c') * sig(o).  Five MUFU.EX2 + three MUFU.RCP per unit: each product
+// of a sigmoid and a tanh shares one reciprocal, sig(a) * tanh(b) = (E - 1) / ((1 + e^-a) (1 + E)), E = e^{2b}.  Arguments
+// are clamped where the functions have saturated below fp32 resolution, so no intermediate overflows.  Absolute error of
+// each factor <= 3e-7 (ex2.approx / rcp.approx are good to 2^-22 relative).
+__device__ __forceinline__ float sig_tanh(float a, float b) {
+  const float ea = ex2_fast(-1.4426950408889634f * fminf(fmaxf(a, -30.f), 30.f));
+  const float eb = ex2_fast(2.8853900817779268f * fminf(fmaxf(b, -15.f), 15.f));
+  return (eb - 1.0f) * rcp_fast((1.0f + ea) * (1.0f + eb));
+}
+__device__ __forceinline__ float sig_fast(float a) {
+  return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * fminf(fmaxf(a, -30.f), 30.f)));
+}
+
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+lstm_cluster_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SLOTS * TILE_BYTES);
+  uint64_t* empty_bar = full_bar + SLOTS;
+  uint64_t* a_ready = empty_bar + SLOTS;
+  uint64_t* d_full = a_ready + 1;
+  uint64_t* x_bar = d_full + 1;           // h slabs of all four CTAs are in the exchange buffer
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(x_bar + 1);
+  float* s_stage = reinterpret_cast<float*>(smem + STAGE_OFFSET);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tile = blockIdx.y;
+  const int m0 = tile * BM;
+  const int n_groups = 1 + p.T;   // gx, then one GEMM per step
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_x);
+    prefetch_tmap(&p.tm_h);
+    for (int s = 0; s < SLOTS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(a_ready, NUM_EPI_WARPS * 32);
+    mbar_init(d_full, 1);
+    mbar_init(x_bar, CLUSTER * NUM_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive can reach them
+  griddep_launch();
+  griddep_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's weight slab (rows rank * NH .. + NH of the permuted W^T), hi and lo tiles =====
+    if (elect_one()) {
+      uint32_t par = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const CUtensorMap* tm = g == 0 ? &p.tm_x : &p.tm_h;
+        const int K = g == 0 ? p.n_enc : NH;
+        const int nkb = ((K + 15) / 16 + 3) / 4;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int hs = kb & 3, ls = 4 + (kb & 1);
+          mbar_wait(&empty_bar[hs], ((par >> hs) & 1) ^ 1);
+          par ^= 1u << hs;
+          mbar_expect_tx(&full_bar[hs], TILE_BYTES);
+          tma_load_2d(smem + hs * TILE_BYTES, tm, kb * BK, (int)rank * NH, &full_bar[hs]);
+          mbar_wait(&empty_bar[ls], ((par >> ls) & 1) ^ 1);
+          par ^= 1u << ls;
+          mbar_expect_tx(&full_bar[ls], TILE_BYTES);
+          tma_load_2d(smem + ls * TILE_BYTES, tm, kb * BK, CLUSTER * NH + (int)rank * NH, &full_bar[ls]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: cross terms first, then main terms (see chain_tc.cuh) =====
+    if (elect_one()) {
+      uint32_t par = 0;
+      constexpr uint32_t idesc = make_idesc_f16(BM, NH);
+      for (int g = 0; g < n_groups; ++g) {
+        const int K = g == 0 ? p.n_enc : NH;
+        const int nsl = (K + 15) / 16, nkb = (nsl + 3) / 4;
+        mbar_wait(a_ready, g & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int hs = kb & 3, ls = 4 + (kb & 1);
+          mbar_wait(&full_bar[hs], (par >> hs) & 1);
+          par ^= 1u << hs;
+          mbar_wait(&full_bar[ls], (par >> ls) & 1);
+          par ^= 1u << ls;
+          tc_fence_after();
+          const uint64_t db_hi = make_smem_desc_sw128(smem + hs * TILE_BYTES);
+          const uint64_t db_lo = make_smem_desc_sw128(smem + ls * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int sl = kb * 4 + k;
+            if (sl < nsl) {
+              const uint32_t a_col = (uint32_t)sl * 8u;
+              const uint64_t adv = (uint64_t)(k * 2);
+              umma_f16_ts(tmem_base + D_COL, tmem_base + A_LO_COL + a_col, db_hi + adv, idesc, sl != 0);
+              umma_f16_ts(tmem_base + D_COL, tmem_base + A_HI_COL + a_col, db_lo + adv, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[ls]);
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int hs = kb & 3;
+          const uint64_t db_hi = make_smem_desc_sw128(smem + hs * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int sl = kb * 4 + k;
+            if (sl < nsl)
+              umma_f16_ts(tmem_base + D_COL, tmem_base + A_HI_COL + (uint32_t)sl * 8u, db_hi + (uint64_t)(k * 2), idesc, 1);
+          }
+          umma_commit(&empty_bar[hs]);
+        }
+        umma_commit(d_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps: thread <-> (row, 16 of this CTA's 64 units) =====
+    const int q = warp & 3, cq = (warp - 2) >> 2;
+    const int row_w = m0 + q * 32;
+    const int rit = q * 32 + lane;          // row inside the tile
+    const int row = m0 + rit;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* stage = s_stage + (warp - 2) * 512;
+    const int u0 = (int)rank * UPC + cq * 16;   // first hidden unit of this thread
+    const int my_slice = (int)rank * 4 + cq;    // == u0 / 16
+    uint32_t ovf = 0;
+
+    // --- operand of the gx GEMM: e rows, fp32 -> hi/lo -> TMEM (each thread: slices cq, cq + 4, ...) ---
+    {
+      const int nsl = (p.n_enc + 15) / 16;
+      for (int s = cq; s < nsl; s += 4) {
+        float v[16];
+        tile_load(stage, lane, v, p.e, p.n_enc, row_w, s * 16, p.n_enc, p.B);
+        uint32_t hi[8], lo[8];
+        split_pack16(v, hi, lo, ovf);
+        tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
+        tmem_st_32x8(t_lane + A_LO_COL + s * 8, lo);
+      }
+    }
+    // cell state of this thread's 16 units, in registers for the whole recurrence
+    float c_reg[16];
+    tile_load(stage, lane, c_reg, p.c, NH, row_w, u0, NH, p.B);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+
+    // --- gx: D + bias -> scratch, in this thread's own read-back order: [gate * 4 + k4][row][4 floats] ---
+    float* gx_mine = p.gx_scr + ((((size_t)tile * CLUSTER + rank) * 4 + cq) * 16 * BM + rit) * 4;
+    mbar_wait(d_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate) {
+      float v[16], b[16];
+      tmem_ld_32x16(t_lane + D_COL + gate * UPC + cq * 16, v);
+      load16(p.bias + (size_t)rank * NH + gate * UPC + cq * 16, b);
+      tmem_ld_wait(v);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        *reinterpret_cast<float4*>(gx_mine + (size_t)(gate * 4 + k4) * BM * 4) =
+            make_float4(fmaf(v[4 * k4], W_UNSCALE, b[4 * k4]), fmaf(v[4 * k4 + 1], W_UNSCALE, b[4 * k4 + 1]),
+                        fmaf(v[4 * k4 + 2], W_UNSCALE, b[4 * k4 + 2]), fmaf(v[4 * k4 + 3], W_UNSCALE, b[4 * k4 + 3]));
+    }
+    // --- operand of step 1: h_init rows ---
+    for (int s = cq; s < NH / 16; s += 4) {
+      float v[16];
+      tile_load(stage, lane, v, p.h_init, NH, row_w, s * 16, NH, p.B);
+      uint32_t hi[8], lo[8];
+      split_pack16(v, hi, lo, ovf);
+      tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
+      tmem_st_32x8(t_lane + A_LO_COL + s * 8, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+
+    for (int t = 0; t < p.T; ++t) {
+      mbar_wait(d_full, (t + 1) & 1);
+      tc_fence_after();
+      // ---- gate math of 16 units, four at a time ----
+      float h_new[16];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        float gi[4], gj[4], gf[4], go[4];
+        tmem_ld_32x4(t_lane + D_COL + 0 * UPC + cq * 16 + k4 * 4, gi);
+        tmem_ld_32x4(t_lane + D_COL + 1 * UPC + cq * 16 + k4 * 4, gj);
+        tmem_ld_32x4(t_lane + D_COL + 2 * UPC + cq * 16 + k4 * 4, gf);
+        tmem_ld_32x4(t_lane + D_COL + 3 * UPC + cq * 16 + k4 * 4, go);
+        const float4 xi = *reinterpret_cast<const float4*>(gx_mine + (size_t)(0 * 4 + k4) * BM * 4);
+        const float4 xj = *reinterpret_cast<const float4*>(gx_mine + (size_t)(1 * 4 + k4) * BM * 4);
+        const float4 xf = *reinterpret_cast<const float4*>(gx_mine + (size_t)(2 * 4 + k4) * BM * 4);
+        const float4 xo = *reinterpret_cast<const float4*>(gx_mine + (size_t)(3 * 4 + k4) * BM * 4);
+        tmem_ld_wait4(gi, gj, gf, go);
+        const float ai[4] = {xi.x, xi.y, xi.z, xi.w}, aj[4] = {xj.x, xj.y, xj.z, xj.w};
+        const float af[4] = {xf.x, xf.y, xf.z, xf.w}, ao[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float pi = fmaf(gi[j], W_UNSCALE, ai[j]), pj = fmaf(gj[j], W_UNSCALE, aj[j]);
+          const float pf = fmaf(gf[j], W_UNSCALE, af[j]), po = fmaf(go[j], W_UNSCALE, ao[j]);
+          const float cn = fmaf(sig_fast(pf + p.forget_bias), c_reg[4 * k4 + j], sig_tanh(pi, pj));
+          c_reg[4 * k4 + j] = cn;
+          h_new[4 * k4 + j] = sig_tanh(po, cn);
+        }
+      }
+      // ---- h_t: fp32 rows (output + final state), hl copy for the heads chain, own slice straight into TMEM, and the
+      //      exchange buffer for the other three CTAs ----
+      tile_store(stage, lane, h_new, p.hs + (size_t)t * p.B * NH, NH, row_w, u0, NH, p.B);
+      uint32_t hi[8], lo[8];
+      split_pack16(h_new, hi, lo, ovf);
+      if (p.hs_hlt.p && row < p.B) {
+        __half* d = p.hs_hlt.p + hl_index(p.hs_hlt, (size_t)t * p.B + row, u0);
+        *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(d + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(d + p.hs_hlt.plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(d + p.hs_hlt.plane + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+      if (t + 1 == p.T) {
+        tile_store(stage, lane, c_reg, p.c, NH, row_w, u0, NH, p.B);
+        break;
+      }
+      tmem_st_32x8(t_lane + A_HI_COL + my_slice * 8, hi);
+      tmem_st_32x8(t_lane + A_LO_COL + my_slice * 8, lo);
+      __half* xb = p.hx + (size_t)(t & 1) * 2 * p.hx_plane + ((size_t)tile * 16 * BM) * 16;   // this tile, this parity
+      {
+        __half* d = xb + ((size_t)my_slice * BM + rit) * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(d + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(d + p.hx_plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(d + p.hx_plane + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (uint32_t r = 0; r < CLUSTER; ++r) mbar_arrive_remote(x_bar, r);
+      }
+      mbar_wait_cluster(x_bar, t & 1);
+      // ---- the other CTAs' slabs: slices 4 r' + cq, r' != rank ----
+#pragma unroll
+      for (int rr = 1; rr < CLUSTER; ++rr) {
+        const int s = ((int)((rank + rr) & 3)) * 4 + cq;
+        const __half* src = xb + ((size_t)s * BM + rit) * 16;
+        const uint4 h0 = ld_cg_u4(src), h1 = ld_cg_u4(src + 8);
+        const uint4 l0 = ld_cg_u4(src + p.hx_plane), l1 = ld_cg_u4(src + p.hx_plane + 8);
+        const uint32_t whi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t wlo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        tmem_st_32x8(t_lane + A_HI_COL + s * 8, whi);
+        tmem_st_32x8(t_lane + A_LO_COL + s * 8, wlo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    }
+    if ((ovf & 0x80008000u) && p.range_flag) atomicOr(p.range_flag, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer may still arrive on its x_bar
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+inline cudaError_t launch_lstm(const Params& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  return launch_k(lstm_cluster_kernel, dim3(CLUSTER, (p.B + BM - 1) / BM), dim3(NUM_THREADS), SMEM_BYTES, st, p);
+}
+
+}  // namespace lstm
+}  // namespace air

@@ -471,6 +471,12 @@ def test_forward_tc_per_layer_schedule(monkeypatch):
     _check_forward(U.oracle_cfg(**U.TINY), 10, O.PriorConfig(), seed=2, global_step=5000, weight_gain=2.0, precision=TC)
 
 
+def test_forward_tc_without_cluster_lstm(monkeypatch):
+    """fused chains on, cluster LSTM kernel off: per-step recurrent GEMM + gate kernel feeding the chains"""
+    monkeypatch.setenv("AIR_NO_LSTM_CLUSTER", "1")
+    _check_forward(U.oracle_cfg(**U.SCRIPT), 130, O.PriorConfig(), seed=4, global_step=20000, precision=TC)
+
+
 def test_forward_tc_chain_deep_and_ragged_widths():
     """3-4 hidden layers of odd widths, na not a multiple of 16, nh > 256 (chunked A operand), 130 rows (tile tail)."""
     cfg = dict(H=20, W=24, h=9, w=7, T=4, na=21, nh=272, enc_hidden=(96, 40), glenc_hidden=(200, 72, 256),
