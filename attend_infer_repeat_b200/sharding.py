@@ -1,0 +1,95 @@
+"""Batch sharding of the AIR path across the GPUs of one node.
+
+Every canvas is independent through the whole unroll (no batch-norm, no cross-sample op): rank r owns a contiguous
+slice of the batch, parameters and optimiser state are replicated, and there is NO data-path collective.  The only
+cross-sample couplings are batch means (model.py:103,151,184,212,248,322) and the REINFORCE [B,B] broadcast
+(model.py:242-248), which factors into three means:
+
+    mean_{i,j}((iw_j - baseline_i) * logq_j) = mean(iw * logq) - mean(baseline) * mean(logq)
+
+so the exchange is one all-reduce of 16 floats per pass, plus (training) one all-reduce of the flat gradient buffer.
+Nothing here computes on the path: these are host-side helpers around torch.distributed (NCCL on the GPUs, gloo in the
+CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import AIR_N_SCALARS, SCALAR_INDEX
+
+# scalars that are plain batch means of per-sample terms (everything else is derived from them)
+_MEAN_SLOTS = ("rec_loss", "kl_num_steps", "kl_what", "kl_where", "num_step", "mean_iw_logq", "mean_logq",
+               "mean_baseline")
+
+
+def shard_range(n_global: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [start, stop) of a batch of n_global canvases owned by `rank` (remainder to the low ranks)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, rem = divmod(int(n_global), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard(t: torch.Tensor, rank: int, world: int, dim: int = 0) -> torch.Tensor:
+    """The rank's slice of a batch-major (dim=0) or time-major (dim=1) tensor."""
+    a, b = shard_range(t.shape[dim], rank, world)
+    return t.narrow(dim, a, b - a)
+
+
+def combine_scalars(scalars: torch.Tensor, n_local: int, steps_weight: float = 1.0, use_prior: bool = True,
+                    use_reinforce: bool = True, group=None) -> torch.Tensor:
+    """Turn the per-shard scalar block of air_forward (16 floats, batch means over the LOCAL shard) into the scalars
+    of the whole batch, in place, on every rank.  Means are re-weighted by the shard size (shards may be ragged); the
+    derived entries (prior_loss, loss, reinforce_loss, opt_loss; elbo_scalars_kernel) are re-formed from the global
+    means exactly as the single-device kernel forms them."""
+    import torch.distributed as dist
+    assert scalars.numel() == AIR_N_SCALARS
+    buf = torch.zeros(AIR_N_SCALARS, dtype=torch.float64, device=scalars.device)
+    for name in _MEAN_SLOTS:
+        buf[SCALAR_INDEX[name]] = scalars[SCALAR_INDEX[name]].double() * n_local
+    buf[AIR_N_SCALARS - 1] = float(n_local)
+    if scalars.device.type == "cuda":
+        buf = buf.float()          # NCCL path: fp32 on the wire (16 floats)
+    dist.all_reduce(buf, group=group)
+    n = buf[AIR_N_SCALARS - 1]
+    m = {name: buf[SCALAR_INDEX[name]] / n for name in _MEAN_SLOTS}
+    prior_loss = m["kl_num_steps"] * steps_weight + m["kl_what"] + m["kl_where"]
+    loss = m["rec_loss"] + prior_loss * (1.0 if use_prior else 0.0)
+    reinforce = (m["mean_iw_logq"] - m["mean_baseline"] * m["mean_logq"]) if use_reinforce else torch.zeros_like(loss)
+    scalars.zero_()
+    for name in _MEAN_SLOTS:
+        scalars[SCALAR_INDEX[name]] = m[name].to(scalars.dtype)
+    scalars[SCALAR_INDEX["prior_loss"]] = prior_loss.to(scalars.dtype)
+    scalars[SCALAR_INDEX["loss"]] = loss.to(scalars.dtype)
+    scalars[SCALAR_INDEX["reinforce_loss"]] = reinforce.to(scalars.dtype)
+    scalars[SCALAR_INDEX["opt_loss"]] = (loss + reinforce).to(scalars.dtype)
+    return scalars
+
+
+def allreduce_gradient(flat_grad: torch.Tensor, n_local: int, n_global: Optional[int] = None, group=None,
+                       async_op: bool = False):
+    """The ONE data-path collective of a training step: sum over ranks of the flat gradient buffer.
+
+    Each rank's buffer holds the gradient of ITS shard's mean loss; the gradient of the global mean is the shard-size
+    weighted average.  With equal shards (the benchmark configuration) that is all-reduce(sum) / world; ragged shards
+    pre-scale by n_local / n_global.  In place; returns the work handle when async_op."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if n_global is None:
+        n_global = n_local * world
+    flat_grad.mul_(float(n_local) / float(n_global))
+    return dist.all_reduce(flat_grad, group=group, async_op=async_op)
+
+
+def global_baseline_mean(baseline_local: torch.Tensor, n_local: int, group=None) -> torch.Tensor:
+    """mean(baseline) over the WHOLE batch (needed by the backward of the REINFORCE term on every rank)."""
+    import torch.distributed as dist
+    buf = torch.stack([baseline_local.double().sum(), torch.tensor(float(n_local), dtype=torch.float64,
+                                                                    device=baseline_local.device)])
+    if buf.device.type == "cuda":
+        buf = buf.float()
+    dist.all_reduce(buf, group=group)
+    return (buf[0] / buf[1]).to(baseline_local.dtype)
