@@ -593,8 +593,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                                                   : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
   }
   a.lp_const = (float)(0.5 * 1.8378770664093453 /* log(2 pi) */ + std::log((double)c.output_std));
-  AIR_CUDA(air::launch_paint_elbo(a, st));
-  ++h->launches;
+  AIR_CUDA(air::launch_paint_elbo(a, st));   // prior_terms_kernel (when a prior is given) + paint_elbo_kernel
+  h->launches += prior ? 2 : 1;
 
   if (prior) {
     AIR_CUDA(air::launch_k(air::elbo_scalars_kernel, dim3(1), dim3(1024), 0, st, o->rec_loss_per_sample,
@@ -1035,16 +1035,8 @@ int32_t air_prior_terms(int32_t B, int32_t T, int32_t na, const float* what_loc,
       !outs->kl_where_per_sample || !outs->loss_per_sample || !outs->num_steps_log_prob)
     return fail(AIR_ERR_ARG, "air_prior_terms: ELBO output buffers are mandatory");
   cudaStream_t st = (cudaStream_t)stream;
-  // a 1x1 all-zero canvas / glimpse and identity where-codes: the paint part of the fused kernel contributes nothing
-  const size_t TB = (size_t)T * B;
-  float* tmp = nullptr;
-  AIR_CUDA(cudaMallocAsync(&tmp, sizeof(float) * (B + TB + 4 * TB), st));
-  AIR_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * (B + TB + 4 * TB), st));
   air::ElboArgs a;
   memset(&a, 0, sizeof(a));
-  a.img = tmp;
-  a.glimpse = tmp + B;
-  a.where = tmp + B + TB;          // zeros: sx = sy = 0 -> the inverse warp is "outside" everywhere -> canvas stays 0
   a.where_loc = where_loc;
   a.where_scale = where_scale;
   a.what_loc = what_loc;
@@ -1060,17 +1052,14 @@ int32_t air_prior_terms(int32_t B, int32_t T, int32_t na, const float* what_loc,
   a.kl_where_per_sample = outs->kl_where_per_sample;
   a.loss_per_sample = outs->loss_per_sample;
   a.num_steps_log_prob = outs->num_steps_log_prob;
-  a.T = T; a.B = B; a.H = 1; a.W = 1; a.h = 1; a.w = 1; a.na = na;
-  a.output_std = 1.0f;
-  a.output_multiplier = 1.0f;
-  a.lp_const = 0.0f;               // with x = mu = 0 the reconstruction term is exactly 0
+  a.T = T; a.B = B; a.na = na;
   a.do_elbo = 1;
   a.prior = *prior;
   for (int k = 0; k <= T; ++k)
     a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
                                                 : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
-  AIR_CUDA(air::launch_paint_elbo(a, st));
-  AIR_CUDA(cudaFreeAsync(tmp, st));
+  // no canvas: the reconstruction term is exactly 0 and prior_terms_kernel completes loss_per_sample itself
+  AIR_CUDA(air::launch_prior_terms(a, /*finalize=*/1, (cudaStream_t)stream));
   return AIR_OK;
 }
 
@@ -1138,10 +1127,10 @@ int32_t air_linear(const float* A, const float* Wt, const float* bias, float* ou
   pe.tiles_n = (N + 31) / 32;
   pe.split_n = 0;
   pe.split_off = 0;
-  AIR_CUDA(cudaMemcpyAsync(table, &pe, sizeof(pe), cudaMemcpyHostToDevice, st));
   pe.bias_src = -1;
   pe.bias_dst = 0;
   pe.perm_nh = 0;
+  AIR_CUDA(cudaMemcpyAsync(table, &pe, sizeof(pe), cudaMemcpyHostToDevice, st));
   tc::prep_weights_kernel<<<pe.tiles_n * ((K + 31) / 32), 256, 0, st>>>(Wt, w_hl, table, 1, flag, nullptr);
   AIR_CUDA(cudaGetLastError());
   const size_t n4 = (size_t)M * ((K + 3) / 4);

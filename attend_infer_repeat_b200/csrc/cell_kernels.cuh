@@ -54,7 +54,7 @@ struct __align__(16) Tap {
   float wf, wc;   // weight of the floor tap (= ceil - coord) and of the ceil tap (= 1 - that); 0 where the tap reads 0
   int i_f, i_c;   // clamped indices of the two taps
 };
-__device__ __forceinline__ Tap make_tap(float coord, int n) {
+__device__ __forceinline__ Tap make_tap(float coord, int n, int stride = 1) {
   Tap t;
   const bool inside = coord > -1.0f && coord < (float)n;
   const float f = floorf(coord);
@@ -62,8 +62,8 @@ __device__ __forceinline__ Tap make_tap(float coord, int n) {
   const float d = (f + 1.0f) - coord;
   t.wf = (inside && fi >= 0 && fi <= n - 1) ? d : 0.f;
   t.wc = (inside && ci >= 0 && ci <= n - 1) ? 1.0f - d : 0.f;
-  t.i_f = min(max(fi, 0), n - 1);
-  t.i_c = min(max(ci, 0), n - 1);
+  t.i_f = min(max(fi, 0), n - 1) * stride;   // stride > 1: row taps pre-multiplied by the source row pitch
+  t.i_c = min(max(ci, 0), n - 1) * stride;
   return t;
 }
 // same association as the reference kernel: dx*dy*D(fx,fy) + (1-dx)(1-dy)*D(cx,cy) + dx(1-dy)*D(fx,cy) + (1-dx)dy*D(cx,fy)
@@ -317,6 +317,8 @@ struct ElboArgs {
   int T, B, H, W, h, w, na;
   float output_std, output_multiplier;
   float lp_const;              // 0.5 log(2 pi) + log(output_std), the constant of Normal.log_prob (host, float64)
+  float inv_sigma;             // 1 / output_std (host)
+  double step_W, step_H;       // np.linspace(-1, 1, n) step 2/(n-1) of the canvas columns / rows (host, float64)
   int do_elbo;
   air_prior prior;
   double steps_prior[AIR_MAX_STEPS + 1];   // geometric_prior(success_prob, T) (prior.py:26-32): the same table for
@@ -363,28 +365,256 @@ __device__ __forceinline__ float tabular_kl_entry(float p, double q, double zero
 }
 
 // ---------------------------------------------------------------------------------------------------
-// paint + ELBO.  One CTA per canvas b.
+// Per-canvas prior terms (model.py:126-216, prior.py:62-90,148-151).  One WARP per canvas, no shared memory:
+//   q(n) (float64 island, lane k owns n = k), KL(q(n) || prior), log q(n_b), the per-step weights,
+//   KL(what) (lanes over the na latents, one warp reduction per step), KL(where).
+// Runs before the paint kernel and leaves prior_weight * prior_per_sample in loss_per_sample[b]; the paint kernel adds
+// the reconstruction term on top (Loss.add, ops.py:12-29).  `finalize` != 0 (air_prior_terms): there is no canvas, so
+// the reconstruction term is exactly 0 and loss_per_sample is complete.
+// ---------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(128) prior_terms_kernel(ElboArgs a, int finalize) {
+  griddep_launch();
+  griddep_wait();
+  const int B = a.B;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const air_prior& pr = a.prior;
+  // step-count posterior q(n): lane k owns n = k (float64 island)
+  const int k = lane;
+  double pi = 0.0;
+  if (k <= T) {
+    double cum = 1.0;
+    for (int j = 0; j < k && j < T; ++j) cum *= (double)a.presence_prob[(size_t)j * B + b];
+    pi = (k < T) ? (1.0 - (double)a.presence_prob[(size_t)k * B + b]) * cum : cum;
+  }
+  double sum = pi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  float q = 0.f, kl = 0.f;
+  if (k <= T) {
+    q = (float)(pi / sum);
+    kl = tabular_kl_entry(q, a.steps_prior[k], 0.0);
+    a.num_steps_posterior[(size_t)b * (T + 1) + k] = q;
+  }
+  float kl_n = 0.f;   // fp32 sum over n in index order (model.py:149)
+  float qs[T + 1];
+#pragma unroll
+  for (int j = 0; j <= T; ++j) {
+    const float v = __shfl_sync(0xffffffffu, kl, j);
+    kl_n = (j == 0) ? v : __fadd_rn(kl_n, v);
+    qs[j] = __shfl_sync(0xffffffffu, q, j);
+  }
+  // KL(what) per step (model.py:174-186): lanes over the latents
+  float klw[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float v = 0.f;
+    const size_t base = ((size_t)t * B + b) * a.na;
+    for (int i = lane; i < a.na; i += 32)
+      v += normal_kl(a.what_loc[base + i], a.what_scale[base + i], pr.what_loc, pr.what_scale);
+    klw[t] = warp_sum(v);
+  }
+  // KL(where) per step (model.py:188-214): lane t owns step t; (sx, sy) vs scale prior, (tx, ty) vs shift prior
+  float klwh_l = 0.f, pres_l = 0.f;
+  if (lane < T) {
+    const float* wlp = a.where_loc + ((size_t)lane * B + b) * 4;
+    const float* wsp = a.where_scale + ((size_t)lane * B + b) * 4;
+    const float4 wl = make_float4(wlp[0], wlp[1], wlp[2], wlp[3]);
+    const float4 ws = make_float4(wsp[0], wsp[1], wsp[2], wsp[3]);
+    const float k_sx = normal_kl(wl.x, ws.x, pr.where_scale_loc, pr.where_scale_scale);
+    const float k_sy = normal_kl(wl.z, ws.z, pr.where_scale_loc, pr.where_scale_scale);
+    const float k_tx = normal_kl(wl.y, ws.y, pr.where_shift_has_loc ? pr.where_shift_loc : wl.y, pr.where_shift_scale);
+    const float k_ty = normal_kl(wl.w, ws.w, pr.where_shift_has_loc ? pr.where_shift_loc : wl.w, pr.where_shift_scale);
+    klwh_l = __fadd_rn(__fadd_rn(k_sx, k_tx), __fadd_rn(k_sy, k_ty));
+    pres_l = a.presence[(size_t)lane * B + b];
+  }
+  float klwh[T], pres[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    klwh[t] = __shfl_sync(0xffffffffu, klwh_l, t);
+    pres[t] = __shfl_sync(0xffffffffu, pres_l, t);
+  }
+  if (lane != 0) return;
+  a.kl_num_steps_per_sample[b] = kl_n;
+  float n = 0.f;
+#pragma unroll
+  for (int t = 0; t < T; ++t) n += pres[t];
+  a.num_step_per_sample[b] = n;
+  int idx = (int)n;
+  idx = idx < 0 ? 0 : (idx > T ? T : idx);
+  float q_sel = qs[0];
+#pragma unroll
+  for (int j = 1; j <= T; ++j) q_sel = (idx == j) ? qs[j] : q_sel;
+  a.num_steps_log_prob[b] = logf(fmaxf(q_sel, 1e-32f));
+  float sw[T];
+  if (pr.analytic) {   // reverse cumsum of q(n)[1:]   (model.py:157-161)
+    float cs = 0.f;
+#pragma unroll
+    for (int t = T - 1; t >= 0; --t) {
+      cs = (t == T - 1) ? qs[t + 1] : __fadd_rn(cs, qs[t + 1]);
+      sw[t] = cs;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < T; ++t) sw[t] = pres[t];
+  }
+  float kl_what = 0.f, kl_where = 0.f;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    a.prior_step_weight[(size_t)t * B + b] = sw[t];
+    const float v = __fmul_rn(klw[t], sw[t]);
+    kl_what = (t == 0) ? v : __fadd_rn(kl_what, v);
+    const float u = __fmul_rn(klwh[t], sw[t]);
+    kl_where = (t == 0) ? u : __fadd_rn(kl_where, u);
+  }
+  a.kl_what_per_sample[b] = kl_what;
+  a.kl_where_per_sample[b] = kl_where;
+  // Loss.add bookkeeping (ops.py:12-29; model.py:154,186,214,332): the prior part of the per-sample loss
+  const float prior_ps = __fadd_rn(__fadd_rn(__fmul_rn(kl_n, pr.steps_weight), kl_what), kl_where);
+  const float part = __fmul_rn(prior_ps, pr.use_prior ? 1.0f : 0.0f);
+  if (finalize) {
+    a.rec_loss_per_sample[b] = 0.f;
+    a.loss_per_sample[b] = __fadd_rn(0.f, part);
+  } else {
+    a.loss_per_sample[b] = part;
+  }
+}
+
+inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStream_t st) {
+  const dim3 grid((a.B + 3) / 4), block(128);
+  switch (a.T) {
+    case 1: return launch_k(prior_terms_kernel<1>, grid, block, 0, st, a, finalize);
+    case 2: return launch_k(prior_terms_kernel<2>, grid, block, 0, st, a, finalize);
+    case 3: return launch_k(prior_terms_kernel<3>, grid, block, 0, st, a, finalize);
+    case 4: return launch_k(prior_terms_kernel<4>, grid, block, 0, st, a, finalize);
+    case 5: return launch_k(prior_terms_kernel<5>, grid, block, 0, st, a, finalize);
+    case 6: return launch_k(prior_terms_kernel<6>, grid, block, 0, st, a, finalize);
+    case 7: return launch_k(prior_terms_kernel<7>, grid, block, 0, st, a, finalize);
+    case 8: return launch_k(prior_terms_kernel<8>, grid, block, 0, st, a, finalize);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// paint + reconstruction term.  One CTA per canvas b.
 //   canvas_t = canvas_{t-1} + presence_t * resampler(glimpse_t, inverse warp(where_t))   (cell.py:159-164)
 //   rec[b]   = sum_px 0.5 ((x - mu)/sigma)^2 + log sigma + 0.5 log 2 pi, mu = multiplier * canvas_T (model.py:319-321)
-//   KL terms per sample (model.py:126-216), q(n) (prior.py:62-68), log q(n_b) (prior.py:148-151)
-// The canvas is never read back from HBM: it accumulates in a register per pixel across the T steps and is
-// written once per step (coalesced rows).  dynamic smem: T*G floats (glimpses) + T*(W+H) taps.
+//   loss_per_sample[b] = rec[b] + (prior part left there by prior_terms_kernel)
+// The canvas is never read back from HBM: it accumulates in registers across the T steps and is written once per step.
+// Thread mapping: a thread owns a fixed column (a column PAIR when W is even: 8-byte stores) and walks down the rows, so
+// "is this column inside glimpse t's footprint" is a loop-invariant bit mask, the row test is one broadcast shared-memory
+// load, and a (row, step) whose footprint misses costs a handful of instructions.  In pass k the CTA's threads cover one
+// contiguous run of W * rows_per_pass pixels: every store instruction is fully coalesced.
+// dynamic smem: T*G floats (glimpses) + T*(W+H) taps.
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) {
   return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H);
+}
+
+// bilinear with the row taps' indices pre-multiplied by the source row pitch (make_tap(..., stride = Ws))
+__device__ __forceinline__ float bilinear_pre(const float* __restrict__ D, const Tap& x, const Tap& y) {
+  const float* rf = D + y.i_f;
+  const float* rc = D + y.i_c;
+  float r = __fmul_rn(__fmul_rn(x.wf, y.wf), rf[x.i_f]);
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wc), rc[x.i_c]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wf, y.wc), rc[x.i_f]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wf), rf[x.i_c]));
+  return r;
+}
+
+template <int T, int CPT>
+__device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const float* __restrict__ s_gl,
+                                            const Tap* __restrict__ s_tx, const Tap* __restrict__ s_ty,
+                                            const float* __restrict__ s_pres) {
+  const int B = a.B, H = a.H, W = a.W;
+  const int P = H * W, G = a.h * a.w;
+  const int NT = blockDim.x;
+  const int TPR = W / CPT;                      // threads per row
+  const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
+  const int RPP = NT / TPRB;                    // rows per pass
+  const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
+  const float mult = a.output_multiplier, inv_sigma = a.inv_sigma, lp_const = a.lp_const;
+  const bool do_elbo = a.do_elbo != 0;
+  float pres[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) pres[t] = s_pres[t];
+  const float* cin = a.canvas_in ? a.canvas_in + (size_t)b * P : nullptr;
+  const float* obs = a.img + (size_t)b * P;
+  float* cbase = a.canvas ? a.canvas + (size_t)b * P : nullptr;
+  const size_t tstride = (size_t)B * P;
+  float rec = 0.f;
+  if (rslot >= RPP) return rec;
+  for (int c = cslot * CPT; c < W; c += TPRB * CPT) {
+    // loop-invariant: which (step, column) pairs lie inside the glimpse footprint (and are present at all)
+    uint32_t colmask = 0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (pres[t] != 0.f) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const Tap tx = s_tx[t * W + c + j];
+          if ((tx.wf != 0.f) | (tx.wc != 0.f)) colmask |= 1u << (t * CPT + j);
+        }
+      }
+    }
+    for (int r = rslot; r < H; r += RPP) {
+      const int p = r * W + c;
+      float acc[CPT], xo[CPT];
+      if (CPT == 2) {
+        const float2 ci = cin ? *reinterpret_cast<const float2*>(cin + p) : make_float2(0.f, 0.f);
+        const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs + p) : make_float2(0.f, 0.f);
+        acc[0] = ci.x; acc[CPT - 1] = ci.y;
+        xo[0] = xv.x; xo[CPT - 1] = xv.y;
+      } else {
+        acc[0] = cin ? cin[p] : 0.f;
+        xo[0] = do_elbo ? obs[p] : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const uint32_t cm = (colmask >> (t * CPT)) & ((1u << CPT) - 1u);
+        if (cm) {
+          const Tap ty = s_ty[t * H + r];
+          if ((ty.wf != 0.f) | (ty.wc != 0.f)) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              if (cm & (1u << j)) {
+                const Tap tx = s_tx[t * W + c + j];
+                const float v = bilinear_pre(s_gl + t * G, tx, ty);
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(pres[t], v));
+              }
+            }
+          }
+        }
+        if (cbase) {
+          float* dst = cbase + (size_t)t * tstride + p;
+          if (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(__fmul_rn(acc[0], mult), __fmul_rn(acc[CPT - 1], mult));
+          else          dst[0] = __fmul_rn(acc[0], mult);
+        }
+      }
+      if (do_elbo) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const float mu = __fmul_rn(acc[j], mult);
+          const float z = __fmul_rn(xo[j] - mu, inv_sigma);   // sigma is a constant: multiply by its reciprocal
+          rec += __fadd_rn(__fmul_rn(__fmul_rn(0.5f, z), z), lp_const);
+        }
+      }
+    }
+  }
+  return rec;
 }
 
 template <int T>
 __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
-  __shared__ float s_pres[AIR_MAX_STEPS], s_w[AIR_MAX_STEPS], s_klw[AIR_MAX_STEPS], s_red[32];
-  __shared__ float s_q[AIR_MAX_STEPS + 1];
-  __shared__ float s_kln;
+  __shared__ float s_pres[AIR_MAX_STEPS], s_red[32];
+  __shared__ float4 s_inv[AIR_MAX_STEPS];
   const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
   const int P = H * W, G = h * w;
   const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
   Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);         // [T][W]
   Tap* s_ty = s_tx + (size_t)T * W;                                                                      // [T][H]
@@ -405,74 +635,21 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
       const int t = i / G, g = i - t * G;
       s_gl[i] = a.glimpse[((size_t)t * B + b) * G + g];
     }
+  // the T inverse transforms of this canvas (two divisions each), one thread per step
+  if (threadIdx.x < T) {
+    const float* wh = a.where + ((size_t)threadIdx.x * B + b) * 4;
+    float4 iv;   // (a', d', -tx', -ty')
+    inv_params(wh[0], wh[1], wh[2], wh[3], iv.x, iv.y, iv.z, iv.w);
+    s_inv[threadIdx.x] = iv;
+    s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
+  }
+  __syncthreads();
   // inverse-warp tap tables while the copy is in flight: glimpse-space taps of every canvas column / row
   for (int i = threadIdx.x; i < T * (W + H); i += blockDim.x) {
     const int t = i / (W + H), j = i - t * (W + H);
-    const float* wh = a.where + ((size_t)t * B + b) * 4;
-    float a_inv, d_inv, ntx, nty;
-    inv_params(wh[0], wh[1], wh[2], wh[3], a_inv, d_inv, ntx, nty);
-    if (j < W) s_tx[t * W + j] = make_tap(inv_coord(a_inv, ntx, j, W, w), w);
-    else       s_ty[t * H + (j - W)] = make_tap(inv_coord(d_inv, nty, j - W, H, h), h);
-  }
-  if (threadIdx.x < T) s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
-
-  const air_prior& pr = a.prior;
-  if (a.do_elbo) {
-    if (warp == 0) {
-      // step-count posterior q(n), KL(q(n) || prior) and the per-step weights: lane k owns n = k (float64 island)
-      const int k = lane;
-      double pi = 0.0;
-      if (k <= T) {
-        double cum = 1.0;
-        for (int j = 0; j < k && j < T; ++j) cum *= (double)a.presence_prob[(size_t)j * B + b];
-        pi = (k < T) ? (1.0 - (double)a.presence_prob[(size_t)k * B + b]) * cum : cum;
-      }
-      double sum = pi;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      float q = 0.f, kl = 0.f;
-      if (k <= T) {
-        q = (float)(pi / sum);
-        kl = tabular_kl_entry(q, a.steps_prior[k], 0.0);
-        s_q[k] = q;
-        a.num_steps_posterior[(size_t)b * (T + 1) + k] = q;
-      }
-      float kl_n = 0.f;   // fp32 sum over n in index order (model.py:149)
-      for (int j = 0; j <= T; ++j) {
-        const float v = __shfl_sync(0xffffffffu, kl, j);
-        kl_n = (j == 0) ? v : __fadd_rn(kl_n, v);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        s_kln = kl_n;
-        a.kl_num_steps_per_sample[b] = kl_n;
-        float n = 0.f;
-        for (int t = 0; t < T; ++t) n += a.presence[(size_t)t * B + b];
-        a.num_step_per_sample[b] = n;
-        int idx = (int)n;
-        idx = idx < 0 ? 0 : (idx > T ? T : idx);
-        a.num_steps_log_prob[b] = logf(fmaxf(s_q[idx], 1e-32f));
-        if (pr.analytic) {   // reverse cumsum of q(n)[1:]   (model.py:157-161)
-          float cs = 0.f;
-          for (int t = T - 1; t >= 0; --t) {
-            cs = (t == T - 1) ? s_q[t + 1] : __fadd_rn(cs, s_q[t + 1]);
-            s_w[t] = cs;
-          }
-        } else {
-          for (int t = 0; t < T; ++t) s_w[t] = a.presence[(size_t)t * B + b];
-        }
-        for (int t = 0; t < T; ++t) a.prior_step_weight[(size_t)t * B + b] = s_w[t];
-      }
-    }
-    // KL(what) per step: one warp per step (model.py:174-186)
-    for (int t = warp; t < T; t += (blockDim.x >> 5)) {
-      float v = 0.f;
-      const size_t base = ((size_t)t * B + b) * a.na;
-      for (int i = lane; i < a.na; i += 32)
-        v += normal_kl(a.what_loc[base + i], a.what_scale[base + i], pr.what_loc, pr.what_scale);
-      v = warp_sum(v);
-      if (lane == 0) s_klw[t] = v;
-    }
+    const float4 iv = s_inv[t];
+    if (j < W) s_tx[t * W + j] = make_tap(inv_coord_s(iv.x, iv.z, j, a.step_W, w), w, 1);
+    else       s_ty[t * H + (j - W)] = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, w);
   }
   __syncthreads();
   if (bulk) mbar_wait(&bar, 0);
@@ -481,83 +658,19 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
   if (a.glimpse_viz) {
     for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
       const int t = i / G, g = i - t * G;
-      a.glimpse_viz[((size_t)t * B + b) * G + g] = __fmul_rn(s_pres[t], sigmoid_f(s_gl[i]));
+      a.glimpse_viz[((size_t)t * B + b) * G + g] = __fmul_rn(s_pres[t], sigmoid_fast(s_gl[i]));
     }
   }
 
-  // ---- paint: per-thread pixels p = tid, tid + 256, ...; (row, col) tracked incrementally; the T-step loop is unrolled
-  // at compile time so every base pointer and presence value sits in a register.  A step whose presence is 0
-  // (block-uniform) or whose inverse-warp footprint misses the pixel (both taps of an axis weightless: the
-  // reference's "outside" case) contributes exactly 0 and is skipped.
-  const float mult = a.output_multiplier, sigma = a.output_std, lp_const = a.lp_const;
-  const int NT = blockDim.x;
-  const int dr = NT / W, dc = NT - dr * W;
-  int r = (int)threadIdx.x / W, c = (int)threadIdx.x - r * W;
-  float pres[T];
-  float* cdst[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    pres[t] = s_pres[t];
-    cdst[t] = a.canvas ? a.canvas + ((size_t)t * B + b) * P : nullptr;
-  }
-  const float* cin = a.canvas_in ? a.canvas_in + (size_t)b * P : nullptr;
-  const float* obs = a.img + (size_t)b * P;
-  float rec = 0.f;
-  for (int p = threadIdx.x; p < P; p += NT) {
-    float acc = cin ? cin[p] : 0.f;
-    const float x_obs = a.do_elbo ? obs[p] : 0.f;
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (pres[t] != 0.f) {
-        const Tap tx = s_tx[t * W + c], ty = s_ty[t * H + r];
-        if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) {
-          const float v = bilinear(s_gl + t * G, w, tx, ty);
-          acc = __fadd_rn(acc, __fmul_rn(pres[t], v));
-        }
-      }
-      if (cdst[t]) cdst[t][p] = __fmul_rn(acc, mult);
-    }
-    if (a.do_elbo) {
-      const float mu = __fmul_rn(acc, mult);
-      const float z = __fdiv_rn(x_obs - mu, sigma);
-      rec += __fadd_rn(__fmul_rn(__fmul_rn(0.5f, z), z), lp_const);
-    }
-    c += dc;
-    r += dr;
-    if (c >= W) {
-      c -= W;
-      ++r;
-    }
-  }
+  // column pairs need an even row pitch and 8-byte aligned rows
+  const bool pair = ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.canvas) & 7) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(a.canvas_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.img) & 7) == 0);
+  float rec = pair ? paint_rows<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
   if (!a.do_elbo) return;
   rec = block_sum(rec, s_red);
-
   if (threadIdx.x == 0) {
-    float kl_what = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float v = __fmul_rn(s_klw[t], s_w[t]);
-      kl_what = (t == 0) ? v : __fadd_rn(kl_what, v);
-    }
-    // KL(where)   (model.py:188-214): (sx, sy) vs scale prior, (tx, ty) vs shift prior
-    float kl_where = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float* wl = a.where_loc + ((size_t)t * B + b) * 4;
-      const float* ws = a.where_scale + ((size_t)t * B + b) * 4;
-      const float k_sx = normal_kl(wl[0], ws[0], pr.where_scale_loc, pr.where_scale_scale);
-      const float k_sy = normal_kl(wl[2], ws[2], pr.where_scale_loc, pr.where_scale_scale);
-      const float k_tx = normal_kl(wl[1], ws[1], pr.where_shift_has_loc ? pr.where_shift_loc : wl[1], pr.where_shift_scale);
-      const float k_ty = normal_kl(wl[3], ws[3], pr.where_shift_has_loc ? pr.where_shift_loc : wl[3], pr.where_shift_scale);
-      const float s = __fadd_rn(__fadd_rn(k_sx, k_tx), __fadd_rn(k_sy, k_ty));
-      const float ws_t = __fmul_rn(s, s_w[t]);
-      kl_where = (t == 0) ? ws_t : __fadd_rn(kl_where, ws_t);
-    }
-    const float kl_n = s_kln;
     a.rec_loss_per_sample[b] = rec;
-    a.kl_what_per_sample[b] = kl_what;
-    a.kl_where_per_sample[b] = kl_where;
-    // Loss.add bookkeeping (ops.py:12-29; model.py:154,186,214,324,332)
-    const float prior_ps = __fadd_rn(__fadd_rn(__fmul_rn(kl_n, pr.steps_weight), kl_what), kl_where);
-    a.loss_per_sample[b] = __fadd_rn(rec, __fmul_rn(prior_ps, pr.use_prior ? 1.0f : 0.0f));
+    a.loss_per_sample[b] = __fadd_rn(rec, a.loss_per_sample[b]);   // + prior part (prior_terms_kernel)
   }
 }
 
@@ -571,7 +684,19 @@ inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStrea
   }
   return launch_k(paint_elbo_kernel<T>, dim3(a.B), dim3(256), smem, st, a);
 }
-inline cudaError_t launch_paint_elbo(const ElboArgs& a, cudaStream_t st) {
+// host-side constants of ElboArgs (float64 maths on the host, exactly what the device code computed per tap before)
+inline void fill_elbo_consts(ElboArgs& a) {
+  a.inv_sigma = 1.0f / a.output_std;
+  a.step_W = a.W > 1 ? 2.0 / (double)(a.W - 1) : 0.0;
+  a.step_H = a.H > 1 ? 2.0 / (double)(a.H - 1) : 0.0;
+}
+// prior terms (when a prior is given) followed by paint + reconstruction term
+inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
+  fill_elbo_consts(a);
+  if (a.do_elbo) {
+    cudaError_t e = launch_prior_terms(a, 0, st);
+    if (e != cudaSuccess) return e;
+  }
   const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);
   switch (a.T) {
     case 1: return launch_paint_elbo_t<1>(a, smem, st);

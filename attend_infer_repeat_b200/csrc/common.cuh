@@ -26,6 +26,9 @@ __device__ __forceinline__ float softplus_f(float x) {
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// visualisation-only sigmoid (glimpse_viz, model.py:90): ex2.approx + fast division, ~2^-21 relative
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 __device__ __forceinline__ float apply_act(float v, int act) { return act == ACT_ELU ? elu_f(v) : v; }
 
 // fp16x2 split operand format of the tensor-core engine (linear_tc.cuh): x = hi + lo, hi = fp16(x), lo = fp16(x - hi)
@@ -163,6 +166,14 @@ __device__ __forceinline__ void inv_params(float sx, float tx, float sy, float t
 __device__ __forceinline__ float inv_coord(float a_inv, float nt, int i, int n_canvas, int n_glimpse) {
   const float S = ((float)n_glimpse - 1.0f) * 0.5f;
   const float US = __fmul_rn(linspace_pm1(i, n_canvas), S);
+  return __fadd_rn(__fadd_rn(__fmul_rn(a_inv, US), __fmul_rn(nt, S)), S);
+}
+
+// inv_coord with np.linspace's float64 step 2/(n_canvas - 1) computed once on the host (same value, no per-tap division)
+__device__ __forceinline__ float inv_coord_s(float a_inv, float nt, int i, double step, int n_glimpse) {
+  const float S = ((float)n_glimpse - 1.0f) * 0.5f;
+  const float U = (float)(-1.0 + (double)i * step);
+  const float US = __fmul_rn(U, S);
   return __fadd_rn(__fadd_rn(__fmul_rn(a_inv, US), __fmul_rn(nt, S)), S);
 }
 
