@@ -124,6 +124,7 @@ struct air_handle {
   Buf ping, pong;                                  // hidden activations of the MLP chains [T*B, max_width]
   Buf x, e, h_init, hs, crop, what_in;             // GEMM A operands produced by non-GEMM kernels (+ e)
   float *gx = nullptr, *gates = nullptr, *cbuf = nullptr, *m = nullptr, *logit = nullptr, *r = nullptr;
+  float* prior_part = nullptr;   // [B] prior part of the per-sample loss (paint grid -> elbo_scalars_kernel)
   // staging for air_forward_host / air_cell_step
   uint8_t* st_img_u8 = nullptr;
   float *st_img = nullptr, *st_eps_where = nullptr, *st_eps_what = nullptr, *st_u = nullptr, *st_pres_in = nullptr;
@@ -497,7 +498,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(256), air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
                          h->m, eps_where, img, o->where, o->where_loc, o->where_scale, tc ? nullptr : h->crop.f32,
                          tc ? (h->chain_ok ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
-                         c.max_crop_size, c.scale_bias));
+                         c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
+                         c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0));
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
@@ -593,13 +595,15 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                                                   : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
   }
   a.lp_const = (float)(0.5 * 1.8378770664093453 /* log(2 pi) */ + std::log((double)c.output_std));
-  AIR_CUDA(air::launch_paint_elbo(a, st));   // prior_terms_kernel (when a prior is given) + paint_elbo_kernel
-  h->launches += prior ? 2 : 1;
+  a.prior_part = h->prior_part;
+  AIR_CUDA(air::launch_paint_elbo(a, st));   // paint CTAs + (when a prior is given) the prior-term CTAs, one grid
+  ++h->launches;
 
   if (prior) {
     AIR_CUDA(air::launch_k(air::elbo_scalars_kernel, dim3(1), dim3(1024), 0, st, o->rec_loss_per_sample,
                            o->kl_num_steps_per_sample, o->kl_what_per_sample, o->kl_where_per_sample,
-                           o->num_step_per_sample, o->num_steps_log_prob, baseline, o->scalars, B, *prior));
+                           o->num_step_per_sample, o->num_steps_log_prob, baseline, o->scalars, B, *prior,
+                           (const float*)h->prior_part, o->loss_per_sample));
     ++h->launches;
   }
   mark(h, AIR_N_STAGES, st);
@@ -658,6 +662,7 @@ void carve_workspace(air_handle* h, Carver& cv) {
   h->st_eps_what = cv.take<float>(TB * c.na);
   h->st_u = cv.take<float>(TB);
   h->st_pres_in = cv.take<float>(B);
+  h->prior_part = cv.take<float>(B);
   // tensor-core side
   if (tc) {
     hl(h->ping, TB_alloc, h->max_width);
@@ -1007,7 +1012,7 @@ int32_t air_elbo_scalars(air_handle* h, const float* baseline, const air_prior* 
   if (rc != AIR_OK) return rc;
   air::elbo_scalars_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
       outs->rec_loss_per_sample, outs->kl_num_steps_per_sample, outs->kl_what_per_sample, outs->kl_where_per_sample,
-      outs->num_step_per_sample, outs->num_steps_log_prob, baseline, outs->scalars, h->cfg.B, *prior);
+      outs->num_step_per_sample, outs->num_steps_log_prob, baseline, outs->scalars, h->cfg.B, *prior, nullptr, nullptr);
   AIR_CUDA(cudaGetLastError());
   return AIR_OK;
 }
@@ -1020,7 +1025,7 @@ int32_t air_elbo_scalars_raw(int32_t B, const float* baseline, const air_prior* 
   AIR_CUDA(air::launch_k(air::elbo_scalars_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream,
                          outs->rec_loss_per_sample, outs->kl_num_steps_per_sample, outs->kl_what_per_sample,
                          outs->kl_where_per_sample, outs->num_step_per_sample, outs->num_steps_log_prob, baseline,
-                         outs->scalars, B, *prior));
+                         outs->scalars, B, *prior, (const float*)nullptr, (float*)nullptr));
   return AIR_OK;
 }
 

@@ -77,6 +77,17 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ D, int Ws, c
   return r;
 }
 
+// bilinear with the row taps' indices pre-multiplied by the source row pitch (make_tap(..., stride = Ws))
+__device__ __forceinline__ float bilinear_pre(const float* __restrict__ D, const Tap& x, const Tap& y) {
+  const float* rf = D + y.i_f;
+  const float* rc = D + y.i_c;
+  float r = __fmul_rn(__fmul_rn(x.wf, y.wf), rf[x.i_f]);
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wc), rc[x.i_c]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wf, y.wc), rc[x.i_f]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wf), rf[x.i_c]));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LSTM state handling (snt.LSTM [upstream], mnist_model.py:35; cell.py:101-114,126-127)
 // ---------------------------------------------------------------------------------------------------
@@ -162,11 +173,11 @@ __host__ __device__ inline size_t where_read_smem(int T, int H, int W, int h, in
   return sizeof(float) * ((size_t)H * W + 4) / 16 * 16 + 16 + sizeof(Tap) * (size_t)T * (w + h);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_where, const float* __restrict__ img,
                   float* __restrict__ where, float* __restrict__ where_loc, float* __restrict__ where_scale,
                   float* __restrict__ crop, HlOut crop_hl, int T, int B, int H, int W, int h, int w, float max_crop,
-                  float scale_bias) {
+                  float scale_bias, double step_w, double step_h) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_where[AIR_MAX_STEPS][4];
@@ -203,12 +214,40 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   __syncthreads();
   for (int i = threadIdx.x; i < T * (w + h); i += blockDim.x) {
     const int t = i / (w + h), j = i - t * (w + h);
-    if (j < w) s_tx[t * w + j] = make_tap(fwd_coord(s_where[t][0], s_where[t][1], j, w, W), W);
-    else       s_ty[t * h + (j - w)] = make_tap(fwd_coord(s_where[t][2], s_where[t][3], j - w, h, H), H);
+    if (j < w) s_tx[t * w + j] = make_tap(fwd_coord_s(s_where[t][0], s_where[t][1], j, step_w, W), W, 1);
+    else       s_ty[t * h + (j - w)] = make_tap(fwd_coord_s(s_where[t][2], s_where[t][3], j - w, step_h, H), H, W);
   }
   __syncthreads();
   if (bulk) mbar_wait(&bar, 0);
   const int NT = blockDim.x;
+  if (!crop && crop_hl.p && crop_hl.nsl > 0 && (G & 7) == 0) {
+    // tensor-core engine, fused-chain operand layout: a thread produces 8 consecutive glimpse pixels = one 16-byte
+    // store into the hi plane and one into the lo plane ([row tile of 128][K slice of 16][128 rows][16 fp16])
+    const int chunks = G >> 3;
+    for (int i = threadIdx.x; i < T * chunks; i += NT) {
+      const int t = i / chunks, g0 = (i - t * chunks) << 3;
+      const size_t row = (size_t)t * B + b;
+      const Tap* txs = s_tx + t * w;
+      const Tap* tys = s_ty + t * h;
+      int r = g0 / w, c = g0 - r * w;
+      __align__(16) __half hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const Tap tx = txs[c], ty = tys[r];
+        float v = 0.f;
+        if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear_pre(s_img, tx, ty);
+        split_f16(v, hi[j], lo[j]);
+        if (++c == w) {
+          c = 0;
+          ++r;
+        }
+      }
+      __half* dst = crop_hl.p + (((row >> 7) * (size_t)crop_hl.nsl + (size_t)(g0 >> 4)) * 128 + (row & 127)) * 16 + (g0 & 15);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(dst + crop_hl.plane) = *reinterpret_cast<const uint4*>(lo);
+    }
+    return;
+  }
   const int dr = NT / w, dc = NT - dr * w;
   for (int t = 0; t < T; ++t) {
     const size_t row = (size_t)t * B + b;
@@ -219,7 +258,7 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
     for (int g = threadIdx.x; g < G; g += NT) {
       const Tap tx = txs[c], ty = tys[r];
       float v = 0.f;
-      if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear(s_img, W, tx, ty);
+      if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear_pre(s_img, tx, ty);
       if (cf) cf[g] = v;
       if (crop_hl.p) hl_store(crop_hl, row, g, v);
       c += dc;
@@ -320,6 +359,8 @@ struct ElboArgs {
   float inv_sigma;             // 1 / output_std (host)
   double step_W, step_H;       // np.linspace(-1, 1, n) step 2/(n-1) of the canvas columns / rows (host, float64)
   int do_elbo;
+  float* prior_part;           // [B] scratch: prior_weight * prior_per_sample (prior CTAs -> elbo_scalars_kernel)
+  int n_prior_ctas;            // leading CTAs of the paint grid that compute the prior terms (launch_paint_elbo)
   air_prior prior;
   double steps_prior[AIR_MAX_STEPS + 1];   // geometric_prior(success_prob, T) (prior.py:26-32): the same table for
                                            // every canvas, computed once on the host (air_api.cu:steps_prior_table)
@@ -368,17 +409,14 @@ __device__ __forceinline__ float tabular_kl_entry(float p, double q, double zero
 // Per-canvas prior terms (model.py:126-216, prior.py:62-90,148-151).  One WARP per canvas, no shared memory:
 //   q(n) (float64 island, lane k owns n = k), KL(q(n) || prior), log q(n_b), the per-step weights,
 //   KL(what) (lanes over the na latents, one warp reduction per step), KL(where).
-// Runs before the paint kernel and leaves prior_weight * prior_per_sample in loss_per_sample[b]; the paint kernel adds
-// the reconstruction term on top (Loss.add, ops.py:12-29).  `finalize` != 0 (air_prior_terms): there is no canvas, so
-// the reconstruction term is exactly 0 and loss_per_sample is complete.
+// Runs inside the paint grid (its leading CTAs) and leaves prior_weight * prior_per_sample in prior_part[b];
+// elbo_scalars_kernel adds the reconstruction term on top (Loss.add, ops.py:12-29).  `finalize` != 0 (air_prior_terms,
+// stand-alone kernel): there is no canvas, the reconstruction term is exactly 0 and loss_per_sample is complete.
 // ---------------------------------------------------------------------------------------------------
 template <int T>
-__global__ void __launch_bounds__(128) prior_terms_kernel(ElboArgs a, int finalize) {
-  griddep_launch();
-  griddep_wait();
+__device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int finalize) {
   const int B = a.B;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const air_prior& pr = a.prior;
   // step-count posterior q(n): lane k owns n = k (float64 island)
@@ -478,8 +516,15 @@ __global__ void __launch_bounds__(128) prior_terms_kernel(ElboArgs a, int finali
     a.rec_loss_per_sample[b] = 0.f;
     a.loss_per_sample[b] = __fadd_rn(0.f, part);
   } else {
-    a.loss_per_sample[b] = part;
+    a.prior_part[b] = part;
   }
+}
+
+template <int T>
+__global__ void __launch_bounds__(128) prior_terms_kernel(ElboArgs a, int finalize) {
+  griddep_launch();
+  griddep_wait();
+  prior_terms_warp<T>(a, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), finalize);
 }
 
 inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStream_t st) {
@@ -501,7 +546,7 @@ inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStrea
 // paint + reconstruction term.  One CTA per canvas b.
 //   canvas_t = canvas_{t-1} + presence_t * resampler(glimpse_t, inverse warp(where_t))   (cell.py:159-164)
 //   rec[b]   = sum_px 0.5 ((x - mu)/sigma)^2 + log sigma + 0.5 log 2 pi, mu = multiplier * canvas_T (model.py:319-321)
-//   loss_per_sample[b] = rec[b] + (prior part left there by prior_terms_kernel)
+//   (loss_per_sample[b] = rec[b] + prior part is completed by elbo_scalars_kernel)
 // The canvas is never read back from HBM: it accumulates in registers across the T steps and is written once per step.
 // Thread mapping: a thread owns a fixed column (a column PAIR when W is even: 8-byte stores) and walks down the rows, so
 // "is this column inside glimpse t's footprint" is a loop-invariant bit mask, the row test is one broadcast shared-memory
@@ -511,17 +556,6 @@ inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStrea
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) {
   return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H);
-}
-
-// bilinear with the row taps' indices pre-multiplied by the source row pitch (make_tap(..., stride = Ws))
-__device__ __forceinline__ float bilinear_pre(const float* __restrict__ D, const Tap& x, const Tap& y) {
-  const float* rf = D + y.i_f;
-  const float* rc = D + y.i_c;
-  float r = __fmul_rn(__fmul_rn(x.wf, y.wf), rf[x.i_f]);
-  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wc), rc[x.i_c]));
-  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wf, y.wc), rc[x.i_f]));
-  r = __fadd_rn(r, __fmul_rn(__fmul_rn(x.wc, y.wf), rf[x.i_c]));
-  return r;
 }
 
 template <int T, int CPT>
@@ -535,7 +569,7 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const floa
   const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
   const int RPP = NT / TPRB;                    // rows per pass
   const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
-  const float mult = a.output_multiplier, inv_sigma = a.inv_sigma, lp_const = a.lp_const;
+  const float mult = a.output_multiplier;
   const bool do_elbo = a.do_elbo != 0;
   float pres[T];
 #pragma unroll
@@ -593,12 +627,11 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const floa
           else          dst[0] = __fmul_rn(acc[0], mult);
         }
       }
-      if (do_elbo) {
+      if (do_elbo) {   // sum of squared residuals; the constants of Normal.log_prob are applied once per canvas
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-          const float mu = __fmul_rn(acc[j], mult);
-          const float z = __fmul_rn(xo[j] - mu, inv_sigma);   // sigma is a constant: multiply by its reciprocal
-          rec += __fadd_rn(__fmul_rn(__fmul_rn(0.5f, z), z), lp_const);
+          const float d = xo[j] - __fmul_rn(acc[j], mult);
+          rec = fmaf(d, d, rec);
         }
       }
     }
@@ -607,20 +640,26 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const floa
 }
 
 template <int T>
-__global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
+__global__ void __launch_bounds__(256, 8) paint_elbo_kernel(ElboArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_pres[AIR_MAX_STEPS], s_red[32];
   __shared__ float4 s_inv[AIR_MAX_STEPS];
   const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
-  const int P = H * W, G = h * w;
-  const int b = blockIdx.x;
+  const int G = h * w;
   float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
   Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);         // [T][W]
   Tap* s_ty = s_tx + (size_t)T * W;                                                                      // [T][H]
 
   griddep_launch();
   griddep_wait();
+  // The first n_prior_ctas CTAs of the grid compute the prior terms (one warp per canvas) while the others paint: the
+  // latency-bound float64 / log chains hide behind the bandwidth-bound paint CTAs instead of costing a launch.
+  if ((int)blockIdx.x < a.n_prior_ctas) {
+    prior_terms_warp<T>(a, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), 0);
+    return;
+  }
+  const int b = blockIdx.x - a.n_prior_ctas;
   // stage the T decoded glimpses of this canvas (TMA bulk copies, one mbarrier)
   const bool bulk = bulk_ok(a.glimpse, G);
   if (threadIdx.x == 0 && bulk) {
@@ -645,20 +684,24 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
   }
   __syncthreads();
   // inverse-warp tap tables while the copy is in flight: glimpse-space taps of every canvas column / row
-  for (int i = threadIdx.x; i < T * (W + H); i += blockDim.x) {
-    const int t = i / (W + H), j = i - t * (W + H);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
     const float4 iv = s_inv[t];
-    if (j < W) s_tx[t * W + j] = make_tap(inv_coord_s(iv.x, iv.z, j, a.step_W, w), w, 1);
-    else       s_ty[t * H + (j - W)] = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, w);
+    for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
+      if (j < W) s_tx[t * W + j] = make_tap(inv_coord_s(iv.x, iv.z, j, a.step_W, w), w, 1);
+      else       s_ty[t * H + (j - W)] = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, w);
+    }
   }
   __syncthreads();
   if (bulk) mbar_wait(&bar, 0);
 
   // optional visualisation output: presence * sigmoid(glimpse)   (model.py:90)
   if (a.glimpse_viz) {
-    for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
-      const int t = i / G, g = i - t * G;
-      a.glimpse_viz[((size_t)t * B + b) * G + g] = __fmul_rn(s_pres[t], sigmoid_fast(s_gl[i]));
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float* dst = a.glimpse_viz + ((size_t)t * B + b) * G;
+      const float pres_t = s_pres[t];
+      for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = __fmul_rn(pres_t, sigmoid_fast(s_gl[t * G + g]));
     }
   }
 
@@ -668,10 +711,9 @@ __global__ void __launch_bounds__(256) paint_elbo_kernel(ElboArgs a) {
   float rec = pair ? paint_rows<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
   if (!a.do_elbo) return;
   rec = block_sum(rec, s_red);
-  if (threadIdx.x == 0) {
-    a.rec_loss_per_sample[b] = rec;
-    a.loss_per_sample[b] = __fadd_rn(rec, a.loss_per_sample[b]);   // + prior part (prior_terms_kernel)
-  }
+  // sum_px 0.5 ((x - mu) / sigma)^2 + (log sigma + 0.5 log 2 pi); elbo_scalars_kernel adds the prior part
+  if (threadIdx.x == 0)
+    a.rec_loss_per_sample[b] = fmaf(__fmul_rn(0.5f * a.inv_sigma, a.inv_sigma), rec, __fmul_rn((float)(H * W), a.lp_const));
 }
 
 template <int T>
@@ -682,7 +724,7 @@ inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStrea
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  return launch_k(paint_elbo_kernel<T>, dim3(a.B), dim3(256), smem, st, a);
+  return launch_k(paint_elbo_kernel<T>, dim3(a.B + a.n_prior_ctas), dim3(256), smem, st, a);
 }
 // host-side constants of ElboArgs (float64 maths on the host, exactly what the device code computed per tap before)
 inline void fill_elbo_consts(ElboArgs& a) {
@@ -693,10 +735,7 @@ inline void fill_elbo_consts(ElboArgs& a) {
 // prior terms (when a prior is given) followed by paint + reconstruction term
 inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
   fill_elbo_consts(a);
-  if (a.do_elbo) {
-    cudaError_t e = launch_prior_terms(a, 0, st);
-    if (e != cudaSuccess) return e;
-  }
+  a.n_prior_ctas = a.do_elbo ? (a.B + 7) / 8 : 0;   // 8 warps per CTA, one canvas per warp
   const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);
   switch (a.T) {
     case 1: return launch_paint_elbo_t<1>(a, smem, st);
@@ -744,26 +783,37 @@ __global__ void __launch_bounds__(1024)
 elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_n, const float* __restrict__ kl_what,
                     const float* __restrict__ kl_where, const float* __restrict__ nsteps,
                     const float* __restrict__ logq, const float* __restrict__ baseline, float* __restrict__ scalars,
-                    int B, air_prior pr) {
-  __shared__ float s_red[32];
+                    int B, air_prior pr, const float* __restrict__ prior_part, float* __restrict__ loss_per_sample) {
+  __shared__ float s_part[32][8];
   griddep_launch();
   griddep_wait();
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float r = rec[b], lq = logq[b];
+    const float r = rec[b], lq = logq[b], k_n = kl_n[b], k_wt = kl_what[b], k_wh = kl_where[b];
+    if (prior_part) loss_per_sample[b] = __fadd_rn(r, prior_part[b]);   // Loss.add (ops.py:12-29), model.py:324,332
     float iw = r;   // REINFORCE importance weight (model.py:337-339)
-    if (!pr.analytic) iw = __fadd_rn(r, __fadd_rn(__fadd_rn(__fmul_rn(kl_n[b], pr.steps_weight), kl_what[b]), kl_where[b]));
+    if (!pr.analytic) iw = __fadd_rn(r, __fadd_rn(__fadd_rn(__fmul_rn(k_n, pr.steps_weight), k_wt), k_wh));
     s[0] += r;
-    s[1] += kl_n[b];
-    s[2] += kl_what[b];
-    s[3] += kl_where[b];
+    s[1] += k_n;
+    s[2] += k_wt;
+    s[3] += k_wh;
     s[4] += nsteps[b];
     s[5] += iw * lq;
     s[6] += lq;
     s[7] += baseline ? baseline[b] : 0.f;
   }
+  // one pass: warp sums -> shared -> the first warp adds the per-warp partials (fixed order: deterministic)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = block_sum(s[i], s_red);
+  for (int i = 0; i < 8; ++i) {
+    s[i] = warp_sum(s[i]);
+    if (lane == 0) s_part[wid][i] = s[i];
+  }
+  __syncthreads();
+  if (wid != 0) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = warp_sum(lane < nw ? s_part[lane][i] : 0.f);
   if (threadIdx.x == 0) {
     const float inv = 1.0f / (float)B;
     const float m_rec = s[0] * inv, m_kln = s[1] * inv, m_klw = s[2] * inv, m_klwh = s[3] * inv;

@@ -152,6 +152,13 @@ __device__ __forceinline__ float fwd_coord(float s, float t, int i, int n_out, i
   return __fadd_rn(__fadd_rn(__fmul_rn(s, uS), __fmul_rn(t, S)), S);
 }
 
+// fwd_coord with np.linspace's float64 step 2/(n_out - 1) computed once on the host (same value, no per-tap division)
+__device__ __forceinline__ float fwd_coord_s(float s, float t, int i, double step, int n_src) {
+  const float S = ((float)n_src - 1.0f) * 0.5f;
+  const float uS = __fmul_rn((float)(-1.0 + (double)i * step), S);
+  return __fadd_rn(__fadd_rn(__fmul_rn(s, uS), __fmul_rn(t, S)), S);
+}
+
 // AffineGridWarper.inverse() for the no-shear case (a = sx, d = sy, b = c = 0):
 //   det = sx * sy; a' = sy / det; d' = sx / det; tx' = a' * tx; ty' = d' * ty
 //   x_g = a' * (U * S_w) + (-tx') * S_w + S_w   (U = linspace(-1, 1, W) over canvas columns), y likewise.
