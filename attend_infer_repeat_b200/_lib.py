@@ -96,6 +96,12 @@ SYMBOLS = {
                                      _P]),
     "air_forward_host_u8": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P, _P,
                                         _P]),
+    "air_train_enable": (C.c_int32, [_P, C.c_int32]),
+    "air_train_workspace_bytes": (C.c_int64, [_P]),
+    "air_backward": (C.c_int32, [_P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), C.c_float, C.c_float,
+                                 C.c_float, _P, _P]),
+    "air_rmsprop_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, _P]),
     "air_elbo_scalars": (C.c_int32, [_P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_elbo_scalars_raw": (C.c_int32, [C.c_int32, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_prior_terms": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior),

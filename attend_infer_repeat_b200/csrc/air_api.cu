@@ -26,9 +26,11 @@
 #include <vector>
 
 #include "../../include/air_b200.h"
+#include "backward_kernels.cuh"
 #include "cell_kernels.cuh"
 #include "chain_tc.cuh"
 #include "common.cuh"
+#include "gemm_simt.cuh"
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
 #include "lstm_tc.cuh"
@@ -136,6 +138,22 @@ struct air_handle {
   int prep_tiles = 0;
   int* range_flag = nullptr;
   std::map<std::pair<const void*, int>, CUtensorMap> tmap_cache;
+  // training (air_train_enable / air_backward; AIR_PREC_FP32 engine): saved activations + gradient scratch, one cudaMalloc
+  bool train = false;
+  bool fwd_saved = false;          // the last forward on this handle ran in training mode with a prior (backward is valid)
+  char* tws = nullptr;
+  size_t tws_bytes = 0;
+  std::vector<float*> sv_enc, sv_where, sv_steps, sv_glenc, sv_dec;   // hidden activations of each MLP (layer outputs)
+  float *sv_q = nullptr;           // glimpse-encoder output [T*B, n_gl]
+  float *gates_all = nullptr;      // [T,B,4nh] pre-activation gates of every step
+  float *c_all = nullptr;          // [T+1,B,nh] cell states (slice 0 = initial)
+  float *hprev = nullptr;          // [T,B,nh] h_{t-1} of every step (slice 0 = initial)
+  float *g_a = nullptr, *g_b = nullptr;            // [T*B, max_width] gradient ping-pong
+  float *g_glimpse = nullptr, *g_crop = nullptr;   // [T*B, G]
+  float *g_what = nullptr, *g_r = nullptr;         // [T*B, na], [T*B, 2na]
+  float *g_wh_paint = nullptr, *g_wh_read = nullptr, *g_m = nullptr, *g_logit = nullptr;   // [T*B,4] x2, [T*B,8], [T*B]
+  float *g_h = nullptr, *g_gates = nullptr;        // [T*B, nh], [T*B, 4nh]
+  float *g_gx = nullptr, *g_hrec = nullptr, *g_c = nullptr, *g_e = nullptr;   // [B,4nh], [B,nh], [B,nh], [B,n_enc]
   // instrumentation: kernel-launch counter and optional per-stage CUDA-event timing (air_profile_*)
   uint64_t launches = 0;
   bool profile = false;
@@ -258,26 +276,30 @@ int32_t dense(air_handle* h, const float* params, const Buf& in, int row0, const
 // neural.MLP (neural.py:63-102): ELU hidden layers, linear output layer.  Hidden activations ping-pong between the two
 // workspace buffers (fp32 rows or hl planes depending on the engine); the last layer writes `out`.
 int32_t run_mlp(air_handle* h, const float* params, const Mlp& mlp, const Buf& in, int M, const Buf& out,
-                bool out_f32, bool out_hl, cudaStream_t st) {
-  const Buf* cur = &in;
+                bool out_f32, bool out_hl, cudaStream_t st, const std::vector<float*>* saves = nullptr) {
+  Buf cur = in;
+  bool to_ping = true;
   const int nl = (int)mlp.layers.size();
   for (int i = 0; i < nl; ++i) {
     const Layer& l = mlp.layers[i];
     const bool last = (i == nl - 1);
-    Buf dst = last ? out : ((cur == &h->ping) ? h->pong : h->ping);
-    if (!last) {
+    Buf dst;
+    if (last) {
+      dst = out;
+    } else if (saves) {   // training mode (fp32 engine): every hidden activation is kept for the backward pass
+      dst.f32 = (*saves)[i];
+      dst.ld = l.N;
+    } else {
+      dst = to_ping ? h->ping : h->pong;
+      to_ping = !to_ping;
       dst.ld = l.N;
       dst.kpad = round_up(l.N, air::tc::BK);
     }
     const int act = (i < mlp.n_hidden) ? air::ACT_ELU : air::ACT_NONE;
-    const int32_t rc = dense(h, params, *cur, 0, l, true, nullptr, 0, dst, last ? out_f32 : !h->use_tc,
+    const int32_t rc = dense(h, params, cur, 0, l, true, nullptr, 0, dst, last ? out_f32 : !h->use_tc,
                              last ? out_hl : h->use_tc, M, act, st);
     if (rc != AIR_OK) return rc;
-    if (!last) {
-      Buf* slot = (cur == &h->ping) ? &h->pong : &h->ping;
-      *slot = dst;
-      cur = slot;
-    }
+    cur = dst;
   }
   return AIR_OK;
 }
@@ -370,6 +392,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   const bool tc = h->use_tc;
   const air::HlOut no_hl{nullptr, 0, 0, 0};
   int32_t rc;
+  // training mode (air_train_enable, fp32 engine): every activation the backward pass needs is kept
+  const bool train = h->train && !tc && prior != nullptr && T_run == c.T && !h_in && !canvas_in;
+  h->fwd_saved = false;
 
   // 0. tensor-core engine: (re)build the fp16-split W^T arena from the current parameters and split the images
   mark(h, AIR_ST_ENCODER, st);
@@ -390,7 +415,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
   const bool lstm_fused = tc && h->lstm_ok;
-  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused, tc && !lstm_fused, st)) != AIR_OK) return rc;
+  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused, tc && !lstm_fused, st,
+                    train ? &h->sv_enc : nullptr)) != AIR_OK)
+    return rc;
   mark(h, AIR_ST_LSTM, st);
 
   // 2. gx = e @ W[:n_enc] + b   (input half of snt.LSTM's [x,h] @ W + b)
@@ -412,7 +439,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     }
   } else {
     AIR_CUDA(air::launch_k(air::lstm_init_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
-                           params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, h->cbuf, B, nh,
+                           params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, train ? h->c_all : h->cbuf, B, nh,
                            (tc && !lstm_fused) ? h->h_init.hl_out() : no_hl));
     ++h->launches;
   }
@@ -445,16 +472,19 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   for (int t = 0; t < (lstm_fused ? 0 : T_run); ++t) {
     const Buf& h_prev = (t == 0) ? h->h_init : h->hs;
     const int row0 = (t == 0) ? 0 : (t - 1) * B;
+    if (train) gates.f32 = h->gates_all + (size_t)t * B * 4 * nh;
     if ((rc = dense(h, params, h_prev, row0, h->lstm_h, false, h->gx, 4 * nh, gates, true, false, B, air::ACT_NONE,
                     st)) != AIR_OK)
       return rc;
+    const float* c_src = train ? h->c_all + (size_t)t * B * nh : h->cbuf;
+    float* c_dst = train ? h->c_all + (size_t)(t + 1) * B * nh : h->cbuf;
     air::HlOut hs_hl = no_hl;
     if (tc) {
       hs_hl = h->hs.hl_out();
       hs_hl.p += (size_t)t * B * h->hs.kpad;
     }
-    AIR_CUDA(air::launch_k(air::lstm_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st, h->gates,
-                           h->cbuf, h->hs.f32 + (size_t)t * B * nh, B, nh, c.forget_bias, hs_hl,
+    AIR_CUDA(air::launch_k(air::lstm_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
+                           (const float*)gates.f32, c_src, c_dst, h->hs.f32 + (size_t)t * B * nh, B, nh, c.forget_bias, hs_hl,
                            (tc && h->chain_ok) ? h->hs.hlt_out() : no_hl, (size_t)t * B));
     ++h->launches;
   }
@@ -462,7 +492,14 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     AIR_CUDA(cudaMemcpyAsync(o->final_h, h->hs.f32 + (size_t)(T_run - 1) * B * nh, sizeof(float) * B * nh,
                              cudaMemcpyDeviceToDevice, st));
   if (o->final_c)
-    AIR_CUDA(cudaMemcpyAsync(o->final_c, h->cbuf, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
+    AIR_CUDA(cudaMemcpyAsync(o->final_c, train ? h->c_all + (size_t)T_run * B * nh : h->cbuf, sizeof(float) * B * nh,
+                             cudaMemcpyDeviceToDevice, st));
+  if (train) {   // h_{t-1} of every step, stacked: the A operand of dW_h = h_prev^T @ dgates
+    AIR_CUDA(cudaMemcpyAsync(h->hprev, h->h_init.f32, sizeof(float) * B * nh, cudaMemcpyDeviceToDevice, st));
+    if (T_run > 1)
+      AIR_CUDA(cudaMemcpyAsync(h->hprev + (size_t)B * nh, h->hs.f32, sizeof(float) * (size_t)(T_run - 1) * B * nh,
+                               cudaMemcpyDeviceToDevice, st));
+  }
 
   // 4. heads over all T*B hidden states at once
   mark(h, AIR_ST_WHERE_MLP, st);
@@ -485,9 +522,12 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     ++h->launches;
     mark(h, AIR_ST_STEPS, st);
   } else {
-    if ((rc = run_mlp(h, params, h->where_mlp, h->hs, TB, m, true, false, st)) != AIR_OK) return rc;   // modules.py:58-63
+    if ((rc = run_mlp(h, params, h->where_mlp, h->hs, TB, m, true, false, st, train ? &h->sv_where : nullptr)) != AIR_OK)
+      return rc;   // modules.py:58-63
     mark(h, AIR_ST_STEPS, st);
-    if ((rc = run_mlp(h, params, h->steps_mlp, h->hs, TB, logit, true, false, st)) != AIR_OK) return rc;   // :119-122
+    if ((rc = run_mlp(h, params, h->steps_mlp, h->hs, TB, logit, true, false, st, train ? &h->sv_steps : nullptr)) !=
+        AIR_OK)
+      return rc;   // modules.py:119-122
   }
   AIR_CUDA(air::launch_k(air::presence_kernel, dim3((B + 127) / 128), dim3(128), 0, st, h->logit, u_pres, presence_in,
                          o->presence_prob, o->presence, T_run, B, c.step_bias, c.explore_eps, c.discrete_steps));
@@ -532,9 +572,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     {
       const Layer& last = h->glenc.layers.back();
       Buf q = (h->glenc.layers.size() & 1) ? h->ping : h->pong;   // where the chain's last layer may land
+      if (train) q.f32 = h->sv_q;
       q.ld = last.N;
       q.kpad = round_up(last.N, air::tc::BK);
-      if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc, tc, st)) != AIR_OK) return rc;
+      if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc, tc, st, train ? &h->sv_glenc : nullptr)) != AIR_OK)
+        return rc;
       Buf r;
       r.f32 = h->r;
       r.ld = 2 * na;
@@ -554,7 +596,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
       Buf glimpse;
       glimpse.f32 = o->glimpse;
       glimpse.ld = G;
-      if ((rc = run_mlp(h, params, h->dec, what, TB, glimpse, true, false, st)) != AIR_OK) return rc;
+      if ((rc = run_mlp(h, params, h->dec, what, TB, glimpse, true, false, st, train ? &h->sv_dec : nullptr)) != AIR_OK)
+        return rc;
     }
   }
   mark(h, AIR_ST_PAINT_ELBO, st);
@@ -607,6 +650,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     ++h->launches;
   }
   mark(h, AIR_N_STAGES, st);
+  h->fwd_saved = train && o->canvas != nullptr;
   return AIR_OK;
 }
 
@@ -695,6 +739,243 @@ void carve_workspace(air_handle* h, Carver& cv) {
     h->prep_table = cv.take<air::tc::PrepEntry>(h->tcw.size());
     h->range_flag = cv.take<int>(1);
   }
+}
+
+// ---- training workspace (air_train_enable): saved activations + gradient scratch --------------------------------
+void carve_train(air_handle* h, Carver& cv) {
+  const air_config& c = h->cfg;
+  const size_t TB = (size_t)c.T * c.B, B = c.B;
+  auto hidden = [&](std::vector<float*>& v, const Mlp& mlp, size_t rows) {
+    v.clear();
+    for (size_t i = 0; i + 1 < mlp.layers.size(); ++i) v.push_back(cv.take<float>(rows * mlp.layers[i].N));
+  };
+  hidden(h->sv_enc, h->enc, B);
+  hidden(h->sv_where, h->where_mlp, TB);
+  hidden(h->sv_steps, h->steps_mlp, TB);
+  hidden(h->sv_glenc, h->glenc, TB);
+  hidden(h->sv_dec, h->dec, TB);
+  h->sv_q = cv.take<float>(TB * h->what_lin.K);
+  h->gates_all = cv.take<float>(TB * 4 * c.nh);
+  h->c_all = cv.take<float>((TB + B) * c.nh);
+  h->hprev = cv.take<float>(TB * c.nh);
+  int wmax = h->max_width;
+  for (int v : {h->G, 2 * c.na, c.nh, 8}) wmax = v > wmax ? v : wmax;
+  h->g_a = cv.take<float>(TB * wmax);
+  h->g_b = cv.take<float>(TB * wmax);
+  h->g_glimpse = cv.take<float>(TB * h->G);
+  h->g_crop = cv.take<float>(TB * h->G);
+  h->g_what = cv.take<float>(TB * c.na);
+  h->g_r = cv.take<float>(TB * 2 * c.na);
+  h->g_wh_paint = cv.take<float>(TB * 4);
+  h->g_wh_read = cv.take<float>(TB * 4);
+  h->g_m = cv.take<float>(TB * 8);
+  h->g_logit = cv.take<float>(TB);
+  h->g_h = cv.take<float>(TB * c.nh);
+  h->g_gates = cv.take<float>(TB * 4 * c.nh);
+  h->g_gx = cv.take<float>(B * 4 * c.nh);
+  h->g_hrec = cv.take<float>(B * c.nh);
+  h->g_c = cv.take<float>(B * c.nh);
+  h->g_e = cv.take<float>(B * h->n_enc);
+}
+
+// split of the batch-row contraction of a weight-gradient GEMM so that the grid fills the machine
+int pick_split(int out_rows, int out_cols, int contraction) {
+  const int tiles = ((out_rows + 127) / 128) * ((out_cols + (out_cols > 32 ? 63 : 15)) / (out_cols > 32 ? 64 : 16));
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int max_s = contraction / 64 > 1 ? contraction / 64 : 1;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+// dW += X^T @ dY, db += colsum(dY) for one dense layer (X [M, l.K] with row pitch ldx, dY [M, l.N] with row pitch ldy)
+int32_t layer_param_grads(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
+                          int M, cudaStream_t st) {
+  AIR_CUDA(air::launch_gemm_simt(true, false, X, ldx, dY, ldy, grad + l.w_off, l.N, l.K, l.N, M, true, nullptr, 0,
+                                 pick_split(l.K, l.N, M), st));
+  ++h->launches;
+  if (l.b_off >= 0) {
+    AIR_CUDA(air::launch_colsum(dY, ldy, grad + l.b_off, M, l.N, st));
+    ++h->launches;
+  }
+  return AIR_OK;
+}
+// dX = dY @ W^T (* elu'(X) when elu_x is the saved forward value of X)
+int32_t layer_input_grad(air_handle* h, const float* params, const Layer& l, const float* dY, int ldy, float* dX, int ldx,
+                         int M, bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st) {
+  AIR_CUDA(air::launch_gemm_simt(false, true, dY, ldy, params + l.w_off, l.N, dX, ldx, M, l.K, l.N, accumulate, elu_x,
+                                 ld_elu, 1, st));
+  ++h->launches;
+  return AIR_OK;
+}
+
+// Backward of a whole neural.MLP (neural.py:63-102).  x0 [M, layers[0].K] is the MLP input, `saves` its hidden
+// activations (outputs of layers 0 .. L-2), dY the gradient with respect to the LAST layer's pre-activation (callers mask
+// with elu' first when the last layer is an ELU layer).  dY is consumed; intermediate gradients ping-pong between
+// h->g_a / h->g_b.  dx0 != null: gradient with respect to x0 (no activation mask) is written (or accumulated) there.
+int32_t mlp_backward(air_handle* h, const float* params, float* grad, const Mlp& mlp, const float* x0, int ld0,
+                     const std::vector<float*>& saves, const float* dY, int ldy, int M, float* dx0, int ld_dx0,
+                     bool dx0_accumulate, cudaStream_t st) {
+  const int nl = (int)mlp.layers.size();
+  const float* cur = dY;
+  int ld_cur = ldy;
+  for (int i = nl - 1; i >= 0; --i) {
+    const Layer& l = mlp.layers[i];
+    const float* X = i == 0 ? x0 : saves[i - 1];
+    const int ldx = i == 0 ? ld0 : mlp.layers[i - 1].N;
+    int32_t rc = layer_param_grads(h, grad, l, X, ldx, cur, ld_cur, M, st);
+    if (rc != AIR_OK) return rc;
+    if (i > 0) {
+      float* dst = (cur == h->g_a) ? h->g_b : h->g_a;
+      rc = layer_input_grad(h, params, l, cur, ld_cur, dst, l.K, M, false, X, ldx, st);   // X is an ELU output
+      if (rc != AIR_OK) return rc;
+      cur = dst;
+      ld_cur = l.K;
+    } else if (dx0) {
+      rc = layer_input_grad(h, params, l, cur, ld_cur, dx0, ld_dx0, M, dx0_accumulate, nullptr, 0, st);
+      if (rc != AIR_OK) return rc;
+    }
+  }
+  return AIR_OK;
+}
+
+int32_t backward_impl(air_handle* h, const float* params, const float* img, const float* eps_where,
+                      const float* eps_what, const air_prior* prior, const air_outputs* o, float baseline_mean,
+                      float inv_batch, float l2_weight, float* grad, cudaStream_t st) {
+  const air_config& c = h->cfg;
+  const int B = c.B, T = c.T, nh = c.nh, P = h->P, G = h->G, na = c.na;
+  const int TB = T * B;
+  const int thr = 256;
+  int32_t rc;
+  AIR_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)h->n_params, st));
+
+  air::BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.img = img;
+  a.canvas_final = o->canvas + (size_t)(T - 1) * B * P;
+  a.glimpse = o->glimpse;
+  a.where = o->where;
+  a.where_loc = o->where_loc;
+  a.where_scale = o->where_scale;
+  a.eps_where = eps_where;
+  a.what_loc = o->what_loc;
+  a.what_scale = o->what_scale;
+  a.eps_what = eps_what;
+  a.presence = o->presence;
+  a.presence_prob = o->presence_prob;
+  a.posterior = o->num_steps_posterior;
+  a.num_step = o->num_step_per_sample;
+  a.step_weight = o->prior_step_weight;
+  a.rec_ps = o->rec_loss_per_sample;
+  a.kl_n_ps = o->kl_num_steps_per_sample;
+  a.kl_what_ps = o->kl_what_per_sample;
+  a.kl_where_ps = o->kl_where_per_sample;
+  a.dglimpse = h->g_glimpse;
+  a.dwhere_paint = h->g_wh_paint;
+  a.dcrop = h->g_crop;
+  a.dwhere_read = h->g_wh_read;
+  a.dwhat = h->g_what;
+  a.dr = h->g_r;
+  a.dm = h->g_m;
+  a.dlogit = h->g_logit;
+  a.T = T; a.B = B; a.H = c.H; a.W = c.W; a.h = c.h; a.w = c.w; a.na = na;
+  a.output_std = c.output_std;
+  a.output_multiplier = c.output_multiplier;
+  a.max_crop = c.max_crop_size;
+  a.explore_eps = c.explore_eps;
+  a.inv_batch = inv_batch > 0.f ? inv_batch : 1.0f / (float)B;
+  a.baseline_mean = baseline_mean;
+  a.step_W = c.W > 1 ? 2.0 / (double)(c.W - 1) : 0.0;
+  a.step_H = c.H > 1 ? 2.0 / (double)(c.H - 1) : 0.0;
+  a.step_w = c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0;
+  a.step_h = c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0;
+  a.prior = *prior;
+  for (int k = 0; k <= T; ++k)
+    a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
+                                                : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
+
+  // 1. reconstruction term -> d glimpse, d where (inverse transformer)            cell.py:159-164, model.py:319-321
+  AIR_CUDA(air::launch_paint_bwd(a, st));
+  ++h->launches;
+  // 2. decoder                                                                    cell.py:158
+  if ((rc = mlp_backward(h, params, grad, h->dec, o->what, na, h->sv_dec, h->g_glimpse, G, TB, h->g_what, na, false,
+                         st)) != AIR_OK)
+    return rc;
+  // 3. what sample + KL(what)                                                     cell.py:154-156, model.py:174-186
+  {
+    const size_t n = (size_t)TB * na;
+    AIR_CUDA(air::launch_k(air::what_bwd_kernel, dim3((unsigned)((n + thr - 1) / thr)), dim3(thr), 0, st, a));
+    ++h->launches;
+  }
+  // 4. what head (linear) and glimpse encoder -> d crop                           cell.py:153, modules.py:20
+  if ((rc = layer_param_grads(h, grad, h->what_lin, h->sv_q, h->what_lin.K, h->g_r, 2 * na, TB, st)) != AIR_OK) return rc;
+  if ((rc = layer_input_grad(h, params, h->what_lin, h->g_r, 2 * na, h->g_a, h->what_lin.K, TB, false, h->sv_q,
+                             h->what_lin.K, st)) != AIR_OK)
+    return rc;
+  if ((rc = mlp_backward(h, params, grad, h->glenc, h->crop.f32, G, h->sv_glenc, h->g_a, h->what_lin.K, TB, h->g_crop, G,
+                         false, st)) != AIR_OK)
+    return rc;
+  // 5. glimpse read -> d where                                                    cell.py:135
+  AIR_CUDA(air::launch_read_bwd(a, st));
+  ++h->launches;
+  // 6. where sample + KL(where) -> dm ; step-count posterior (KL(n), q(n) weights, REINFORCE) -> dlogit
+  AIR_CUDA(air::launch_latent_bwd(a, st));
+  ++h->launches;
+  // 7. the two heads on h_t -> dh                                                 modules.py:58-63,119-122
+  if ((rc = mlp_backward(h, params, grad, h->where_mlp, h->hs.f32, nh, h->sv_where, h->g_m, 8, TB, h->g_h, nh, false,
+                         st)) != AIR_OK)
+    return rc;
+  if ((rc = mlp_backward(h, params, grad, h->steps_mlp, h->hs.f32, nh, h->sv_steps, h->g_logit, 1, TB, h->g_h, nh, true,
+                         st)) != AIR_OK)
+    return rc;
+  // 8. LSTM through time                                                          cell.py:126-127
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t off = (size_t)t * B;
+    AIR_CUDA(air::launch_k(air::lstm_bwd_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
+                           (const float*)(h->gates_all + off * 4 * nh), (const float*)(h->c_all + off * nh),
+                           (const float*)(h->c_all + (off + B) * nh), (const float*)(h->g_h + off * nh),
+                           (const float*)(t == T - 1 ? nullptr : h->g_hrec), h->g_c, h->g_gates + off * 4 * nh, B, nh,
+                           c.forget_bias, t == T - 1 ? 1 : 0));
+    ++h->launches;
+    // d h_{t-1} = dgates_t @ W_h^T  (t = 0: gradient of the trainable initial state)
+    if ((rc = layer_input_grad(h, params, h->lstm_h, h->g_gates + off * 4 * nh, 4 * nh, h->g_hrec, nh, B, false, nullptr,
+                               0, st)) != AIR_OK)
+      return rc;
+  }
+  AIR_CUDA(air::launch_colsum(h->g_hrec, nh, grad + h->lstm_h0, B, nh, st));
+  AIR_CUDA(air::launch_colsum(h->g_c, nh, grad + h->lstm_c0, B, nh, st));
+  h->launches += 2;
+  {
+    Layer wh = h->lstm_h;
+    wh.b_off = h->lstm_b;   // db = colsum over all T*B gate rows
+    if ((rc = layer_param_grads(h, grad, wh, h->hprev, nh, h->g_gates, 4 * nh, TB, st)) != AIR_OK) return rc;
+    const size_t n = (size_t)B * 4 * nh;
+    AIR_CUDA(air::launch_k(air::sum_steps_kernel, dim3((unsigned)((n + thr - 1) / thr)), dim3(thr), 0, st,
+                           (const float*)h->g_gates, h->g_gx, T, n));
+    ++h->launches;
+    Layer wx = h->lstm_x;
+    wx.b_off = -1;
+    if ((rc = layer_param_grads(h, grad, wx, h->e.f32, h->n_enc, h->g_gx, 4 * nh, B, st)) != AIR_OK) return rc;
+    // 9. input encoder (its last layer is an ELU layer: mask with the saved output e)   cell.py:125
+    if ((rc = layer_input_grad(h, params, wx, h->g_gx, 4 * nh, h->g_e, h->n_enc, B, false, h->e.f32, h->n_enc, st)) !=
+        AIR_OK)
+      return rc;
+    if ((rc = mlp_backward(h, params, grad, h->enc, img, P, h->sv_enc, h->g_e, h->n_enc, B, nullptr, 0, false, st)) !=
+        AIR_OK)
+      return rc;
+  }
+  // l2_weight * sum of tf.nn.l2_loss over the 2-D variables (model.py:345-350): weights and the [1,nh] initial state
+  if (l2_weight > 0.f) {
+    for (const ParamEntry& e : h->entries) {
+      const bool two_d = e.name.size() > 2 && (e.name.compare(e.name.size() - 2, 2, ".w") == 0 || e.name == "lstm.h0" ||
+                                               e.name == "lstm.c0");
+      if (!two_d) continue;
+      const size_t n = (size_t)e.rows * e.cols;
+      air::l2_grad_kernel<<<(unsigned)((n + thr - 1) / thr), thr, 0, st>>>(params + e.offset, grad + e.offset, l2_weight, n);
+      ++h->launches;
+    }
+    AIR_CUDA(cudaGetLastError());
+  }
+  return AIR_OK;
 }
 
 }  // namespace
@@ -884,6 +1165,7 @@ int32_t air_destroy(air_handle* h) {
   for (cudaEvent_t e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
+  if (h->tws) cudaFree(h->tws);
   if (h->trace) cudaFree(h->trace);
   delete h;
   return AIR_OK;
@@ -936,6 +1218,59 @@ int32_t air_check_range(air_handle* h, void* stream) {
   }
   return AIR_OK;
 }
+
+int32_t air_train_enable(air_handle* h, int32_t on) {
+  if (!h) return fail(AIR_ERR_ARG, "air_train_enable: NULL handle");
+  if (on && h->use_tc)
+    return fail(AIR_ERR_ARG, "air_train_enable: the backward pass is built on the AIR_PREC_FP32 engine; create the "
+                             "handle with precision = AIR_PREC_FP32");
+  if (on && !h->cfg.discrete_steps)
+    return fail(AIR_ERR_ARG, "air_train_enable: the backward pass covers discrete_steps = 1 (the script configuration)");
+  if (on && !h->tws) {
+    Carver sizing(nullptr);
+    carve_train(h, sizing);
+    cudaError_t e = cudaMalloc(&h->tws, sizing.off);
+    if (e != cudaSuccess) return fail(AIR_ERR_NOMEM, std::string("air_train_enable: cudaMalloc: ") + cudaGetErrorString(e));
+    h->tws_bytes = sizing.off;
+    Carver real(h->tws);
+    carve_train(h, real);
+    const size_t smem = air::paint_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
+    const size_t smem_r = air::read_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
+    if (smem > 200 * 1024 || smem_r > 200 * 1024)
+      return fail(AIR_ERR_ARG, "air_train_enable: image / glimpse tile does not fit in shared memory");
+  }
+  h->train = on != 0;
+  h->fwd_saved = false;
+  return AIR_OK;
+}
+
+int32_t air_backward(air_handle* h, const float* params, const float* img, const float* eps_where,
+                     const float* eps_what, const air_prior* prior, const air_outputs* outs, float baseline_mean,
+                     float inv_batch, float l2_weight, float* grad_params, void* stream) {
+  if (!h || !params || !img || !eps_where || !eps_what || !prior || !grad_params)
+    return fail(AIR_ERR_ARG, "air_backward: NULL argument");
+  if (!h->train || !h->fwd_saved)
+    return fail(AIR_ERR_ARG, "air_backward: needs air_train_enable(h, 1) and a preceding air_forward on this handle with a "
+                             "prior and a materialised canvas");
+  const int32_t rc = check_outs(outs, true);
+  if (rc != AIR_OK) return rc;
+  if (!outs->canvas) return fail(AIR_ERR_ARG, "air_backward: the canvas output of the forward pass is required");
+  return backward_impl(h, params, img, eps_where, eps_what, prior, outs, baseline_mean, inv_batch, l2_weight,
+                       grad_params, (cudaStream_t)stream);
+}
+
+int32_t air_rmsprop_step(float* params, const float* grad, float* mg, float* ms, float* mom, int64_t n,
+                         float learning_rate, float decay, float momentum, float epsilon, float grad_scale,
+                         void* stream) {
+  if (!params || !grad || !mg || !ms || !mom || n < 0) return fail(AIR_ERR_ARG, "air_rmsprop_step: bad argument");
+  if (n == 0) return AIR_OK;
+  air::rmsprop_centered_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grad, mg, ms, mom, (size_t)n, learning_rate, decay, momentum, epsilon, grad_scale);
+  AIR_CUDA(cudaGetLastError());
+  return AIR_OK;
+}
+
+int64_t air_train_workspace_bytes(const air_handle* h) { return h ? (int64_t)h->tws_bytes : 0; }
 
 int32_t air_forward(air_handle* h, const float* params, const float* img, const float* eps_where,
                     const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
@@ -1177,7 +1512,7 @@ int32_t air_lstm_step(const float* x, float* hstate, float* cstate, const float*
   AIR_CUDA(air::launch_linear_simt(x, nx, W, 4 * nh, b, nullptr, 0, gx, 4 * nh, B, 4 * nh, nx, air::ACT_NONE, st));
   AIR_CUDA(air::launch_linear_simt(hstate, nh, W + (size_t)nx * 4 * nh, 4 * nh, nullptr, gx, 4 * nh, gates, 4 * nh, B,
                                    4 * nh, nh, air::ACT_NONE, st));
-  air::lstm_pointwise_kernel<<<(B * nh + 255) / 256, 256, 0, st>>>(gates, cstate, hstate, B, nh, forget_bias,
+  air::lstm_pointwise_kernel<<<(B * nh + 255) / 256, 256, 0, st>>>(gates, cstate, cstate, hstate, B, nh, forget_bias,
                                                                   air::HlOut{nullptr, 0, 0, 0},
                                                                   air::HlOut{nullptr, 0, 0, 0}, 0);
   AIR_CUDA(cudaGetLastError());

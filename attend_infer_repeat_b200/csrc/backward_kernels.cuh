@@ -1,0 +1,546 @@
+// Non-GEMM stages of the backward pass: the hand-derived gradients of the stages in cell_kernels.cuh,
+// i.e. what tf.gradients(opt_loss, model_vars) (model.py:355-356) computes for
+//   * the reconstruction term through the canvas and the inverse spatial transformer (cell.py:159-164, model.py:319-321;
+//     snt.resampler's registered gradient [upstream]: d/d data = scatter of the bilinear weights, d/d warp = data
+//     differences, floor() treated as a constant),
+//   * the glimpse read (cell.py:135) with respect to the where code,
+//   * the what / where reparameterisation and their Normal||Normal KL terms (modules.py:11-63, model.py:174-214),
+//   * the step-count posterior: KL(q(n)||prior), the q(n)-weighted KL terms and the REINFORCE term
+//     (prior.py:62-90,148-151; model.py:143-161,218-251), float64 island like the forward,
+//   * the LSTM gates (snt.LSTM [upstream]),
+// plus the centered RMSProp update (tf.train.RMSPropOptimizer(centered=True, momentum=.9), model.py:265,355-360).
+// Per-canvas kernels: one CTA (or warp) per canvas, the tile staged in shared memory, warp-shuffle reductions.
+#pragma once
+#include "cell_kernels.cuh"
+
+namespace air {
+
+// bilinear tap along one axis for the backward pass: the raw fractional weight plus validity bits (the forward Tap
+// folds validity into zeroed weights, which loses the distinction the derivative needs)
+struct __align__(16) BTap {
+  float d;       // ceil - coord: weight of the floor tap
+  float aux;     // paint: the coordinate itself; read: the pre-scaled grid feature u * S of this output column / row
+  int i_f;       // clamped floor index * stride
+  int i_c_fl;    // clamped ceil index * stride | flags << 24   (bit 0: floor tap valid, 1: ceil tap valid, 2: inside)
+};
+__device__ __forceinline__ BTap make_btap(float coord, int n, int stride, float aux) {
+  BTap t;
+  const bool inside = coord > -1.0f && coord < (float)n;
+  const float f = floorf(coord);
+  const int fi = (int)f, ci = fi + 1;
+  t.d = (f + 1.0f) - coord;
+  t.aux = aux;
+  const int fl = ((fi >= 0 && fi <= n - 1) ? 1 : 0) | ((ci >= 0 && ci <= n - 1) ? 2 : 0) | (inside ? 4 : 0);
+  t.i_f = min(max(fi, 0), n - 1) * stride;
+  t.i_c_fl = (min(max(ci, 0), n - 1) * stride) | (fl << 24);
+  return t;
+}
+// value-gradient pieces of one bilinear sample: the four (validity-masked) data values
+struct Quad {
+  float ff, cc, fc, cf;
+};
+__device__ __forceinline__ Quad load_quad(const float* __restrict__ D, const BTap& x, const BTap& y) {
+  const int xc = x.i_c_fl & 0xffffff, yc = y.i_c_fl & 0xffffff;
+  const int xf_ok = (x.i_c_fl >> 24) & 1, xc_ok = (x.i_c_fl >> 25) & 1;
+  const int yf_ok = (y.i_c_fl >> 24) & 1, yc_ok = (y.i_c_fl >> 25) & 1;
+  Quad q;
+  q.ff = (xf_ok & yf_ok) ? D[y.i_f + x.i_f] : 0.f;
+  q.cc = (xc_ok & yc_ok) ? D[yc + xc] : 0.f;
+  q.fc = (xf_ok & yc_ok) ? D[yc + x.i_f] : 0.f;   // (fx, cy)
+  q.cf = (xc_ok & yf_ok) ? D[y.i_f + xc] : 0.f;   // (cx, fy)
+  return q;
+}
+__device__ __forceinline__ bool btap_inside(const BTap& t) { return (t.i_c_fl >> 26) & 1; }
+
+struct BwdArgs {
+  // forward tensors
+  const float* img;            // [B,P]
+  const float* canvas_final;   // [B,P] = output_multiplier * canvas_T (the last slice of the `canvas` output)
+  const float* glimpse;        // [T,B,G]
+  const float* where;          // [T,B,4]
+  const float* where_loc;
+  const float* where_scale;
+  const float* eps_where;
+  const float* what_loc;       // [T,B,na]
+  const float* what_scale;
+  const float* eps_what;
+  const float* presence;       // [T,B]
+  const float* presence_prob;  // [T,B]
+  const float* posterior;      // [B,T+1]
+  const float* num_step;       // [B]
+  const float* step_weight;    // [T,B]
+  const float* rec_ps;         // [B]
+  const float* kl_n_ps;
+  const float* kl_what_ps;
+  const float* kl_where_ps;
+  // gradient tensors
+  float* dglimpse;             // [T,B,G]
+  float* dwhere_paint;         // [T,B,4]
+  const float* dcrop;          // [T,B,G]
+  float* dwhere_read;          // [T,B,4]
+  const float* dwhat;          // [T,B,na]
+  float* dr;                   // [T,B,2na]
+  float* dm;                   // [T,B,8]
+  float* dlogit;               // [T,B]
+  int T, B, H, W, h, w, na;
+  float output_std, output_multiplier, max_crop, explore_eps;
+  float inv_batch;             // 1 / (global batch): every per-sample term enters the loss through a batch mean
+  float baseline_mean;         // mean over the global batch of the REINFORCE baseline (0 without one)
+  double step_W, step_H, step_w, step_h;   // np.linspace steps (host, float64) as in the forward
+  air_prior prior;
+  double steps_prior[AIR_MAX_STEPS + 1];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// d rec / d glimpse_t (scatter) and d rec / d where_t through the inverse transformer.  One CTA per canvas.
+//   rec = sum_p 0.5 ((x_p - mu_p)/sigma)^2 + const, mu = mult * (sum_t presence_t * inv_t)
+//   d rec / d inv_t[p] = -presence_t * mult * (x_p - mu_p) / sigma^2
+// dynamic smem: 2 * T*G floats (glimpses, their gradient accumulators) + T*(W+H) taps
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t paint_bwd_smem(int T, int H, int W, int h, int w) {
+  return (2 * sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(BTap) * (size_t)T * (W + H);
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ float4 s_inv[AIR_MAX_STEPS];
+  __shared__ float s_pres[AIR_MAX_STEPS];
+  __shared__ float s_red[8][4 * T];
+  const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
+  const int P = H * W, G = h * w;
+  const int b = blockIdx.x;
+  float* s_gl = reinterpret_cast<float*>(smem_raw);   // [T][G]
+  float* s_dgl = s_gl + (size_t)T * G;                // [T][G]
+  BTap* s_tx = reinterpret_cast<BTap*>(smem_raw + (2 * sizeof(float) * (size_t)T * G + 15) / 16 * 16);   // [T][W]
+  BTap* s_ty = s_tx + (size_t)T * W;                                                                     // [T][H]
+  griddep_launch();
+  griddep_wait();
+  for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
+    const int t = i / G, g = i - t * G;
+    s_gl[i] = a.glimpse[((size_t)t * B + b) * G + g];
+    s_dgl[i] = 0.f;
+  }
+  if (threadIdx.x < T) {
+    const float* wh = a.where + ((size_t)threadIdx.x * B + b) * 4;
+    float4 iv;
+    inv_params(wh[0], wh[1], wh[2], wh[3], iv.x, iv.y, iv.z, iv.w);
+    s_inv[threadIdx.x] = iv;
+    s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const float4 iv = s_inv[t];
+    for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
+      if (j < W) {
+        const float xg = inv_coord_s(iv.x, iv.z, j, a.step_W, w);
+        s_tx[t * W + j] = make_btap(xg, w, 1, xg);
+      } else {
+        const float yg = inv_coord_s(iv.y, iv.w, j - W, a.step_H, h);
+        s_ty[t * H + (j - W)] = make_btap(yg, h, w, yg);
+      }
+    }
+  }
+  __syncthreads();
+
+  const float S_w = ((float)w - 1.0f) * 0.5f, S_h = ((float)h - 1.0f) * 0.5f;
+  const float coef = -a.inv_batch * a.output_multiplier / (a.output_std * a.output_std);
+  float acc[T][4];   // per step: sum gx * (xg - S_w), sum gx, sum gy * (yg - S_h), sum gy
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const int r = p / W, c = p - r * W;
+    const float dC = coef * (a.img[(size_t)b * P + p] - a.canvas_final[(size_t)b * P + p]);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float pres = s_pres[t];
+      if (pres == 0.f) continue;
+      const BTap bx = s_tx[t * W + c], by = s_ty[t * H + r];
+      if (!(btap_inside(bx) && btap_inside(by))) continue;
+      const float gv = pres * dC;
+      const float dx = bx.d, dy = by.d;
+      const float* D = s_gl + t * G;
+      float* dD = s_dgl + t * G;
+      const Quad q = load_quad(D, bx, by);
+      const int xc = bx.i_c_fl & 0xffffff, yc = by.i_c_fl & 0xffffff;
+      const int xf_ok = (bx.i_c_fl >> 24) & 1, xc_ok = (bx.i_c_fl >> 25) & 1;
+      const int yf_ok = (by.i_c_fl >> 24) & 1, yc_ok = (by.i_c_fl >> 25) & 1;
+      if (xf_ok & yf_ok) atomicAdd(dD + by.i_f + bx.i_f, gv * dx * dy);
+      if (xc_ok & yc_ok) atomicAdd(dD + yc + xc, gv * (1.0f - dx) * (1.0f - dy));
+      if (xf_ok & yc_ok) atomicAdd(dD + yc + bx.i_f, gv * dx * (1.0f - dy));
+      if (xc_ok & yf_ok) atomicAdd(dD + by.i_f + xc, gv * (1.0f - dx) * dy);
+      const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
+      const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
+      acc[t][0] = fmaf(gx, bx.aux - S_w, acc[t][0]);
+      acc[t][1] += gx;
+      acc[t][2] = fmaf(gy, by.aux - S_h, acc[t][2]);
+      acc[t][3] += gy;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = warp_sum(acc[t][k]);
+      if (lane == 0) s_red[wid][t * 4 + k] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
+    const int t = i / G, g = i - t * G;
+    a.dglimpse[((size_t)t * B + b) * G + g] = s_dgl[i];
+  }
+  if (threadIdx.x < T) {
+    const int t = threadIdx.x;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi)
+      for (int k = 0; k < 4; ++k) s[k] += s_red[wi][t * 4 + k];
+    const float* wh = a.where + ((size_t)t * B + b) * 4;
+    float* o = a.dwhere_paint + ((size_t)t * B + b) * 4;
+    // x_g - S_w = (U S_w - tx S_w) / sx  ->  d x_g / d sx = -(x_g - S_w) / sx,  d x_g / d tx = -S_w / sx
+    o[0] = -s[0] / wh[0];
+    o[1] = -S_w * s[1] / wh[0];
+    o[2] = -s[2] / wh[2];
+    o[3] = -S_h * s[3] / wh[2];
+  }
+}
+
+template <int T>
+inline cudaError_t launch_paint_bwd_t(const BwdArgs& a, cudaStream_t st) {
+  const size_t smem = paint_bwd_smem(a.T, a.H, a.W, a.h, a.w);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(paint_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  return launch_k(paint_bwd_kernel<T>, dim3(a.B), dim3(256), smem, st, a);
+}
+inline cudaError_t launch_paint_bwd(const BwdArgs& a, cudaStream_t st) {
+  switch (a.T) {
+    case 1: return launch_paint_bwd_t<1>(a, st);
+    case 2: return launch_paint_bwd_t<2>(a, st);
+    case 3: return launch_paint_bwd_t<3>(a, st);
+    case 4: return launch_paint_bwd_t<4>(a, st);
+    case 5: return launch_paint_bwd_t<5>(a, st);
+    case 6: return launch_paint_bwd_t<6>(a, st);
+    case 7: return launch_paint_bwd_t<7>(a, st);
+    case 8: return launch_paint_bwd_t<8>(a, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// d L / d where_t through the glimpse read: crop_t[g] = resampler(img, x = sx u S_W + tx S_W + S_W, y likewise).
+// One CTA per canvas; dynamic smem: H*W floats (image) + T*(w+h) taps.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t read_bwd_smem(int T, int H, int W, int h, int w) {
+  return (sizeof(float) * (size_t)H * W + 15) / 16 * 16 + sizeof(BTap) * (size_t)T * (w + h);
+}
+__global__ void __launch_bounds__(256) read_bwd_kernel(BwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ float s_red[8][4];
+  const int T = a.T, B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
+  const int P = H * W, G = h * w;
+  const int b = blockIdx.x;
+  float* s_img = reinterpret_cast<float*>(smem_raw);
+  BTap* s_tx = reinterpret_cast<BTap*>(smem_raw + (sizeof(float) * (size_t)P + 15) / 16 * 16);   // [T][w]
+  BTap* s_ty = s_tx + (size_t)T * w;                                                             // [T][h]
+  griddep_launch();
+  griddep_wait();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s_img[i] = a.img[(size_t)b * P + i];
+  const float S_W = ((float)W - 1.0f) * 0.5f, S_H = ((float)H - 1.0f) * 0.5f;
+  for (int i = threadIdx.x; i < T * (w + h); i += blockDim.x) {
+    const int t = i / (w + h), j = i - t * (w + h);
+    const float* wh = a.where + ((size_t)t * B + b) * 4;
+    if (j < w) {
+      const float uS = __fmul_rn((float)(-1.0 + (double)j * a.step_w), S_W);
+      s_tx[t * w + j] = make_btap(fwd_coord_s(wh[0], wh[1], j, a.step_w, W), W, 1, uS);
+    } else {
+      const float vS = __fmul_rn((float)(-1.0 + (double)(j - w) * a.step_h), S_H);
+      s_ty[t * h + (j - w)] = make_btap(fwd_coord_s(wh[2], wh[3], j - w, a.step_h, H), H, W, vS);
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int t = 0; t < T; ++t) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* dc = a.dcrop + ((size_t)t * B + b) * G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const int r = g / w, c = g - r * w;
+      const BTap bx = s_tx[t * w + c], by = s_ty[t * h + r];
+      if (!(btap_inside(bx) && btap_inside(by))) continue;
+      const float gv = dc[g];
+      const float dx = bx.d, dy = by.d;
+      const Quad q = load_quad(s_img, bx, by);
+      const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
+      const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
+      acc[0] = fmaf(gx, bx.aux, acc[0]);
+      acc[1] += gx;
+      acc[2] = fmaf(gy, by.aux, acc[2]);
+      acc[3] += gy;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) s_red[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      float s = 0.f;
+      for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) s += s_red[wi][threadIdx.x];
+      const int k = threadIdx.x;
+      // d x / d sx = u S_W, d x / d tx = S_W, d y / d sy = v S_H, d y / d ty = S_H
+      a.dwhere_read[((size_t)t * B + b) * 4 + k] = (k == 1) ? S_W * s : (k == 3) ? S_H * s : s;
+    }
+    __syncthreads();
+  }
+}
+inline cudaError_t launch_read_bwd(const BwdArgs& a, cudaStream_t st) {
+  const size_t smem = read_bwd_smem(a.T, a.H, a.W, a.h, a.w);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(read_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  return launch_k(read_bwd_kernel, dim3(a.B), dim3(256), smem, st, a);
+}
+
+// d Normal||Normal KL / d (mu_a, s_a)   [upstream _kl_normal_normal]
+__device__ __forceinline__ void normal_kl_grad(float mu_a, float s_a, float mu_b, float s_b, float& d_mu, float& d_s) {
+  const float sb2 = s_b * s_b;
+  d_mu = (mu_a - mu_b) / sb2;
+  d_s = s_a / sb2 - 1.0f / s_a;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// what head backward (modules.py:11-24, cell.py:154-156, model.py:174-186): what = loc + softplus(raw + offset) * eps
+//   d loc = d what + c * w_t * dKL/d loc;  d scale = d what * eps + c * w_t * dKL/d scale;  d raw = d scale * sigmoid(.)
+// with sigmoid(x) = 1 - exp(-softplus(x)), c = prior_weight / batch, w_t = the q(n) step weight.  -> dr [T*B, 2 na]
+// ---------------------------------------------------------------------------------------------------
+__global__ void what_bwd_kernel(BwdArgs a) {
+  griddep_launch();
+  griddep_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t rows = (size_t)a.T * a.B;
+  if (idx >= rows * (size_t)a.na) return;
+  const size_t row = idx / a.na;
+  const int j = (int)(idx % a.na);
+  const float c = a.inv_batch * (a.prior.use_prior ? 1.0f : 0.0f) * a.step_weight[row];
+  const float loc = a.what_loc[idx], sc = a.what_scale[idx], g = a.dwhat[idx];
+  float k_mu, k_s;
+  normal_kl_grad(loc, sc, a.prior.what_loc, a.prior.what_scale, k_mu, k_s);
+  const float d_loc = fmaf(c, k_mu, g);
+  const float d_sc = fmaf(c, k_s, g * a.eps_what[idx]);
+  a.dr[row * 2 * a.na + j] = d_loc;
+  a.dr[row * 2 * a.na + a.na + j] = d_sc * (1.0f - expf(-sc));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// where head + step-count backward.  One warp per canvas.
+//   where: d where_t = d(paint) + d(read); where = loc + scale * eps; loc = (max_crop sig, tanh, max_crop sig, tanh)(m[0:4]);
+//          scale = softplus(m[4:8] + bias); KL(where) terms weighted by w_t                       -> dm [T*B, 8]
+//   steps: L depends on p_t = presence_prob through q(n) (prior.py:62-68): KL(q||prior), the weights w_t = sum_{k>t} q_k
+//          (analytic mode, model.py:157-161) and REINFORCE's log q(n_b) (clip straight-through, ops.py:67-76),
+//          float64 like the forward island; p = eps/2 + (1 - eps) sigmoid(logit + bias)            -> dlogit [T*B]
+// ---------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(128) latent_bwd_kernel(BwdArgs a) {
+  griddep_launch();
+  griddep_wait();
+  const int B = a.B;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const air_prior& pr = a.prior;
+  const float pw = pr.use_prior ? 1.0f : 0.0f;
+  const float coef = a.inv_batch * pw;
+  // KL(what) per step, recomputed (model.py:174-186)
+  float klw[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float v = 0.f;
+    const size_t base = ((size_t)t * B + b) * a.na;
+    for (int i = lane; i < a.na; i += 32)
+      v += normal_kl(a.what_loc[base + i], a.what_scale[base + i], pr.what_loc, pr.what_scale);
+    klw[t] = warp_sum(v);
+  }
+  // where head: lane t owns step t
+  float klwh_l = 0.f;
+  if (lane < T) {
+    const size_t row = (size_t)lane * B + b;
+    const float sw = a.step_weight[row];
+    float dmv[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float loc = a.where_loc[row * 4 + k], sc = a.where_scale[row * 4 + k];
+      const float g = a.dwhere_paint[row * 4 + k] + a.dwhere_read[row * 4 + k];
+      const bool shift = k & 1;
+      const float mu_b = shift ? (pr.where_shift_has_loc ? pr.where_shift_loc : loc) : pr.where_scale_loc;
+      const float s_b = shift ? pr.where_shift_scale : pr.where_scale_scale;
+      float k_mu, k_s;
+      normal_kl_grad(loc, sc, mu_b, s_b, k_mu, k_s);
+      klwh_l += normal_kl(loc, sc, mu_b, s_b);
+      const float d_loc = fmaf(coef * sw, k_mu, g);
+      const float d_sc = fmaf(coef * sw, k_s, g * a.eps_where[row * 4 + k]);
+      dmv[k] = d_loc * (shift ? (1.0f - loc * loc) : loc * (1.0f - loc / a.max_crop));
+      dmv[4 + k] = d_sc * (1.0f - expf(-sc));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.dm[row * 8 + k] = dmv[k];
+  }
+  float klwh[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) klwh[t] = __shfl_sync(0xffffffffu, klwh_l, t);
+  if (lane != 0) return;
+
+  // ---- step-count posterior backward (float64) ----
+  double p[T], q[T + 1], dq[T + 1];
+#pragma unroll
+  for (int t = 0; t < T; ++t) p[t] = (double)a.presence_prob[(size_t)t * B + b];
+#pragma unroll
+  for (int k = 0; k <= T; ++k) q[k] = (double)a.posterior[(size_t)b * (T + 1) + k];
+  // REINFORCE coefficient on log q(n_b): stop_gradient(importance weight - baseline) / batch   (model.py:242-248)
+  double cq = 0.0;
+  int n_idx = (int)a.num_step[b];
+  n_idx = n_idx < 0 ? 0 : (n_idx > T ? T : n_idx);
+  if (pr.use_reinforce) {
+    float iw = a.rec_ps[b];
+    if (!pr.analytic)
+      iw = __fadd_rn(iw, __fadd_rn(__fadd_rn(__fmul_rn(a.kl_n_ps[b], pr.steps_weight), a.kl_what_ps[b]), a.kl_where_ps[b]));
+    cq = (double)a.inv_batch * ((double)iw - (double)a.baseline_mean);
+  }
+  double dsw_run = 0.0;   // sum_{t < k} dL/dw_t
+#pragma unroll
+  for (int k = 0; k <= T; ++k) {
+    double g = 0.0;
+    if (q[k] > 0.0) g = (double)coef * (double)pr.steps_weight * (log(q[k] / a.steps_prior[k]) + 1.0);
+    if (k >= 1 && pr.analytic) {
+      dsw_run += (double)coef * ((double)klw[k - 1] + (double)klwh[k - 1]);
+      g += dsw_run;
+    }
+    if (k == n_idx) g += cq / fmax(q[k], 1e-32);
+    dq[k] = g;
+  }
+  // q = pi / sum(pi)
+  double pi[T + 1], cum[T + 1];
+  double run = 1.0, S = 0.0;
+#pragma unroll
+  for (int k = 0; k <= T; ++k) {
+    cum[k] = run;                                   // prod_{j<k} p_j
+    pi[k] = (k < T) ? (1.0 - p[k]) * run : run;
+    if (k < T) run *= p[k];
+    S += pi[k];
+  }
+  double dot = 0.0;
+#pragma unroll
+  for (int k = 0; k <= T; ++k) dot += dq[k] * (pi[k] / S);
+  double dpi[T + 1];
+#pragma unroll
+  for (int k = 0; k <= T; ++k) dpi[k] = (dq[k] - dot) / S;
+  const float ee = a.explore_eps;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    // d pi_j / d p_j = -cum_j;  d pi_k / d p_j (k > j) = (1 - p_k [k < T]) * prod_{i < k, i != j} p_i
+    double g = -dpi[j] * cum[j];
+#pragma unroll
+    for (int k = j + 1; k <= T; ++k) {
+      double prod = 1.0;
+#pragma unroll
+      for (int i = 0; i < k; ++i)
+        if (i != j) prod *= p[i];
+      g += dpi[k] * ((k < T) ? (1.0 - p[k]) * prod : prod);
+    }
+    double s = p[j], scale = 1.0;   // p = eps/2 + (1 - eps) * sigmoid(.)   (cell.py:140-141)
+    if (ee >= 0.f) {
+      scale = 1.0 - (double)ee;
+      s = (p[j] - 0.5 * (double)ee) / scale;
+    }
+    a.dlogit[(size_t)j * B + b] = (float)(g * scale * s * (1.0 - s));
+  }
+}
+inline cudaError_t launch_latent_bwd(const BwdArgs& a, cudaStream_t st) {
+  const dim3 grid((a.B + 3) / 4), block(128);
+  switch (a.T) {
+    case 1: return launch_k(latent_bwd_kernel<1>, grid, block, 0, st, a);
+    case 2: return launch_k(latent_bwd_kernel<2>, grid, block, 0, st, a);
+    case 3: return launch_k(latent_bwd_kernel<3>, grid, block, 0, st, a);
+    case 4: return launch_k(latent_bwd_kernel<4>, grid, block, 0, st, a);
+    case 5: return launch_k(latent_bwd_kernel<5>, grid, block, 0, st, a);
+    case 6: return launch_k(latent_bwd_kernel<6>, grid, block, 0, st, a);
+    case 7: return launch_k(latent_bwd_kernel<7>, grid, block, 0, st, a);
+    case 8: return launch_k(latent_bwd_kernel<8>, grid, block, 0, st, a);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LSTM gate backward for one step (snt.LSTM [upstream]; gates order i, j, f, o; forget bias added inside the sigmoid).
+//   gates [B,4nh] pre-activation of this step, c_prev / c_new [B,nh], dh_heads [B,nh] (from the where / steps heads),
+//   dh_rec [B,nh] (from step t+1 through W_h, null at the last step), dc [B,nh] in: d L / d c_t from step t+1, out: for t-1
+//   -> dgates [B,4nh]
+// ---------------------------------------------------------------------------------------------------
+__global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                          const float* __restrict__ c_new, const float* __restrict__ dh_heads,
+                                          const float* __restrict__ dh_rec, float* __restrict__ dc,
+                                          float* __restrict__ dgates, int B, int nh, float forget_bias, int first) {
+  griddep_launch();
+  griddep_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * nh) return;
+  const size_t b = idx / nh;
+  const int u = (int)(idx % nh);
+  const float* g = gates + b * 4 * (size_t)nh;
+  const float si = sigmoid_f(g[u]), tj = tanhf(g[nh + u]), sf = sigmoid_f(g[2 * nh + u] + forget_bias),
+              so = sigmoid_f(g[3 * nh + u]);
+  const float tc = tanhf(c_new[idx]);
+  const float dh = dh_heads[idx] + (dh_rec ? dh_rec[idx] : 0.f);
+  const float dcv = (first ? 0.f : dc[idx]) + dh * so * (1.0f - tc * tc);
+  float* dg = dgates + b * 4 * (size_t)nh;
+  dg[u] = dcv * tj * si * (1.0f - si);
+  dg[nh + u] = dcv * si * (1.0f - tj * tj);
+  dg[2 * nh + u] = dcv * c_prev[idx] * sf * (1.0f - sf);
+  dg[3 * nh + u] = dh * tc * so * (1.0f - so);
+  dc[idx] = dcv * sf;
+}
+
+// out[b, :] = sum_t x[t, b, :]   (the LSTM's input half sees the same encoder output at every step)
+__global__ void sum_steps_kernel(const float* __restrict__ x, float* __restrict__ out, int T, size_t n) {
+  griddep_launch();
+  griddep_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += x[(size_t)t * n + i];
+  out[i] = s;
+}
+
+// grad[i] += l2 * w[i]   (l2_weight * tf.nn.l2_loss(w) on the 2-D variables, model.py:345-350)
+__global__ void l2_grad_kernel(const float* __restrict__ w, float* __restrict__ grad, float l2, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) grad[i] = fmaf(l2, w[i], grad[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tf.train.RMSPropOptimizer(lr, decay, momentum, epsilon, centered=True) [upstream ApplyCenteredRMSProp]:
+//   mg <- mg + (1 - rho)(g - mg);  ms <- ms + (1 - rho)(g^2 - ms);  mom <- mu mom + lr g / sqrt(ms - mg^2 + eps);
+//   theta <- theta - mom.     (ms starts at 1, mg and mom at 0; epsilon inside the square root)
+// One pass over the flat parameter buffer; grad_scale folds the 1 / world of a summed all-reduce.
+// ---------------------------------------------------------------------------------------------------
+__global__ void rmsprop_centered_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ mg,
+                                        float* __restrict__ ms, float* __restrict__ mom, size_t n, float lr, float rho,
+                                        float mu, float eps, float grad_scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = grad[i] * grad_scale;
+  const float mgi = mg[i] + (1.0f - rho) * (g - mg[i]);
+  const float msi = ms[i] + (1.0f - rho) * (g * g - ms[i]);
+  const float mo = mu * mom[i] + lr * g / sqrtf(msi - mgi * mgi + eps);
+  mg[i] = mgi;
+  ms[i] = msi;
+  mom[i] = mo;
+  theta[i] -= mo;
+}
+
+}  // namespace air

@@ -114,7 +114,8 @@ __global__ void split_state_kernel(const float* __restrict__ h, int B, int nh, H
 
 // gates[B,4nh] (order i, j, f, o) already hold [x,h] @ W + b.  c <- sig(f + fb) * c + sig(i) * tanh(j);
 // h <- tanh(c) * sig(o).
-__global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ c,
+// c_out may alias c (in-place state) or be the next slice of the saved cell-state history (training mode).
+__global__ void lstm_pointwise_kernel(const float* __restrict__ gates, const float* c, float* c_out,
                                       float* __restrict__ h_out, int B, int nh, float forget_bias, HlOut h_hl,
                                       HlOut h_hl2, size_t row0_hl2) {
   griddep_launch();
@@ -126,7 +127,7 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __
   const float* g = gates + b * 4 * (size_t)nh;
   const float gi = g[u], gj = g[nh + u], gf = g[2 * nh + u], go = g[3 * nh + u];
   const float c_new = __fadd_rn(__fmul_rn(sigmoid_f(gf + forget_bias), c[idx]), __fmul_rn(sigmoid_f(gi), tanhf(gj)));
-  c[idx] = c_new;
+  c_out[idx] = c_new;
   const float h_new = __fmul_rn(tanhf(c_new), sigmoid_f(go));
   h_out[idx] = h_new;
   if (h_hl.p) hl_store(h_hl, b, u, h_new);

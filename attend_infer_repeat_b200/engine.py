@@ -277,6 +277,38 @@ class Engine:
                                                current_stream_ptr()), "air_forward_host_u8")
         return scalars_host, loss_per_sample_host
 
+    # -- training step -----------------------------------------------------------------
+    def train_enable(self, on: bool = True):
+        """Keep the activations of every following forward() for backward() (fp32 engine only)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.air_train_enable(self._handle, int(on)), "air_train_enable")
+
+    @property
+    def train_workspace_bytes(self) -> int:
+        return int(self.lib.air_train_workspace_bytes(self._handle))
+
+    def backward(self, params, img, eps_where, eps_what, prior: air_prior, grad: Optional[torch.Tensor] = None,
+                 baseline_mean: float = 0.0, inv_batch: float = 0.0, l2_weight: float = 0.0) -> torch.Tensor:
+        """d opt_loss / d params for the batch of the LAST forward() (model.py:355-356).  Returns the flat gradient."""
+        if grad is None:
+            grad = torch.empty(self.n_params, device=self.device, dtype=torch.float32)
+        self._chk(grad, (self.n_params,), "grad")
+        with torch.cuda.device(self.device):
+            check(self.lib.air_backward(self._handle, ptr(params), ptr(img), ptr(eps_where), ptr(eps_what),
+                                        C.byref(prior), C.byref(self._c_out), float(baseline_mean), float(inv_batch),
+                                        float(l2_weight), ptr(grad), current_stream_ptr()), "air_backward")
+        return grad
+
+    def rmsprop_step(self, params, grad, mg, ms, mom, learning_rate, decay=0.9, momentum=0.9, epsilon=1e-10,
+                     grad_scale=1.0):
+        """Centered RMSProp with momentum, TF semantics (model.py:265,355-360), in place on the flat buffers."""
+        for t in (params, grad, mg, ms, mom):
+            self._chk(t, (params.numel(),), "rmsprop buffer")
+        with torch.cuda.device(self.device):
+            check(self.lib.air_rmsprop_step(ptr(params), ptr(grad), ptr(mg), ptr(ms), ptr(mom), params.numel(),
+                                            float(learning_rate), float(decay), float(momentum), float(epsilon),
+                                            float(grad_scale), current_stream_ptr()), "air_rmsprop_step")
+
     def cell_step(self, params, img, canvas, h, c, presence, eps_where, eps_what, u_pres):
         """One AIRCell step (cell.py:116-171); canvas / h / c / presence are updated IN PLACE.  Returns the per-step
         outputs glimpse, what, what_loc, what_scale, where, where_loc, where_scale, presence_prob."""

@@ -210,6 +210,34 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
                             const float* u_pres_host, const air_prior* prior, const air_outputs* outs,
                             float* scalars_host, float* loss_per_sample_host, void* stream);
 
+/* ---- training step: opt.compute_gradients(opt_loss, model_vars) + opt.apply_gradients of
+ *      AIRModel.train_step (model.py:261-265,335-360) ------------------------------------------------------- */
+/* Switch a handle (AIR_PREC_FP32 engine, discrete_steps = 1) to training mode: allocates the second workspace
+ * (saved activations + gradient scratch, air_train_workspace_bytes) once; from then on air_forward with a prior keeps
+ * every activation the backward pass needs. */
+int32_t air_train_enable(air_handle* h, int32_t on);
+int64_t air_train_workspace_bytes(const air_handle* h);
+/* Gradient of opt_loss = loss.value + reinforce_loss (+ l2) with respect to the flat parameter buffer, for the batch the
+ * LAST air_forward on this handle saw (same params / img / noise / prior / outs must be passed again; `outs` must have a
+ * materialised canvas).  tf.gradients semantics: reparameterised what / where samples, presence samples and the REINFORCE
+ * importance weight are constants (stop_gradient, model.py:246), log q(n) clips straight-through (ops.py:67-76).
+ *   baseline_mean  mean over the GLOBAL batch of the baseline (0 without one): the [B]-[B,1] broadcast of model.py:231
+ *                  reduces the REINFORCE coefficient of sample j to (iw_j - mean_i baseline_i) / B  
+ *   inv_batch      1 / (global batch size); <= 0 selects 1 / B.  With batch sharding every rank passes 1 / (N * B) and the
+ *                  gradient buffers are SUMMED by one all-reduce
+ *   l2_weight      model.py:345-350 (2-D variables only)
+ *   grad_params    [air_param_count] overwritten */
+int32_t air_backward(air_handle* h, const float* params, const float* img, const float* eps_where,
+                     const float* eps_what, const air_prior* prior, const air_outputs* outs, float baseline_mean,
+                     float inv_batch, float l2_weight, float* grad_params, void* stream);
+/* tf.train.RMSPropOptimizer(learning_rate, decay=.9, momentum=.9, epsilon=1e-10, centered=True) on a flat buffer
+ * [upstream ApplyCenteredRMSProp]: mg <- mg + (1-decay)(g - mg); ms <- ms + (1-decay)(g^2 - ms);
+ * mom <- momentum * mom + lr * g / sqrt(ms - mg^2 + epsilon); params <- params - mom.  Slots: ms starts at 1, mg and mom
+ * at 0 (caller-owned).  g = grad * grad_scale. */
+int32_t air_rmsprop_step(float* params, const float* grad, float* mg, float* ms, float* mom, int64_t n,
+                         float learning_rate, float decay, float momentum, float epsilon, float grad_scale,
+                         void* stream);
+
 /* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
  * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be
  * known after the forward pass): AIRModel._reinforce, model.py:218-251. */
