@@ -99,8 +99,12 @@ class AIRCell:
             what_scale_offset=self._what_distrib._scale_offset, forget_bias=self._transition.forget_bias,
             max_crop_size=te._max_crop_size, discrete_steps=self._sample_presence, precision=self._precision)
 
-    def engine(self, B: int, T: int, **kw) -> Engine:
+    def engine(self, B: int, T: int, precision=None, **kw) -> Engine:
+        """The fused-path handle for (B, T); ``precision`` overrides the cell's arithmetic mode (the training step runs on
+        the AIR_PREC_FP32 engine, which keeps the activations the backward pass needs)."""
         cfg = self.config
+        if precision is not None:
+            cfg.precision = precision
         key = (B, T, repr(cfg), tuple(sorted(kw.items())))
         if key not in self._engines:
             self._engines[key] = Engine(cfg, B, T, device=self.device, **kw)

@@ -114,6 +114,7 @@ class AIRModel:
         if noise is None:
             noise = self.cell.draw_noise(B, T)
         eps_where, eps_what, u_pres = (n.contiguous() for n in noise)
+        self._last_noise = (eps_where, eps_what, u_pres)
         self._prior_struct = self._current_prior()
         o = self.engine.forward(self.cell.params, self.obs, eps_where, eps_what, u_pres, self._prior_struct)
 
@@ -183,16 +184,23 @@ class AIRModel:
                    optimizer=None, opt_kwargs=dict(momentum=.9, centered=True)):
         """Creates the train step and the global_step (model.py:261-376).
 
-        Built so far: the whole loss side (rec / KL / REINFORCE terms, Loss bookkeeping, annealed step prior).  The
-        gradient + centered-RMSProp update is SURVEY 8(f) row 1 ("next") and is not built yet, so the returned
-        ``train_op`` evaluates forward + ELBO on a fresh batch and advances ``global_step`` (which drives the prior
-        annealing) but leaves the parameters untouched."""
+        The returned ``train_op(obs=None, nums=None, noise=None)`` is the sess.run(train_step) of the reference: forward +
+        ELBO on the batch, ``opt.compute_gradients(opt_loss)`` (air_backward), one all-reduce of the flat gradient buffer
+        when torch.distributed is initialised (batch shards), and the centered-RMSProp update of the flat
+        parameter buffer (air_rmsprop_step, TF semantics).  It runs on the AIR_PREC_FP32 engine, which keeps the
+        activations the backward pass needs.  Not built: the baseline's own optimiser (SURVEY 8f row 2 -- a baseline
+        module is evaluated and enters REINFORCE, but its parameters are not trained) and NVIL moment normalisation."""
         if decay_rate is not None:
             raise NotImplementedError("NVIL moving-average normalisation (decay_rate) is not built")
-        if l2_weight:
-            raise NotImplementedError("l2_weight > 0 only affects the optimiser, which is not built")
         if num_steps_prior is None:
             raise ValueError("num_steps_prior is required (model.py:292 dereferences it)")
+        if optimizer is not None:
+            raise NotImplementedError("only the reference's default optimiser (tf.train.RMSPropOptimizer) is built")
+        opt = dict(decay=.9, momentum=0., epsilon=1e-10, centered=False)     # tf.train.RMSPropOptimizer defaults
+        opt.update(opt_kwargs or {})
+        if not opt.pop("centered"):
+            raise NotImplementedError("only centered RMSProp (the reference's opt_kwargs) is built")
+        self._opt = opt
         self.l2_weight = l2_weight
         self.what_prior, self.where_scale_prior = what_prior, where_scale_prior
         self.where_shift_prior, self.num_steps_prior = where_shift_prior, num_steps_prior
@@ -206,15 +214,44 @@ class AIRModel:
         self._train_cfg = dict(what_prior=what_prior, where_scale_prior=where_scale_prior,
                                where_shift_prior=where_shift_prior, num_steps_prior=num_steps_prior,
                                use_reinforce=use_reinforce)
+        # the training engine: fp32 arithmetic, activations kept; it replaces the inference engine for this model
+        self.engine = self.cell.engine(self.batch_size, self.max_steps, precision=_lib.AIR_PREC_FP32,
+                                       materialise_canvas=True, materialise_viz=self._materialise_canvas)
+        self.engine.train_enable(True)
+        n = self.engine.n_params
+        dev = self.obs.device
+        self._grad = torch.zeros(n, device=dev)
+        self._slots = dict(mg=torch.zeros(n, device=dev), ms=torch.ones(n, device=dev), mom=torch.zeros(n, device=dev))
         self.forward()
 
         def train_op(obs=None, nums=None, noise=None):
-            out = self.forward(obs, nums, noise)
-            self.global_step += 1
-            return out
+            return self._run_train_step(obs, nums, noise)
 
         self._train_step = train_op
         return self._train_step, lambda: self.global_step
+
+    def _run_train_step(self, obs=None, nums=None, noise=None):
+        import torch.distributed as dist
+        from . import sharding
+        out = self.forward(obs, nums, noise)
+        eng, pr = self.engine, self._prior_struct
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        B = self.batch_size
+        bmean = 0.0
+        if self._train_cfg["use_reinforce"] and self.baseline_module is not None:
+            b = self.baseline.reshape(-1)
+            bmean = float(sharding.global_baseline_mean(b, B)) if world > 1 else float(b.mean())
+        eps_where, eps_what, _ = self._last_noise
+        eng.backward(self.cell.params, self.obs, eps_where, eps_what, pr, self._grad, baseline_mean=bmean,
+                     inv_batch=1.0 / (world * B), l2_weight=float(self.l2_weight) / world)
+        if world > 1:
+            dist.all_reduce(self._grad)          # the ONE data-path collective: sum of the per-shard partial gradients
+            sharding.combine_scalars(out["scalars"], B, pr.steps_weight, bool(pr.use_prior), bool(pr.use_reinforce))
+        o = self._opt
+        eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
+                         float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
+        self.global_step += 1
+        return out
 
     def toggle_prior(self):
         """use_prior.assign(not use_prior) (model.py:306-308)."""

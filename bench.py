@@ -325,12 +325,55 @@ def run_native(args, rank, local_rank, world):
     paint_bytes = B * (T * cfg.P * 4 + cfg.P * 4 + 2 * T * cfg.G * 4)
     roofline["paint_elbo_gbs"] = paint_bytes / (acc["paint_elbo"] * 1e-3) / 1e9
 
+    # ---- full training step (BASELINE.json configs[2] per GPU): forward + ELBO with saved activations, backward,
+    # one all-reduce of the flat gradient buffer (N > 1), centered RMSProp -- AIR_PREC_FP32 engine
+    train = None
+    if not args.no_train:
+        teng = air.Engine(air.CellConfig(precision=air.AIR_PREC_FP32), B, T, device=dev)
+        teng.train_enable(True)
+        tparams = params.clone()
+        n = tparams.numel()
+        grad = torch.empty(n, device=dev)
+        mg, ms_, mom = torch.zeros(n, device=dev), torch.ones(n, device=dev), torch.zeros(n, device=dev)
+
+        def train_step(i):
+            img, ew, ea, u = sets[i % len(sets)]
+            teng.forward(tparams, img, ew, ea, u, prior)
+            teng.backward(tparams, img, ew, ea, prior, grad, inv_batch=1.0 / (world * B))
+            if dist is not None:
+                dist.all_reduce(grad)
+            teng.rmsprop_step(tparams, grad, mg, ms_, mom, 1e-5)
+
+        for i in range(3):
+            train_step(i)
+        barrier()
+        l0 = teng.launch_count
+        n_train = max(5, args.steps // 5)
+        ev0.record()
+        for i in range(n_train):
+            train_step(i)
+        ev1.record()
+        barrier()
+        tms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        train = {"value": world * B * T * n_train / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms / n_train,
+                 "steps": n_train, "global_batch": world * B, "engine": "AIR_PREC_FP32 (SIMT fp32 GEMMs; tensor-core backward pending)",
+                 "gpu_launches_per_step": (teng.launch_count - l0) / n_train + 1,
+                 "allreduce_bytes_per_step": n * 4 if world > 1 else 0,
+                 "what": "forward+ELBO (activations kept) + backward + gradient all-reduce + centered RMSProp",
+                 "train_workspace_mb": round(teng.train_workspace_bytes / 1e6, 1),
+                 "final_loss": float(teng.scalar("loss"))}
+        teng.close()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu_baseline(args) if world == 1 else None,
+                "roofline": roofline, "train_step": train, "cpu_baseline": cpu_baseline(args) if world == 1 else None,
                 "elbo": -float(eng.scalar("loss")) / world}
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -348,6 +391,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="canvases per GPU")
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc"])
     ap.add_argument("--input-sets", type=int, default=4)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

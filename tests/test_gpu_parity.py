@@ -302,11 +302,13 @@ def test_air_on_mnist_surface():
     pr = dict(loc=0., scale=1.)
     train_op, global_step = model.train_step(1e-4, 0., pr, pr, pr, num_steps_prior)
     noise = model.cell.draw_noise(B, T, generator=torch.Generator(device=DEV).manual_seed(3))
+    params_before = model.params.detach().cpu().clone()
     train_op(noise=noise)
     assert global_step() == 1
-    # cross-check every exposed loss attribute against the oracle, with the model's own weights and its baseline
+    assert not torch.equal(params_before, model.params.detach().cpu()), "train_op must update the parameters"
+    # cross-check every exposed loss attribute against the oracle, with the weights the step was evaluated at
     ocfg = U.oracle_cfg(**U.SCRIPT)
-    params = O.unflatten_params(ocfg, model.params.detach().cpu())
+    params = O.unflatten_params(ocfg, params_before)
     bl = model.baseline.detach().cpu()
     ref = O.forward(ocfg, O.PriorConfig(), params, img, *(n.cpu() for n in noise), global_step=0, baseline=bl)
     bview = {k.replace("baseline.", "baseline."): v.detach().cpu() for k, v in model.baseline_module.views.items()}
