@@ -186,6 +186,8 @@ def run_native(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to STDOUT: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     prec = air.AIR_PREC_TC_SPLIT if args.precision == "tc" else air.AIR_PREC_FP32
