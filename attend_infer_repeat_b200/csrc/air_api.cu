@@ -1272,6 +1272,26 @@ int32_t air_rmsprop_step(float* params, const float* grad, float* mg, float* ms,
 
 int64_t air_train_workspace_bytes(const air_handle* h) { return h ? (int64_t)h->tws_bytes : 0; }
 
+int32_t air_linear_backward(const float* X, const float* W, const float* dY, const float* elu_x, float* dW, float* db,
+                            float* dX, int32_t M, int32_t N, int32_t K, void* stream) {
+  if (!X || !W || !dY || M < 1 || N < 1 || K < 1) return fail(AIR_ERR_ARG, "air_linear_backward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dW)
+    AIR_CUDA(air::launch_gemm_simt(true, false, X, K, dY, N, dW, N, K, N, M, true, nullptr, 0, pick_split(K, N, M), st));
+  if (db) AIR_CUDA(air::launch_colsum(dY, N, db, M, N, st));
+  if (dX) AIR_CUDA(air::launch_gemm_simt(false, true, dY, N, W, N, dX, K, M, K, N, false, elu_x, K, 1, st));
+  return AIR_OK;
+}
+
+int32_t air_baseline_grad(const float* target, const float* baseline, float target_mean, float inv_batch, float* d_baseline,
+                          int32_t B, void* stream) {
+  if (!target || !baseline || !d_baseline || B < 1) return fail(AIR_ERR_ARG, "air_baseline_grad: bad argument");
+  air::baseline_grad_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(baseline, target_mean, inv_batch,
+                                                                                d_baseline, B);
+  AIR_CUDA(cudaGetLastError());
+  return AIR_OK;
+}
+
 int32_t air_forward(air_handle* h, const float* params, const float* img, const float* eps_where,
                     const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
                     const air_outputs* outs, void* stream) {

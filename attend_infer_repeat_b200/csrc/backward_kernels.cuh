@@ -522,6 +522,14 @@ __global__ void l2_grad_kernel(const float* __restrict__ w, float* __restrict__ 
   if (i < n) grad[i] = fmaf(l2, w[i], grad[i]);
 }
 
+// baseline_loss = .5 * mean((stop_gradient(iw) - baseline)^2) with iw [B] and baseline [B,1] broadcasting to [B,B]
+// (model.py:253-259): d / d baseline_i = -(mean_j iw_j - baseline_i) / B
+__global__ void baseline_grad_kernel(const float* __restrict__ baseline, float target_mean, float inv_batch,
+                                     float* __restrict__ d_baseline, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) d_baseline[i] = -inv_batch * (target_mean - baseline[i]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tf.train.RMSPropOptimizer(lr, decay, momentum, epsilon, centered=True) [upstream ApplyCenteredRMSProp]:
 //   mg <- mg + (1 - rho)(g - mg);  ms <- ms + (1 - rho)(g^2 - ms);  mom <- mu mom + lr g / sqrt(ms - mg^2 + eps);

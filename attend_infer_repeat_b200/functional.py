@@ -37,6 +37,34 @@ def linear(x, w, b=None, act=ACT_NONE, precision=_lib.AIR_PREC_FP32):
     return out
 
 
+def linear_backward(x, w, dy, dw=None, db=None, need_dx=False, x_is_elu_output=False):
+    """Backward of one snt.Linear (+ the ELU of the layer that produced x): dw += x^T dy, db += colsum(dy) in place
+    (callers zero them), returns dx = (dy @ w^T) * elu'(x) or None.  dy is the gradient at the layer's pre-activation."""
+    x, w, dy = _cuda_f32(x, "x"), _cuda_f32(w, "w"), _cuda_f32(dy, "dy")
+    M, K = x.shape
+    N = w.shape[1]
+    assert w.shape[0] == K and tuple(dy.shape) == (M, N)
+    for t in (dw, db):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    dx = torch.empty(M, K, device=x.device, dtype=torch.float32) if need_dx else None
+    with torch.cuda.device(x.device):
+        check(_lib.lib().air_linear_backward(ptr(x), ptr(w), ptr(dy), ptr(x) if (x_is_elu_output and need_dx) else None,
+                                             ptr(dw), ptr(db), ptr(dx), M, N, K, current_stream_ptr()),
+              "air_linear_backward")
+    return dx
+
+
+def baseline_grad(target, baseline, target_mean, inv_batch):
+    """d baseline_loss / d baseline (model.py:253-259 with the [B]-[B,1] broadcast) -> [B,1]."""
+    target, baseline = _cuda_f32(target.reshape(-1), "target"), _cuda_f32(baseline.reshape(-1), "baseline")
+    B = baseline.numel()
+    out = torch.empty(B, 1, device=baseline.device, dtype=torch.float32)
+    with torch.cuda.device(baseline.device):
+        check(_lib.lib().air_baseline_grad(ptr(target), ptr(baseline), float(target_mean), float(inv_batch), ptr(out), B,
+                                           current_stream_ptr()), "air_baseline_grad")
+    return out
+
+
 def lstm_step(x, h, c, w, b, forget_bias=1.0):
     """snt.LSTM step; returns new (h, c).  Gate order i, j, f, o; w is [nx + nh, 4 nh]."""
     x, w, b = _cuda_f32(x, "x"), _cuda_f32(w, "w"), _cuda_f32(b, "b")

@@ -169,7 +169,9 @@ class AIRModel:
                 eng.elbo_scalars(b.reshape(-1), self._prior_struct)               # REINFORCE with the baseline mean
                 # [B] - [B,1] broadcasts to [B,B] in the reference; exposed as written, lazily
                 self.importance_weight = self.reinforce_imp_weight - b
-                self.baseline_loss = .5 * ((self.reinforce_imp_weight - b) ** 2).mean()
+                # .5 * mean over the [B,B] broadcast of (iw_j - b_i)^2, without materialising it a second time
+                iw, bb = self.reinforce_imp_weight.double(), b.reshape(-1).double()
+                self.baseline_loss = (.5 * ((iw * iw).mean() - 2. * iw.mean() * bb.mean() + (bb * bb).mean())).float()
             else:
                 self.importance_weight = self.reinforce_imp_weight
             self.reinforce_loss = eng.scalar("reinforce_loss")
@@ -188,8 +190,9 @@ class AIRModel:
         ELBO on the batch, ``opt.compute_gradients(opt_loss)`` (air_backward), one all-reduce of the flat gradient buffer
         when torch.distributed is initialised (batch shards), and the centered-RMSProp update of the flat
         parameter buffer (air_rmsprop_step, TF semantics).  It runs on the AIR_PREC_FP32 engine, which keeps the
-        activations the backward pass needs.  Not built: the baseline's own optimiser (SURVEY 8f row 2 -- a baseline
-        module is evaluated and enters REINFORCE, but its parameters are not trained) and NVIL moment normalisation."""
+        activations the backward pass needs.  A baseline module (BaselineMLP) is trained by its own RMSProp at 10x the
+        learning rate on .5 * mean((stop_gradient(iw) - baseline)^2) (model.py:253-259,362-367).  Not built: NVIL moment
+        normalisation (decay_rate)."""
         if decay_rate is not None:
             raise NotImplementedError("NVIL moving-average normalisation (decay_rate) is not built")
         if num_steps_prior is None:
@@ -250,6 +253,18 @@ class AIRModel:
         o = self._opt
         eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
                          float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
+        # the baseline's own train step at 10x the learning rate (model.py:362-367, _make_baseline_train_step :253-259)
+        if self._train_cfg["use_reinforce"] and self.baseline_module is not None:
+            bm = self.baseline_module
+            target = self.reinforce_imp_weight
+            tmean = None
+            if world > 1:
+                tmean = float(sharding.global_baseline_mean(target.reshape(-1), B))
+            g = bm.backward(target, self.baseline, tmean, 1.0 / (world * B))
+            if world > 1:
+                dist.all_reduce(g)
+            eng.rmsprop_step(bm.params, g, bm.slots["mg"], bm.slots["ms"], bm.slots["mom"],
+                             10.0 * float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
         self.global_step += 1
         return out
 

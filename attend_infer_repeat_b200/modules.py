@@ -146,8 +146,27 @@ class BaselineMLP:
             spec += [(f"baseline.{i}.w", (d, n)), (f"baseline.{i}.b", (1, n))]
             d = n
         spec += [("baseline.out.w", (d, 1)), ("baseline.out.b", (1, 1))]
+        self._spec = spec
         self.params, self.views = _init_flat(spec, device, seed)
         self.mlp = MLP(self._n_hidden, n_out=1).bind(self.views, "baseline")
+        # gradient buffer + optimiser slots of the baseline's own optimiser (model.py:362-367; RMSProp slots: ms = 1)
+        from .engine import make_views
+        self.grad = torch.zeros_like(self.params)
+        self.grad_views = make_views(spec, self.grad)
+        self.slots = dict(mg=torch.zeros_like(self.params), ms=torch.ones_like(self.params),
+                          mom=torch.zeros_like(self.params))
+
+    def backward(self, target, baseline, target_mean=None, inv_batch=None):
+        """Gradient of baseline_loss = .5 * mean((stop_gradient(target) - baseline)^2) (model.py:253-259; target [B],
+        baseline [B,1] -> [B,B] broadcast) with respect to the baseline's parameters, for the LAST
+        call; left in ``self.grad`` (flat).  ``target_mean`` / ``inv_batch`` are the global-batch values under sharding."""
+        from . import functional as F
+        B = baseline.shape[0]
+        tm = float(target.mean()) if target_mean is None else float(target_mean)
+        d_out = F.baseline_grad(target, baseline, tm, 1.0 / B if inv_batch is None else inv_batch)
+        self.grad.zero_()
+        self.mlp.backward(d_out, self.grad_views)
+        return self.grad
 
     def __call__(self, img, what, where, presence_prob, state=None):
         B = img.shape[0]

@@ -47,8 +47,22 @@ class MLP:
         if self._views is None:
             raise RuntimeError("MLP is not bound to parameters (build it through AIRCell / AIRModel)")
         x = inpt.reshape(inpt.shape[0], -1)
+        self._saved = [x]          # layer inputs, kept for backward()
         for i in range(len(self._n_hiddens)):
             x = F.linear(x, self._views[f"{self._prefix}.{i}.w"], self._views[f"{self._prefix}.{i}.b"], F.ACT_ELU)
+            self._saved.append(x)
         if self._n_out is not None:
             x = F.linear(x, self._views[f"{self._prefix}.out.w"], self._views[f"{self._prefix}.out.b"], F.ACT_NONE)
         return x
+
+    def backward(self, d_out: torch.Tensor, grad_views: Dict[str, torch.Tensor]):
+        """Accumulate d loss / d parameters of the LAST call into ``grad_views`` (same names as the parameter views, zeroed
+        by the caller); d_out is the gradient at the MLP's output (requires the linear output layer, n_out)."""
+        if self._n_out is None:
+            raise NotImplementedError("backward() is built for MLPs with a linear output layer (BaselineMLP)")
+        names = [f"{self._prefix}.{i}" for i in range(len(self._n_hiddens))] + [f"{self._prefix}.out"]
+        dy = d_out
+        for li in range(len(names) - 1, -1, -1):
+            x = self._saved[li]
+            dy = F.linear_backward(x, self._views[names[li] + ".w"], dy, grad_views[names[li] + ".w"],
+                                   grad_views[names[li] + ".b"], need_dx=li > 0, x_is_elu_output=li > 0)

@@ -238,6 +238,18 @@ int32_t air_rmsprop_step(float* params, const float* grad, float* mg, float* ms,
                          float learning_rate, float decay, float momentum, float epsilon, float grad_scale,
                          void* stream);
 
+/* Backward of ONE dense layer y = act(x @ W + b) (neural.py:42-60) for callers that own their own MLP parameters -- the
+ * BaselineMLP of modules.py:125-143, trained by its own optimiser (model.py:253-259,362-367):
+ *   dW[K,N] += X^T @ dY, db[N] += colsum(dY)  (accumulated: zero them first), dX[M,K] = dY @ W^T (overwritten),
+ *   multiplied by elu'(x) when elu_x (the forward value of X, itself an ELU layer's output) is given.
+ * dY is the gradient with respect to the layer's PRE-activation.  Any of dW / db / dX may be NULL. */
+int32_t air_linear_backward(const float* X, const float* W, const float* dY, const float* elu_x, float* dW, float* db,
+                            float* dX, int32_t M, int32_t N, int32_t K, void* stream);
+/* d baseline_loss / d baseline for baseline_loss = .5 mean((stop_gradient(target) - baseline)^2) with target [B] and
+ * baseline [B,1] broadcasting to [B,B] (model.py:253-259): -(target_mean - baseline_i) * inv_batch. */
+int32_t air_baseline_grad(const float* target, const float* baseline, float target_mean, float inv_batch,
+                          float* d_baseline, int32_t B, void* stream);
+
 /* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
  * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be
  * known after the forward pass): AIRModel._reinforce, model.py:218-251. */

@@ -233,3 +233,40 @@ def test_model_train_op_decreases_the_loss():
     first, last = sum(losses[:5]) / 5, sum(losses[-5:]) / 5
     print(f"loss {first:.1f} -> {last:.1f}")
     assert last < 0.8 * first, (first, last)
+
+
+def test_baseline_mlp_training_step_matches_oracle():
+    """BaselineMLP (modules.py:125-143) forward, the gradient of baseline_loss (model.py:253-259, [B]-[B,1] broadcast) and
+    one RMSProp step at 10x lr against autograd on the oracle's baseline_mlp."""
+    B, T, na, nh, P = 24, 3, 50, 256, 2500
+    g = torch.Generator().manual_seed(4)
+    img = torch.rand(B, 50, 50, generator=g)
+    what, where, pres = torch.randn(T, B, na, generator=g), torch.randn(T, B, 4, generator=g), torch.rand(T, B, 1, generator=g)
+    h, c = torch.randn(B, nh, generator=g), torch.randn(B, nh, generator=g)
+    target = 300.0 + 40.0 * torch.randn(B, generator=g)
+    bm = air.BaselineMLP([256, 128])
+    d = lambda t: t.cuda()
+    b = bm(d(img), d(what), d(where), d(pres), (d(h), d(c)))
+    # oracle with the module's own initial parameters
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in bm.views.items()}
+    b_ref = O.baseline_mlp(p, 2, img, what, where, pres, h, c)
+    U.assert_close(b.cpu(), b_ref.detach(), atol=2e-4, rtol=1e-4, name="baseline")
+    loss = 0.5 * ((target[None, :] - b_ref) ** 2).mean()          # [B] - [B,1] -> [B,B]
+    loss.backward()
+    theta0 = bm.params.detach().cpu().clone()
+    grad = bm.backward(d(target), b).cpu()
+    off = 0
+    for name, (r, cc) in bm._spec:
+        ref = p[name].grad.reshape(-1)
+        got = grad[off:off + r * cc]
+        off += r * cc
+        tol = 2e-4 * float(ref.abs().max()) + 1e-7
+        assert float((got - ref).abs().max()) <= tol, (name, float((got - ref).abs().max()), tol)
+    eng = air.Engine(U.cell_cfg(U.oracle_cfg(**U.TINY)), 2, 3, device="cuda")
+    eng.rmsprop_step(bm.params, bm.grad, bm.slots["mg"], bm.slots["ms"], bm.slots["mom"], 1e-3)
+    n = theta0.numel()
+    ref_theta, _, _, _ = O.centered_rmsprop_step(theta0, O.flatten_params, None, None, None, 0) if False else \
+        O.centered_rmsprop_step(theta0, torch.cat([p[nm].grad.reshape(-1) for nm, _ in bm._spec]), torch.zeros(n),
+                                torch.ones(n), torch.zeros(n), 1e-3)
+    U.assert_close(bm.params.cpu() - theta0, ref_theta - theta0, atol=2e-6, rtol=2e-3, name="baseline update")
+    eng.close()

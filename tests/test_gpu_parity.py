@@ -303,6 +303,7 @@ def test_air_on_mnist_surface():
     train_op, global_step = model.train_step(1e-4, 0., pr, pr, pr, num_steps_prior)
     noise = model.cell.draw_noise(B, T, generator=torch.Generator(device=DEV).manual_seed(3))
     params_before = model.params.detach().cpu().clone()
+    bview = {k: v.detach().cpu().clone() for k, v in model.baseline_module.views.items()}
     train_op(noise=noise)
     assert global_step() == 1
     assert not torch.equal(params_before, model.params.detach().cpu()), "train_op must update the parameters"
@@ -311,7 +312,8 @@ def test_air_on_mnist_surface():
     params = O.unflatten_params(ocfg, params_before)
     bl = model.baseline.detach().cpu()
     ref = O.forward(ocfg, O.PriorConfig(), params, img, *(n.cpu() for n in noise), global_step=0, baseline=bl)
-    bview = {k.replace("baseline.", "baseline."): v.detach().cpu() for k, v in model.baseline_module.views.items()}
+    assert any(not torch.equal(v, model.baseline_module.views[k].cpu()) for k, v in bview.items()), \
+        "train_op must also run the baseline's own optimiser (model.py:362-367)"
     bl_ref = O.baseline_mlp(bview, 2, img, ref["outs"]["what"], ref["outs"]["where"], ref["outs"]["presence"],
                             ref["final_h"], ref["final_c"])
     U.assert_close(bl, bl_ref, atol=2e-4, rtol=1e-4, name="baseline")
