@@ -102,6 +102,9 @@ SYMBOLS = {
                                  C.c_float, _P, _P]),
     "air_rmsprop_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, _P]),
+    "air_forward_dataset_u8": (C.c_int32, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(air_prior),
+                                           C.POINTER(air_outputs), _P, _P]),
+    "air_gather_u8": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "air_linear_backward": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "air_baseline_grad": (C.c_int32, [_P, _P, C.c_float, C.c_float, _P, C.c_int32, _P]),
     "air_elbo_scalars": (C.c_int32, [_P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),

@@ -1346,7 +1346,7 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
                          (const uint8_t*)h->st_img_u8, h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(),
-                         h->x.kpad, c.B, h->P));
+                         h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
   ++h->launches;
   rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
                     nullptr, nullptr, nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
@@ -1357,6 +1357,36 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
     AIR_CUDA(cudaMemcpyAsync(loss_per_sample_host, outs->loss_per_sample, sizeof(float) * c.B, cudaMemcpyDeviceToHost,
                              st));
   AIR_CUDA(cudaStreamSynchronize(st));
+  return AIR_OK;
+}
+
+int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t* dataset_u8, int64_t n_dataset,
+                               const int32_t* idx, const float* eps_where, const float* eps_what, const float* u_pres,
+                               const float* baseline, const air_prior* prior, const air_outputs* outs, float* img_out,
+                               void* stream) {
+  if (!h || !params || !dataset_u8 || !idx || !eps_where || !eps_what || n_dataset < 1)
+    return fail(AIR_ERR_ARG, "air_forward_dataset_u8: bad argument");
+  if (h->cfg.discrete_steps && !u_pres) return fail(AIR_ERR_ARG, "air_forward_dataset_u8: u_pres is required");
+  int32_t rc = check_outs(outs, prior != nullptr);
+  if (rc != AIR_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const air_config& c = h->cfg;
+  float* img = img_out ? img_out : h->st_img;
+  // gather + uint8 -> float32 / 255 (data.py:116,131-132) + the first layer's operand split, one pass, all on the device
+  const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
+  AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dataset_u8,
+                         img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(), h->x.kpad, c.B, h->P, idx));
+  ++h->launches;
+  return forward_impl(h, params, img, eps_where, eps_what, u_pres, baseline, prior, outs, c.T, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
+}
+
+int32_t air_gather_u8(const uint8_t* dataset_u8, const int32_t* idx, float* img_out, int32_t B, int32_t P, void* stream) {
+  if (!dataset_u8 || !idx || !img_out || B < 1 || P < 1) return fail(AIR_ERR_ARG, "air_gather_u8: bad argument");
+  const size_t n4 = (size_t)B * ((P + 3) / 4);
+  air::tc::u8_to_f32_hl_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      dataset_u8, img_out, nullptr, 0, 0, B, P, idx);
+  AIR_CUDA(cudaGetLastError());
   return AIR_OK;
 }
 

@@ -403,15 +403,17 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __h
 // uint8 pixels (the reference's dataset format, data.py:35-107) -> float32 / 255 (load_data, data.py:116) written both
 // as fp32 rows (read by the glimpse-read and paint kernels) and, for the tensor-core engine, as the hl operand of the
 // first encoder layer.  One pass over the image batch.
+// gather != null: row r of the batch is row gather[r] of a device-resident uint8 dataset (the minibatch indices of
+// tensors_from_data, data.py:121-158), so the host never touches the pixels.
 __global__ void u8_to_f32_hl_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, __half* __restrict__ hl,
-                                    size_t plane, int ld_hl, int M, int K) {
+                                    size_t plane, int ld_hl, int M, int K, const int32_t* __restrict__ gather) {
   griddep_launch();
   griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 pixels
   const int kq = (K + 3) / 4;
   if (idx >= (size_t)M * kq) return;
   const int row = (int)(idx / kq), k = (int)(idx % kq) * 4;
-  const uint8_t* s = src + (size_t)row * K + k;
+  const uint8_t* s = src + (size_t)(gather ? gather[row] : row) * K + k;
   float f[4] = {0.f, 0.f, 0.f, 0.f};
   const bool vec = (k + 3 < K) && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
   if (vec) {

@@ -309,6 +309,26 @@ class Engine:
                                             float(learning_rate), float(decay), float(momentum), float(epsilon),
                                             float(grad_scale), current_stream_ptr()), "air_rmsprop_step")
 
+    def forward_dataset_u8(self, params, dataset_u8, idx, eps_where, eps_what, u_pres, prior: Optional[air_prior] = None,
+                           baseline=None, img_out=None):
+        """forward() on the minibatch ``dataset_u8[idx]`` of a device-resident uint8 dataset [N,H,W]:
+        gather, /255 and operand preparation run on the device.  ``img_out`` [B,H,W] receives the float32 minibatch."""
+        T, B, cfg = self.T, self.B, self.cfg
+        assert dataset_u8.is_cuda and dataset_u8.dtype == torch.uint8 and dataset_u8.is_contiguous()
+        assert tuple(dataset_u8.shape[1:]) == (cfg.H, cfg.W)
+        assert idx.is_cuda and idx.dtype == torch.int32 and idx.numel() == B and idx.is_contiguous()
+        self._chk(params, (self.n_params,), "params")
+        self._chk(eps_where, (T, B, 4), "eps_where")
+        self._chk(eps_what, (T, B, cfg.na), "eps_what")
+        self._chk(u_pres, (T, B, 1), "u_pres")
+        self._chk(img_out, (B, cfg.H, cfg.W), "img_out")
+        with torch.cuda.device(self.device):
+            check(self.lib.air_forward_dataset_u8(self._handle, ptr(params), ptr(dataset_u8), dataset_u8.shape[0], ptr(idx),
+                                                  ptr(eps_where), ptr(eps_what), ptr(u_pres), ptr(baseline),
+                                                  C.byref(prior) if prior is not None else None, C.byref(self._c_out),
+                                                  ptr(img_out), current_stream_ptr()), "air_forward_dataset_u8")
+        return self.out
+
     def cell_step(self, params, img, canvas, h, c, presence, eps_where, eps_what, u_pres):
         """One AIRCell step (cell.py:116-171); canvas / h / c / presence are updated IN PLACE.  Returns the per-step
         outputs glimpse, what, what_loc, what_scale, where, where_loc, where_scale, presence_prob."""

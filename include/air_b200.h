@@ -210,6 +210,17 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
                             const float* u_pres_host, const air_prior* prior, const air_outputs* outs,
                             float* scalars_host, float* loss_per_sample_host, void* stream);
 
+/* Same with the whole DATASET resident on the device: dataset_u8 [n_dataset,H,W] uint8 as pickled by
+ * data.py:35-107, idx [B] int32 = the minibatch indices tensors_from_data draws (data.py:121-158).  Gather, /255 and the
+ * first layer's operand preparation run in one device pass; no host buffer is touched.  img_out [B,H,W] (optional)
+ * receives the float32 minibatch (what a following air_backward needs); every pointer is a DEVICE pointer. */
+int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t* dataset_u8, int64_t n_dataset,
+                               const int32_t* idx, const float* eps_where, const float* eps_what, const float* u_pres,
+                               const float* baseline, const air_prior* prior, const air_outputs* outs, float* img_out,
+                               void* stream);
+/* stand-alone minibatch gather: img_out[b] = float32(dataset_u8[idx[b]]) / 255  (data.py:116,131-132) */
+int32_t air_gather_u8(const uint8_t* dataset_u8, const int32_t* idx, float* img_out, int32_t B, int32_t P, void* stream);
+
 /* ---- training step: opt.compute_gradients(opt_loss, model_vars) + opt.apply_gradients of
  *      AIRModel.train_step (model.py:261-265,335-360) ------------------------------------------------------- */
 /* Switch a handle (AIR_PREC_FP32 engine, discrete_steps = 1) to training mode: allocates the second workspace

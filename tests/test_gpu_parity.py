@@ -491,3 +491,32 @@ def test_forward_tc_chain_deep_and_ragged_widths():
 def test_forward_tc_wide_hidden_falls_back_to_per_layer():
     cfg = dict(U.SCRIPT, where_hidden=(320, 64), T=2)
     _check_forward(U.oracle_cfg(**cfg), 20, O.PriorConfig(), seed=7, global_step=15000, precision=TC, noise_floor=True)
+
+
+def test_resident_dataset_forward_matches_host_fed_forward():
+    """the uint8 dataset stays in HBM; the minibatch gather + /255 inside the library gives exactly the
+    forward pass of the same canvases fed as float32 (both engines), and air_gather_u8 is exact."""
+    from attend_infer_repeat_b200.data import ResidentDataset, synthetic_multi_mnist_u8
+    imgs_u8, nums_u8 = synthetic_multi_mnist_u8(200, 50, 50, seed=2)
+    ds = ResidentDataset(imgs_u8, nums_u8, device=DEV, seed=1)
+    B, T = 48, 3
+    idx = ds.next_indices(B)
+    assert idx.dtype == torch.int32 and int(idx.min()) >= 0 and int(idx.max()) < 200
+    img, nums = ds.gather(idx)
+    ref = torch.from_numpy(imgs_u8.astype("float32") / 255.)[idx.cpu().long()]
+    assert torch.equal(img.cpu(), ref)
+    assert torch.equal(nums.cpu(), torch.from_numpy(nums_u8.astype("float32"))[:, idx.cpu().long()])
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    params = O.flatten_params(ocfg, O.init_params(ocfg, 0)).to(DEV)
+    noise = tuple(n.to(DEV).contiguous() for n in O.make_noise(ocfg, B, 4))
+    pr = U.prior_struct(O.PriorConfig(), 20000)
+    for prec in (air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT):
+        eng = air.Engine(U.cell_cfg(ocfg, prec), B, T, device=DEV)
+        a = {k: v.clone() for k, v in eng.forward(params, img, *noise, pr).items() if v is not None}
+        img_out = torch.empty(B, 50, 50, device=DEV)
+        b = eng.forward_dataset_u8(params, ds.imgs, idx, *noise, pr, img_out=img_out)
+        torch.cuda.synchronize()
+        assert torch.equal(img_out, img)
+        for k in ("canvas", "what", "where", "presence", "loss_per_sample", "scalars"):
+            assert torch.equal(a[k], b[k]), (prec, k)
+        eng.close()

@@ -117,3 +117,26 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_data_pickle_round_trip_and_loaders(tmp_path):
+    """The reference's dataset format (data.py:35-118): uint8 pickle -> load_data float32 / 255; tensors_from_data draws
+    with replacement when shuffling and (as written, data.py:136-139) always returns the first batch otherwise."""
+    import numpy as np
+    from attend_infer_repeat_b200 import data as D
+    imgs, nums = D.synthetic_multi_mnist_u8(40, 50, 50, seed=3)
+    path = os.path.join(str(tmp_path), "mnist_train.pickle")
+    D.save_data(path, imgs, nums)
+    raw = D.load_raw("mnist_train.pickle", str(tmp_path))
+    assert raw["imgs"].dtype == np.uint8 and raw["imgs"].shape == (40, 50, 50) and raw["nums"].shape == (3, 40, 1)
+    data = D.load_data("mnist_train.pickle", str(tmp_path))
+    assert data["imgs"].dtype == np.float32 and float(data["imgs"].max()) <= 1.0
+    np.testing.assert_array_equal(data["imgs"], imgs.astype(np.float32) / 255.)
+    axes = {'imgs': 0, 'labels': 0, 'nums': 1}
+    t = D.tensors_from_data(data, 8, axes, shuffle=True, seed=0)
+    b = t["next_batch"]()
+    assert b["imgs"].shape == (8, 50, 50) and b["nums"].shape == (3, 8, 1) and b["labels"].shape[0] == 8
+    t = D.tensors_from_data(data, 8, axes, shuffle=False)
+    b1, b2 = t["next_batch"](), t["next_batch"]()
+    np.testing.assert_array_equal(b1["imgs"], data["imgs"][:8])
+    np.testing.assert_array_equal(b2["imgs"], data["imgs"][:8])
