@@ -19,8 +19,10 @@
 
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <utility>
 #include <vector>
@@ -154,6 +156,13 @@ struct air_handle {
   float *g_wh_paint = nullptr, *g_wh_read = nullptr, *g_m = nullptr, *g_logit = nullptr;   // [T*B,4] x2, [T*B,8], [T*B]
   float *g_h = nullptr, *g_gates = nullptr;        // [T*B, nh], [T*B, 4nh]
   float *g_gx = nullptr, *g_hrec = nullptr, *g_c = nullptr, *g_e = nullptr;   // [B,4nh], [B,nh], [B,nh], [B,n_enc]
+  // tensor-core weight gradients (dW = X^T @ dY on the tcgen05 split engine): transposed hl operands, M contiguous
+  bool tc_bwd = false;
+  float bwd_lift = 1.0f;   // power of two >= 1 / inv_batch of the current backward pass
+  __half *hl_xt = nullptr, *hl_yt = nullptr;
+  size_t hl_xt_halves = 0, hl_yt_halves = 0;   // per plane
+  int* t_range_flag = nullptr;
+  std::map<std::tuple<const void*, int, long long, int>, CUtensorMap> tmap_cache2;
   // instrumentation: kernel-launch counter and optional per-stage CUDA-event timing (air_profile_*)
   uint64_t launches = 0;
   bool profile = false;
@@ -776,6 +785,26 @@ void carve_train(air_handle* h, Carver& cv) {
   h->g_hrec = cv.take<float>(B * c.nh);
   h->g_c = cv.take<float>(B * c.nh);
   h->g_e = cv.take<float>(B * h->n_enc);
+  if (h->tc_bwd) {
+    // largest transposed operands over all dense layers: X^T [round_up(K,128)][round_up(rows,64)], dY^T [round_up(N,64)][..]
+    size_t xt = 0, yt = 0;
+    auto visit = [&](const Layer& l, size_t rows) {
+      const size_t mp = (size_t)round_up((int)rows, 64);
+      xt = std::max(xt, (size_t)round_up(l.K, 128) * mp);
+      yt = std::max(yt, (size_t)round_up(l.N, 64) * mp);
+    };
+    for (const Layer& l : h->enc.layers) visit(l, B);
+    for (const Mlp* m : {&h->where_mlp, &h->steps_mlp, &h->glenc, &h->dec})
+      for (const Layer& l : m->layers) visit(l, TB);
+    visit(h->what_lin, TB);
+    visit(h->lstm_h, TB);
+    visit(h->lstm_x, B);
+    h->hl_xt_halves = xt;
+    h->hl_yt_halves = yt;
+    h->hl_xt = cv.take<__half>(2 * xt);
+    h->hl_yt = cv.take<__half>(2 * yt);
+    h->t_range_flag = cv.take<int>(1);
+  }
 }
 
 // split of the batch-row contraction of a weight-gradient GEMM so that the grid fills the machine
@@ -788,8 +817,71 @@ int pick_split(int out_rows, int out_cols, int contraction) {
 }
 
 // dW += X^T @ dY, db += colsum(dY) for one dense layer (X [M, l.K] with row pitch ldx, dY [M, l.N] with row pitch ldy)
+int32_t get_tmap2(air_handle* h, const __half* base, int kpad, long long rows_total, int box_rows, const CUtensorMap** out) {
+  const auto key = std::make_tuple((const void*)base, kpad, rows_total, box_rows);
+  auto it = h->tmap_cache2.find(key);
+  if (it == h->tmap_cache2.end()) {
+    CUtensorMap tm;
+    if (!air::tc::make_tmap(&tm, base, kpad, rows_total, box_rows))
+      return fail(AIR_ERR_CUDA, "cuTensorMapEncodeTiled failed for a backward operand");
+    it = h->tmap_cache2.emplace(key, tm).first;
+  }
+  *out = &it->second;
+  return AIR_OK;
+}
+
+// dW += X^T @ dY on the tensor-core split engine: both operands are re-laid out contraction-major (the batch rows) by
+// split_transpose_kernel as bf16 hi/lo planes (16 significant bits each; per-sample gradients span the fp32 exponent
+// range -- the 1 / s_x factors of the inverse transformer -- which fp16 planes cannot hold), three tcgen05.mma per K slice
+// as in the forward, the contraction split over gridDim.z with fp32 atomics into the zeroed gradient buffer.
+int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
+                             int M, float lift, cudaStream_t st) {
+  namespace tc = air::tc;
+  const int mp = round_up(M, 64), KA = round_up(l.K, 128), NA = round_up(l.N, 64);
+  if ((size_t)KA * mp > h->hl_xt_halves || (size_t)NA * mp > h->hl_yt_halves)
+    return fail(AIR_ERR_ARG, "internal: transposed operand does not fit the training workspace");
+  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.K + 31) / 32, (mp + 31) / 32), dim3(256), 0, st, X, ldx, M, l.K,
+                         1.0f, h->hl_xt, (size_t)KA * mp, mp, h->t_range_flag, 1));
+  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.N + 31) / 32, (mp + 31) / 32), dim3(256), 0, st, dY, ldy, M, l.N,
+                         lift, h->hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1));
+  const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
+  int32_t rc = get_tmap2(h, h->hl_xt, mp, 2LL * KA, tc::BM, &tm_a);
+  if (rc != AIR_OK) return rc;
+  if ((rc = get_tmap2(h, h->hl_yt, mp, 2LL * NA, 64, &tm_b)) != AIR_OK) return rc;
+  tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out_f32 = grad + l.w_off;
+  p.ldc = l.N;
+  p.M = l.K;
+  p.N = l.N;
+  p.num_k_blocks = mp / tc::BK;
+  p.a_lo_row = KA;
+  p.b_lo_row = NA;
+  p.act = air::ACT_NONE;
+  p.range_flag = h->t_range_flag;
+  p.out_scale = 1.0f / lift;
+  p.atomic_out = 1;
+  p.ab_bf16 = 1;
+  const int tiles = (KA / tc::BM) * (NA / 64);
+  int split = (2 * 148 + tiles - 1) / tiles;
+  split = std::max(1, std::min(split, p.num_k_blocks));
+  p.kb_per_z = (p.num_k_blocks + split - 1) / split;
+  AIR_CUDA(tc::launch_gemm(64, *tm_a, *tm_b, p, NA, st));
+  h->launches += 3;
+  return AIR_OK;
+}
+
 int32_t layer_param_grads(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
                           int M, cudaStream_t st) {
+  if (h->tc_bwd && M >= 64) {
+    const int32_t rc = layer_weight_grad_tc(h, grad, l, X, ldx, dY, ldy, M, 1.0f, st);
+    if (rc != AIR_OK) return rc;
+    if (l.b_off >= 0) {
+      AIR_CUDA(air::launch_colsum(dY, ldy, grad + l.b_off, M, l.N, st));
+      ++h->launches;
+    }
+    return AIR_OK;
+  }
   AIR_CUDA(air::launch_gemm_simt(true, false, X, ldx, dY, ldy, grad + l.w_off, l.N, l.K, l.N, M, true, nullptr, 0,
                                  pick_split(l.K, l.N, M), st));
   ++h->launches;
@@ -883,6 +975,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   a.max_crop = c.max_crop_size;
   a.explore_eps = c.explore_eps;
   a.inv_batch = inv_batch > 0.f ? inv_batch : 1.0f / (float)B;
+  h->bwd_lift = exp2f(ceilf(log2f(1.0f / a.inv_batch)));
   a.baseline_mean = baseline_mean;
   a.step_W = c.W > 1 ? 2.0 / (double)(c.W - 1) : 0.0;
   a.step_H = c.H > 1 ? 2.0 / (double)(c.H - 1) : 0.0;
@@ -1207,10 +1300,18 @@ const char* air_stage_name(int32_t i) { return (i >= 0 && i < AIR_N_STAGES) ? kS
 
 int32_t air_check_range(air_handle* h, void* stream) {
   if (!h) return fail(AIR_ERR_ARG, "air_check_range: NULL handle");
-  if (!h->use_tc) return AIR_OK;
-  int flag = 0;
-  AIR_CUDA(cudaMemcpyAsync(&flag, h->range_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (!h->use_tc && !h->t_range_flag) return AIR_OK;
+  int flag = 0, tflag = 0;
+  if (h->use_tc)
+    AIR_CUDA(cudaMemcpyAsync(&flag, h->range_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (h->t_range_flag)
+    AIR_CUDA(cudaMemcpyAsync(&tflag, h->t_range_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   AIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (tflag) {
+    AIR_CUDA(cudaMemsetAsync(h->t_range_flag, 0, sizeof(int), (cudaStream_t)stream));
+    return fail(AIR_ERR_RANGE, "an activation or a lifted gradient exceeded the fp16 range (65504) in the tensor-core "
+                               "weight-gradient GEMMs; set AIR_NO_TC_BWD=1 for this model");
+  }
   if (flag) {
     AIR_CUDA(cudaMemsetAsync(h->range_flag, 0, sizeof(int), (cudaStream_t)stream));
     return fail(AIR_ERR_RANGE, "a weight*2^8 or an activation exceeded the fp16 range (65504) in the tensor-core "
@@ -1227,6 +1328,7 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
   if (on && !h->cfg.discrete_steps)
     return fail(AIR_ERR_ARG, "air_train_enable: the backward pass covers discrete_steps = 1 (the script configuration)");
   if (on && !h->tws) {
+    h->tc_bwd = getenv("AIR_NO_TC_BWD") == nullptr && air::tc::get_encode_fn() != nullptr;
     Carver sizing(nullptr);
     carve_train(h, sizing);
     cudaError_t e = cudaMalloc(&h->tws, sizing.off);
@@ -1234,6 +1336,7 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
     h->tws_bytes = sizing.off;
     Carver real(h->tws);
     carve_train(h, real);
+    if (h->t_range_flag) AIR_CUDA(cudaMemset(h->t_range_flag, 0, sizeof(int)));
     const size_t smem = air::paint_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
     const size_t smem_r = air::read_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
     if (smem > 200 * 1024 || smem_r > 200 * 1024)

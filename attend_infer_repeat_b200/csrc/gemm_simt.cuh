@@ -229,7 +229,9 @@ colsum_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, int
 }
 inline cudaError_t launch_colsum(const float* X, int ldx, float* out, int M, int N, cudaStream_t st) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  const int rows_per_cta = 512;
+  // enough CTAs to pull the operand at HBM speed: ~1200 CTAs for a [12288, 256] gradient
+  int rows_per_cta = 512;
+  while (rows_per_cta > 64 && (long long)((N + 31) / 32) * ((M + rows_per_cta - 1) / rows_per_cta) < 1184) rows_per_cta >>= 1;
   return launch_k(colsum_kernel, dim3((N + 31) / 32, (M + rows_per_cta - 1) / rows_per_cta), dim3(256), 0, st, X, ldx, out,
                   M, N, rows_per_cta);
 }

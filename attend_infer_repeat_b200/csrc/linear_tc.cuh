@@ -24,6 +24,7 @@
 //               activation, fp32 and/or hi/lo fp16 vector stores
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "cell_kernels.cuh"   // mbarrier helpers
@@ -148,6 +149,13 @@ struct GemmParams {
   int b_lo_row;          // row coordinate of the lo plane in the W^T tensor map (= N_alloc)
   int act;
   int* range_flag;       // set to 1 if a produced activation overflows fp16
+  // ---- backward-pass extensions (all zero = the forward behaviour) ----
+  float out_scale;       // factor applied to the accumulator; 0 selects W_UNSCALE (operand B prepared with W_SCALE)
+  int kb_per_z;          // > 0: the K loop is split over gridDim.z, kb_per_z blocks of 64 per slice (every slice non-empty)
+  int atomic_out;        // out_f32 += result with atomicAdd (split-K weight gradients into the zeroed gradient buffer)
+  const float* mask_y;   // [M, ld_mask] forward ELU output: result *= (y > 0 ? 1 : y + 1)   (tf.nn.elu gradient)
+  int ld_mask;
+  int ab_bf16;           // both operands hold bf16 hi/lo planes (fp32 exponent range, 16 significant bits) instead of fp16
   long long* trace;      // AIR_TC_TRACE builds only: [n_ctas][16] SM-clock timestamps of the pipeline phases
 };
 
@@ -186,7 +194,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = p.num_k_blocks;
+  const int kb0 = p.kb_per_z > 0 ? (int)blockIdx.z * p.kb_per_z : 0;
+  const int nkb = p.kb_per_z > 0 ? min(p.kb_per_z, p.num_k_blocks - kb0) : p.num_k_blocks;
   if (threadIdx.x == 0) TC_TRACE(0);
 
   if (warp == 0 && lane == 0) {
@@ -219,7 +228,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (kb == 0) TC_TRACE(2);
         uint8_t* st = smem + s * L::STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        const int k0 = kb * BK;
+        const int k0 = (kb0 + kb) * BK;
         tma_load_2d(st, &tm_a, k0, p.a_row0 + m0, &full_bar[s]);
         tma_load_2d(st + L::A_BYTES, &tm_a, k0, p.a_lo_row + p.a_row0 + m0, &full_bar[s]);
         tma_load_2d(st + 2 * L::A_BYTES, &tm_b, k0, n0, &full_bar[s]);
@@ -231,7 +240,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      // instruction descriptor bits [7,10) / [10,13): A / B element format, 0 = f16, 1 = bf16 (kind::f16 wants both alike:
+      // a mixed f16 x bf16 descriptor traps as an illegal instruction on sm_100a); bf16 x bf16 products are exact in fp32
+      const uint32_t idesc = make_idesc_f16(BM, BN) | (p.ab_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -290,7 +301,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     mbar_wait(tmem_full_bar, 0);
     if (threadIdx.x == 64) TC_TRACE(7);
     tc_fence_after();
-    const bool f32_vec = p.out_f32 && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+    const bool f32_vec = p.out_f32 && !p.atomic_out && ((p.ldc & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+    const float osc = p.out_scale != 0.f ? p.out_scale : W_UNSCALE;
     float amax = 0.f;   // NaN-propagating running max |x| of what is written as fp16 hi halves
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
 #pragma unroll
@@ -306,12 +319,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (p.act == ACT_ELU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float x = (v[j] + vx[j]) * W_UNSCALE + s_bias[c0 + j] + addf[hf * 16 + j];
+            const float x = (v[j] + vx[j]) * osc + s_bias[c0 + j] + addf[hf * 16 + j];
             v[j] = x > 0.f ? x : __expf(x) - 1.0f;   // ex2.approx path: <= 2.4e-7 absolute on (-1, 0]
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = (v[j] + vx[j]) * W_UNSCALE + s_bias[c0 + j] + addf[hf * 16 + j];
+          for (int j = 0; j < 16; ++j) v[j] = (v[j] + vx[j]) * osc + s_bias[c0 + j] + addf[hf * 16 + j];
+        }
+        if (p.mask_y) {   // backward: gradient through the ELU that produced the saved activation y
+          const float* my = p.mask_y + (size_t)row * p.ld_mask + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (n0 + c0 + j < p.N) {
+              const float y = my[j];
+              v[j] *= (y > 0.f) ? 1.0f : y + 1.0f;
+            }
+          }
         }
         if (n0 + c0 + 16 > p.N) {   // only the last, partial column tile
 #pragma unroll
@@ -321,7 +344,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (threadIdx.x == 64) TC_TRACE(11 + 3 * hf);
         if (p.out_f32) {
           float* dst = p.out_f32 + (size_t)row * p.ldc + n0 + c0;
-          if (f32_vec && n0 + c0 + 16 <= p.N) {
+          if (p.atomic_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.N) atomicAdd(dst + j, v[j]);
+          } else if (f32_vec && n0 + c0 + 16 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -394,6 +421,51 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __h
         overflow |= __hisinf(hi) || __hisnan(hi);
         dh[j] = hi;
         dh[plane + j] = lo;
+      }
+    }
+  }
+  if (overflow && range_flag) atomicOr(range_flag, 1);
+}
+
+// fp32 [M, C] rows (row pitch ld) -> hl planes of the TRANSPOSE, [2][C_alloc][ld_dst] with M contiguous: the operands of a
+// weight-gradient GEMM dW = X^T @ dY, whose contraction runs over the batch rows.  `scale` (a power of two) lifts small
+// gradients into the fp16 normal range; columns m in [M, ld_dst) are zero-filled so that the contraction padding is
+// exact whatever the buffer held before.  One 32 x 32 tile per CTA through shared memory.
+// as_bf16: the planes hold bf16 hi / lo (x = hi + lo to 16 significant bits, fp32 exponent range) -- per-sample gradients
+// span too many decades for fp16 (1 / s_x factors of the inverse transformer).
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, float scale, __half* __restrict__ dst,
+                       size_t plane, int ld_dst, int* range_flag, int as_bf16) {
+  __shared__ float tile[32][33];
+  griddep_launch();
+  griddep_wait();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int m = m0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (m < M && c < C) ? src[(size_t)m * ld + c] * scale : 0.f;
+  }
+  __syncthreads();
+  bool overflow = false;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, m = m0 + tx;
+    if (c < C && m < ld_dst) {
+      const float x = tile[tx][ty + i];
+      __half* d = dst + (size_t)c * ld_dst + m;
+      if (as_bf16) {
+        const __nv_bfloat16 bh = __float2bfloat16_rn(x);
+        const __nv_bfloat16 bl = __float2bfloat16_rn(x - __bfloat162float(bh));
+        overflow |= !(fabsf(x) <= 3.0e38f);
+        reinterpret_cast<__nv_bfloat16*>(d)[0] = bh;
+        reinterpret_cast<__nv_bfloat16*>(d)[plane] = bl;
+      } else {
+        __half hi, lo;
+        split_f16(x, hi, lo);
+        overflow |= __hisinf(hi) || __hisnan(hi);
+        d[0] = hi;
+        d[plane] = lo;
       }
     }
   }
@@ -552,7 +624,8 @@ inline cudaError_t launch_gemm_cfg(const CUtensorMap& tm_a, const CUtensorMap& t
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid(n_alloc / BN, (p.M + BM - 1) / BM);
+  const int nz = p.kb_per_z > 0 ? (p.num_k_blocks + p.kb_per_z - 1) / p.kb_per_z : 1;
+  dim3 grid(n_alloc / BN, (p.M + BM - 1) / BM, nz);
   return launch_k(linear_tc_kernel<BN, STAGES>, grid, dim3(num_threads(BN)), L::TOTAL, st, tm_a, tm_b, p);
 }
 
@@ -561,7 +634,7 @@ inline cudaError_t launch_gemm_cfg(const CUtensorMap& tm_a, const CUtensorMap& t
 // layer) use 4 stages.
 inline cudaError_t launch_gemm(int bn, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p,
                                int n_alloc, cudaStream_t st) {
-  const bool deep = p.num_k_blocks > 8;
+  const bool deep = (p.kb_per_z > 0 ? p.kb_per_z : p.num_k_blocks) > 8;
   if (bn == 32) return deep ? launch_gemm_cfg<32, 4>(tm_a, tm_b, p, n_alloc, st) : launch_gemm_cfg<32, 2>(tm_a, tm_b, p, n_alloc, st);
   return deep ? launch_gemm_cfg<64, 4>(tm_a, tm_b, p, n_alloc, st) : launch_gemm_cfg<64, 2>(tm_a, tm_b, p, n_alloc, st);
 }
