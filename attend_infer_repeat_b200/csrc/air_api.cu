@@ -161,6 +161,10 @@ struct air_handle {
   float bwd_lift = 1.0f;   // power of two >= 1 / inv_batch of the current backward pass
   __half *hl_xt = nullptr, *hl_yt = nullptr;
   size_t hl_xt_halves = 0, hl_yt_halves = 0;   // per plane
+  // tensor-core input gradients (dX = dY @ W^T): dY row-major planes, W as stored ([in][out]) planes per layer
+  __half *hl_dy = nullptr, *wnt_arena = nullptr;
+  size_t hl_dy_halves = 0;
+  std::map<int64_t, std::pair<size_t, int>> wnt_index;   // Layer::w_off -> (half offset of the hi plane, Npad)
   int* t_range_flag = nullptr;
   std::map<std::tuple<const void*, int, long long, int>, CUtensorMap> tmap_cache2;
   // instrumentation: kernel-launch counter and optional per-stage CUDA-event timing (air_profile_*)
@@ -804,6 +808,24 @@ void carve_train(air_handle* h, Carver& cv) {
     h->hl_xt = cv.take<__half>(2 * xt);
     h->hl_yt = cv.take<__half>(2 * yt);
     h->t_range_flag = cv.take<int>(1);
+    // input gradients: the widest dY (rows padded to the 128-row tile) and one [round_up(K,64)][round_up(N,64)] pair
+    // of planes per weight matrix
+    size_t dy = 0, wnt = 0;
+    h->wnt_index.clear();
+    auto visit2 = [&](const Layer& l, size_t rows) {
+      dy = std::max(dy, (size_t)round_up((int)rows, 128) * round_up(l.N, 64));
+      h->wnt_index[l.w_off] = std::make_pair(wnt, round_up(l.N, 64));
+      wnt += 2 * (size_t)round_up(l.K, 64) * round_up(l.N, 64);
+    };
+    for (const Layer& l : h->enc.layers) visit2(l, B);
+    for (const Mlp* m : {&h->where_mlp, &h->steps_mlp, &h->glenc, &h->dec})
+      for (const Layer& l : m->layers) visit2(l, TB);
+    visit2(h->what_lin, TB);
+    visit2(h->lstm_h, TB);
+    visit2(h->lstm_x, B);
+    h->hl_dy_halves = dy;
+    h->hl_dy = cv.take<__half>(2 * dy);
+    h->wnt_arena = cv.take<__half>(wnt);
   }
 }
 
@@ -891,9 +913,70 @@ int32_t layer_param_grads(air_handle* h, float* grad, const Layer& l, const floa
   }
   return AIR_OK;
 }
+// dX = dY @ W^T on the tensor-core split engine: dY [M, N] as row-major bf16 hi/lo planes (A operand, contraction over the
+// layer's N outputs), W [K, N] exactly as stored (its rows are the output columns of dX) from the per-step weight arena
+// prepared by prep_backward_weights; elu' mask, accumulation (atomicAdd) in the epilogue.
+int32_t layer_input_grad_tc(air_handle* h, const Layer& l, const float* dY, int ldy, float* dX, int ldx, int M,
+                            bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st) {
+  namespace tc = air::tc;
+  const int np = round_up(l.N, 64), MA = round_up(M, 128), KA = round_up(l.K, 64);
+  if ((size_t)MA * np > h->hl_dy_halves) return fail(AIR_ERR_ARG, "internal: dY does not fit the training workspace");
+  const auto it = h->wnt_index.find(l.w_off);
+  if (it == h->wnt_index.end()) return fail(AIR_ERR_ARG, "internal: weight not in the backward arena");
+  const size_t n4 = (size_t)M * (np / 4);
+  AIR_CUDA(air::launch_k(tc::split_rows_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dY, ldy, M, l.N,
+                         h->hl_dy, (size_t)MA * np, np, h->t_range_flag));
+  const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
+  int32_t rc = get_tmap2(h, h->hl_dy, np, 2LL * MA, tc::BM, &tm_a);
+  if (rc != AIR_OK) return rc;
+  if ((rc = get_tmap2(h, h->wnt_arena + it->second.first, np, 2LL * KA, 64, &tm_b)) != AIR_OK) return rc;
+  tc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out_f32 = dX;
+  p.ldc = ldx;
+  p.M = M;
+  p.N = l.K;
+  p.num_k_blocks = np / tc::BK;
+  p.a_lo_row = MA;
+  p.b_lo_row = KA;
+  p.act = air::ACT_NONE;
+  p.range_flag = h->t_range_flag;
+  p.out_scale = 1.0f;
+  p.atomic_out = accumulate ? 1 : 0;
+  p.ab_bf16 = 1;
+  p.mask_y = elu_x;
+  p.ld_mask = ld_elu;
+  AIR_CUDA(tc::launch_gemm(64, *tm_a, *tm_b, p, KA, st));
+  h->launches += 2;
+  return AIR_OK;
+}
+
+// all weight matrices, as stored, -> bf16 hi/lo planes with zero-padded columns (once per backward pass)
+int32_t prep_backward_weights(air_handle* h, const float* params, cudaStream_t st) {
+  auto one = [&](const Layer& l) -> int32_t {
+    const auto it = h->wnt_index.find(l.w_off);
+    if (it == h->wnt_index.end()) return fail(AIR_ERR_ARG, "internal: weight not in the backward arena");
+    const int np = it->second.second, KA = round_up(l.K, 64);
+    const size_t n4 = (size_t)l.K * (np / 4);
+    AIR_CUDA(air::launch_k(air::tc::split_rows_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
+                           params + l.w_off, l.N, l.K, l.N, h->wnt_arena + it->second.first, (size_t)KA * np, np,
+                           h->t_range_flag));
+    ++h->launches;
+    return AIR_OK;
+  };
+  int32_t rc;
+  for (const Mlp* m : {&h->enc, &h->where_mlp, &h->steps_mlp, &h->glenc, &h->dec})
+    for (size_t i = (m == &h->enc ? 1 : 0); i < m->layers.size(); ++i)   // the first encoder layer needs no dX
+      if ((rc = one(m->layers[i])) != AIR_OK) return rc;
+  for (const Layer* l : {&h->what_lin, &h->lstm_h, &h->lstm_x})
+    if ((rc = one(*l)) != AIR_OK) return rc;
+  return AIR_OK;
+}
+
 // dX = dY @ W^T (* elu'(X) when elu_x is the saved forward value of X)
 int32_t layer_input_grad(air_handle* h, const float* params, const Layer& l, const float* dY, int ldy, float* dX, int ldx,
                          int M, bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st) {
+  if (h->tc_bwd && M >= 64) return layer_input_grad_tc(h, l, dY, ldy, dX, ldx, M, accumulate, elu_x, ld_elu, st);
   AIR_CUDA(air::launch_gemm_simt(false, true, dY, ldy, params + l.w_off, l.N, dX, ldx, M, l.K, l.N, accumulate, elu_x,
                                  ld_elu, 1, st));
   ++h->launches;
@@ -939,6 +1022,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   const int thr = 256;
   int32_t rc;
   AIR_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)h->n_params, st));
+  if (h->tc_bwd && TB >= 64 && (rc = prep_backward_weights(h, params, st)) != AIR_OK) return rc;
 
   air::BwdArgs a;
   memset(&a, 0, sizeof(a));

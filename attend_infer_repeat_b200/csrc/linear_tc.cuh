@@ -472,6 +472,41 @@ split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, floa
   if (overflow && range_flag) atomicOr(range_flag, 1);
 }
 
+// fp32 [M, C] rows (row pitch ld) -> bf16 hi/lo planes [2][rows_alloc][ld_dst], row-major, columns [C, ld_dst) zero-filled:
+// the A operand (dY, contraction over the layer's outputs) and the B operand (W as stored, [in][out]) of the
+// input-gradient GEMM dX = dY @ W^T.
+__global__ void split_rows_bf16_kernel(const float* __restrict__ src, int ld, int M, int C, __half* __restrict__ dst,
+                                       size_t plane, int ld_dst, int* range_flag) {
+  griddep_launch();
+  griddep_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 destination columns
+  const int cq = ld_dst >> 2;
+  if (idx >= (size_t)M * cq) return;
+  const int row = (int)(idx / cq), c = (int)(idx % cq) * 4;
+  const float* sp = src + (size_t)row * ld + c;
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c + 3 < C && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(sp);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < C) f[j] = sp[j];
+  }
+  __align__(8) __nv_bfloat16 hi[4], lo[4];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __float2bfloat16_rn(f[j]);
+    lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+    bad |= !(fabsf(f[j]) <= 3.0e38f);
+  }
+  __half* d = dst + (size_t)row * ld_dst + c;
+  *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(d + plane) = *reinterpret_cast<const uint2*>(lo);
+  if (bad && range_flag) atomicOr(range_flag, 1);
+}
+
 // uint8 pixels (the reference's dataset format, data.py:35-107) -> float32 / 255 (load_data, data.py:116) written both
 // as fp32 rows (read by the glimpse-read and paint kernels) and, for the tensor-core engine, as the hl operand of the
 // first encoder layer.  One pass over the image batch.
