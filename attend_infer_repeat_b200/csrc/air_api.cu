@@ -299,7 +299,12 @@ int32_t run_mlp(air_handle* h, const float* params, const Mlp& mlp, const Buf& i
     Buf dst;
     if (last) {
       dst = out;
-    } else if (saves) {   // training mode (fp32 engine): every hidden activation is kept for the backward pass
+    } else if (saves) {   // training mode: every hidden activation is kept (fp32 rows) for the backward pass
+      if (h->use_tc) {
+        dst = to_ping ? h->ping : h->pong;   // + the hl planes the next tensor-core layer reads
+        to_ping = !to_ping;
+        dst.kpad = round_up(l.N, air::tc::BK);
+      }
       dst.f32 = (*saves)[i];
       dst.ld = l.N;
     } else {
@@ -309,7 +314,7 @@ int32_t run_mlp(air_handle* h, const float* params, const Mlp& mlp, const Buf& i
       dst.kpad = round_up(l.N, air::tc::BK);
     }
     const int act = (i < mlp.n_hidden) ? air::ACT_ELU : air::ACT_NONE;
-    const int32_t rc = dense(h, params, cur, 0, l, true, nullptr, 0, dst, last ? out_f32 : !h->use_tc,
+    const int32_t rc = dense(h, params, cur, 0, l, true, nullptr, 0, dst, last ? out_f32 : (!h->use_tc || saves != nullptr),
                              last ? out_hl : h->use_tc, M, act, st);
     if (rc != AIR_OK) return rc;
     cur = dst;
@@ -406,7 +411,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   const air::HlOut no_hl{nullptr, 0, 0, 0};
   int32_t rc;
   // training mode (air_train_enable, fp32 engine): every activation the backward pass needs is kept
-  const bool train = h->train && !tc && prior != nullptr && T_run == c.T && !h_in && !canvas_in;
+  const bool train = h->train && prior != nullptr && T_run == c.T && !h_in && !canvas_in;
+  // the fused chains / the cluster LSTM keep their hidden activations in TMEM / registers: training mode takes the
+  // layer-by-layer tensor-core path, whose epilogues write every activation as fp32 rows (kept) + hl planes (next operand)
+  const bool chain = tc && h->chain_ok && !train;
   h->fwd_saved = false;
 
   // 0. tensor-core engine: (re)build the fp16-split W^T arena from the current parameters and split the images
@@ -427,8 +435,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   }
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
-  const bool lstm_fused = tc && h->lstm_ok;
-  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused, tc && !lstm_fused, st,
+  const bool lstm_fused = tc && h->lstm_ok && !train;
+  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
                     train ? &h->sv_enc : nullptr)) != AIR_OK)
     return rc;
   mark(h, AIR_ST_LSTM, st);
@@ -498,7 +506,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     }
     AIR_CUDA(air::launch_k(air::lstm_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
                            (const float*)gates.f32, c_src, c_dst, h->hs.f32 + (size_t)t * B * nh, B, nh, c.forget_bias, hs_hl,
-                           (tc && h->chain_ok) ? h->hs.hlt_out() : no_hl, (size_t)t * B));
+                           chain ? h->hs.hlt_out() : no_hl, (size_t)t * B));
     ++h->launches;
   }
   if (o->final_h)
@@ -522,7 +530,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   Buf logit;
   logit.f32 = h->logit;
   logit.ld = 1;
-  if (tc && h->chain_ok) {
+  if (chain) {
     // both heads of every (t, canvas) row in ONE launch: hs -> where MLP -> m ; hs -> steps MLP -> logit
     air::chain::Params cp;
     memset(&cp, 0, sizeof(cp));
@@ -549,15 +557,16 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
 
   // 5. where sampling + glimpse read   (cell.py:129-135)
   AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(256), air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
-                         h->m, eps_where, img, o->where, o->where_loc, o->where_scale, tc ? nullptr : h->crop.f32,
-                         tc ? (h->chain_ok ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
+                         h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
+                         (tc && !train) ? nullptr : h->crop.f32,
+                         tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
                          c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
                          c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0));
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
   // 6. glimpse encoder -> what   (cell.py:153-156)   7. decoder   (cell.py:158)
-  if (tc && h->chain_ok) {
+  if (chain) {
     // crop -> glimpse Encoder -> what head (sample) -> Decoder -> glimpse, one launch, activations resident in TMEM
     air::chain::Params cp;
     memset(&cp, 0, sizeof(cp));
@@ -588,7 +597,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
       if (train) q.f32 = h->sv_q;
       q.ld = last.N;
       q.kpad = round_up(last.N, air::tc::BK);
-      if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc, tc, st, train ? &h->sv_glenc : nullptr)) != AIR_OK)
+      if ((rc = run_mlp(h, params, h->glenc, h->crop, TB, q, !tc || train, tc, st, train ? &h->sv_glenc : nullptr)) != AIR_OK)
         return rc;
       Buf r;
       r.f32 = h->r;
@@ -768,6 +777,10 @@ void carve_train(air_handle* h, Carver& cv) {
   hidden(h->sv_glenc, h->glenc, TB);
   hidden(h->sv_dec, h->dec, TB);
   h->sv_q = cv.take<float>(TB * h->what_lin.K);
+  if (h->use_tc) {   // the tensor-core engine keeps the crops as hl planes only; the backward pass wants fp32 rows too
+    h->crop.f32 = cv.take<float>(TB * h->G);
+    h->crop.ld = h->G;
+  }
   h->gates_all = cv.take<float>(TB * 4 * c.nh);
   h->c_all = cv.take<float>((TB + B) * c.nh);
   h->hprev = cv.take<float>(TB * c.nh);
@@ -1406,9 +1419,6 @@ int32_t air_check_range(air_handle* h, void* stream) {
 
 int32_t air_train_enable(air_handle* h, int32_t on) {
   if (!h) return fail(AIR_ERR_ARG, "air_train_enable: NULL handle");
-  if (on && h->use_tc)
-    return fail(AIR_ERR_ARG, "air_train_enable: the backward pass is built on the AIR_PREC_FP32 engine; create the "
-                             "handle with precision = AIR_PREC_FP32");
   if (on && !h->cfg.discrete_steps)
     return fail(AIR_ERR_ARG, "air_train_enable: the backward pass covers discrete_steps = 1 (the script configuration)");
   if (on && !h->tws) {

@@ -189,8 +189,8 @@ class AIRModel:
         The returned ``train_op(obs=None, nums=None, noise=None)`` is the sess.run(train_step) of the reference: forward +
         ELBO on the batch, ``opt.compute_gradients(opt_loss)`` (air_backward), one all-reduce of the flat gradient buffer
         when torch.distributed is initialised (batch shards), and the centered-RMSProp update of the flat
-        parameter buffer (air_rmsprop_step, TF semantics).  It runs on the AIR_PREC_FP32 engine, which keeps the
-        activations the backward pass needs.  A baseline module (BaselineMLP) is trained by its own RMSProp at 10x the
+        parameter buffer (air_rmsprop_step, TF semantics).  The engine is switched to training mode, in which every
+        activation the backward pass needs is kept.  A baseline module (BaselineMLP) is trained by its own RMSProp at 10x the
         learning rate on .5 * mean((stop_gradient(iw) - baseline)^2) (model.py:253-259,362-367).  Not built: NVIL moment
         normalisation (decay_rate)."""
         if decay_rate is not None:
@@ -217,9 +217,9 @@ class AIRModel:
         self._train_cfg = dict(what_prior=what_prior, where_scale_prior=where_scale_prior,
                                where_shift_prior=where_shift_prior, num_steps_prior=num_steps_prior,
                                use_reinforce=use_reinforce)
-        # the training engine: fp32 arithmetic, activations kept; it replaces the inference engine for this model
-        self.engine = self.cell.engine(self.batch_size, self.max_steps, precision=_lib.AIR_PREC_FP32,
-                                       materialise_canvas=True, materialise_viz=self._materialise_canvas)
+        # the training engine (same arithmetic mode as the model, activations kept) replaces the inference engine
+        self.engine = self.cell.engine(self.batch_size, self.max_steps, materialise_canvas=True,
+                                       materialise_viz=self._materialise_canvas)
         self.engine.train_enable(True)
         n = self.engine.n_params
         dev = self.obs.device

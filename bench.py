@@ -331,7 +331,7 @@ def run_native(args, rank, local_rank, world):
     # one all-reduce of the flat gradient buffer (N > 1), centered RMSProp -- AIR_PREC_FP32 engine
     train = None
     if not args.no_train:
-        teng = air.Engine(air.CellConfig(precision=air.AIR_PREC_FP32), B, T, device=dev)
+        teng = air.Engine(air.CellConfig(precision=prec), B, T, device=dev)
         teng.train_enable(True)
         tparams = params.clone()
         n = tparams.numel()
@@ -362,7 +362,8 @@ def run_native(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tms = float(t.item())
         train = {"value": world * B * T * n_train / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms / n_train,
-                 "steps": n_train, "global_batch": world * B, "engine": "AIR_PREC_FP32 (SIMT fp32 GEMMs; tensor-core backward pending)",
+                 "steps": n_train, "global_batch": world * B, "engine": ("tcgen05 split engine: fp16 hi/lo forward layers, bf16 hi/lo gradient GEMMs" if prec == air.AIR_PREC_TC_SPLIT
+                            else "AIR_PREC_FP32 forward (SIMT), tcgen05 bf16 hi/lo gradient GEMMs"),
                  "gpu_launches_per_step": (teng.launch_count - l0) / n_train + 1,
                  "allreduce_bytes_per_step": n * 4 if world > 1 else 0,
                  "what": "forward+ELBO (activations kept) + backward + gradient all-reduce + centered RMSProp",

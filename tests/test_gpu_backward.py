@@ -27,10 +27,11 @@ def oracle_grads(ocfg, pc, params, img, noise, global_step, baseline=None, l2_we
     return res, grads
 
 
-def cuda_grads(ocfg, pc, params, img, noise, global_step, baseline=None, l2_weight=0.0, inv_batch=0.0):
+def cuda_grads(ocfg, pc, params, img, noise, global_step, baseline=None, l2_weight=0.0, inv_batch=0.0,
+               precision=air.AIR_PREC_FP32):
     B = img.shape[0]
     dev = "cuda"
-    eng = air.Engine(U.cell_cfg(ocfg, air.AIR_PREC_FP32), B, ocfg.T, device=dev)
+    eng = air.Engine(U.cell_cfg(ocfg, precision), B, ocfg.T, device=dev)
     eng.train_enable(True)
     flat = O.flatten_params(ocfg, params).to(dev)
     ew, ea, u = (n.to(dev).contiguous() for n in noise)
@@ -103,10 +104,12 @@ def test_backward_matches_oracle_autograd(shape, case):
     print(f"{shape}/{case}: worst {worst[1]} ({worst[0]:.2f} of tolerance)")
 
 
-@pytest.mark.parametrize("tc_bwd", [True, False])
-def test_backward_batch64_tensor_core_weight_gradients(tc_bwd, monkeypatch):
-    """At >= 64 batch rows the weight gradients dW = X^T dY run on the tcgen05 split engine (transposed hl operands,
-    split-K); AIR_NO_TC_BWD=1 keeps them on the fp32 SIMT GEMMs.  Both must meet the same bar."""
+@pytest.mark.parametrize("tc_bwd,precision", [(True, air.AIR_PREC_FP32), (False, air.AIR_PREC_FP32),
+                                              (True, air.AIR_PREC_TC_SPLIT)])
+def test_backward_batch64_tensor_core_weight_gradients(tc_bwd, precision, monkeypatch):
+    """At >= 64 batch rows the gradient GEMMs (dW = X^T dY, dX = dY W^T) run on the tcgen05 split engine (bf16 hi/lo
+    planes, split-K); AIR_NO_TC_BWD=1 keeps them on the fp32 SIMT GEMMs; with an AIR_PREC_TC_SPLIT handle the training
+    forward runs on the tensor cores as well.  All three must meet the same bar."""
     if not tc_bwd:
         monkeypatch.setenv("AIR_NO_TC_BWD", "1")
     ocfg = U.oracle_cfg(**U.SCRIPT)
@@ -114,10 +117,10 @@ def test_backward_batch64_tensor_core_weight_gradients(tc_bwd, monkeypatch):
     params, img, nums, noise = U.make_problem(ocfg, 64, seed=13)
     noise, n_fixed = well_conditioned(ocfg, pc, params, img, noise)
     res_o, g_ref = oracle_grads(ocfg, pc, params, img, noise, 20000, dtype=torch.float64)
-    res_c, g = cuda_grads(ocfg, pc, params, img, noise, 20000)
+    res_c, g = cuda_grads(ocfg, pc, params, img, noise, 20000, precision=precision)
     assert torch.equal(res_c["presence"].reshape(-1), res_o["outs"]["presence"].detach().float().reshape(-1))
     worst = compare(ocfg, g, g_ref)
-    print(f"B=64 tc_bwd={tc_bwd} ({n_fixed} ill-conditioned draws replaced): worst {worst[1]} ({worst[0]:.2f} of tolerance)")
+    print(f"B=64 tc_bwd={tc_bwd} precision={precision} ({n_fixed} ill-conditioned draws replaced): worst {worst[1]} ({worst[0]:.2f} of tolerance)")
 
 
 def test_backward_with_baseline_and_l2():
@@ -163,7 +166,20 @@ def test_sharded_gradients_sum_to_the_whole_batch_gradient():
     compare(ocfg, total, g_ref)
 
 
-def test_backward_requires_training_mode_and_fp32_engine():
+def test_backward_small_batch_on_the_tensor_core_engine():
+    """AIR_PREC_TC_SPLIT handle, batch below the tensor-core gradient threshold: tcgen05 forward with kept activations,
+    SIMT gradient GEMMs."""
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    pc = O.PriorConfig()
+    params, img, nums, noise = U.make_problem(ocfg, 16, seed=5)
+    res_o, g_ref = oracle_grads(ocfg, pc, params, img, noise, 20000)
+    res_c, g = cuda_grads(ocfg, pc, params, img, noise, 20000, precision=air.AIR_PREC_TC_SPLIT)
+    assert torch.equal(res_c["presence"].reshape(-1), res_o["outs"]["presence"].detach().reshape(-1))
+    U.assert_close(res_c["loss_per_sample"], res_o["loss_per_sample"].detach(), atol=0, rtol=1e-4, name="loss_per_sample")
+    compare(ocfg, g, g_ref)
+
+
+def test_backward_requires_training_mode_and_discrete_steps():
     ocfg = U.oracle_cfg(**U.TINY)
     eng = air.Engine(U.cell_cfg(ocfg, air.AIR_PREC_FP32), 4, ocfg.T, device="cuda")
     flat = torch.zeros(eng.n_params, device="cuda")
@@ -171,8 +187,9 @@ def test_backward_requires_training_mode_and_fp32_engine():
     with pytest.raises(air.AirError):
         eng.backward(flat, z(4, 3, 3), z(3, 4, 4), z(3, 4, 10), U.prior_struct(O.PriorConfig(), 0))
     eng.close()
-    eng = air.Engine(U.cell_cfg(U.oracle_cfg(**U.SCRIPT), air.AIR_PREC_TC_SPLIT), 4, 3, device="cuda")
-    with pytest.raises(air.AirError):
+    ocfg = U.oracle_cfg(**U.SCRIPT, discrete_steps=False)
+    eng = air.Engine(U.cell_cfg(ocfg), 4, 3, device="cuda")
+    with pytest.raises(air.AirError):       # the backward pass covers sampled (discrete) presence only
         eng.train_enable(True)
     eng.close()
 
