@@ -165,6 +165,10 @@ struct air_handle {
   __half *hl_dy = nullptr, *wnt_arena = nullptr;
   size_t hl_dy_halves = 0;
   std::map<int64_t, std::pair<size_t, int>> wnt_index;   // Layer::w_off -> (half offset of the hi plane, Npad)
+  air::tc::RowsEntry* wnt_table = nullptr;               // device copy of the per-matrix table (prep_weights_rows_kernel)
+  int wnt_entries = 0, wnt_blocks = 0;
+  const float* dy_ready = nullptr;                       // dY whose row-major planes currently sit in hl_dy ...
+  int dy_ready_m = 0, dy_ready_n = 0;                    // ... with these dimensions
   int* t_range_flag = nullptr;
   std::map<std::tuple<const void*, int, long long, int>, CUtensorMap> tmap_cache2;
   // instrumentation: kernel-launch counter and optional per-stage CUDA-event timing (air_profile_*)
@@ -839,6 +843,7 @@ void carve_train(air_handle* h, Carver& cv) {
     h->hl_dy_halves = dy;
     h->hl_dy = cv.take<__half>(2 * dy);
     h->wnt_arena = cv.take<__half>(wnt);
+    h->wnt_table = cv.take<air::tc::RowsEntry>(h->wnt_index.size());
   }
 }
 
@@ -870,15 +875,23 @@ int32_t get_tmap2(air_handle* h, const __half* base, int kpad, long long rows_to
 // range -- the 1 / s_x factors of the inverse transformer -- which fp16 planes cannot hold), three tcgen05.mma per K slice
 // as in the forward, the contraction split over gridDim.z with fp32 atomics into the zeroed gradient buffer.
 int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
-                             int M, float lift, cudaStream_t st) {
+                             int M, bool dx_follows, cudaStream_t st) {
   namespace tc = air::tc;
   const int mp = round_up(M, 64), KA = round_up(l.K, 128), NA = round_up(l.N, 64);
-  if ((size_t)KA * mp > h->hl_xt_halves || (size_t)NA * mp > h->hl_yt_halves)
+  const int np = NA, MA = round_up(M, 128);
+  if ((size_t)KA * mp > h->hl_xt_halves || (size_t)NA * mp > h->hl_yt_halves || (size_t)MA * np > h->hl_dy_halves)
     return fail(AIR_ERR_ARG, "internal: transposed operand does not fit the training workspace");
   AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.K + 31) / 32, (mp + 31) / 32), dim3(256), 0, st, X, ldx, M, l.K,
-                         1.0f, h->hl_xt, (size_t)KA * mp, mp, h->t_range_flag, 1));
-  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.N + 31) / 32, (mp + 31) / 32), dim3(256), 0, st, dY, ldy, M, l.N,
-                         lift, h->hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1));
+                         1.0f, h->hl_xt, (size_t)KA * mp, mp, h->t_range_flag, 1, (__half*)nullptr, (size_t)0, 0,
+                         (float*)nullptr));
+  // one read of dY: transposed planes (this GEMM), the bias gradient, and the row-major planes of the dX GEMM that follows
+  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((dx_follows ? np : l.N + 31) / 32, (mp + 31) / 32), dim3(256), 0,
+                         st, dY, ldy, M, l.N, 1.0f, h->hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1,
+                         dx_follows ? h->hl_dy : (__half*)nullptr, (size_t)MA * np, np,
+                         l.b_off >= 0 ? grad + l.b_off : (float*)nullptr));
+  h->dy_ready = dx_follows ? dY : nullptr;
+  h->dy_ready_m = M;
+  h->dy_ready_n = l.N;
   const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
   int32_t rc = get_tmap2(h, h->hl_xt, mp, 2LL * KA, tc::BM, &tm_a);
   if (rc != AIR_OK) return rc;
@@ -894,7 +907,7 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
   p.b_lo_row = NA;
   p.act = air::ACT_NONE;
   p.range_flag = h->t_range_flag;
-  p.out_scale = 1.0f / lift;
+  p.out_scale = 1.0f;
   p.atomic_out = 1;
   p.ab_bf16 = 1;
   const int tiles = (KA / tc::BM) * (NA / 64);
@@ -907,16 +920,8 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
 }
 
 int32_t layer_param_grads(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
-                          int M, cudaStream_t st) {
-  if (h->tc_bwd && M >= 64) {
-    const int32_t rc = layer_weight_grad_tc(h, grad, l, X, ldx, dY, ldy, M, 1.0f, st);
-    if (rc != AIR_OK) return rc;
-    if (l.b_off >= 0) {
-      AIR_CUDA(air::launch_colsum(dY, ldy, grad + l.b_off, M, l.N, st));
-      ++h->launches;
-    }
-    return AIR_OK;
-  }
+                          int M, cudaStream_t st, bool dx_follows = false) {
+  if (h->tc_bwd && M >= 64) return layer_weight_grad_tc(h, grad, l, X, ldx, dY, ldy, M, dx_follows, st);
   AIR_CUDA(air::launch_gemm_simt(true, false, X, ldx, dY, ldy, grad + l.w_off, l.N, l.K, l.N, M, true, nullptr, 0,
                                  pick_split(l.K, l.N, M), st));
   ++h->launches;
@@ -936,9 +941,13 @@ int32_t layer_input_grad_tc(air_handle* h, const Layer& l, const float* dY, int 
   if ((size_t)MA * np > h->hl_dy_halves) return fail(AIR_ERR_ARG, "internal: dY does not fit the training workspace");
   const auto it = h->wnt_index.find(l.w_off);
   if (it == h->wnt_index.end()) return fail(AIR_ERR_ARG, "internal: weight not in the backward arena");
-  const size_t n4 = (size_t)M * (np / 4);
-  AIR_CUDA(air::launch_k(tc::split_rows_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dY, ldy, M, l.N,
-                         h->hl_dy, (size_t)MA * np, np, h->t_range_flag));
+  if (h->dy_ready != dY || h->dy_ready_m != M || h->dy_ready_n != l.N) {   // not left behind by layer_weight_grad_tc
+    const size_t n4 = (size_t)M * (np / 4);
+    AIR_CUDA(air::launch_k(tc::split_rows_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dY, ldy, M, l.N,
+                           h->hl_dy, (size_t)MA * np, np, h->t_range_flag));
+    ++h->launches;
+  }
+  h->dy_ready = nullptr;
   const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
   int32_t rc = get_tmap2(h, h->hl_dy, np, 2LL * MA, tc::BM, &tm_a);
   if (rc != AIR_OK) return rc;
@@ -960,29 +969,40 @@ int32_t layer_input_grad_tc(air_handle* h, const Layer& l, const float* dY, int 
   p.mask_y = elu_x;
   p.ld_mask = ld_elu;
   AIR_CUDA(tc::launch_gemm(64, *tm_a, *tm_b, p, KA, st));
-  h->launches += 2;
+  ++h->launches;
   return AIR_OK;
 }
 
 // all weight matrices, as stored, -> bf16 hi/lo planes with zero-padded columns (once per backward pass)
 int32_t prep_backward_weights(air_handle* h, const float* params, cudaStream_t st) {
-  auto one = [&](const Layer& l) -> int32_t {
+  AIR_CUDA(air::launch_k(air::tc::prep_weights_rows_kernel, dim3(h->wnt_blocks), dim3(256), 0, st, params, h->wnt_arena,
+                         (const air::tc::RowsEntry*)h->wnt_table, h->wnt_entries));
+  ++h->launches;
+  return AIR_OK;
+}
+// host table of prep_weights_rows_kernel (uploaded once by air_train_enable)
+int32_t upload_backward_weight_table(air_handle* h) {
+  std::vector<air::tc::RowsEntry> table;
+  int blocks = 0;
+  auto one = [&](const Layer& l) {
     const auto it = h->wnt_index.find(l.w_off);
-    if (it == h->wnt_index.end()) return fail(AIR_ERR_ARG, "internal: weight not in the backward arena");
-    const int np = it->second.second, KA = round_up(l.K, 64);
-    const size_t n4 = (size_t)l.K * (np / 4);
-    AIR_CUDA(air::launch_k(air::tc::split_rows_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
-                           params + l.w_off, l.N, l.K, l.N, h->wnt_arena + it->second.first, (size_t)KA * np, np,
-                           h->t_range_flag));
-    ++h->launches;
-    return AIR_OK;
+    air::tc::RowsEntry e;
+    e.src_off = l.w_off;
+    e.dst_off = (int64_t)it->second.first;
+    e.np = it->second.second;
+    e.plane = (int64_t)round_up(l.K, 64) * e.np;
+    e.K = l.K;
+    e.N = l.N;
+    e.block_begin = blocks;
+    blocks += (int)(((size_t)l.K * (e.np / 4) + 255) / 256);
+    table.push_back(e);
   };
-  int32_t rc;
   for (const Mlp* m : {&h->enc, &h->where_mlp, &h->steps_mlp, &h->glenc, &h->dec})
-    for (size_t i = (m == &h->enc ? 1 : 0); i < m->layers.size(); ++i)   // the first encoder layer needs no dX
-      if ((rc = one(m->layers[i])) != AIR_OK) return rc;
-  for (const Layer* l : {&h->what_lin, &h->lstm_h, &h->lstm_x})
-    if ((rc = one(*l)) != AIR_OK) return rc;
+    for (size_t i = (m == &h->enc ? 1 : 0); i < m->layers.size(); ++i) one(m->layers[i]);   // enc layer 0 needs no dX
+  for (const Layer* l : {&h->what_lin, &h->lstm_h, &h->lstm_x}) one(*l);
+  h->wnt_entries = (int)table.size();
+  h->wnt_blocks = blocks;
+  AIR_CUDA(cudaMemcpy(h->wnt_table, table.data(), sizeof(air::tc::RowsEntry) * table.size(), cudaMemcpyHostToDevice));
   return AIR_OK;
 }
 
@@ -1010,7 +1030,7 @@ int32_t mlp_backward(air_handle* h, const float* params, float* grad, const Mlp&
     const Layer& l = mlp.layers[i];
     const float* X = i == 0 ? x0 : saves[i - 1];
     const int ldx = i == 0 ? ld0 : mlp.layers[i - 1].N;
-    int32_t rc = layer_param_grads(h, grad, l, X, ldx, cur, ld_cur, M, st);
+    int32_t rc = layer_param_grads(h, grad, l, X, ldx, cur, ld_cur, M, st, i > 0 || dx0 != nullptr);
     if (rc != AIR_OK) return rc;
     if (i > 0) {
       float* dst = (cur == h->g_a) ? h->g_b : h->g_a;
@@ -1097,7 +1117,8 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
     ++h->launches;
   }
   // 4. what head (linear) and glimpse encoder -> d crop                           cell.py:153, modules.py:20
-  if ((rc = layer_param_grads(h, grad, h->what_lin, h->sv_q, h->what_lin.K, h->g_r, 2 * na, TB, st)) != AIR_OK) return rc;
+  if ((rc = layer_param_grads(h, grad, h->what_lin, h->sv_q, h->what_lin.K, h->g_r, 2 * na, TB, st, true)) != AIR_OK)
+    return rc;
   if ((rc = layer_input_grad(h, params, h->what_lin, h->g_r, 2 * na, h->g_a, h->what_lin.K, TB, false, h->sv_q,
                              h->what_lin.K, st)) != AIR_OK)
     return rc;
@@ -1144,7 +1165,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
     ++h->launches;
     Layer wx = h->lstm_x;
     wx.b_off = -1;
-    if ((rc = layer_param_grads(h, grad, wx, h->e.f32, h->n_enc, h->g_gx, 4 * nh, B, st)) != AIR_OK) return rc;
+    if ((rc = layer_param_grads(h, grad, wx, h->e.f32, h->n_enc, h->g_gx, 4 * nh, B, st, true)) != AIR_OK) return rc;
     // 9. input encoder (its last layer is an ELU layer: mask with the saved output e)   cell.py:125
     if ((rc = layer_input_grad(h, params, wx, h->g_gx, 4 * nh, h->g_e, h->n_enc, B, false, h->e.f32, h->n_enc, st)) !=
         AIR_OK)
@@ -1431,6 +1452,10 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
     Carver real(h->tws);
     carve_train(h, real);
     if (h->t_range_flag) AIR_CUDA(cudaMemset(h->t_range_flag, 0, sizeof(int)));
+    if (h->tc_bwd) {
+      const int32_t rc = upload_backward_weight_table(h);
+      if (rc != AIR_OK) return rc;
+    }
     const size_t smem = air::paint_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
     const size_t smem_r = air::read_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
     if (smem > 200 * 1024 || smem_r > 200 * 1024)

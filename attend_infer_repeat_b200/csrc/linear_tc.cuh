@@ -435,7 +435,11 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __h
 // span too many decades for fp16 (1 / s_x factors of the inverse transformer).
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, float scale, __half* __restrict__ dst,
-                       size_t plane, int ld_dst, int* range_flag, int as_bf16) {
+                       size_t plane, int ld_dst, int* range_flag, int as_bf16, __half* __restrict__ rm, size_t plane_rm,
+                       int ld_rm, float* __restrict__ colsum) {
+  // optional by-products of the same read (gradient tensors dY): `rm` = the row-major bf16 planes [2][..][ld_rm] with
+  // columns [C, ld_rm) zero-filled (A operand of dX = dY @ W^T; the grid must then cover ld_rm columns), `colsum` += the
+  // column sums (bias gradient, fp32 atomics)
   __shared__ float tile[32][33];
   griddep_launch();
   griddep_wait();
@@ -444,9 +448,23 @@ split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, floa
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int m = m0 + ty + i, c = c0 + tx;
-    tile[ty + i][tx] = (m < M && c < C) ? src[(size_t)m * ld + c] * scale : 0.f;
+    const float x = (m < M && c < C) ? src[(size_t)m * ld + c] * scale : 0.f;
+    tile[ty + i][tx] = x;
+    if (rm && m < M && c < ld_rm) {
+      const __nv_bfloat16 bh = __float2bfloat16_rn(x);
+      const __nv_bfloat16 bl = __float2bfloat16_rn(x - __bfloat162float(bh));
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(rm) + (size_t)m * ld_rm + c;
+      d[0] = bh;
+      d[plane_rm] = bl;
+    }
   }
   __syncthreads();
+  if (colsum && ty == 0 && c0 + tx < C) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += tile[i][tx];
+    atomicAdd(colsum + c0 + tx, sum);
+  }
   bool overflow = false;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
@@ -470,6 +488,40 @@ split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, floa
     }
   }
   if (overflow && range_flag) atomicOr(range_flag, 1);
+}
+
+// every weight matrix of the model, as stored ([in][out] row-major), -> bf16 hi/lo planes [2][round_up(in,64)][np] with
+// columns [N, np) zero-filled, one launch: the B operands of the input-gradient GEMMs.
+struct RowsEntry {
+  int64_t src_off;   // float offset into params
+  int64_t dst_off;   // half offset of the hi plane in the arena
+  int64_t plane;     // halves between the hi and the lo plane
+  int K, N, np;
+  int block_begin;   // first CTA of this matrix
+};
+__global__ void __launch_bounds__(256)
+prep_weights_rows_kernel(const float* __restrict__ params, __half* __restrict__ arena, const RowsEntry* __restrict__ table,
+                         int n_entries) {
+  griddep_launch();
+  griddep_wait();
+  int e = 0;
+  while (e + 1 < n_entries && (int)blockIdx.x >= table[e + 1].block_begin) ++e;
+  const RowsEntry t = table[e];
+  const size_t idx = (size_t)(blockIdx.x - t.block_begin) * blockDim.x + threadIdx.x;   // 4 destination columns each
+  const int cq = t.np >> 2;
+  if (idx >= (size_t)t.K * cq) return;
+  const int row = (int)(idx / cq), c = (int)(idx % cq) * 4;
+  const float* sp = params + t.src_off + (size_t)row * t.N + c;
+  __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float f = (c + j < t.N) ? sp[j] : 0.f;
+    hi[j] = __float2bfloat16_rn(f);
+    lo[j] = __float2bfloat16_rn(f - __bfloat162float(hi[j]));
+  }
+  __half* d = arena + t.dst_off + (size_t)row * t.np + c;
+  *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(d + t.plane) = *reinterpret_cast<const uint2*>(lo);
 }
 
 // fp32 [M, C] rows (row pitch ld) -> bf16 hi/lo planes [2][rows_alloc][ld_dst], row-major, columns [C, ld_dst) zero-filled:

@@ -1,4 +1,5 @@
 """One B=4096 training step (forward with saved activations + backward + RMSProp) for ncu launch lists / profiles."""
+import os
 import sys
 import torch
 import attend_infer_repeat_b200 as air
@@ -8,7 +9,7 @@ from attend_infer_repeat_b200.data import synthetic_multi_mnist_u8
 B, T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 3
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
-cfg = air.CellConfig(precision=air.AIR_PREC_FP32)
+cfg = air.CellConfig(precision=air.AIR_PREC_TC_SPLIT if os.environ.get("AIR_PROBE_FP32") is None else air.AIR_PREC_FP32)
 eng = air.Engine(cfg, B, T, device=dev)
 eng.train_enable(True)
 params, _ = _init_flat(air.param_spec(cfg), dev, seed=0)
