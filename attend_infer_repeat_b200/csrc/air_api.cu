@@ -881,11 +881,11 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
   const int np = NA, MA = round_up(M, 128);
   if ((size_t)KA * mp > h->hl_xt_halves || (size_t)NA * mp > h->hl_yt_halves || (size_t)MA * np > h->hl_dy_halves)
     return fail(AIR_ERR_ARG, "internal: transposed operand does not fit the training workspace");
-  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.K + 31) / 32, (mp + 31) / 32), dim3(256), 0, st, X, ldx, M, l.K,
+  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.K + 31) / 32, (mp + tc::ST_M - 1) / tc::ST_M), dim3(256), 0, st, X, ldx, M, l.K,
                          1.0f, h->hl_xt, (size_t)KA * mp, mp, h->t_range_flag, 1, (__half*)nullptr, (size_t)0, 0,
                          (float*)nullptr));
   // one read of dY: transposed planes (this GEMM), the bias gradient, and the row-major planes of the dX GEMM that follows
-  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((dx_follows ? np : l.N + 31) / 32, (mp + 31) / 32), dim3(256), 0,
+  AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((dx_follows ? np : l.N + 31) / 32, (mp + tc::ST_M - 1) / tc::ST_M), dim3(256), 0,
                          st, dY, ldy, M, l.N, 1.0f, h->hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1,
                          dx_follows ? h->hl_dy : (__half*)nullptr, (size_t)MA * np, np,
                          l.b_off >= 0 ? grad + l.b_off : (float*)nullptr));
@@ -911,8 +911,9 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
   p.atomic_out = 1;
   p.ab_bf16 = 1;
   const int tiles = (KA / tc::BM) * (NA / 64);
+  // enough slices to fill the machine, but at least 8 K blocks per slice: a slice ends in 128 x 64 fp32 atomics
   int split = (2 * 148 + tiles - 1) / tiles;
-  split = std::max(1, std::min(split, p.num_k_blocks));
+  split = std::max(1, std::min(split, p.num_k_blocks / 8));
   p.kb_per_z = (p.num_k_blocks + split - 1) / split;
   AIR_CUDA(tc::launch_gemm(64, *tm_a, *tm_b, p, NA, st));
   h->launches += 3;

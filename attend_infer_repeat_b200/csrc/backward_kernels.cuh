@@ -148,33 +148,52 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   float acc[T][4];   // per step: sum gx * (xg - S_w), sum gx, sum gy * (yg - S_h), sum gy
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    const int r = p / W, c = p - r * W;
-    const float dC = coef * (a.img[(size_t)b * P + p] - a.canvas_final[(size_t)b * P + p]);
+  // A thread owns a fixed canvas column and walks down the rows (same mapping as the forward paint kernel): whether the
+  // column lies inside glimpse t's footprint is loop-invariant, and a pixel no present glimpse covers costs no global load.
+  const int NT = blockDim.x;
+  const int TPRB = W < NT ? W : NT, RPP = NT / TPRB;
+  const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
+  const float* obs = a.img + (size_t)b * P;
+  const float* mu = a.canvas_final + (size_t)b * P;
+  if (rslot < RPP) {
+    for (int c = cslot; c < W; c += TPRB) {
+      uint32_t colmask = 0;
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const float pres = s_pres[t];
-      if (pres == 0.f) continue;
-      const BTap bx = s_tx[t * W + c], by = s_ty[t * H + r];
-      if (!(btap_inside(bx) && btap_inside(by))) continue;
-      const float gv = pres * dC;
-      const float dx = bx.d, dy = by.d;
-      const float* D = s_gl + t * G;
-      float* dD = s_dgl + t * G;
-      const Quad q = load_quad(D, bx, by);
-      const int xc = bx.i_c_fl & 0xffffff, yc = by.i_c_fl & 0xffffff;
-      const int xf_ok = (bx.i_c_fl >> 24) & 1, xc_ok = (bx.i_c_fl >> 25) & 1;
-      const int yf_ok = (by.i_c_fl >> 24) & 1, yc_ok = (by.i_c_fl >> 25) & 1;
-      if (xf_ok & yf_ok) atomicAdd(dD + by.i_f + bx.i_f, gv * dx * dy);
-      if (xc_ok & yc_ok) atomicAdd(dD + yc + xc, gv * (1.0f - dx) * (1.0f - dy));
-      if (xf_ok & yc_ok) atomicAdd(dD + yc + bx.i_f, gv * dx * (1.0f - dy));
-      if (xc_ok & yf_ok) atomicAdd(dD + by.i_f + xc, gv * (1.0f - dx) * dy);
-      const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
-      const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
-      acc[t][0] = fmaf(gx, bx.aux - S_w, acc[t][0]);
-      acc[t][1] += gx;
-      acc[t][2] = fmaf(gy, by.aux - S_h, acc[t][2]);
-      acc[t][3] += gy;
+      for (int t = 0; t < T; ++t)
+        if (s_pres[t] != 0.f && btap_inside(s_tx[t * W + c])) colmask |= 1u << t;
+      if (!colmask) continue;
+      for (int r = rslot; r < H; r += RPP) {
+        uint32_t act = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          if (((colmask >> t) & 1u) && btap_inside(s_ty[t * H + r])) act |= 1u << t;
+        if (!act) continue;
+        const int p = r * W + c;
+        const float dC = coef * (obs[p] - mu[p]);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          if (!((act >> t) & 1u)) continue;
+          const BTap bx = s_tx[t * W + c], by = s_ty[t * H + r];
+          const float gv = s_pres[t] * dC;
+          const float dx = bx.d, dy = by.d;
+          const float* D = s_gl + t * G;
+          float* dD = s_dgl + t * G;
+          const Quad q = load_quad(D, bx, by);
+          const int xc = bx.i_c_fl & 0xffffff, yc = by.i_c_fl & 0xffffff;
+          const int xf_ok = (bx.i_c_fl >> 24) & 1, xc_ok = (bx.i_c_fl >> 25) & 1;
+          const int yf_ok = (by.i_c_fl >> 24) & 1, yc_ok = (by.i_c_fl >> 25) & 1;
+          if (xf_ok & yf_ok) atomicAdd(dD + by.i_f + bx.i_f, gv * dx * dy);
+          if (xc_ok & yc_ok) atomicAdd(dD + yc + xc, gv * (1.0f - dx) * (1.0f - dy));
+          if (xf_ok & yc_ok) atomicAdd(dD + yc + bx.i_f, gv * dx * (1.0f - dy));
+          if (xc_ok & yf_ok) atomicAdd(dD + by.i_f + xc, gv * (1.0f - dx) * dy);
+          const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
+          const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
+          acc[t][0] = fmaf(gx, bx.aux - S_w, acc[t][0]);
+          acc[t][1] += gx;
+          acc[t][2] = fmaf(gy, by.aux - S_h, acc[t][2]);
+          acc[t][3] += gy;
+        }
+      }
     }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

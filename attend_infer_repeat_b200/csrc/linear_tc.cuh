@@ -433,6 +433,7 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __h
 // exact whatever the buffer held before.  One 32 x 32 tile per CTA through shared memory.
 // as_bf16: the planes hold bf16 hi / lo (x = hi + lo to 16 significant bits, fp32 exponent range) -- per-sample gradients
 // span too many decades for fp16 (1 / s_x factors of the inverse transformer).
+constexpr int ST_M = 32;    // batch rows per CTA of split_transpose_kernel
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, float scale, __half* __restrict__ dst,
                        size_t plane, int ld_dst, int* range_flag, int as_bf16, __half* __restrict__ rm, size_t plane_rm,
