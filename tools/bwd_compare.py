@@ -16,24 +16,27 @@ img = (u8[torch.randint(0, 256, (B,), generator=torch.Generator().manual_seed(0)
 g = torch.Generator(device=dev).manual_seed(0)
 ew, ea, u = torch.randn(T, B, 4, device=dev, generator=g), torch.randn(T, B, 50, device=dev, generator=g), torch.rand(T, B, 1, device=dev, generator=g)
 grads = {}
-for mode in ("simt", "tc"):
+losses = {}
+for mode in ("simt", "tc", "tc_fwd"):
     if mode == "simt":
         os.environ["AIR_NO_TC_BWD"] = "1"
     else:
         os.environ.pop("AIR_NO_TC_BWD", None)
-    eng = air.Engine(cfg, B, T, device=dev)
+    eng = air.Engine(air.CellConfig(precision=air.AIR_PREC_TC_SPLIT) if mode == "tc_fwd" else cfg, B, T, device=dev)
     eng.train_enable(True)
     eng.forward(params, img, ew, ea, u, prior)
     grads[mode] = eng.backward(params, img, ew, ea, prior).clone()
+    losses[mode] = float(eng.scalar("loss"))
     torch.cuda.synchronize()
     try:
         eng.check_range()
     except Exception as e:
         print(mode, "RANGE:", e)
     eng.close()
+print("loss", losses)
 off = 0
 for name, (r, c) in air.param_spec(cfg):
-    a, b = grads["simt"][off:off + r * c], grads["tc"][off:off + r * c]
+    a, b, f = (grads[m][off:off + r * c] for m in ("simt", "tc", "tc_fwd"))
     off += r * c
-    err = float((a - b).abs().max()); sc = float(a.abs().max())
-    print(f"{name:28s} max|g| {sc:.3e} err {err:.3e} rel {err / (sc + 1e-30):.2e} nan_tc {int(torch.isnan(b).sum())} nan_simt {int(torch.isnan(a).sum())}")
+    err = float((a - b).abs().max()); sc = float(a.abs().max()); errf = float((a - f).abs().max())
+    print(f"{name:28s} max|g| {sc:.3e} err {err:.3e} rel {err / (sc + 1e-30):.2e} nan_tc {int(torch.isnan(b).sum())} tcfwd_rel {errf / (sc + 1e-30):.2e}")
