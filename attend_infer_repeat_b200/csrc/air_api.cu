@@ -141,6 +141,9 @@ struct air_handle {
   int* range_flag = nullptr;
   std::map<std::pair<const void*, int>, CUtensorMap> tmap_cache;
   // training (air_train_enable / air_backward; AIR_PREC_FP32 engine): saved activations + gradient scratch, one cudaMalloc
+  // inference: the prepared fp16-split weight arena is reused while the caller vouches that `params` is unchanged
+  bool cache_weights = false;
+  const float* weights_ready = nullptr;
   bool train = false;
   bool fwd_saved = false;          // the last forward on this handle ran in training mode with a prior (backward is valid)
   char* tws = nullptr;
@@ -426,10 +429,13 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   Buf x = h->x;
   x.f32 = const_cast<float*>(img);
   x.ld = P;
-  if (tc) {
+  if (tc && !(h->cache_weights && h->weights_ready == params)) {
     AIR_CUDA(air::launch_k(air::tc::prep_weights_kernel, dim3(h->prep_tiles), dim3(256), 0, st, params, h->arena,
                            h->prep_table, (int)h->tcw.size(), h->range_flag, h->bias_arena));
     ++h->launches;
+    h->weights_ready = params;
+  }
+  if (tc) {
     if (!x_hl_ready) {
       const size_t n4 = (size_t)B * ((P + 3) / 4);
       AIR_CUDA(air::launch_k(air::tc::split_rows_kernel, dim3((unsigned)((n4 + thr - 1) / thr)), dim3(thr), 0, st, img,
@@ -462,7 +468,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                              h->h_init.hl_out()));
       ++h->launches;
     }
-  } else {
+  } else if (!lstm_fused) {   // (the cluster LSTM kernel broadcasts the trainable initial state itself)
     AIR_CUDA(air::launch_k(air::lstm_init_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
                            params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, train ? h->c_all : h->cbuf, B, nh,
                            (tc && !lstm_fused) ? h->h_init.hl_out() : no_hl));
@@ -480,7 +486,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     lp.bias = h->bias_arena + h->tcw[h->lstm_x_perm].bias_off;
     lp.e = h->e.f32;
     lp.n_enc = h->n_enc;
-    lp.h_init = h->h_init.f32;
+    lp.h_init = h_in ? h->h_init.f32 : params + h->lstm_h0;   // cell.py:103: (h0, c0) [1,nh] tiled to the batch
+    lp.h_init_ld = h_in ? nh : 0;
+    lp.c_in = h_in ? h->cbuf : params + h->lstm_c0;
+    lp.c_in_ld = h_in ? nh : 0;
     lp.c = h->cbuf;
     lp.hs = h->hs.f32;
     lp.hs_hlt = h->hs.hlt_out();
@@ -554,9 +563,16 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
         AIR_OK)
       return rc;   // modules.py:119-122
   }
-  AIR_CUDA(air::launch_k(air::presence_kernel, dim3((B + 127) / 128), dim3(128), 0, st, h->logit, u_pres, presence_in,
-                         o->presence_prob, o->presence, T_run, B, c.step_bias, c.explore_eps, c.discrete_steps));
-  ++h->launches;
+  // the presence scan (cell.py:137-151) rides in the glimpse-read kernel: one thread of each canvas's CTA
+  air::PresenceArgs pa;
+  pa.logit = h->logit;
+  pa.u_pres = u_pres;
+  pa.presence_in = presence_in;
+  pa.presence_prob = o->presence_prob;
+  pa.presence = o->presence;
+  pa.step_bias = c.step_bias;
+  pa.explore_eps = c.explore_eps;
+  pa.discrete = c.discrete_steps;
   mark(h, AIR_ST_READ, st);
 
   // 5. where sampling + glimpse read   (cell.py:129-135)
@@ -565,7 +581,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                          (tc && !train) ? nullptr : h->crop.f32,
                          tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
                          c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
-                         c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0));
+                         c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0, pa));
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
@@ -1494,6 +1510,18 @@ int32_t air_rmsprop_step(float* params, const float* grad, float* mg, float* ms,
 }
 
 int64_t air_train_workspace_bytes(const air_handle* h) { return h ? (int64_t)h->tws_bytes : 0; }
+
+int32_t air_cache_weights(air_handle* h, int32_t on) {
+  if (!h) return fail(AIR_ERR_ARG, "air_cache_weights: NULL handle");
+  h->cache_weights = on != 0;
+  h->weights_ready = nullptr;
+  return AIR_OK;
+}
+int32_t air_params_updated(air_handle* h) {
+  if (!h) return fail(AIR_ERR_ARG, "air_params_updated: NULL handle");
+  h->weights_ready = nullptr;
+  return AIR_OK;
+}
 
 int32_t air_linear_backward(const float* X, const float* W, const float* dY, const float* elu_x, float* dW, float* db,
                             float* dX, int32_t M, int32_t N, int32_t K, void* stream) {

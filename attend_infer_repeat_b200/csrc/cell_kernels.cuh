@@ -138,29 +138,7 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, const flo
 // presence: StepsPredictor sigmoid + explore-eps mix + Bernoulli draw + cumulative product over steps
 // (modules.py:119-122, cell.py:137-151)
 // ---------------------------------------------------------------------------------------------------
-__global__ void presence_kernel(const float* __restrict__ logit /*[T,B]*/, const float* __restrict__ u_pres /*[T,B]*/,
-                                const float* __restrict__ presence_in /*[B] or null (=1)*/,
-                                float* __restrict__ presence_prob /*[T,B]*/, float* __restrict__ presence /*[T,B]*/,
-                                int T, int B, float step_bias, float explore_eps, int discrete) {
-  griddep_launch();
-  griddep_wait();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float pres = presence_in ? presence_in[b] : 1.0f;
-  for (int t = 0; t < T; ++t) {
-    const size_t i = (size_t)t * B + b;
-    float p = sigmoid_f(logit[i] + step_bias);
-    if (explore_eps >= 0.f) p = __fadd_rn(explore_eps / 2.0f, __fmul_rn(1.0f - explore_eps, p));
-    presence_prob[i] = p;
-    if (discrete) {
-      const float z = (u_pres[i] < p) ? 1.0f : 0.0f;
-      pres *= z;
-    } else {
-      pres = p;
-    }
-    presence[i] = pres;
-  }
-}
+// (implemented by presence_scan() below: one thread of each canvas's where_read CTA)
 
 // ---------------------------------------------------------------------------------------------------
 // where head + glimpse read.  One CTA per canvas b: the image is staged once in shared memory and all
@@ -174,11 +152,38 @@ __host__ __device__ inline size_t where_read_smem(int T, int H, int W, int h, in
   return sizeof(float) * ((size_t)H * W + 4) / 16 * 16 + 16 + sizeof(Tap) * (size_t)T * (w + h);
 }
 
+// presence scan of one canvas, run by one thread of the canvas's where_read CTA
+struct PresenceArgs {
+  const float* logit;        // [T,B]; null: no scan
+  const float* u_pres;       // [T,B]
+  const float* presence_in;  // [B] or null (= 1)
+  float* presence_prob;      // [T,B]
+  float* presence;           // [T,B]
+  float step_bias, explore_eps;
+  int discrete;
+};
+__device__ __forceinline__ void presence_scan(const PresenceArgs& pa, int b, int T, int B) {
+  float pres = pa.presence_in ? pa.presence_in[b] : 1.0f;
+  for (int t = 0; t < T; ++t) {
+    const size_t i = (size_t)t * B + b;
+    float p = sigmoid_f(pa.logit[i] + pa.step_bias);
+    if (pa.explore_eps >= 0.f) p = __fadd_rn(pa.explore_eps / 2.0f, __fmul_rn(1.0f - pa.explore_eps, p));
+    pa.presence_prob[i] = p;
+    if (pa.discrete) {
+      const float z = (pa.u_pres[i] < p) ? 1.0f : 0.0f;
+      pres *= z;
+    } else {
+      pres = p;
+    }
+    pa.presence[i] = pres;
+  }
+}
+
 __global__ void __launch_bounds__(256, 8)
 where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_where, const float* __restrict__ img,
                   float* __restrict__ where, float* __restrict__ where_loc, float* __restrict__ where_scale,
                   float* __restrict__ crop, HlOut crop_hl, int T, int B, int H, int W, int h, int w, float max_crop,
-                  float scale_bias, double step_w, double step_h) {
+                  float scale_bias, double step_w, double step_h, PresenceArgs pa) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_where[AIR_MAX_STEPS][4];
@@ -210,6 +215,7 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
     where[row * 4 + k] = wv;
     s_where[t][k] = wv;
   }
+  if (pa.logit && threadIdx.x == 64) presence_scan(pa, b, T, B);   // StepsPredictor + Bernoulli draw (cell.py:137-151)
   if (!bulk)
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_img[i] = src[i];
   __syncthreads();

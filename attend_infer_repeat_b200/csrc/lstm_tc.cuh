@@ -26,7 +26,10 @@ struct Params {
   const float* bias;      // lstm.b permuted the same way (bias arena), [4 * NH]
   const float* e;         // [B, n_enc] fp32: input-encoder output
   int n_enc;
-  const float* h_init;    // [B, NH] fp32
+  const float* h_init;    // [B, NH] fp32 (row pitch h_init_ld; 0 = one [NH] vector broadcast to every canvas)
+  int h_init_ld;
+  const float* c_in;      // initial cell state, row pitch c_in_ld (0 = broadcast vector); the final state goes to `c`
+  int c_in_ld;
   float* c;               // [B, NH] fp32: initial cell state in, final cell state out
   float* hs;              // [T, B, NH] fp32 out
   HlOut hs_hlt;           // slice-major tiled hl copy of hs (operand of the heads chain), row = t * B + b
@@ -244,7 +247,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     }
     // cell state of this thread's 16 units, in registers for the whole recurrence
     float c_reg[16];
-    tile_load(stage, lane, c_reg, p.c, NH, row_w, u0, NH, p.B);
+    tile_load(stage, lane, c_reg, p.c_in, p.c_in_ld, row_w, u0, NH, p.B);
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(a_ready);
@@ -268,7 +271,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     // --- operand of step 1: h_init rows ---
     for (int s = cq; s < NH / 16; s += 4) {
       float v[16];
-      tile_load(stage, lane, v, p.h_init, NH, row_w, s * 16, NH, p.B);
+      tile_load(stage, lane, v, p.h_init, p.h_init_ld, row_w, s * 16, NH, p.B);
       uint32_t hi[8], lo[8];
       split_pack16(v, hi, lo, ovf);
       tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);

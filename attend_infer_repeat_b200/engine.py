@@ -277,6 +277,14 @@ class Engine:
                                                current_stream_ptr()), "air_forward_host_u8")
         return scalars_host, loss_per_sample_host
 
+    def cache_weights(self, on: bool = True):
+        """Inference loops: reuse the prepared tensor-core weight arena while `params` is unchanged (call
+        params_updated() after writing to the buffer)."""
+        check(self.lib.air_cache_weights(self._handle, int(on)), "air_cache_weights")
+
+    def params_updated(self):
+        check(self.lib.air_params_updated(self._handle), "air_params_updated")
+
     # -- training step (SURVEY 8f row 1) -----------------------------------------------------------------
     def train_enable(self, on: bool = True):
         """Keep the activations of every following forward() for backward() (fp32 engine only)."""

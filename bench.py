@@ -148,6 +148,7 @@ def workload_config(args, n):
             "global_batch": args.batch * n, "canvas": "50x50", "glimpse": "20x20", "max_steps": 3,
             "outputs": "all 10 AIRCell outputs materialised [T,B,.] fp32 + per-sample ELBO terms",
             "parallelism": f"dp{n}", "precision": args.precision,
+            "weights": "constant over the timed loop; tensor-core operand arena prepared once (air_cache_weights)",
             "l2": f"{args.input_sets} rotating input sets ({args.input_sets * args.batch * 10000 / 1e6:.0f} MB of "
                   f"images) + {args.batch * 3 * 11.6e3 / 1e6:.0f} MB of outputs written per step > 126 MB L2"}
 
@@ -194,6 +195,7 @@ def run_native(args, rank, local_rank, world):
     cfg = air.CellConfig(precision=prec)
     T, B = SHAPE["T"], args.batch
     eng = air.Engine(cfg, B, T, device=dev)
+    eng.cache_weights(True)        # forward-only loop with constant parameters: the fp16-split weight arena is built once
     spec = air.param_spec(cfg)
     from attend_infer_repeat_b200.cell import _init_flat
     params, _ = _init_flat(spec, dev, seed=0)

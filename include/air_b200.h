@@ -221,6 +221,13 @@ int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t
 /* stand-alone minibatch gather: img_out[b] = float32(dataset_u8[idx[b]]) / 255  (data.py:116,131-132) */
 int32_t air_gather_u8(const uint8_t* dataset_u8, const int32_t* idx, float* img_out, int32_t B, int32_t P, void* stream);
 
+/* Inference loops (AIR_PREC_TC_SPLIT): by default every forward call re-derives the fp16-split weight arena from `params`
+ * (7 MB, one kernel), so that an optimiser step needs no extra call.  air_cache_weights(h, 1) keeps the arena across calls
+ * made with the SAME params pointer; the caller must then call air_params_updated(h) after changing the buffer's contents
+ * (a TF graph has the same contract between a variable assignment and the ops that read it). */
+int32_t air_cache_weights(air_handle* h, int32_t on);
+int32_t air_params_updated(air_handle* h);
+
 /* ---- training step: opt.compute_gradients(opt_loss, model_vars) + opt.apply_gradients of
  *      AIRModel.train_step (model.py:261-265,335-360) ------------------------------------------------------- */
 /* Switch a handle (AIR_PREC_FP32 engine, discrete_steps = 1) to training mode: allocates the second workspace
