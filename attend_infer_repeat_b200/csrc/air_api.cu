@@ -1611,6 +1611,55 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
   return AIR_OK;
 }
 
+namespace {
+int32_t draw_noise_impl(air_handle* h, uint64_t seed, float* eps_where, float* eps_what, float* u_pres, cudaStream_t st) {
+  const air_config& c = h->cfg;
+  const size_t TB = (size_t)c.T * c.B;
+  struct { float* p; size_t n; uint32_t id; int normal; } jobs[3] = {
+      {eps_where, TB * 4, 0u, 1}, {eps_what, TB * (size_t)c.na, 1u, 1}, {u_pres, TB, 2u, 0}};
+  for (auto& j : jobs) {
+    if (!j.p) continue;
+    const size_t threads = (j.n + 3) / 4;
+    AIR_CUDA(air::launch_k(air::philox_fill_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, j.p, j.n,
+                           (unsigned long long)seed, j.id, j.normal));
+    ++h->launches;
+  }
+  return AIR_OK;
+}
+}  // namespace
+
+int32_t air_draw_noise(air_handle* h, uint64_t seed, float* eps_where, float* eps_what, float* u_pres, void* stream) {
+  if (!h) return fail(AIR_ERR_ARG, "air_draw_noise: NULL handle");
+  return draw_noise_impl(h, seed, eps_where, eps_what, u_pres, (cudaStream_t)stream);
+}
+
+int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_t* img_u8_host, uint64_t seed,
+                                const air_prior* prior, const air_outputs* outs, float* scalars_host,
+                                float* loss_per_sample_host, void* stream) {
+  if (!h || !params || !img_u8_host) return fail(AIR_ERR_ARG, "air_forward_host_u8_rng: NULL argument");
+  int32_t rc = check_outs(outs, prior != nullptr);
+  if (rc != AIR_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const air_config& c = h->cfg;
+  AIR_CUDA(cudaMemcpyAsync(h->st_img_u8, img_u8_host, (size_t)c.B * h->P, cudaMemcpyHostToDevice, st));
+  if ((rc = draw_noise_impl(h, seed, h->st_eps_where, h->st_eps_what, h->st_u, st)) != AIR_OK) return rc;
+  const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
+  AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
+                         (const uint8_t*)h->st_img_u8, h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(),
+                         h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
+  ++h->launches;
+  rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
+                    nullptr, nullptr, nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
+  if (rc != AIR_OK) return rc;
+  if (prior && scalars_host)
+    AIR_CUDA(cudaMemcpyAsync(scalars_host, outs->scalars, sizeof(float) * AIR_N_SCALARS, cudaMemcpyDeviceToHost, st));
+  if (prior && loss_per_sample_host)
+    AIR_CUDA(cudaMemcpyAsync(loss_per_sample_host, outs->loss_per_sample, sizeof(float) * c.B, cudaMemcpyDeviceToHost,
+                             st));
+  AIR_CUDA(cudaStreamSynchronize(st));
+  return AIR_OK;
+}
+
 int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t* dataset_u8, int64_t n_dataset,
                                const int32_t* idx, const float* eps_where, const float* eps_what, const float* u_pres,
                                const float* baseline, const air_prior* prior, const air_outputs* outs, float* img_out,

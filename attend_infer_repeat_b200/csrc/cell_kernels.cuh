@@ -89,6 +89,51 @@ __device__ __forceinline__ float bilinear_pre(const float* __restrict__ D, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// In-library noise (SURVEY 8d "perf mode"): the reference draws where / what / presence noise inside the graph
+// (cell.py:133,147,156), so a caller that feeds only images needs no noise bytes from the host.  Counter-based
+// Philox4x32-10 (Salmon et al., SC'11): element i of stream `stream_id` under `seed` is a pure function of
+// (seed, stream_id, i) -- reproducible across launches, batch shards and devices.  Normals by Box-Muller.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// (0, 1]: never 0, so log() below is finite; 24 random bits
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+// one thread per 4 outputs; normal != 0: N(0,1) (two Box-Muller pairs), else U[0,1)
+__global__ void philox_fill_kernel(float* __restrict__ out, size_t n, unsigned long long seed, uint32_t stream_id,
+                                   int normal) {
+  griddep_launch();
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), stream_id, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float v[4];
+  if (normal) {
+    const float r0 = sqrtf(-2.0f * logf(u01_open(r.x))), r1 = sqrtf(-2.0f * logf(u01_open(r.z)));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u01_open(r.y), &s0, &c0);
+    sincospif(2.0f * u01_open(r.w), &s1, &c1);
+    v[0] = r0 * c0; v[1] = r0 * s0; v[2] = r1 * c1; v[3] = r1 * s1;
+  } else {
+    v[0] = (float)(r.x >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+    v[1] = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+    v[2] = (float)(r.z >> 8) * (1.0f / 16777216.0f);
+    v[3] = (float)(r.w >> 8) * (1.0f / 16777216.0f);
+  }
+  griddep_wait();   // the buffer may still be read by the previous pass
+  for (int j = 0; j < 4 && q * 4 + j < n; ++j) out[q * 4 + j] = v[j];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // LSTM state handling (snt.LSTM [upstream], mnist_model.py:35; cell.py:101-114,126-127)
 // ---------------------------------------------------------------------------------------------------
 // trainable initial state (h0, c0) [nh] tiled to the batch (cell.py:103)

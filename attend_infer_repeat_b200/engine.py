@@ -317,6 +317,27 @@ class Engine:
                                             float(learning_rate), float(decay), float(momentum), float(epsilon),
                                             float(grad_scale), current_stream_ptr()), "air_rmsprop_step")
 
+    def draw_noise(self, seed: int):
+        """(eps_where[T,B,4], eps_what[T,B,na], u_pres[T,B,1]) drawn inside the library (Philox4x32-10, counter-based:
+        the same seed gives the same tensors on any device / shard layout)."""
+        T, B, cfg, dev = self.T, self.B, self.cfg, self.device
+        ew = torch.empty(T, B, 4, device=dev)
+        ea = torch.empty(T, B, cfg.na, device=dev)
+        u = torch.empty(T, B, 1, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.air_draw_noise(self._handle, int(seed), ptr(ew), ptr(ea), ptr(u), current_stream_ptr()),
+                  "air_draw_noise")
+        return ew, ea, u
+
+    def forward_host_u8_rng(self, params, img_u8_host, seed: int, prior: air_prior, scalars_host, loss_per_sample_host):
+        """forward_host_u8 with the noise drawn on the device from ``seed``: only the uint8 images cross the bus."""
+        assert img_u8_host.dtype == torch.uint8 and not img_u8_host.is_cuda and img_u8_host.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.air_forward_host_u8_rng(self._handle, ptr(params), ptr(img_u8_host), int(seed), C.byref(prior),
+                                                   C.byref(self._c_out), ptr(scalars_host), ptr(loss_per_sample_host),
+                                                   current_stream_ptr()), "air_forward_host_u8_rng")
+        return scalars_host, loss_per_sample_host
+
     def forward_dataset_u8(self, params, dataset_u8, idx, eps_where, eps_what, u_pres, prior: Optional[air_prior] = None,
                            baseline=None, img_out=None):
         """forward() on the minibatch ``dataset_u8[idx]`` of a device-resident uint8 dataset [N,H,W]:

@@ -263,6 +263,9 @@ def run_native(args, rank, local_rank, world):
         _, ew, ea, u = host[i % len(host)]
         eng.forward_host_u8(params, host_u8[i % len(host)], ew, ea, u, prior, scal_h, lps_h)
 
+    def e2e_step_u8_rng(i):
+        eng.forward_host_u8_rng(params, host_u8[i % len(host)], 1000 + i, prior, scal_h, lps_h)
+
     def e2e_step_f32(i):
         img, ew, ea, u = host[i % len(host)]
         eng.forward_host(params, img, ew, ea, u, prior, scal_h, lps_h)
@@ -282,14 +285,21 @@ def run_native(args, rank, local_rank, world):
             ms_ = float(t.item())
         return ms_
 
+    e2e_rng_ms = time_e2e(e2e_step_u8_rng)
     e2e_ms = time_e2e(e2e_step_u8)
     e2e_f32_ms = time_e2e(e2e_step_f32)
     noise_bytes = sum(t.numel() * 4 for t in host[0][1:])
     d2h = (scal_h.numel() + lps_h.numel()) * 4
-    e2e = {"value": world * B * T * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": host_u8[0].numel() + noise_bytes, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_ms / args.steps,
-           "api": "air_forward_host_u8 (pinned host uint8 images + float32 noise in, loss scalars + per-sample loss out)",
+    # headline: what sess.run(train_step, feed_dict={imgs}) moves in the reference -- the uint8 image batch in, the loss out;
+    # where / what / presence noise is drawn inside the library like the reference's in-graph draws (cell.py:133,147,156)
+    e2e = {"value": world * B * T * args.steps / (e2e_rng_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": host_u8[0].numel(), "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_rng_ms / args.steps,
+           "api": "air_forward_host_u8_rng (pinned host uint8 images in, in-library Philox noise, loss scalars + "
+                  "per-sample loss out)",
+           "host_noise": {"value": world * B * T * args.steps / (e2e_ms * 1e-3), "ms_per_step": e2e_ms / args.steps,
+                          "h2d_bytes_per_step": host_u8[0].numel() + noise_bytes,
+                          "api": "air_forward_host_u8 (images + pre-drawn float32 noise from the host)"},
            "f32_images": {"value": world * B * T * args.steps / (e2e_f32_ms * 1e-3), "ms_per_step": e2e_f32_ms / args.steps,
                           "h2d_bytes_per_step": host[0][0].numel() * 4 + noise_bytes, "api": "air_forward_host"}}
 

@@ -210,6 +210,16 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
                             const float* u_pres_host, const air_prior* prior, const air_outputs* outs,
                             float* scalars_host, float* loss_per_sample_host, void* stream);
 
+/* In-library noise: fills eps_where [T,B,4] ~ N(0,1), eps_what [T,B,na] ~ N(0,1), u_pres [T,B,1] ~ U[0,1)
+ * (DEVICE buffers, any may be NULL) from a counter-based Philox4x32-10 generator: a pure function of (seed, tensor,
+ * element index), like the in-graph draws of cell.py:133,147,156 under a fixed graph seed. */
+int32_t air_draw_noise(air_handle* h, uint64_t seed, float* eps_where, float* eps_what, float* u_pres, void* stream);
+/* air_forward_host_u8 with the noise drawn on the device (air_draw_noise(seed)): the only host->device traffic is the
+ * uint8 image batch -- what sess.run(train_step, feed_dict={imgs}) moves in the reference. */
+int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_t* img_u8_host, uint64_t seed,
+                                const air_prior* prior, const air_outputs* outs, float* scalars_host,
+                                float* loss_per_sample_host, void* stream);
+
 /* Same with the whole DATASET resident on the device: dataset_u8 [n_dataset,H,W] uint8 as pickled by
  * data.py:35-107, idx [B] int32 = the minibatch indices tensors_from_data draws (data.py:121-158).  Gather, /255 and the
  * first layer's operand preparation run in one device pass; no host buffer is touched.  img_out [B,H,W] (optional)
