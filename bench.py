@@ -329,7 +329,12 @@ def run_native(args, rank, local_rank, world):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     stage_share = {k: round(v / sum(acc.values()), 4) for k, v in acc.items()}
     roofline = {"bound": "tensor", "kernel": engine_name, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf_peak, "peak_kind": f"bf16 dense sustained, {peak_kind}", "traffic": None,
+                "frac": achieved / tf_peak, "peak_kind": f"bf16 dense sustained, {peak_kind}",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the two chain_kernel launches of one pass at B=4096, from
+                # the committed `ncu --set full` capture (profiles/r01c_full_tc.md: 13.36 + 23.80 MB read, 0.07 MB written;
+                # the 37 MB of outputs they produce are still in the 126 MB L2 when the kernels end)
+                "traffic": 37.23e6 if (prec == air.AIR_PREC_TC_SPLIT and B == 4096) else None,
+                "traffic_unit": "bytes per launch set",
                 "flops_per_launch_set": gemm_flops, "ms_per_launch_set": gemm_ms,
                 "stages_timed": gemm_stages, "stage_ms": {k: round(v, 4) for k, v in acc.items()},
                 "stage_share": stage_share,
