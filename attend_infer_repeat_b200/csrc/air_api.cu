@@ -170,6 +170,11 @@ struct air_handle {
   std::map<int64_t, std::pair<size_t, int>> wnt_index;   // Layer::w_off -> (half offset of the hi plane, Npad)
   air::tc::RowsEntry* wnt_table = nullptr;               // device copy of the per-matrix table (prep_weights_rows_kernel)
   int wnt_entries = 0, wnt_blocks = 0;
+  // the weight-gradient work of a backward pass runs on a second stream, beside the dX / pointwise critical path
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  std::map<const float*, cudaEvent_t> dy_consumed;       // gradient buffer -> "the side stream has re-laid it out"
   const float* dy_ready = nullptr;                       // dY whose row-major planes currently sit in hl_dy ...
   int dy_ready_m = 0, dy_ready_n = 0;                    // ... with these dimensions
   int* t_range_flag = nullptr;
@@ -890,9 +895,34 @@ int32_t get_tmap2(air_handle* h, const __half* base, int kpad, long long rows_to
 // split_transpose_kernel as bf16 hi/lo planes (16 significant bits each; per-sample gradients span the fp32 exponent
 // range -- the 1 / s_x factors of the inverse transformer -- which fp16 planes cannot hold), three tcgen05.mma per K slice
 // as in the forward, the contraction split over gridDim.z with fp32 atomics into the zeroed gradient buffer.
+cudaEvent_t next_event(air_handle* h) {
+  cudaEvent_t e = h->ev_pool[h->ev_next];
+  h->ev_next = (h->ev_next + 1) % h->ev_pool.size();
+  return e;
+}
+// before the main stream overwrites a gradient buffer: wait until the side stream has finished reading it
+int32_t wait_consumed(air_handle* h, const float* buf, cudaStream_t st) {
+  auto it = h->dy_consumed.find(buf);
+  if (it != h->dy_consumed.end()) {
+    AIR_CUDA(cudaStreamWaitEvent(st, it->second, 0));
+    h->dy_consumed.erase(it);
+  }
+  return AIR_OK;
+}
+
 int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
-                             int M, bool dx_follows, cudaStream_t st) {
+                             int M, bool dx_follows, cudaStream_t main_st) {
   namespace tc = air::tc;
+  // fork: everything below runs on the side stream once X and dY are complete on the main stream; the main stream goes on
+  // with the input gradient of this layer (its own row-major copy of dY) and the layers below
+  cudaStream_t st = main_st;
+  if (h->side) {
+    cudaEvent_t ready = next_event(h);
+    AIR_CUDA(cudaEventRecord(ready, main_st));
+    AIR_CUDA(cudaStreamWaitEvent(h->side, ready, 0));
+    st = h->side;
+    dx_follows = false;
+  }
   const int mp = round_up(M, 64), KA = round_up(l.K, 128), NA = round_up(l.N, 64);
   const int np = NA, MA = round_up(M, 128);
   if ((size_t)KA * mp > h->hl_xt_halves || (size_t)NA * mp > h->hl_yt_halves || (size_t)MA * np > h->hl_dy_halves)
@@ -908,6 +938,11 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
   h->dy_ready = dx_follows ? dY : nullptr;
   h->dy_ready_m = M;
   h->dy_ready_n = l.N;
+  if (h->side) {   // dY (and X, which nobody overwrites within a pass) have been read
+    cudaEvent_t done = next_event(h);
+    AIR_CUDA(cudaEventRecord(done, st));
+    h->dy_consumed[dY] = done;
+  }
   const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
   int32_t rc = get_tmap2(h, h->hl_xt, mp, 2LL * KA, tc::BM, &tm_a);
   if (rc != AIR_OK) return rc;
@@ -1026,6 +1061,8 @@ int32_t upload_backward_weight_table(air_handle* h) {
 // dX = dY @ W^T (* elu'(X) when elu_x is the saved forward value of X)
 int32_t layer_input_grad(air_handle* h, const float* params, const Layer& l, const float* dY, int ldy, float* dX, int ldx,
                          int M, bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st) {
+  const int32_t rcw = wait_consumed(h, dX, st);
+  if (rcw != AIR_OK) return rcw;
   if (h->tc_bwd && M >= 64) return layer_input_grad_tc(h, l, dY, ldy, dX, ldx, M, accumulate, elu_x, ld_elu, st);
   AIR_CUDA(air::launch_gemm_simt(false, true, dY, ldy, params + l.w_off, l.N, dX, ldx, M, l.K, l.N, accumulate, elu_x,
                                  ld_elu, 1, st));
@@ -1072,6 +1109,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   const int thr = 256;
   int32_t rc;
   AIR_CUDA(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)h->n_params, st));
+  h->dy_consumed.clear();
   if (h->tc_bwd && TB >= 64 && (rc = prep_backward_weights(h, params, st)) != AIR_OK) return rc;
 
   air::BwdArgs a;
@@ -1190,6 +1228,13 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
     if ((rc = mlp_backward(h, params, grad, h->enc, img, P, h->sv_enc, h->g_e, h->n_enc, B, nullptr, 0, false, st)) !=
         AIR_OK)
       return rc;
+  }
+  // join: the weight gradients of the side stream are part of this call's result
+  if (h->side) {
+    cudaEvent_t done = next_event(h);
+    AIR_CUDA(cudaEventRecord(done, h->side));
+    AIR_CUDA(cudaStreamWaitEvent(st, done, 0));
+    h->dy_consumed.clear();
   }
   // l2_weight * sum of tf.nn.l2_loss over the 2-D variables (model.py:345-350): weights and the [1,nh] initial state
   if (l2_weight > 0.f) {
@@ -1394,6 +1439,8 @@ int32_t air_destroy(air_handle* h) {
     if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
   if (h->tws) cudaFree(h->tws);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->trace) cudaFree(h->trace);
   delete h;
   return AIR_OK;
@@ -1472,6 +1519,11 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
     if (h->tc_bwd) {
       const int32_t rc = upload_backward_weight_table(h);
       if (rc != AIR_OK) return rc;
+      if (getenv("AIR_NO_SIDE_STREAM") == nullptr) {
+        AIR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        h->ev_pool.resize(96);
+        for (cudaEvent_t& e : h->ev_pool) AIR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
     }
     const size_t smem = air::paint_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
     const size_t smem_r = air::read_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
