@@ -304,6 +304,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const bool f32_vec = p.out_f32 && !p.atomic_out && ((p.ldc & 3) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
     const float osc = p.out_scale != 0.f ? p.out_scale : W_UNSCALE;
+    const bool mask_vec = p.mask_y && ((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0);
     float amax = 0.f;   // NaN-propagating running max |x| of what is written as fp16 hi halves
     const uint32_t t_lane = (uint32_t)(lane_grp * 32) << 16;
 #pragma unroll
@@ -328,11 +329,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         if (p.mask_y) {   // backward: gradient through the ELU that produced the saved activation y
           const float* my = p.mask_y + (size_t)row * p.ld_mask + n0 + c0;
+          if (mask_vec && n0 + c0 + 16 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (n0 + c0 + j < p.N) {
-              const float y = my[j];
-              v[j] *= (y > 0.f) ? 1.0f : y + 1.0f;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 y = __ldg(reinterpret_cast<const float4*>(my + j));
+              v[j] *= (y.x > 0.f) ? 1.0f : y.x + 1.0f;
+              v[j + 1] *= (y.y > 0.f) ? 1.0f : y.y + 1.0f;
+              v[j + 2] *= (y.z > 0.f) ? 1.0f : y.z + 1.0f;
+              v[j + 3] *= (y.w > 0.f) ? 1.0f : y.w + 1.0f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n0 + c0 + j < p.N) {
+                const float y = my[j];
+                v[j] *= (y > 0.f) ? 1.0f : y + 1.0f;
+              }
             }
           }
         }
