@@ -356,7 +356,7 @@ int32_t check_outs_elbo_only(const air_outputs* o) {
 
 // One layer of a fused chain (chain_tc.cuh) from a prepared weight.
 void chain_add(const air_handle* h, air::chain::Params& p, const float* params, const Layer& l, int epi, int a_src,
-               int a_buf, float* out, int ldo) {
+               int a_buf, float* out, int ldo, float* save = nullptr) {
   const TcWeight& w = h->tcw[l.tc];
   air::chain::Layer& L = p.layer[p.n_layers];
   p.tm[p.n_layers] = w.tm_chain;
@@ -371,16 +371,19 @@ void chain_add(const air_handle* h, air::chain::Params& p, const float* params, 
   L.bias = h->bias_arena + w.bias_off;
   L.out = out;
   L.ldo = ldo;
+  L.save = epi == air::chain::EPI_ELU_A ? save : nullptr;
   ++p.n_layers;
 }
 // a whole neural.MLP whose first layer reads in[a_buf] and whose last layer writes fp32 rows to `out`
+// `saves` (training mode): fp32 destinations of the hidden activations, one per ELU layer in order (null: not kept)
 void chain_add_mlp(const air_handle* h, air::chain::Params& p, const float* params, const Mlp& mlp, int a_buf,
-                   bool first_loads, float* out, int ldo) {
+                   bool first_loads, float* out, int ldo, const std::vector<float*>* saves = nullptr) {
   const int nl = (int)mlp.layers.size();
   for (int i = 0; i < nl; ++i) {
     const bool last = i == nl - 1;
+    float* save = (saves && i < (int)saves->size()) ? (*saves)[i] : nullptr;
     chain_add(h, p, params, mlp.layers[i], last && out ? air::chain::EPI_F32 : air::chain::EPI_ELU_A,
-              (i == 0 && first_loads) ? air::chain::A_LOAD : air::chain::A_KEEP, a_buf, last ? out : nullptr, ldo);
+              (i == 0 && first_loads) ? air::chain::A_LOAD : air::chain::A_KEEP, a_buf, last ? out : nullptr, ldo, save);
   }
 }
 // debug: AIR_CHAIN_TRACE=<prefix> dumps the per-group SM-clock stamps of every chain launch to <prefix>.<seq>.bin
@@ -424,9 +427,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   int32_t rc;
   // training mode (air_train_enable, fp32 engine): every activation the backward pass needs is kept
   const bool train = h->train && prior != nullptr && T_run == c.T && !h_in && !canvas_in;
-  // the fused chains / the cluster LSTM keep their hidden activations in TMEM / registers: training mode takes the
-  // layer-by-layer tensor-core path, whose epilogues write every activation as fp32 rows (kept) + hl planes (next operand)
-  const bool chain = tc && h->chain_ok && !train;
+  // training mode: the fused chains / the cluster LSTM additionally write the activations they otherwise keep in TMEM /
+  // registers as fp32 rows (Layer::save, gates_save / c_save); AIR_TRAIN_LAYERWISE=1 selects the layer-by-layer path
+  static const bool layerwise = getenv("AIR_TRAIN_LAYERWISE") != nullptr;
+  const bool chain = tc && h->chain_ok && !(train && layerwise);
   h->fwd_saved = false;
 
   // 0. tensor-core engine: (re)build the fp16-split W^T arena from the current parameters and split the images
@@ -450,7 +454,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   }
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
-  const bool lstm_fused = tc && h->lstm_ok && !train;
+  const bool lstm_fused = tc && h->lstm_ok && !(train && layerwise);
   if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
                     train ? &h->sv_enc : nullptr)) != AIR_OK)
     return rc;
@@ -473,7 +477,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                              h->h_init.hl_out()));
       ++h->launches;
     }
-  } else if (!lstm_fused) {   // (the cluster LSTM kernel broadcasts the trainable initial state itself)
+  } else if (!lstm_fused || train) {   // (the cluster LSTM kernel broadcasts the trainable initial state itself)
     AIR_CUDA(air::launch_k(air::lstm_init_state_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
                            params + h->lstm_h0, params + h->lstm_c0, h->h_init.f32, train ? h->c_all : h->cbuf, B, nh,
                            (tc && !lstm_fused) ? h->h_init.hl_out() : no_hl));
@@ -491,11 +495,14 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     lp.bias = h->bias_arena + h->tcw[h->lstm_x_perm].bias_off;
     lp.e = h->e.f32;
     lp.n_enc = h->n_enc;
-    lp.h_init = h_in ? h->h_init.f32 : params + h->lstm_h0;   // cell.py:103: (h0, c0) [1,nh] tiled to the batch
-    lp.h_init_ld = h_in ? nh : 0;
-    lp.c_in = h_in ? h->cbuf : params + h->lstm_c0;
-    lp.c_in_ld = h_in ? nh : 0;
+    const bool rows = h_in || train;   // explicit per-canvas state (air_cell_step) or the tiled copy kept for the backward
+    lp.h_init = rows ? h->h_init.f32 : params + h->lstm_h0;   // cell.py:103: (h0, c0) [1,nh] tiled to the batch
+    lp.h_init_ld = rows ? nh : 0;
+    lp.c_in = rows ? (train ? h->c_all : h->cbuf) : params + h->lstm_c0;
+    lp.c_in_ld = rows ? nh : 0;
     lp.c = h->cbuf;
+    lp.gates_save = train ? h->gates_all : nullptr;
+    lp.c_save = train ? h->c_all + (size_t)B * nh : nullptr;
     lp.hs = h->hs.f32;
     lp.hs_hlt = h->hs.hlt_out();
     lp.gx_scr = h->gx_scr;
@@ -555,8 +562,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     cp.M = TB;
     cp.in[0] = chain_in(h->hs);
     cp.range_flag = h->range_flag;
-    chain_add_mlp(h, cp, params, h->where_mlp, 0, true, h->m, 8);       // modules.py:58-63
-    chain_add_mlp(h, cp, params, h->steps_mlp, 0, true, h->logit, 1);   // modules.py:119-122
+    chain_add_mlp(h, cp, params, h->where_mlp, 0, true, h->m, 8, train ? &h->sv_where : nullptr);       // modules.py:58-63
+    chain_add_mlp(h, cp, params, h->steps_mlp, 0, true, h->logit, 1, train ? &h->sv_steps : nullptr);   // modules.py:119-122
     if ((rc = launch_chain_traced(h, cp, st)) != AIR_OK) return rc;
     ++h->launches;
     mark(h, AIR_ST_STEPS, st);
@@ -605,12 +612,17 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     cp.na = na;
     cp.na_off = h->na_off;
     cp.what_offset = c.what_scale_offset;
-    chain_add_mlp(h, cp, params, h->glenc, 0, true, nullptr, 0);
+    std::vector<float*> glenc_saves;   // every glimpse-encoder layer is an ELU layer; the last one feeds the what head
+    if (train) {
+      glenc_saves = h->sv_glenc;
+      glenc_saves.push_back(h->sv_q);
+    }
+    chain_add_mlp(h, cp, params, h->glenc, 0, true, nullptr, 0, train ? &glenc_saves : nullptr);
     chain_add(h, cp, params, h->what_chain, air::chain::EPI_WHAT, air::chain::A_KEEP, 0, nullptr, 0);
     {
       Mlp dec = h->dec;
       dec.layers[0].K = na;
-      chain_add_mlp(h, cp, params, dec, 0, false, o->glimpse, G);
+      chain_add_mlp(h, cp, params, dec, 0, false, o->glimpse, G, train ? &h->sv_dec : nullptr);
     }
     if ((rc = launch_chain_traced(h, cp, st)) != AIR_OK) return rc;
     ++h->launches;

@@ -53,6 +53,7 @@ struct Layer {
   const float* bias;   // zero-padded to n_pass * n_box entries (prepared with the weights)
   float* out;    // EPI_F32: fp32 [rows, ldo]
   int ldo;
+  float* save;   // EPI_ELU_A, training mode: the activation is also kept as fp32 rows [rows, N] for the backward pass
 };
 struct HlIn {
   const __half* p;   // slice-major tiled hl operand: [row tile of 128][K slice][128 rows][16 fp16]; lo plane at + plane
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) chain_kernel(const __grid_cons
               split_pack16(v, hi, lo, ovf);
               tmem_st_32x8(t_lane + A_HI_COL + gi * 8, hi);
               tmem_st_32x8(t_lane + A_LO_COL + gi * 8, lo);
+              if (L.save) tile_store(stage, lane, v, L.save, L.N, row_w, gi * 16, L.N, p.M);
             }
           } else if (L.epi == EPI_F32) {
             const int n_base = pass * L.n_box;

@@ -36,6 +36,8 @@ struct Params {
   float* gx_scr;          // [tiles][4][4][16][128][4] fp32 scratch: gx in the layout of the thread that re-reads it
   __half* hx;             // [2][2 planes][tiles][16 slices][128][16] fp16: h exchange buffer, double buffered by step parity
   size_t hx_plane;        // halves per plane = tiles * 16 * 128 * 16
+  float* gates_save;      // training mode: [T, B, 4 NH] pre-activation gates (order i, j, f, o) of every step, or null
+  float* c_save;          // training mode: [T, B, NH] cell state after every step, or null
   int B, T;
   float forget_bias;
   int* range_flag;
@@ -308,7 +310,19 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
           c_reg[4 * k4 + j] = cn;
           h_new[4 * k4 + j] = sig_tanh(po, cn);
         }
+        if (p.gates_save && row < p.B) {   // kept for the backward pass: 16-byte pieces of this row's four gate vectors
+          float* gs = p.gates_save + ((size_t)t * p.B + row) * (4 * NH) + u0 + 4 * k4;
+          *reinterpret_cast<float4*>(gs) = make_float4(fmaf(gi[0], W_UNSCALE, ai[0]), fmaf(gi[1], W_UNSCALE, ai[1]),
+                                                       fmaf(gi[2], W_UNSCALE, ai[2]), fmaf(gi[3], W_UNSCALE, ai[3]));
+          *reinterpret_cast<float4*>(gs + NH) = make_float4(fmaf(gj[0], W_UNSCALE, aj[0]), fmaf(gj[1], W_UNSCALE, aj[1]),
+                                                            fmaf(gj[2], W_UNSCALE, aj[2]), fmaf(gj[3], W_UNSCALE, aj[3]));
+          *reinterpret_cast<float4*>(gs + 2 * NH) = make_float4(fmaf(gf[0], W_UNSCALE, af[0]), fmaf(gf[1], W_UNSCALE, af[1]),
+                                                                fmaf(gf[2], W_UNSCALE, af[2]), fmaf(gf[3], W_UNSCALE, af[3]));
+          *reinterpret_cast<float4*>(gs + 3 * NH) = make_float4(fmaf(go[0], W_UNSCALE, ao[0]), fmaf(go[1], W_UNSCALE, ao[1]),
+                                                                fmaf(go[2], W_UNSCALE, ao[2]), fmaf(go[3], W_UNSCALE, ao[3]));
+        }
       }
+      if (p.c_save) tile_store(stage, lane, c_reg, p.c_save + (size_t)t * p.B * NH, NH, row_w, u0, NH, p.B);
       // ---- h_t: fp32 rows (output + final state), hl copy for the heads chain, own slice straight into TMEM, and the
       //      exchange buffer for the other three CTAs ----
       tile_store(stage, lane, h_new, p.hs + (size_t)t * p.B * NH, NH, row_w, u0, NH, p.B);
