@@ -139,7 +139,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n):
@@ -187,8 +187,6 @@ def run_native(args, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to STDOUT: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     prec = air.AIR_PREC_TC_SPLIT if args.precision == "tc" else air.AIR_PREC_FP32
@@ -395,14 +393,30 @@ def run_native(args, rank, local_rank, world):
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "train_step": train, "cpu_baseline": cpu_baseline(args) if world == 1 else None,
                 "elbo": -float(eng.scalar("loss")) / world}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # libraries print to fd 1 behind our back (NCCL's version banner at communicator creation): keep the original stdout
+    # for the JSON line and point fd 1 at stderr for everything else
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -423,7 +437,7 @@ def main():
         # launched without torchrun: spawn one rank per GPU ourselves
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_native(args, rank, local_rank, world)
 
 
