@@ -25,7 +25,8 @@ AIR_PREC_FP32 = 0
 AIR_PREC_TC_SPLIT = 1
 
 SCALAR_INDEX = dict(rec_loss=0, kl_num_steps=1, kl_what=2, kl_where=3, prior_loss=4, loss=5, reinforce_loss=6,
-                    opt_loss=7, num_step=8, mean_iw_logq=9, mean_logq=10, mean_baseline=11)
+                    opt_loss=7, num_step=8, mean_iw_logq=9, mean_logq=10, mean_baseline=11, mean_iw=12, mean_iw2=13,
+                    mean_baseline2=14)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -61,6 +62,7 @@ class air_prior(C.Structure):
         ("steps_prob_is_f64", C.c_int32),
         ("steps_weight", C.c_float),
         ("analytic", C.c_int32), ("use_prior", C.c_int32), ("use_reinforce", C.c_int32),
+        ("nvil_shift", C.c_float), ("nvil_scale", C.c_float),
     ]
 
 

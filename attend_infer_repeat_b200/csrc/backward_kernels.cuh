@@ -428,7 +428,9 @@ __global__ void __launch_bounds__(128) latent_bwd_kernel(BwdArgs a) {
     float iw = a.rec_ps[b];
     if (!pr.analytic)
       iw = __fadd_rn(iw, __fadd_rn(__fadd_rn(__fmul_rn(a.kl_n_ps[b], pr.steps_weight), a.kl_what_ps[b]), a.kl_where_ps[b]));
-    cq = (double)a.inv_batch * ((double)iw - (double)a.baseline_mean);
+    const double nv_scale = pr.nvil_scale != 0.f ? (double)pr.nvil_scale : 1.0;
+    const double nv_shift = pr.nvil_scale != 0.f ? (double)pr.nvil_shift : 0.0;
+    cq = (double)a.inv_batch * ((double)iw - (double)a.baseline_mean - nv_shift) * nv_scale;
   }
   double dsw_run = 0.0;   // sum_{t < k} dL/dw_t
 #pragma unroll

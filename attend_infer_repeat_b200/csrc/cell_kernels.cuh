@@ -836,10 +836,10 @@ elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_
                     const float* __restrict__ kl_where, const float* __restrict__ nsteps,
                     const float* __restrict__ logq, const float* __restrict__ baseline, float* __restrict__ scalars,
                     int B, air_prior pr, const float* __restrict__ prior_part, float* __restrict__ loss_per_sample) {
-  __shared__ float s_part[32][8];
+  __shared__ float s_part[32][11];
   griddep_launch();
   griddep_wait();
-  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float s[11] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const float r = rec[b], lq = logq[b], k_n = kl_n[b], k_wt = kl_what[b], k_wh = kl_where[b];
@@ -853,19 +853,23 @@ elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_
     s[4] += nsteps[b];
     s[5] += iw * lq;
     s[6] += lq;
-    s[7] += baseline ? baseline[b] : 0.f;
+    const float bl = baseline ? baseline[b] : 0.f;
+    s[7] += bl;
+    s[8] += iw;
+    s[9] += iw * iw;
+    s[10] += bl * bl;
   }
   // one pass: warp sums -> shared -> the first warp adds the per-warp partials (fixed order: deterministic)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 11; ++i) {
     s[i] = warp_sum(s[i]);
     if (lane == 0) s_part[wid][i] = s[i];
   }
   __syncthreads();
   if (wid != 0) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = warp_sum(lane < nw ? s_part[lane][i] : 0.f);
+  for (int i = 0; i < 11; ++i) s[i] = warp_sum(lane < nw ? s_part[lane][i] : 0.f);
   if (threadIdx.x == 0) {
     const float inv = 1.0f / (float)B;
     const float m_rec = s[0] * inv, m_kln = s[1] * inv, m_klw = s[2] * inv, m_klwh = s[3] * inv;
@@ -873,7 +877,9 @@ elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_
     const float loss = m_rec + prior_loss * (pr.use_prior ? 1.0f : 0.0f);
     const float m_iwlq = s[5] * inv, m_lq = s[6] * inv, m_base = s[7] * inv;
     // mean over the [B,B] broadcast of (iw_j - baseline_i) * logq_j  ==  mean(iw*logq) - mean(baseline)*mean(logq)
-    const float reinforce = pr.use_reinforce ? (m_iwlq - m_base * m_lq) : 0.f;
+    // with NVIL normalisation (model.py:232-239): iw' = (iw - baseline - shift) * scale
+    const float nv_scale = pr.nvil_scale != 0.f ? pr.nvil_scale : 1.0f, nv_shift = pr.nvil_scale != 0.f ? pr.nvil_shift : 0.f;
+    const float reinforce = pr.use_reinforce ? nv_scale * (m_iwlq - (m_base + nv_shift) * m_lq) : 0.f;
     scalars[AIR_S_REC_LOSS] = m_rec;
     scalars[AIR_S_KL_NUM_STEPS] = m_kln;
     scalars[AIR_S_KL_WHAT] = m_klw;
@@ -886,7 +892,10 @@ elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_
     scalars[AIR_S_MEAN_REC_LOGQ] = m_iwlq;
     scalars[AIR_S_MEAN_LOGQ] = m_lq;
     scalars[AIR_S_MEAN_BASELINE] = m_base;
-    for (int i = AIR_S_MEAN_BASELINE + 1; i < AIR_N_SCALARS; ++i) scalars[i] = 0.f;
+    scalars[AIR_S_MEAN_IW] = s[8] * inv;
+    scalars[AIR_S_MEAN_IW2] = s[9] * inv;
+    scalars[AIR_S_MEAN_BASELINE2] = s[10] * inv;
+    for (int i = AIR_S_MEAN_BASELINE2 + 1; i < AIR_N_SCALARS; ++i) scalars[i] = 0.f;
   }
 }
 

@@ -107,7 +107,8 @@ def _fill_hidden(dst, src):
 
 
 def make_prior(what_prior=None, where_scale_prior=None, where_shift_prior=None, steps_success_prob=0.5,
-               steps_prob_is_f64=True, steps_weight=1.0, analytic=True, use_prior=True, use_reinforce=True) -> air_prior:
+               steps_prob_is_f64=True, steps_weight=1.0, analytic=True, use_prior=True, use_reinforce=True,
+               nvil_shift=0.0, nvil_scale=0.0) -> air_prior:
     """Pack the AttrDict-style priors of AIRModel.train_step (model.py:261-265) into the C struct."""
     def get(d, k, default):
         if d is None:
@@ -131,6 +132,7 @@ def make_prior(what_prior=None, where_scale_prior=None, where_shift_prior=None, 
     p.analytic = int(bool(analytic))
     p.use_prior = int(bool(use_prior))
     p.use_reinforce = int(bool(use_reinforce))
+    p.nvil_shift, p.nvil_scale = float(nvil_shift), float(nvil_scale)      # scale 0 = normalisation off
     return p
 
 

@@ -98,9 +98,13 @@ class AIRModel:
         else:
             s, is64 = float(_get(nsp, "init")), False
         self.steps_prior_success_prob = s
+        nvil_shift = nvil_scale = 0.0
+        if getattr(self, "decay_rate", None) is not None:
+            nvil_shift = float(self.imp_weight_moving_mean)
+            nvil_scale = 1.0 / max(float(self.imp_weight_moving_var) ** 0.5, 1.0)
         return make_prior(tc["what_prior"], tc["where_scale_prior"], tc["where_shift_prior"], s, is64,
                           _get(nsp, "weight", 1.), _get(nsp, "analytic", True), bool(self.use_prior),
-                          tc["use_reinforce"])
+                          tc["use_reinforce"], nvil_shift, nvil_scale)
 
     def forward(self, obs=None, nums=None, noise=None):
         """Re-evaluate the model on a batch (the sess.run of the reference): T fused cell steps + ELBO terms.
@@ -191,10 +195,8 @@ class AIRModel:
         when torch.distributed is initialised (batch shards), and the centered-RMSProp update of the flat
         parameter buffer (air_rmsprop_step, TF semantics).  The engine is switched to training mode, in which every
         activation the backward pass needs is kept.  A baseline module (BaselineMLP) is trained by its own RMSProp at 10x the
-        learning rate on .5 * mean((stop_gradient(iw) - baseline)^2) (model.py:253-259,362-367).  Not built: NVIL moment
-        normalisation (decay_rate)."""
-        if decay_rate is not None:
-            raise NotImplementedError("NVIL moving-average normalisation (decay_rate) is not built")
+        learning rate on .5 * mean((stop_gradient(iw) - baseline)^2) (model.py:253-259,362-367); decay_rate switches on
+        the NVIL normalisation of the importance weight by its moving moments (model.py:232-239)."""
         if num_steps_prior is None:
             raise ValueError("num_steps_prior is required (model.py:292 dereferences it)")
         if optimizer is not None:
@@ -214,6 +216,9 @@ class AIRModel:
         self.use_prior = use_prior
         self.use_reinforce = use_reinforce
         self.learning_rate = learning_rate
+        # NVIL normalisation of the importance weight (model.py:232-239; make_moving_average, ops.py:46-64)
+        self.decay_rate = decay_rate
+        self.imp_weight_moving_mean, self.imp_weight_moving_var = 0.0, 1.0
         self._train_cfg = dict(what_prior=what_prior, where_scale_prior=where_scale_prior,
                                where_shift_prior=where_shift_prior, num_steps_prior=num_steps_prior,
                                use_reinforce=use_reinforce)
@@ -249,7 +254,8 @@ class AIRModel:
                      inv_batch=1.0 / (world * B), l2_weight=float(self.l2_weight) / world)
         if world > 1:
             dist.all_reduce(self._grad)          # the ONE data-path collective: sum of the per-shard partial gradients
-            sharding.combine_scalars(out["scalars"], B, pr.steps_weight, bool(pr.use_prior), bool(pr.use_reinforce))
+            sharding.combine_scalars(out["scalars"], B, pr.steps_weight, bool(pr.use_prior), bool(pr.use_reinforce),
+                                     nvil_shift=pr.nvil_shift, nvil_scale=pr.nvil_scale)
         o = self._opt
         eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
                          float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
@@ -265,6 +271,18 @@ class AIRModel:
                 dist.all_reduce(g)
             eng.rmsprop_step(bm.params, g, bm.slots["mg"], bm.slots["ms"], bm.slots["mom"],
                              10.0 * float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
+        # UPDATE_OPS (model.py:357-360): the moving moments of the importance weight absorb this batch AFTER the gradient
+        # was taken with their previous values (TF leaves the order of the read and the assign unspecified)
+        if self.decay_rate is not None and self._train_cfg["use_reinforce"]:
+            sc = out["scalars"].double().cpu()
+            from ._lib import SCALAR_INDEX as SI
+            m_iw, m_iw2 = float(sc[SI["mean_iw"]]), float(sc[SI["mean_iw2"]])
+            m_b, m_b2 = float(sc[SI["mean_baseline"]]), float(sc[SI["mean_baseline2"]])
+            # tf.nn.moments over the [B,B] broadcast of iw_j - baseline_i: mean = E iw - E b, var = Var iw + Var b
+            mean, var = m_iw - m_b, max(m_iw2 - m_iw * m_iw, 0.0) + max(m_b2 - m_b * m_b, 0.0)
+            d = float(self.decay_rate)
+            self.imp_weight_moving_mean -= (1.0 - d) * (self.imp_weight_moving_mean - mean)
+            self.imp_weight_moving_var -= (1.0 - d) * (self.imp_weight_moving_var - var)
         self.global_step += 1
         return out
 

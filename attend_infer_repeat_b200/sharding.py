@@ -21,7 +21,7 @@ from ._lib import AIR_N_SCALARS, SCALAR_INDEX
 
 # scalars that are plain batch means of per-sample terms (everything else is derived from them)
 _MEAN_SLOTS = ("rec_loss", "kl_num_steps", "kl_what", "kl_where", "num_step", "mean_iw_logq", "mean_logq",
-               "mean_baseline")
+               "mean_baseline", "mean_iw", "mean_iw2", "mean_baseline2")
 
 
 def shard_range(n_global: int, rank: int, world: int) -> Tuple[int, int]:
@@ -40,7 +40,7 @@ def shard(t: torch.Tensor, rank: int, world: int, dim: int = 0) -> torch.Tensor:
 
 
 def combine_scalars(scalars: torch.Tensor, n_local: int, steps_weight: float = 1.0, use_prior: bool = True,
-                    use_reinforce: bool = True, group=None) -> torch.Tensor:
+                    use_reinforce: bool = True, group=None, nvil_shift: float = 0.0, nvil_scale: float = 0.0) -> torch.Tensor:
     """Turn the per-shard scalar block of air_forward (16 floats, batch means over the LOCAL shard) into the scalars
     of the whole batch, in place, on every rank.  Means are re-weighted by the shard size (shards may be ragged); the
     derived entries (prior_loss, loss, reinforce_loss, opt_loss; elbo_scalars_kernel) are re-formed from the global
@@ -58,7 +58,9 @@ def combine_scalars(scalars: torch.Tensor, n_local: int, steps_weight: float = 1
     m = {name: buf[SCALAR_INDEX[name]] / n for name in _MEAN_SLOTS}
     prior_loss = m["kl_num_steps"] * steps_weight + m["kl_what"] + m["kl_where"]
     loss = m["rec_loss"] + prior_loss * (1.0 if use_prior else 0.0)
-    reinforce = (m["mean_iw_logq"] - m["mean_baseline"] * m["mean_logq"]) if use_reinforce else torch.zeros_like(loss)
+    nv_scale, nv_shift = (nvil_scale, nvil_shift) if nvil_scale != 0.0 else (1.0, 0.0)
+    reinforce = (nv_scale * (m["mean_iw_logq"] - (m["mean_baseline"] + nv_shift) * m["mean_logq"])
+                 if use_reinforce else torch.zeros_like(loss))
     scalars.zero_()
     for name in _MEAN_SLOTS:
         scalars[SCALAR_INDEX[name]] = m[name].to(scalars.dtype)

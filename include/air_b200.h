@@ -87,6 +87,10 @@ typedef struct air_prior {
   int32_t analytic;                           /* num_steps_prior.analytic (model.py:157)  */
   int32_t use_prior;                          /* prior_weight = float(use_prior), model.py:331 */
   int32_t use_reinforce;                      /* model.py:335                             */
+  /* NVIL normalisation of the REINFORCE importance weight (decay_rate, model.py:232-239):
+   * iw <- (iw - nvil_shift) * nvil_scale, shift = imp_weight_moving_mean, scale = 1 / max(sqrt(moving_var), 1).
+   * nvil_scale == 0 selects "off" (shift 0, scale 1). */
+  float nvil_shift, nvil_scale;
 } air_prior;
 
 /* Caller-owned output buffers of one unrolled forward pass (+ ELBO terms).  A NULL pointer means
@@ -134,6 +138,9 @@ typedef enum air_scalar {
   AIR_S_MEAN_REC_LOGQ = 9,   /* mean_j rec_j * log q(n_j)   (REINFORCE pieces) */
   AIR_S_MEAN_LOGQ = 10,      /* mean_j log q(n_j)                              */
   AIR_S_MEAN_BASELINE = 11,  /* mean_i baseline_i                              */
+  AIR_S_MEAN_IW = 12,        /* mean_j iw_j            (moments of the importance weight, model.py:233-234) */
+  AIR_S_MEAN_IW2 = 13,       /* mean_j iw_j^2                                  */
+  AIR_S_MEAN_BASELINE2 = 14, /* mean_i baseline_i^2                            */
   AIR_N_SCALARS = 16
 } air_scalar;
 

@@ -627,18 +627,24 @@ def rec_loss(cfg: AirConfig, obs, final_canvas):
     return (-lp).sum((1, 2))
 
 
-def reinforce(joint, num_step_per_sample, importance_weight, baseline=None):
-    """model.py:218-251 without the NVIL moving-average option (decay_rate=None in the script).
-    baseline is [B,1] -> importance weight broadcasts to [B,B], reproduced as written."""
+def reinforce(joint, num_step_per_sample, importance_weight, baseline=None, nvil=None):
+    """model.py:218-251.  baseline is [B,1] -> importance weight broadcasts to [B,B], reproduced as
+    written.  nvil = (imp_weight_moving_mean, imp_weight_moving_var) switches on the decay_rate branch (model.py:232-239):
+    iw <- (iw - moving_mean) / max(sqrt(moving_var), 1); the batch moments that feed the moving averages
+    (tf.nn.moments over every axis of the squeezed weight, population variance) are returned as well."""
     log_prob = num_steps_log_prob(joint, num_step_per_sample)
     iw = importance_weight
     if baseline is not None:
         iw = iw - baseline
+    moments = (iw.detach().mean(), iw.detach().var(unbiased=False))
+    if nvil is not None:
+        mm, mv = (torch.as_tensor(v, dtype=iw.dtype) for v in nvil)
+        iw = (iw - mm) / torch.maximum(torch.sqrt(mv), torch.ones_like(mv))
     rl = (iw.detach() * log_prob).mean()
-    return rl, iw, log_prob
+    return rl, iw, log_prob, moments
 
 
-def elbo(cfg: AirConfig, pc: PriorConfig, obs, outs, global_step=0, baseline=None):
+def elbo(cfg: AirConfig, pc: PriorConfig, obs, outs, global_step=0, baseline=None, nvil=None):
     """model.py:319-343: loss.value = rec + prior_weight * (kl_n + kl_what + kl_where); ELBO = -loss.value."""
     post = postprocess(cfg, outs)
     res = dict(post)
@@ -659,7 +665,9 @@ def elbo(cfg: AirConfig, pc: PriorConfig, obs, outs, global_step=0, baseline=Non
         iw = rps
         if not pc.analytic:
             iw = iw + pl.per_sample
-        rl, iw_full, log_prob = reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, baseline)
+        rl, iw_full, log_prob, moments = reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, baseline,
+                                                   nvil)
+        res["imp_weight_moments"] = moments
         res["reinforce_loss"] = rl
         res["importance_weight"] = iw_full
         res["num_steps_log_prob"] = log_prob
@@ -669,10 +677,11 @@ def elbo(cfg: AirConfig, pc: PriorConfig, obs, outs, global_step=0, baseline=Non
     return res
 
 
-def forward(cfg: AirConfig, pc: PriorConfig, params, img, eps_where, eps_what, u_pres, global_step=0, baseline=None):
+def forward(cfg: AirConfig, pc: PriorConfig, params, img, eps_where, eps_what, u_pres, global_step=0, baseline=None,
+            nvil=None):
     """Whole hot path: unroll + ELBO.  The encoder is NOT hoisted (as written in the reference)."""
     outs, state = unroll(cfg, params, img, eps_where, eps_what, u_pres)
-    res = elbo(cfg, pc, img, outs, global_step, baseline)
+    res = elbo(cfg, pc, img, outs, global_step, baseline, nvil)
     res["outs"] = outs
     res["final_h"], res["final_c"] = state["h"], state["c"]
     return res
@@ -684,6 +693,11 @@ def baseline_mlp(params_b, n_hidden, img, what, where, presence, h, c):
     parts = [t.transpose(0, 1).reshape(B, -1) for t in (what, where, presence)] + [h, c]
     x = torch.cat([img.reshape(B, -1)] + parts, -1)
     return mlp(x, params_b, "baseline", n_hidden, True)
+
+
+def moving_average(var, value, decay):
+    """ops.py:46-64 [upstream assign_moving_average, zero_debias=False]: var <- var - (1 - decay) * (var - value)."""
+    return var - (1.0 - decay) * (var - value)
 
 
 def centered_rmsprop_step(theta, g, mg, ms, mom, lr, decay=0.9, momentum=0.9, eps=1e-10):

@@ -320,3 +320,65 @@ def test_baseline_mlp_training_step_matches_oracle():
                                 torch.ones(n), torch.zeros(n), 1e-3)
     U.assert_close(bm.params.cpu() - theta0, ref_theta - theta0, atol=2e-6, rtol=2e-3, name="baseline update")
     eng.close()
+
+
+def test_nvil_normalised_reinforce_matches_oracle():
+    """decay_rate branch of _reinforce (model.py:232-239): importance weight shifted by the moving mean and divided by
+    max(sqrt(moving var), 1) -- loss scalars, the batch moments that feed the moving averages, and the gradient."""
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    pc = O.PriorConfig()
+    B = 16
+    params, img, nums, noise = U.make_problem(ocfg, B, seed=21)
+    baseline = 250.0 + 30.0 * torch.randn(B, 1, generator=torch.Generator().manual_seed(2))
+    mm, mv = 40.0, 900.0
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    res = O.forward(ocfg, pc, p, img, *noise, global_step=20000, baseline=baseline, nvil=(mm, mv))
+    res["opt_loss"].backward()
+    g_ref = {k: v.grad for k, v in p.items()}
+    dev = "cuda"
+    eng = air.Engine(U.cell_cfg(ocfg, air.AIR_PREC_FP32), B, ocfg.T, device=dev)
+    eng.train_enable(True)
+    flat = O.flatten_params(ocfg, params).to(dev)
+    ew, ea, u = (n.to(dev).contiguous() for n in noise)
+    img_d = img.to(dev).contiguous()
+    pr = U.prior_struct(pc, 20000)
+    pr.nvil_shift, pr.nvil_scale = mm, 1.0 / max(mv ** 0.5, 1.0)
+    out = eng.forward(flat, img_d, ew, ea, u, pr, baseline.reshape(-1).to(dev).contiguous())
+    g = eng.backward(flat, img_d, ew, ea, pr, baseline_mean=float(baseline.mean())).cpu()
+    sc = out["scalars"].cpu()
+    SI = air._lib.SCALAR_INDEX
+    U.assert_close(sc[SI["reinforce_loss"]], res["reinforce_loss"].detach(), atol=1e-3, rtol=2e-4, name="reinforce_loss")
+    U.assert_close(sc[SI["opt_loss"]], res["opt_loss"].detach(), atol=1e-3, rtol=2e-4, name="opt_loss")
+    mean_ref, var_ref = (float(v) for v in res["imp_weight_moments"])
+    mean = float(sc[SI["mean_iw"]] - sc[SI["mean_baseline"]])
+    var = float(sc[SI["mean_iw2"]] - sc[SI["mean_iw"]] ** 2 + sc[SI["mean_baseline2"]] - sc[SI["mean_baseline"]] ** 2)
+    assert abs(mean - mean_ref) <= 1e-4 * abs(mean_ref) + 1e-3, (mean, mean_ref)
+    assert abs(var - var_ref) <= 2e-3 * abs(var_ref), (var, var_ref)
+    compare(ocfg, g, g_ref)
+    eng.close()
+
+
+def test_model_decay_rate_tracks_the_moving_moments():
+    """AIRModel.train_step(decay_rate=...): after one train_op the moving mean / variance of the importance weight are
+    make_moving_average(init 0 / 1) of the batch moments (ops.py:46-64)."""
+    from functools import partial
+    B, T = 32, 3
+    img, nums = O.synthetic_multi_mnist(B, 50, 50, seed=6)
+    model = air.AIRModel(img.cuda(), nums.cuda(), T, (20, 20), 50, air.LSTM(256), partial(air.Encoder, [256, 256]),
+                         partial(air.Encoder, [256, 256]), partial(air.Decoder, [256, 256]),
+                         partial(air.StochasticTransformParam, [256, 256], scale_bias=.5),
+                         partial(air.StepsPredictor, [128, 64], .75), output_std=.3, output_multiplier=.5,
+                         explore_eps=1e-3)
+    pr = dict(loc=0., scale=1.)
+    nsp = dict(anneal='exp', init=1. - 1e-15, final=1e-7, steps_div=1e4, steps=1e5, hold_init=1e3)
+    train_op, _ = model.train_step(1e-5, 0., pr, pr, pr, nsp, decay_rate=0.9)
+    noise = model.cell.draw_noise(B, T, generator=torch.Generator(device="cuda").manual_seed(1))
+    train_op(noise=noise)
+    iw = model.rec_loss_per_sample.double().cpu()
+    mean, var = float(iw.mean()), float(iw.var(unbiased=False))
+    assert abs(model.imp_weight_moving_mean - 0.1 * mean) <= 1e-4 * abs(mean)
+    assert abs(model.imp_weight_moving_var - (0.9 + 0.1 * var)) <= 2e-3 * var
+    assert model._prior_struct.nvil_scale == 1.0 and model._prior_struct.nvil_shift == 0.0   # values BEFORE the update
+    train_op(noise=noise)
+    assert abs(model._prior_struct.nvil_shift - 0.1 * mean) <= 1e-4 * abs(mean)
+    assert abs(model._prior_struct.nvil_scale - 1.0 / max((0.9 + 0.1 * var) ** 0.5, 1.0)) < 1e-3

@@ -34,8 +34,8 @@ def test_struct_layouts_match_header_sizes():
     # air_config: 8 ints + 5 * (1 + AIR_MAX_HIDDEN) ints + 8 floats + 2 ints ; all 4-byte fields -> no padding
     assert ctypes.sizeof(_lib.air_config) == 4 * (8 + 5 * (1 + _lib.AIR_MAX_HIDDEN) + 8 + 2)
     assert ctypes.sizeof(_lib.air_outputs) == 8 * len(_lib.OUTPUT_FIELDS)
-    # air_prior: 6 floats, int, (pad), double, int, float, 3 ints (+ tail pad) with 8-byte alignment
-    assert ctypes.sizeof(_lib.air_prior) == 64
+    # air_prior: 6 floats, int, (pad), double, int, float, 3 ints, 2 floats with 8-byte alignment
+    assert ctypes.sizeof(_lib.air_prior) == 72
     assert _lib.air_prior.steps_success_prob.offset == 32
 
 

@@ -123,7 +123,7 @@ def test_reinforce_broadcast_identity():
     n = torch.randint(0, 4, (B,), generator=g).float()
     rec = torch.randn(B, generator=g) * 100
     base = torch.randn(B, 1, generator=g)
-    rl, iw, lp = O.reinforce(joint, n, rec, base)
+    rl, iw, lp, _ = O.reinforce(joint, n, rec, base)
     assert iw.shape == (B, B)
     want = ((rec - base.mean()) * lp).mean()
     assert torch.allclose(rl, want, rtol=1e-5)

@@ -90,9 +90,9 @@ def test_prior_loss_and_reinforce(i):
     assert close(float(pl.value), g["prior_value"]) and close(pl.per_sample.numpy(), g["prior_per_sample"])
     rec = T32(g["rec"])
     iw = rec if pc.analytic else rec + pl.per_sample
-    r0, iw0, lp = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, None)
+    r0, iw0, lp, _ = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, None)
     assert close(float(r0), g["reinforce_nobaseline"], 1e-5) and close(iw0.numpy(), g["imp_weight_nobaseline"])
     assert close(lp.numpy(), g["log_prob"])
-    r1, iw1, _ = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, T32(g["baseline"]))
+    r1, iw1, _, _ = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, T32(g["baseline"]))
     assert tuple(iw1.shape) == (B, B) == g["imp_weight_baseline"].shape
     assert close(iw1.numpy(), g["imp_weight_baseline"]) and close(float(r1), g["reinforce_baseline"], 1e-5)
