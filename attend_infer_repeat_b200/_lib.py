@@ -204,5 +204,10 @@ def ptr(t):
 
 
 def current_stream_ptr():
+    """torch's current stream on the current device as a cudaStream_t (torch._C entry point: ~0.3 us instead of the
+    ~15 us of torch.cuda.current_stream(), which matters for the launch-bound small-batch training loop)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:      # private entry point moved: fall back to the public (slower) API
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)

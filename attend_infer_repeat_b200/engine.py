@@ -7,6 +7,7 @@ stream; nothing is computed in torch.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -227,7 +228,7 @@ class Engine:
             return None
         if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
             raise _lib.AirError(f"{name} must be a contiguous CUDA float32 tensor")
-        if int(np.prod(t.shape)) != int(np.prod(shape)):
+        if t.numel() != math.prod(shape):
             raise _lib.AirError(f"{name} has {tuple(t.shape)}, expected {tuple(shape)}")
         return t
 
