@@ -165,7 +165,9 @@ struct air_handle {
   __half *hl_xt = nullptr, *hl_yt = nullptr;
   size_t hl_xt_halves = 0, hl_yt_halves = 0;   // per plane
   // tensor-core input gradients (dX = dY @ W^T): dY row-major planes, W as stored ([in][out]) planes per layer
-  __half *hl_dy = nullptr, *wnt_arena = nullptr;
+  __half *hl_dy2[2] = {nullptr, nullptr}, *wnt_arena = nullptr;   // dY planes, double buffered: a dX GEMM's epilogue
+                                                                  // writes the planes the next dX GEMM reads
+  int dy_ready_buf = 0;
   size_t hl_dy_halves = 0;
   std::map<int64_t, std::pair<size_t, int>> wnt_index;   // Layer::w_off -> (half offset of the hi plane, Npad)
   air::tc::RowsEntry* wnt_table = nullptr;               // device copy of the per-matrix table (prep_weights_rows_kernel)
@@ -874,7 +876,8 @@ void carve_train(air_handle* h, Carver& cv) {
     visit2(h->lstm_h, TB);
     visit2(h->lstm_x, B);
     h->hl_dy_halves = dy;
-    h->hl_dy = cv.take<__half>(2 * dy);
+    h->hl_dy2[0] = cv.take<__half>(2 * dy);
+    h->hl_dy2[1] = cv.take<__half>(2 * dy);
     h->wnt_arena = cv.take<__half>(wnt);
     h->wnt_table = cv.take<air::tc::RowsEntry>(h->wnt_index.size());
   }
@@ -945,11 +948,14 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
   // one read of dY: transposed planes (this GEMM), the bias gradient, and the row-major planes of the dX GEMM that follows
   AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((dx_follows ? np : l.N + 31) / 32, (mp + tc::ST_M - 1) / tc::ST_M), dim3(256), 0,
                          st, dY, ldy, M, l.N, 1.0f, h->hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1,
-                         dx_follows ? h->hl_dy : (__half*)nullptr, (size_t)MA * np, np,
+                         dx_follows ? h->hl_dy2[0] : (__half*)nullptr, (size_t)MA * np, np,
                          l.b_off >= 0 ? grad + l.b_off : (float*)nullptr));
-  h->dy_ready = dx_follows ? dY : nullptr;
-  h->dy_ready_m = M;
-  h->dy_ready_n = l.N;
+  if (dx_follows) {
+    h->dy_ready = dY;
+    h->dy_ready_m = M;
+    h->dy_ready_n = l.N;
+    h->dy_ready_buf = 0;
+  }
   if (h->side) {   // dY (and X, which nobody overwrites within a pass) have been read
     cudaEvent_t done = next_event(h);
     AIR_CUDA(cudaEventRecord(done, st));
@@ -999,21 +1005,23 @@ int32_t layer_param_grads(air_handle* h, float* grad, const Layer& l, const floa
 // layer's N outputs), W [K, N] exactly as stored (its rows are the output columns of dX) from the per-step weight arena
 // prepared by prep_backward_weights; elu' mask, accumulation (atomicAdd) in the epilogue.
 int32_t layer_input_grad_tc(air_handle* h, const Layer& l, const float* dY, int ldy, float* dX, int ldx, int M,
-                            bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st) {
+                            bool accumulate, const float* elu_x, int ld_elu, bool planes_for_next, cudaStream_t st) {
   namespace tc = air::tc;
   const int np = round_up(l.N, 64), MA = round_up(M, 128), KA = round_up(l.K, 64);
   if ((size_t)MA * np > h->hl_dy_halves) return fail(AIR_ERR_ARG, "internal: dY does not fit the training workspace");
   const auto it = h->wnt_index.find(l.w_off);
   if (it == h->wnt_index.end()) return fail(AIR_ERR_ARG, "internal: weight not in the backward arena");
-  if (h->dy_ready != dY || h->dy_ready_m != M || h->dy_ready_n != l.N) {   // not left behind by layer_weight_grad_tc
+  int buf = h->dy_ready_buf;
+  if (h->dy_ready != dY || h->dy_ready_m != M || h->dy_ready_n != l.N) {   // not left behind by the previous GEMM's epilogue
+    buf = 0;
     const size_t n4 = (size_t)M * (np / 4);
     AIR_CUDA(air::launch_k(tc::split_rows_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dY, ldy, M, l.N,
-                           h->hl_dy, (size_t)MA * np, np, h->t_range_flag));
+                           h->hl_dy2[0], (size_t)MA * np, np, h->t_range_flag));
     ++h->launches;
   }
   h->dy_ready = nullptr;
   const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
-  int32_t rc = get_tmap2(h, h->hl_dy, np, 2LL * MA, tc::BM, &tm_a);
+  int32_t rc = get_tmap2(h, h->hl_dy2[buf], np, 2LL * MA, tc::BM, &tm_a);
   if (rc != AIR_OK) return rc;
   if ((rc = get_tmap2(h, h->wnt_arena + it->second.first, np, 2LL * KA, 64, &tm_b)) != AIR_OK) return rc;
   tc::GemmParams p;
@@ -1032,6 +1040,17 @@ int32_t layer_input_grad_tc(air_handle* h, const Layer& l, const float* dY, int 
   p.ab_bf16 = 1;
   p.mask_y = elu_x;
   p.ld_mask = ld_elu;
+  if (planes_for_next && !accumulate && (size_t)MA * KA <= h->hl_dy_halves) {
+    // dX is the dY of the layer below: its row-major bf16 planes come straight out of this epilogue
+    p.out_hl = h->hl_dy2[buf ^ 1];
+    p.hl_plane = (size_t)MA * KA;
+    p.ld_hl = KA;
+    p.hl_bf16 = 1;
+    h->dy_ready = dX;
+    h->dy_ready_m = M;
+    h->dy_ready_n = l.K;
+    h->dy_ready_buf = buf ^ 1;
+  }
   AIR_CUDA(tc::launch_gemm(64, *tm_a, *tm_b, p, KA, st));
   ++h->launches;
   return AIR_OK;
@@ -1072,10 +1091,12 @@ int32_t upload_backward_weight_table(air_handle* h) {
 
 // dX = dY @ W^T (* elu'(X) when elu_x is the saved forward value of X)
 int32_t layer_input_grad(air_handle* h, const float* params, const Layer& l, const float* dY, int ldy, float* dX, int ldx,
-                         int M, bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st) {
+                         int M, bool accumulate, const float* elu_x, int ld_elu, cudaStream_t st,
+                         bool planes_for_next = false) {
   const int32_t rcw = wait_consumed(h, dX, st);
   if (rcw != AIR_OK) return rcw;
-  if (h->tc_bwd && M >= 64) return layer_input_grad_tc(h, l, dY, ldy, dX, ldx, M, accumulate, elu_x, ld_elu, st);
+  if (h->tc_bwd && M >= 64)
+    return layer_input_grad_tc(h, l, dY, ldy, dX, ldx, M, accumulate, elu_x, ld_elu, planes_for_next, st);
   AIR_CUDA(air::launch_gemm_simt(false, true, dY, ldy, params + l.w_off, l.N, dX, ldx, M, l.K, l.N, accumulate, elu_x,
                                  ld_elu, 1, st));
   ++h->launches;
@@ -1100,7 +1121,8 @@ int32_t mlp_backward(air_handle* h, const float* params, float* grad, const Mlp&
     if (rc != AIR_OK) return rc;
     if (i > 0) {
       float* dst = (cur == h->g_a) ? h->g_b : h->g_a;
-      rc = layer_input_grad(h, params, l, cur, ld_cur, dst, l.K, M, false, X, ldx, st);   // X is an ELU output
+      rc = layer_input_grad(h, params, l, cur, ld_cur, dst, l.K, M, false, X, ldx, st,   // X is an ELU output
+                            /*planes_for_next=*/i - 1 > 0 || dx0 != nullptr);
       if (rc != AIR_OK) return rc;
       cur = dst;
       ld_cur = l.K;
@@ -1187,7 +1209,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   if ((rc = layer_param_grads(h, grad, h->what_lin, h->sv_q, h->what_lin.K, h->g_r, 2 * na, TB, st, true)) != AIR_OK)
     return rc;
   if ((rc = layer_input_grad(h, params, h->what_lin, h->g_r, 2 * na, h->g_a, h->what_lin.K, TB, false, h->sv_q,
-                             h->what_lin.K, st)) != AIR_OK)
+                             h->what_lin.K, st, /*planes_for_next=*/true)) != AIR_OK)
     return rc;
   if ((rc = mlp_backward(h, params, grad, h->glenc, h->crop.f32, G, h->sv_glenc, h->g_a, h->what_lin.K, TB, h->g_crop, G,
                          false, st)) != AIR_OK)
@@ -1212,7 +1234,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
                            (const float*)(h->gates_all + off * 4 * nh), (const float*)(h->c_all + off * nh),
                            (const float*)(h->c_all + (off + B) * nh), (const float*)(h->g_h + off * nh),
                            (const float*)(t == T - 1 ? nullptr : h->g_hrec), h->g_c, h->g_gates + off * 4 * nh, B, nh,
-                           c.forget_bias, t == T - 1 ? 1 : 0));
+                           c.forget_bias, t == T - 1 ? 1 : 0, h->g_gx));
     ++h->launches;
     // d h_{t-1} = dgates_t @ W_h^T  (t = 0: gradient of the trainable initial state)
     if ((rc = layer_input_grad(h, params, h->lstm_h, h->g_gates + off * 4 * nh, 4 * nh, h->g_hrec, nh, B, false, nullptr,
@@ -1226,16 +1248,12 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
     Layer wh = h->lstm_h;
     wh.b_off = h->lstm_b;   // db = colsum over all T*B gate rows
     if ((rc = layer_param_grads(h, grad, wh, h->hprev, nh, h->g_gates, 4 * nh, TB, st)) != AIR_OK) return rc;
-    const size_t n = (size_t)B * 4 * nh;
-    AIR_CUDA(air::launch_k(air::sum_steps_kernel, dim3((unsigned)((n + thr - 1) / thr)), dim3(thr), 0, st,
-                           (const float*)h->g_gates, h->g_gx, T, n));
-    ++h->launches;
-    Layer wx = h->lstm_x;
+    Layer wx = h->lstm_x;   // (d gx = sum_t dgates_t was accumulated by the gate kernels)
     wx.b_off = -1;
     if ((rc = layer_param_grads(h, grad, wx, h->e.f32, h->n_enc, h->g_gx, 4 * nh, B, st, true)) != AIR_OK) return rc;
     // 9. input encoder (its last layer is an ELU layer: mask with the saved output e)   cell.py:125
-    if ((rc = layer_input_grad(h, params, wx, h->g_gx, 4 * nh, h->g_e, h->n_enc, B, false, h->e.f32, h->n_enc, st)) !=
-        AIR_OK)
+    if ((rc = layer_input_grad(h, params, wx, h->g_gx, 4 * nh, h->g_e, h->n_enc, B, false, h->e.f32, h->n_enc, st,
+                               /*planes_for_next=*/h->enc.layers.size() > 1)) != AIR_OK)
       return rc;
     if ((rc = mlp_backward(h, params, grad, h->enc, img, P, h->sv_enc, h->g_e, h->n_enc, B, nullptr, 0, false, st)) !=
         AIR_OK)

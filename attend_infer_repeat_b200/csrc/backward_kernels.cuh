@@ -505,7 +505,8 @@ inline cudaError_t launch_latent_bwd(const BwdArgs& a, cudaStream_t st) {
 __global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
                                           const float* __restrict__ c_new, const float* __restrict__ dh_heads,
                                           const float* __restrict__ dh_rec, float* __restrict__ dc,
-                                          float* __restrict__ dgates, int B, int nh, float forget_bias, int first) {
+                                          float* __restrict__ dgates, int B, int nh, float forget_bias, int first,
+                                          float* __restrict__ dgx) {
   griddep_launch();
   griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -519,22 +520,20 @@ __global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const
   const float dh = dh_heads[idx] + (dh_rec ? dh_rec[idx] : 0.f);
   const float dcv = (first ? 0.f : dc[idx]) + dh * so * (1.0f - tc * tc);
   float* dg = dgates + b * 4 * (size_t)nh;
-  dg[u] = dcv * tj * si * (1.0f - si);
-  dg[nh + u] = dcv * si * (1.0f - tj * tj);
-  dg[2 * nh + u] = dcv * c_prev[idx] * sf * (1.0f - sf);
-  dg[3 * nh + u] = dh * tc * so * (1.0f - so);
+  const float d_i = dcv * tj * si * (1.0f - si), d_j = dcv * si * (1.0f - tj * tj);
+  const float d_f = dcv * c_prev[idx] * sf * (1.0f - sf), d_o = dh * tc * so * (1.0f - so);
+  dg[u] = d_i;
+  dg[nh + u] = d_j;
+  dg[2 * nh + u] = d_f;
+  dg[3 * nh + u] = d_o;
   dc[idx] = dcv * sf;
-}
-
-// out[b, :] = sum_t x[t, b, :]   (the LSTM's input half sees the same encoder output at every step)
-__global__ void sum_steps_kernel(const float* __restrict__ x, float* __restrict__ out, int T, size_t n) {
-  griddep_launch();
-  griddep_wait();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int t = 0; t < T; ++t) s += x[(size_t)t * n + i];
-  out[i] = s;
+  if (dgx) {   // the LSTM's input half sees the same encoder output at every step: d gx = sum_t dgates_t, accumulated here
+    float* sx = dgx + b * 4 * (size_t)nh;
+    sx[u] = (first ? 0.f : sx[u]) + d_i;
+    sx[nh + u] = (first ? 0.f : sx[nh + u]) + d_j;
+    sx[2 * nh + u] = (first ? 0.f : sx[2 * nh + u]) + d_f;
+    sx[3 * nh + u] = (first ? 0.f : sx[3 * nh + u]) + d_o;
+  }
 }
 
 // grad[i] += l2 * w[i]   (l2_weight * tf.nn.l2_loss(w) on the 2-D variables, model.py:345-350)

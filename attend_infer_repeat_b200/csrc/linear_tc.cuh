@@ -155,6 +155,7 @@ struct GemmParams {
   int atomic_out;        // out_f32 += result with atomicAdd (split-K weight gradients into the zeroed gradient buffer)
   const float* mask_y;   // [M, ld_mask] forward ELU output: result *= (y > 0 ? 1 : y + 1)   (tf.nn.elu gradient)
   int ld_mask;
+  int hl_bf16;           // out_hl receives bf16 hi/lo planes (the next gradient GEMM's A operand) instead of fp16 ones
   int ab_bf16;           // both operands hold bf16 hi/lo planes (fp32 exponent range, 16 significant bits) instead of fp16
   long long* trace;      // AIR_TC_TRACE builds only: [n_ctas][16] SM-clock timestamps of the pipeline phases
 };
@@ -372,10 +373,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         if (p.out_hl && n0 + c0 < p.ld_hl) {
           __align__(16) __half hi[16], lo[16];
+          if (p.hl_bf16) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            split_f16(v[j], hi[j], lo[j]);
-            amax = fmax_nan(amax, fabsf(v[j]));
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat16 bh = __float2bfloat16_rn(v[j]);
+              const __nv_bfloat16 bl = __float2bfloat16_rn(v[j] - __bfloat162float(bh));
+              hi[j] = __ushort_as_half(__bfloat16_as_ushort(bh));
+              lo[j] = __ushort_as_half(__bfloat16_as_ushort(bl));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              split_f16(v[j], hi[j], lo[j]);
+              amax = fmax_nan(amax, fabsf(v[j]));
+            }
           }
           __half* dh = p.out_hl + (size_t)row * p.ld_hl + n0 + c0;
           __half* dl = dh + p.hl_plane;
