@@ -116,10 +116,13 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   BTap* s_ty = s_tx + (size_t)T * W;                                                                     // [T][H]
   griddep_launch();
   griddep_wait();
-  for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
-    const int t = i / G, g = i - t * G;
-    s_gl[i] = a.glimpse[((size_t)t * B + b) * G + g];
-    s_dgl[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float* src = a.glimpse + ((size_t)t * B + b) * G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      s_gl[t * G + g] = src[g];
+      s_dgl[t * G + g] = 0.f;
+    }
   }
   if (threadIdx.x < T) {
     const float* wh = a.where + ((size_t)threadIdx.x * B + b) * 4;
@@ -205,9 +208,10 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
       if (lane == 0) s_red[wid][t * 4 + k] = v;
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
-    const int t = i / G, g = i - t * G;
-    a.dglimpse[((size_t)t * B + b) * G + g] = s_dgl[i];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float* dst = a.dglimpse + ((size_t)t * B + b) * G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = s_dgl[t * G + g];
   }
   if (threadIdx.x < T) {
     const int t = threadIdx.x;
