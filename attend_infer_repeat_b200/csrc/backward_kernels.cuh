@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   __shared__ float4 s_inv[AIR_MAX_STEPS];
   __shared__ float s_pres[AIR_MAX_STEPS];
   __shared__ float s_red[8][4 * T];
+  __shared__ int s_rect[T][4];   // canvas rectangle inside glimpse t's footprint: c_lo, c_hi, r_lo, r_hi
   const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
   const int P = H * W, G = h * w;
   const int b = blockIdx.x;
@@ -130,6 +131,10 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
     inv_params(wh[0], wh[1], wh[2], wh[3], iv.x, iv.y, iv.z, iv.w);
     s_inv[threadIdx.x] = iv;
     s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
+    s_rect[threadIdx.x][0] = W;
+    s_rect[threadIdx.x][1] = -1;
+    s_rect[threadIdx.x][2] = H;
+    s_rect[threadIdx.x][3] = -1;
   }
   __syncthreads();
   for (int t = 0; t < T; ++t) {
@@ -137,10 +142,20 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
     for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
       if (j < W) {
         const float xg = inv_coord_s(iv.x, iv.z, j, a.step_W, w);
-        s_tx[t * W + j] = make_btap(xg, w, 1, xg);
+        const BTap tp = make_btap(xg, w, 1, xg);
+        s_tx[t * W + j] = tp;
+        if (btap_inside(tp)) {
+          atomicMin(&s_rect[t][0], j);
+          atomicMax(&s_rect[t][1], j);
+        }
       } else {
         const float yg = inv_coord_s(iv.y, iv.w, j - W, a.step_H, h);
-        s_ty[t * H + (j - W)] = make_btap(yg, h, w, yg);
+        const BTap tp = make_btap(yg, h, w, yg);
+        s_ty[t * H + (j - W)] = tp;
+        if (btap_inside(tp)) {
+          atomicMin(&s_rect[t][2], j - W);
+          atomicMax(&s_rect[t][3], j - W);
+        }
       }
     }
   }
@@ -151,51 +166,43 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   float acc[T][4];   // per step: sum gx * (xg - S_w), sum gx, sum gy * (yg - S_h), sum gy
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-  // A thread owns a fixed canvas column and walks down the rows (same mapping as the forward paint kernel): whether the
-  // column lies inside glimpse t's footprint is loop-invariant, and a pixel no present glimpse covers costs no global load.
-  const int NT = blockDim.x;
-  const int TPRB = W < NT ? W : NT, RPP = NT / TPRB;
-  const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
+  // The inverse warp is axis-aligned and monotone, so the canvas pixels glimpse t covers form ONE rectangle
+  // [c_lo, c_hi] x [r_lo, r_hi] (s_rect, found while the tap tables were built).  The CTA tiles that rectangle -- a warp per
+  // row, a lane per column -- so every thread-iteration is a pixel that contributes: no footprint tests, no idle threads
+  // beside the ragged edge of a 32-wide row chunk.
   const float* obs = a.img + (size_t)b * P;
   const float* mu = a.canvas_final + (size_t)b * P;
-  if (rslot < RPP) {
-    for (int c = cslot; c < W; c += TPRB) {
-      uint32_t colmask = 0;
+  const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 #pragma unroll
-      for (int t = 0; t < T; ++t)
-        if (s_pres[t] != 0.f && btap_inside(s_tx[t * W + c])) colmask |= 1u << t;
-      if (!colmask) continue;
-      for (int r = rslot; r < H; r += RPP) {
-        uint32_t act = 0;
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-          if (((colmask >> t) & 1u) && btap_inside(s_ty[t * H + r])) act |= 1u << t;
-        if (!act) continue;
+  for (int t = 0; t < T; ++t) {
+    const float pres = s_pres[t];
+    const int c_lo = s_rect[t][0], c_hi = s_rect[t][1], r_lo = s_rect[t][2], r_hi = s_rect[t][3];
+    if (pres == 0.f || c_hi < c_lo || r_hi < r_lo) continue;
+    const float* D = s_gl + t * G;
+    float* dD = s_dgl + t * G;
+    for (int r = r_lo + warp_; r <= r_hi; r += n_warps) {
+      const BTap by = s_ty[t * H + r];
+      const int yc = by.i_c_fl & 0xffffff;
+      const int yf_ok = (by.i_c_fl >> 24) & 1, yc_ok = (by.i_c_fl >> 25) & 1;
+      const float dy = by.d;
+      for (int c = c_lo + lane_; c <= c_hi; c += 32) {
+        const BTap bx = s_tx[t * W + c];
         const int p = r * W + c;
-        const float dC = coef * (obs[p] - mu[p]);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          if (!((act >> t) & 1u)) continue;
-          const BTap bx = s_tx[t * W + c], by = s_ty[t * H + r];
-          const float gv = s_pres[t] * dC;
-          const float dx = bx.d, dy = by.d;
-          const float* D = s_gl + t * G;
-          float* dD = s_dgl + t * G;
-          const Quad q = load_quad(D, bx, by);
-          const int xc = bx.i_c_fl & 0xffffff, yc = by.i_c_fl & 0xffffff;
-          const int xf_ok = (bx.i_c_fl >> 24) & 1, xc_ok = (bx.i_c_fl >> 25) & 1;
-          const int yf_ok = (by.i_c_fl >> 24) & 1, yc_ok = (by.i_c_fl >> 25) & 1;
-          if (xf_ok & yf_ok) atomicAdd(dD + by.i_f + bx.i_f, gv * dx * dy);
-          if (xc_ok & yc_ok) atomicAdd(dD + yc + xc, gv * (1.0f - dx) * (1.0f - dy));
-          if (xf_ok & yc_ok) atomicAdd(dD + yc + bx.i_f, gv * dx * (1.0f - dy));
-          if (xc_ok & yf_ok) atomicAdd(dD + by.i_f + xc, gv * (1.0f - dx) * dy);
-          const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
-          const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
-          acc[t][0] = fmaf(gx, bx.aux - S_w, acc[t][0]);
-          acc[t][1] += gx;
-          acc[t][2] = fmaf(gy, by.aux - S_h, acc[t][2]);
-          acc[t][3] += gy;
-        }
+        const float gv = pres * coef * (obs[p] - mu[p]);
+        const float dx = bx.d;
+        const Quad q = load_quad(D, bx, by);
+        const int xc = bx.i_c_fl & 0xffffff;
+        const int xf_ok = (bx.i_c_fl >> 24) & 1, xc_ok = (bx.i_c_fl >> 25) & 1;
+        if (xf_ok & yf_ok) atomicAdd(dD + by.i_f + bx.i_f, gv * dx * dy);
+        if (xc_ok & yc_ok) atomicAdd(dD + yc + xc, gv * (1.0f - dx) * (1.0f - dy));
+        if (xf_ok & yc_ok) atomicAdd(dD + yc + bx.i_f, gv * dx * (1.0f - dy));
+        if (xc_ok & yf_ok) atomicAdd(dD + by.i_f + xc, gv * (1.0f - dx) * dy);
+        const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
+        const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
+        acc[t][0] = fmaf(gx, bx.aux - S_w, acc[t][0]);
+        acc[t][1] += gx;
+        acc[t][2] = fmaf(gy, by.aux - S_h, acc[t][2]);
+        acc[t][3] += gy;
       }
     }
   }
