@@ -118,6 +118,8 @@ SYMBOLS = {
     "air_elbo_scalars_raw": (C.c_int32, [C.c_int32, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_prior_terms": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior),
                                     C.POINTER(air_outputs), _P]),
+    "air_iwae_bound": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_P] * 9 + [C.POINTER(air_prior), _P, _P,
+                                                                                              _P, _P]),
     "air_cell_step": (C.c_int32, [_P] * 19),
     "air_linear": (C.c_int32, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "air_lstm_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P]),

@@ -1835,6 +1835,39 @@ int32_t air_prior_terms(int32_t B, int32_t T, int32_t na, const float* what_loc,
   return AIR_OK;
 }
 
+int32_t air_iwae_bound(int32_t n_canvases, int32_t K, int32_t T, int32_t na, const float* what, const float* what_loc,
+                       const float* what_scale, const float* where, const float* where_loc, const float* where_scale,
+                       const float* presence, const float* rec_loss_per_row, const float* num_steps_log_prob_per_row,
+                       const air_prior* prior, float* log_w, float* bound_per_canvas, float* bound_mean, void* stream) {
+  if (n_canvases < 1 || K < 1 || T < 1 || T > AIR_MAX_STEPS || na < 1 || !what || !what_loc || !what_scale || !where ||
+      !where_loc || !where_scale || !presence || !rec_loss_per_row || !num_steps_log_prob_per_row || !prior || !log_w ||
+      !bound_per_canvas)
+    return fail(AIR_ERR_ARG, "air_iwae_bound: bad argument");
+  if (!prior->where_shift_has_loc)
+    return fail(AIR_ERR_ARG, "air_iwae_bound: the where-shift prior needs a location (a density, not a KL, is evaluated)");
+  air::IwaeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.what = what; a.what_loc = what_loc; a.what_scale = what_scale;
+  a.where = where; a.where_loc = where_loc; a.where_scale = where_scale;
+  a.presence = presence;
+  a.rec_loss = rec_loss_per_row;
+  a.log_q_n = num_steps_log_prob_per_row;
+  a.log_w = log_w;
+  a.T = T;
+  a.R = n_canvases * K;
+  a.na = na;
+  a.prior = *prior;
+  for (int k = 0; k <= T; ++k)
+    a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
+                                                : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
+  cudaStream_t st = (cudaStream_t)stream;
+  air::iwae_logw_kernel<<<(a.R + 3) / 4, 128, 0, st>>>(a);
+  AIR_CUDA(cudaGetLastError());
+  air::iwae_reduce_kernel<<<1, 1024, 0, st>>>(log_w, bound_per_canvas, bound_mean, n_canvases, K);
+  AIR_CUDA(cudaGetLastError());
+  return AIR_OK;
+}
+
 int32_t air_cell_step(air_handle* h, const float* params, const float* img, float* canvas, float* hstate,
                       float* cstate, float* presence, const float* eps_where, const float* eps_what,
                       const float* u_pres, float* out_glimpse, float* out_what, float* out_what_loc,

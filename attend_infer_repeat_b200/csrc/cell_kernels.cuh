@@ -900,6 +900,83 @@ elbo_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Importance-weighted bound (BASELINE.json configs[4]; an EXTENSION -- the reference has no IWAE).
+// K particles per canvas are K rows of the ordinary forward pass (row = canvas * K + particle, same image, own noise).
+//   log w = log p(x | z) + log p(z, n) - log q(z, n | x)
+//   log p(x | z)      = -rec_loss                                           (Normal(canvas, sigma), model.py:319-321)
+//   log q(z, n | x)   = log q(n) + sum_{t < n} [log N(what_t; loc, scale) + log N(where_t; loc, scale)]
+//   log p(z, n)       = log prior(n) + sum_{t < n} [log N(what_t; what prior) + log N(where_t; scale / shift priors)]
+// with n = the sampled number of steps (steps whose presence is 1 -- later latents never reach the canvas), q(n) the
+// NumStepsDistribution (prior.py:119-151), prior(n) the geometric prior table (prior.py:26-32), Normal priors as in
+// multi_mnist.py:49-51.  One warp per row (lanes over the what latents), float64 for the step-count terms.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float normal_logpdf(float x, float mu, float s) {
+  const float z = (x - mu) / s;
+  return -0.5f * z * z - logf(s) - 0.9189385332046727f;   // 0.5 log(2 pi)
+}
+struct IwaeArgs {
+  const float *what, *what_loc, *what_scale;      // [T, R, na]
+  const float *where, *where_loc, *where_scale;   // [T, R, 4]
+  const float* presence;                          // [T, R]
+  const float* rec_loss;                          // [R]
+  const float* log_q_n;                           // [R]  num_steps_log_prob
+  float* log_w;                                   // [R]
+  int T, R, na;
+  air_prior prior;
+  double steps_prior[AIR_MAX_STEPS + 1];
+};
+__global__ void __launch_bounds__(128) iwae_logw_kernel(IwaeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const air_prior& pr = a.prior;
+  float lq = 0.f, lp = 0.f;
+  int n = 0;
+  for (int t = 0; t < a.T; ++t) {
+    const size_t row = (size_t)t * a.R + r;
+    if (a.presence[row] == 0.f) break;   // presence is a cumulative product: once 0 it stays 0 (cell.py:148)
+    ++n;
+    const size_t base = row * a.na;
+    for (int i = lane; i < a.na; i += 32) {
+      const float x = a.what[base + i];
+      lq += normal_logpdf(x, a.what_loc[base + i], a.what_scale[base + i]);
+      lp += normal_logpdf(x, pr.what_loc, pr.what_scale);
+    }
+    if (lane < 4) {
+      const float x = a.where[row * 4 + lane];
+      const bool shift = lane & 1;
+      lq += normal_logpdf(x, a.where_loc[row * 4 + lane], a.where_scale[row * 4 + lane]);
+      lp += normal_logpdf(x, shift ? pr.where_shift_loc : pr.where_scale_loc,
+                          shift ? pr.where_shift_scale : pr.where_scale_scale);
+    }
+  }
+  lq = warp_sum(lq);
+  lp = warp_sum(lp);
+  if (lane == 0) {
+    const double log_pn = log(a.steps_prior[n]);
+    a.log_w[r] = (float)((double)(-a.rec_loss[r]) + ((double)lp + log_pn) - ((double)lq + (double)a.log_q_n[r]));
+  }
+}
+// bound[b] = logsumexp_k log_w[b*K + k] - log K; *mean = batch mean (one CTA, fixed order)
+__global__ void __launch_bounds__(1024)
+iwae_reduce_kernel(const float* __restrict__ log_w, float* __restrict__ bound, float* __restrict__ mean, int n, int K) {
+  __shared__ float s_red[32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < n; b += blockDim.x) {
+    const float* lw = log_w + (size_t)b * K;
+    float m = lw[0];
+    for (int k = 1; k < K; ++k) m = fmaxf(m, lw[k]);
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) sum += exp((double)lw[k] - (double)m);
+    const float v = (float)((double)m + log(sum) - log((double)K));
+    bound[b] = v;
+    acc += v;
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0 && mean) *mean = acc / (float)n;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // prior.py building blocks as stand-alone kernels (unit parity with test/prior_test.py)
 // ---------------------------------------------------------------------------------------------------
 __global__ void modified_geometric_kernel(const float* __restrict__ probs, float* __restrict__ pmf, int64_t n, int T) {

@@ -361,6 +361,24 @@ class Engine:
                                                   ptr(img_out), current_stream_ptr()), "air_forward_dataset_u8")
         return self.out
 
+    def iwae_bound(self, K: int, prior: air_prior):
+        """Importance-weighted bound of the LAST forward(), whose B rows are B/K canvases x K particles (row = canvas * K +
+        particle; feed ``img.repeat_interleave(K, 0)`` and independent noise).  Returns (mean bound [scalar tensor],
+        bound per canvas [B/K], log_w [B])."""
+        if self.B % K:
+            raise _lib.AirError(f"batch {self.B} is not a multiple of K = {K}")
+        n, o, dev = self.B // K, self.out, self.device
+        log_w = torch.empty(self.B, device=dev)
+        bound = torch.empty(n, device=dev)
+        mean = torch.empty(1, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.air_iwae_bound(n, K, self.T, self.cfg.na, ptr(o["what"]), ptr(o["what_loc"]),
+                                          ptr(o["what_scale"]), ptr(o["where"]), ptr(o["where_loc"]),
+                                          ptr(o["where_scale"]), ptr(o["presence"]), ptr(o["rec_loss_per_sample"]),
+                                          ptr(o["num_steps_log_prob"]), C.byref(prior), ptr(log_w), ptr(bound), ptr(mean),
+                                          current_stream_ptr()), "air_iwae_bound")
+        return mean[0], bound, log_w
+
     def cell_step(self, params, img, canvas, h, c, presence, eps_where, eps_what, u_pres):
         """One AIRCell step (cell.py:116-171); canvas / h / c / presence are updated IN PLACE.  Returns the per-step
         outputs glimpse, what, what_loc, what_scale, where, where_loc, where_scale, presence_prob."""

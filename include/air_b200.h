@@ -245,6 +245,17 @@ int32_t air_gather_u8(const uint8_t* dataset_u8, const int32_t* idx, float* img_
 int32_t air_cache_weights(air_handle* h, int32_t on);
 int32_t air_params_updated(air_handle* h);
 
+/* Importance-weighted bound (BASELINE.json configs[4]; an EXTENSION: the reference has no IWAE).  The K particles of a
+ * canvas are K consecutive rows (row = canvas * K + particle: same image, own noise) of an ordinary air_forward over
+ * R = n_canvases * K rows with a prior; this call turns that pass's outputs into
+ *   log_w[R]              = log p(x|z) + log p(z,n) - log q(z,n|x)   (Normal priors, geometric step prior, NumStepsDistribution)
+ *   bound_per_canvas[n]   = logsumexp_k log_w - log K,    *bound_mean = their batch mean (may be NULL).
+ * All particles of a canvas live on one device, so batch sharding needs no extra collective. */
+int32_t air_iwae_bound(int32_t n_canvases, int32_t K, int32_t T, int32_t na, const float* what, const float* what_loc,
+                       const float* what_scale, const float* where, const float* where_loc, const float* where_scale,
+                       const float* presence, const float* rec_loss_per_row, const float* num_steps_log_prob_per_row,
+                       const air_prior* prior, float* log_w, float* bound_per_canvas, float* bound_mean, void* stream);
+
 /* ---- training step: opt.compute_gradients(opt_loss, model_vars) + opt.apply_gradients of
  *      AIRModel.train_step (model.py:261-265,335-360) ------------------------------------------------------- */
 /* Switch a handle (AIR_PREC_FP32 engine, discrete_steps = 1) to training mode: allocates the second workspace

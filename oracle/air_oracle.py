@@ -687,6 +687,35 @@ def forward(cfg: AirConfig, pc: PriorConfig, params, img, eps_where, eps_what, u
     return res
 
 
+def iwae_bound(cfg: AirConfig, pc: PriorConfig, res, K: int, global_step=0):
+    """Importance-weighted bound from a forward() result whose rows are canvases x K particles (row = canvas * K + k).
+    NOT in the reference: float64 restatement of log(1/K sum_k w_k),
+    log w = log p(x|z) + log p(z,n) - log q(z,n|x), from the same distributions the ELBO uses (Normal priors
+    multi_mnist.py:49-51, geometric step prior prior.py:26-32, NumStepsDistribution.log_prob prior.py:148-151);
+    latents of steps whose sampled presence is 0 never reach the canvas and are left out.  PARITY UNPINNED."""
+    outs = res["outs"]
+    T, R = outs["presence"].shape[:2]
+    d = lambda t: t.detach().to(F64)
+    pres = d(outs["presence"]).reshape(T, R)
+
+    def logpdf(x, mu, s):
+        mu, s = torch.as_tensor(mu, dtype=F64), torch.as_tensor(s, dtype=F64)
+        return -0.5 * ((x - mu) / s) ** 2 - torch.log(s) - 0.5 * math.log(2.0 * math.pi)
+
+    what, where = d(outs["what"]), d(outs["where"])
+    lq = (logpdf(what, d(outs["what_loc"]), d(outs["what_scale"])).sum(-1)
+          + logpdf(where, d(outs["where_loc"]), d(outs["where_scale"])).sum(-1))
+    lp_where = (logpdf(where[..., 0::2], pc.where_scale_loc, pc.where_scale_scale).sum(-1)
+                + logpdf(where[..., 1::2], pc.where_shift_loc, pc.where_shift_scale).sum(-1))
+    lp = logpdf(what, pc.what_loc, pc.what_scale).sum(-1) + lp_where
+    lq, lp = (lq * pres).sum(0), (lp * pres).sum(0)                      # only steps that were taken
+    n = pres.sum(0).long()
+    prior_n = geometric_prior(steps_prior_success_prob(pc, global_step), cfg.T).to(F64)
+    log_w = -d(res["rec_loss_per_sample"]) + (lp + torch.log(prior_n[n])) - (lq + d(res["num_steps_log_prob"]))
+    per_canvas = torch.logsumexp(log_w.reshape(R // K, K), dim=1) - math.log(K)
+    return dict(log_w=log_w, bound_per_canvas=per_canvas, bound=per_canvas.mean())
+
+
 def baseline_mlp(params_b, n_hidden, img, what, where, presence, h, c):
     """modules.py:125-143: concat[img, what (batch-major), where, presence, h, c] -> MLP -> [B,1]."""
     B = img.shape[0]

@@ -577,3 +577,33 @@ def test_in_library_noise_is_reproducible_and_well_distributed():
     eng.forward_host_u8_rng(params, u8.pin_memory(), 7, pr, sc, lps)
     assert torch.equal(lps, ref["loss_per_sample"].cpu()) and torch.equal(sc, ref["scalars"].cpu())
     eng.close()
+
+
+@pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT])
+def test_iwae_bound_matches_oracle(precision):
+    """BASELINE.json configs[4] shapes in small: K = 5 particles per canvas as consecutive rows of one forward pass;
+    log w, the per-canvas bound log(1/K sum_k w_k) and its batch mean against the float64 oracle restatement (the
+    reference has no IWAE: parity unpinned), and the bound is never below the same pass's mean ELBO estimate."""
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    pc = O.PriorConfig()
+    n, K = 12, 5
+    params, img, nums, _ = U.make_problem(ocfg, n, seed=17)
+    img_k = img.repeat_interleave(K, 0)
+    noise = O.make_noise(ocfg, n * K, seed=18)
+    ref = O.forward(ocfg, pc, params, img_k, *noise, global_step=20000)
+    ref_iw = O.iwae_bound(ocfg, pc, ref, K, global_step=20000)
+    eng = air.Engine(U.cell_cfg(ocfg, precision), n * K, ocfg.T, device=DEV)
+    pr = U.prior_struct(pc, 20000)
+    eng.forward(O.flatten_params(ocfg, params).to(DEV), img_k.to(DEV).contiguous(),
+                *(t.to(DEV).contiguous() for t in noise), pr)
+    mean, bound, log_w = eng.iwae_bound(K, pr)
+    torch.cuda.synchronize()
+    eng.check_range()
+    U.assert_close(log_w.cpu(), ref_iw["log_w"], atol=1e-3, rtol=1e-4, name="log_w")
+    U.assert_close(bound.cpu(), ref_iw["bound_per_canvas"], atol=1e-3, rtol=1e-4, name="bound per canvas")
+    U.assert_close(mean.cpu(), ref_iw["bound"], atol=1e-3, rtol=1e-4, name="bound")
+    # Jensen: log mean_k w >= mean_k log w, per canvas
+    assert bool((bound.cpu() >= log_w.cpu().reshape(n, K).mean(1) - 1e-3).all())
+    with pytest.raises(air.AirError):
+        eng.iwae_bound(7, pr)
+    eng.close()
