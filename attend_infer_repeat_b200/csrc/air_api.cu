@@ -161,7 +161,6 @@ struct air_handle {
   float *g_gx = nullptr, *g_hrec = nullptr, *g_c = nullptr, *g_e = nullptr;   // [B,4nh], [B,nh], [B,nh], [B,n_enc]
   // tensor-core weight gradients (dW = X^T @ dY on the tcgen05 split engine): transposed hl operands, M contiguous
   bool tc_bwd = false;
-  float bwd_lift = 1.0f;   // power of two >= 1 / inv_batch of the current backward pass
   __half *hl_xt = nullptr, *hl_yt = nullptr;
   size_t hl_xt_halves = 0, hl_yt_halves = 0;   // per plane
   // tensor-core input gradients (dX = dY @ W^T): dY row-major planes, W as stored ([in][out]) planes per layer
@@ -177,7 +176,7 @@ struct air_handle {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   std::map<const float*, cudaEvent_t> dy_consumed;       // gradient buffer -> "the side stream has re-laid it out"
-  const float* dy_ready = nullptr;                       // dY whose row-major planes currently sit in hl_dy ...
+  const float* dy_ready = nullptr;                       // dY whose row-major planes currently sit in hl_dy2[dy_ready_buf]
   int dy_ready_m = 0, dy_ready_n = 0;                    // ... with these dimensions
   int* t_range_flag = nullptr;
   std::map<std::tuple<const void*, int, long long, int>, CUtensorMap> tmap_cache2;
@@ -1181,7 +1180,6 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   a.max_crop = c.max_crop_size;
   a.explore_eps = c.explore_eps;
   a.inv_batch = inv_batch > 0.f ? inv_batch : 1.0f / (float)B;
-  h->bwd_lift = exp2f(ceilf(log2f(1.0f / a.inv_batch)));
   a.baseline_mean = baseline_mean;
   a.step_W = c.W > 1 ? 2.0 / (double)(c.W - 1) : 0.0;
   a.step_H = c.H > 1 ? 2.0 / (double)(c.H - 1) : 0.0;
@@ -1521,8 +1519,8 @@ int32_t air_check_range(air_handle* h, void* stream) {
   AIR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (tflag) {
     AIR_CUDA(cudaMemsetAsync(h->t_range_flag, 0, sizeof(int), (cudaStream_t)stream));
-    return fail(AIR_ERR_RANGE, "an activation or a lifted gradient exceeded the fp16 range (65504) in the tensor-core "
-                               "weight-gradient GEMMs; set AIR_NO_TC_BWD=1 for this model");
+    return fail(AIR_ERR_RANGE, "a non-finite activation or gradient reached the tensor-core gradient GEMMs (bf16 hi/lo "
+                               "planes cover the whole fp32 range); AIR_NO_TC_BWD=1 selects the fp32 SIMT GEMMs");
   }
   if (flag) {
     AIR_CUDA(cudaMemsetAsync(h->range_flag, 0, sizeof(int), (cudaStream_t)stream));
