@@ -382,3 +382,18 @@ def test_model_decay_rate_tracks_the_moving_moments():
     train_op(noise=noise)
     assert abs(model._prior_struct.nvil_shift - 0.1 * mean) <= 1e-4 * abs(mean)
     assert abs(model._prior_struct.nvil_scale - 1.0 / max((0.9 + 0.1 * var) ** 0.5, 1.0)) < 1e-3
+
+
+@pytest.mark.parametrize("T,B", [(1, 5), (8, 3), (2, 1)])
+def test_backward_edge_step_counts_and_batch_sizes(T, B):
+    """One step, AIR_MAX_STEPS steps, a single canvas: every templated backward kernel at the ends of its range."""
+    kw = dict(U.TINY)
+    kw["T"] = T
+    ocfg = U.oracle_cfg(**kw)
+    pc = O.PriorConfig()
+    params, img, nums, noise = U.make_problem(ocfg, B, seed=31 + T)
+    noise, _ = well_conditioned(ocfg, pc, params, img, noise, min_scale=0.1)
+    res_o, g_ref = oracle_grads(ocfg, pc, params, img, noise, 20000, dtype=torch.float64)
+    res_c, g = cuda_grads(ocfg, pc, params, img, noise, 20000)
+    assert torch.equal(res_c["presence"].reshape(-1), res_o["outs"]["presence"].detach().float().reshape(-1))
+    compare(ocfg, g, g_ref)
