@@ -92,13 +92,32 @@ struct BwdArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// d rec / d glimpse_t (scatter) and d rec / d where_t through the inverse transformer.  One CTA per canvas.
+// d rec / d glimpse_t and d rec / d where_t through the inverse transformer.  One CTA per canvas.
 //   rec = sum_p 0.5 ((x_p - mu_p)/sigma)^2 + const, mu = mult * (sum_t presence_t * inv_t)
-//   d rec / d inv_t[p] = -presence_t * mult * (x_p - mu_p) / sigma^2
-// dynamic smem: 2 * T*G floats (glimpses, their gradient accumulators) + T*(W+H) taps
+//   d rec / d inv_t[p] = dC_p * presence_t,  dC_p = -mult * (x_p - mu_p) / sigma^2 / batch
+// snt.resampler's gradient with respect to its data is the scatter of the bilinear weights.  The inverse warp being
+// axis-aligned, the weights factor, w(p; j, i) = wy(r, j) * wx(c, i), and being monotone, the canvas columns that touch
+// glimpse column i (rows that touch glimpse row j) form ONE contiguous range.  So the scatter is evaluated as a two-pass
+// GATHER with no atomics (shared-memory fp32 atomics are CAS loops on sm_100):
+//   U[r][i]            = sum_{c in cols(i)} wx(c, i) * dC[r][c]          (rows of the footprint rectangle x glimpse columns)
+//   d glimpse_t[j][i]  = presence_t * sum_{r in rows(j)} wy(r, j) * U[r][i]
+// d rec / d where_t comes from the data differences along each axis (one pass over the footprint rectangle).
+// dynamic smem: T*G floats (glimpses) + T*(W+H) taps + P floats (dC) + H*w floats (U) + 2*T*(w+h) ints (ranges)
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t paint_bwd_smem(int T, int H, int W, int h, int w) {
-  return (2 * sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(BTap) * (size_t)T * (W + H);
+  return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(BTap) * (size_t)T * (W + H) +
+         sizeof(float) * ((size_t)H * W + (size_t)H * w) + sizeof(int) * 2 * (size_t)T * (w + h);
+}
+
+// weight with which a canvas column / row (tap) contributes to glimpse column / row `idx` (idx pre-multiplied by the tap's
+// index stride)
+__device__ __forceinline__ float btap_weight(const BTap& t, int idx) {
+  const int ic = t.i_c_fl & 0xffffff;
+  const int f_ok = (t.i_c_fl >> 24) & 1, c_ok = (t.i_c_fl >> 25) & 1;
+  float wgt = 0.f;
+  if (f_ok && t.i_f == idx) wgt += t.d;
+  if (c_ok && ic == idx) wgt += 1.0f - t.d;
+  return wgt;
 }
 
 template <int T>
@@ -111,19 +130,35 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
   const int P = H * W, G = h * w;
   const int b = blockIdx.x;
-  float* s_gl = reinterpret_cast<float*>(smem_raw);   // [T][G]
-  float* s_dgl = s_gl + (size_t)T * G;                // [T][G]
-  BTap* s_tx = reinterpret_cast<BTap*>(smem_raw + (2 * sizeof(float) * (size_t)T * G + 15) / 16 * 16);   // [T][W]
+  float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
+  BTap* s_tx = reinterpret_cast<BTap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);       // [T][W]
   BTap* s_ty = s_tx + (size_t)T * W;                                                                     // [T][H]
+  float* s_dC = reinterpret_cast<float*>(s_ty + (size_t)T * H);                                          // [P]
+  float* s_U = s_dC + P;                                                                                 // [H][w]
+  int* s_clo = reinterpret_cast<int*>(s_U + (size_t)H * w);   // [T][w] first / last canvas column touching glimpse column i
+  int* s_chi = s_clo + T * w;
+  int* s_rlo = s_chi + T * w;                                 // [T][h] first / last canvas row touching glimpse row j
+  int* s_rhi = s_rlo + T * h;
   griddep_launch();
   griddep_wait();
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float* src = a.glimpse + ((size_t)t * B + b) * G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      s_gl[t * G + g] = src[g];
-      s_dgl[t * G + g] = 0.f;
-    }
+    for (int g = threadIdx.x; g < G; g += blockDim.x) s_gl[t * G + g] = src[g];
+  }
+  {
+    const float cf = -a.inv_batch * a.output_multiplier / (a.output_std * a.output_std);
+    const float* obs = a.img + (size_t)b * P;
+    const float* mu = a.canvas_final + (size_t)b * P;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) s_dC[p] = cf * (obs[p] - mu[p]);
+  }
+  for (int i = threadIdx.x; i < T * w; i += blockDim.x) {
+    s_clo[i] = W;
+    s_chi[i] = -1;
+  }
+  for (int i = threadIdx.x; i < T * h; i += blockDim.x) {
+    s_rlo[i] = H;
+    s_rhi[i] = -1;
   }
   if (threadIdx.x < T) {
     const float* wh = a.where + ((size_t)threadIdx.x * B + b) * 4;
@@ -147,14 +182,31 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
         if (btap_inside(tp)) {
           atomicMin(&s_rect[t][0], j);
           atomicMax(&s_rect[t][1], j);
+          if ((tp.i_c_fl >> 24) & 1) {
+            atomicMin(&s_clo[t * w + tp.i_f], j);
+            atomicMax(&s_chi[t * w + tp.i_f], j);
+          }
+          if ((tp.i_c_fl >> 25) & 1) {
+            atomicMin(&s_clo[t * w + (tp.i_c_fl & 0xffffff)], j);
+            atomicMax(&s_chi[t * w + (tp.i_c_fl & 0xffffff)], j);
+          }
         }
       } else {
-        const float yg = inv_coord_s(iv.y, iv.w, j - W, a.step_H, h);
-        const BTap tp = make_btap(yg, h, w, yg);
-        s_ty[t * H + (j - W)] = tp;
+        const int r = j - W;
+        const float yg = inv_coord_s(iv.y, iv.w, r, a.step_H, h);
+        const BTap tp = make_btap(yg, h, w, yg);   // indices pre-multiplied by the glimpse row pitch
+        s_ty[t * H + r] = tp;
         if (btap_inside(tp)) {
-          atomicMin(&s_rect[t][2], j - W);
-          atomicMax(&s_rect[t][3], j - W);
+          atomicMin(&s_rect[t][2], r);
+          atomicMax(&s_rect[t][3], r);
+          if ((tp.i_c_fl >> 24) & 1) {
+            atomicMin(&s_rlo[t * h + tp.i_f / w], r);
+            atomicMax(&s_rhi[t * h + tp.i_f / w], r);
+          }
+          if ((tp.i_c_fl >> 25) & 1) {
+            atomicMin(&s_rlo[t * h + (tp.i_c_fl & 0xffffff) / w], r);
+            atomicMax(&s_rhi[t * h + (tp.i_c_fl & 0xffffff) / w], r);
+          }
         }
       }
     }
@@ -162,41 +214,29 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   __syncthreads();
 
   const float S_w = ((float)w - 1.0f) * 0.5f, S_h = ((float)h - 1.0f) * 0.5f;
-  const float coef = -a.inv_batch * a.output_multiplier / (a.output_std * a.output_std);
   float acc[T][4];   // per step: sum gx * (xg - S_w), sum gx, sum gy * (yg - S_h), sum gy
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-  // The inverse warp is axis-aligned and monotone, so the canvas pixels glimpse t covers form ONE rectangle
-  // [c_lo, c_hi] x [r_lo, r_hi] (s_rect, found while the tap tables were built).  The CTA tiles that rectangle -- a warp per
-  // row, a lane per column -- so every thread-iteration is a pixel that contributes: no footprint tests, no idle threads
-  // beside the ragged edge of a 32-wide row chunk.
-  const float* obs = a.img + (size_t)b * P;
-  const float* mu = a.canvas_final + (size_t)b * P;
   const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float pres = s_pres[t];
     const int c_lo = s_rect[t][0], c_hi = s_rect[t][1], r_lo = s_rect[t][2], r_hi = s_rect[t][3];
-    if (pres == 0.f || c_hi < c_lo || r_hi < r_lo) continue;
+    float* dgl = a.dglimpse + ((size_t)t * B + b) * G;
+    if (pres == 0.f || c_hi < c_lo || r_hi < r_lo) {   // CTA-uniform: this glimpse never reached the canvas
+      for (int g = threadIdx.x; g < G; g += blockDim.x) dgl[g] = 0.f;
+      continue;
+    }
     const float* D = s_gl + t * G;
-    float* dD = s_dgl + t * G;
+    // (1) d rec / d where_t: the footprint rectangle, a warp per row, a lane per column
     for (int r = r_lo + warp_; r <= r_hi; r += n_warps) {
       const BTap by = s_ty[t * H + r];
-      const int yc = by.i_c_fl & 0xffffff;
-      const int yf_ok = (by.i_c_fl >> 24) & 1, yc_ok = (by.i_c_fl >> 25) & 1;
       const float dy = by.d;
       for (int c = c_lo + lane_; c <= c_hi; c += 32) {
         const BTap bx = s_tx[t * W + c];
-        const int p = r * W + c;
-        const float gv = pres * coef * (obs[p] - mu[p]);
+        const float gv = pres * s_dC[r * W + c];
         const float dx = bx.d;
         const Quad q = load_quad(D, bx, by);
-        const int xc = bx.i_c_fl & 0xffffff;
-        const int xf_ok = (bx.i_c_fl >> 24) & 1, xc_ok = (bx.i_c_fl >> 25) & 1;
-        if (xf_ok & yf_ok) atomicAdd(dD + by.i_f + bx.i_f, gv * dx * dy);
-        if (xc_ok & yc_ok) atomicAdd(dD + yc + xc, gv * (1.0f - dx) * (1.0f - dy));
-        if (xf_ok & yc_ok) atomicAdd(dD + yc + bx.i_f, gv * dx * (1.0f - dy));
-        if (xc_ok & yf_ok) atomicAdd(dD + by.i_f + xc, gv * (1.0f - dx) * dy);
         const float gx = gv * (((1.0f - dy) * q.cc + dy * q.cf) - (dy * q.ff + (1.0f - dy) * q.fc));
         const float gy = gv * ((dx * q.fc + (1.0f - dx) * q.cc) - (dx * q.ff + (1.0f - dx) * q.cf));
         acc[t][0] = fmaf(gx, bx.aux - S_w, acc[t][0]);
@@ -205,6 +245,26 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
         acc[t][3] += gy;
       }
     }
+    // (2) U[r][i] = sum_c wx(c, i) dC[r][c] over the rectangle's rows
+    const int nr = r_hi - r_lo + 1;
+    for (int idx = threadIdx.x; idx < nr * w; idx += blockDim.x) {
+      const int rr = idx / w, i = idx - rr * w;
+      const int lo = s_clo[t * w + i], hi = s_chi[t * w + i];
+      const float* dCr = s_dC + (r_lo + rr) * W;
+      float sum = 0.f;
+      for (int c = lo; c <= hi; ++c) sum = fmaf(btap_weight(s_tx[t * W + c], i), dCr[c], sum);
+      s_U[rr * w + i] = sum;
+    }
+    __syncthreads();
+    // (3) d glimpse_t[j][i] = presence_t * sum_r wy(r, j) U[r][i]
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const int j = g / w, i = g - j * w;
+      const int lo = s_rlo[t * h + j], hi = s_rhi[t * h + j];
+      float sum = 0.f;
+      for (int r = lo; r <= hi; ++r) sum = fmaf(btap_weight(s_ty[t * H + r], j * w), s_U[(r - r_lo) * w + i], sum);
+      dgl[g] = pres * sum;
+    }
+    __syncthreads();   // s_U is reused by the next step
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -215,11 +275,6 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
       if (lane == 0) s_red[wid][t * 4 + k] = v;
     }
   __syncthreads();
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    float* dst = a.dglimpse + ((size_t)t * B + b) * G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = s_dgl[t * G + g];
-  }
   if (threadIdx.x < T) {
     const int t = threadIdx.x;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
