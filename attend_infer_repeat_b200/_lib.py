@@ -109,6 +109,10 @@ SYMBOLS = {
     "air_draw_noise": (C.c_int32, [_P, C.c_uint64, _P, _P, _P, _P]),
     "air_forward_host_u8_rng": (C.c_int32, [_P, _P, _P, C.c_uint64, C.POINTER(air_prior), C.POINTER(air_outputs), _P, _P,
                                             _P]),
+    "air_feed_host_u8": (C.c_int32, [_P, C.c_int32, _P]),
+    "air_forward_fed_u8_rng": (C.c_int32, [_P, _P, C.c_int32, C.c_uint64, C.POINTER(air_prior), C.POINTER(air_outputs), _P,
+                                           _P, _P]),
+    "air_feed_wait": (C.c_int32, [_P, C.c_int32]),
     "air_forward_dataset_u8": (C.c_int32, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(air_prior),
                                            C.POINTER(air_outputs), _P, _P]),
     "air_gather_u8": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, _P]),

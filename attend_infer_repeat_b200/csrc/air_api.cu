@@ -186,6 +186,11 @@ struct air_handle {
   cudaEvent_t ev[AIR_N_STAGES + 1] = {};
   long long* trace = nullptr;      // AIR_CHAIN_TRACE=<file prefix>: per-group clock stamps of the chain kernels (debug)
   int trace_seq = 0;
+  // double-buffered host feed (air_feed_host_u8 / air_forward_fed_u8_rng / air_feed_wait), created on first use
+  cudaStream_t feed_stream = nullptr;
+  uint8_t* feed_buf[2] = {nullptr, nullptr};       // one cudaMalloc, two uint8 batches
+  cudaEvent_t feed_fed[2] = {}, feed_consumed[2] = {}, feed_done[2] = {};
+  bool feed_pending[2] = {false, false};           // a copy into the slot has been enqueued and not yet run through a pass
 };
 
 namespace {
@@ -1470,6 +1475,16 @@ int32_t air_destroy(air_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->trace) cudaFree(h->trace);
+  if (h->feed_stream) {
+    cudaStreamSynchronize(h->feed_stream);
+    cudaStreamDestroy(h->feed_stream);
+    for (int s = 0; s < 2; ++s) {
+      cudaEventDestroy(h->feed_fed[s]);
+      cudaEventDestroy(h->feed_consumed[s]);
+      cudaEventDestroy(h->feed_done[s]);
+    }
+    cudaFree(h->feed_buf[0]);
+  }
   delete h;
   return AIR_OK;
 }
@@ -1737,6 +1752,80 @@ int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_
     AIR_CUDA(cudaMemcpyAsync(loss_per_sample_host, outs->loss_per_sample, sizeof(float) * c.B, cudaMemcpyDeviceToHost,
                              st));
   AIR_CUDA(cudaStreamSynchronize(st));
+  return AIR_OK;
+}
+
+// ---- double-buffered host feed -------------------------------------------------------------------------------------
+namespace {
+int32_t feed_init(air_handle* h) {
+  if (h->feed_stream) return AIR_OK;
+  const size_t bytes = align_up((size_t)h->cfg.B * h->P, 256);
+  uint8_t* buf = nullptr;
+  AIR_CUDA(cudaMalloc(&buf, 2 * bytes));
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaFree(buf);
+    return fail(AIR_ERR_CUDA, "air_feed_host_u8: cudaStreamCreate failed");
+  }
+  for (int i = 0; i < 2; ++i) {
+    AIR_CUDA(cudaEventCreateWithFlags(&h->feed_fed[i], cudaEventDisableTiming));
+    AIR_CUDA(cudaEventCreateWithFlags(&h->feed_consumed[i], cudaEventDisableTiming));
+    AIR_CUDA(cudaEventCreateWithFlags(&h->feed_done[i], cudaEventDisableTiming));
+  }
+  h->feed_buf[0] = buf;
+  h->feed_buf[1] = buf + bytes;
+  h->feed_stream = s;
+  return AIR_OK;
+}
+}  // namespace
+
+int32_t air_feed_host_u8(air_handle* h, int32_t slot, const uint8_t* img_u8_host) {
+  if (!h || !img_u8_host || slot < 0 || slot > 1) return fail(AIR_ERR_ARG, "air_feed_host_u8: bad argument");
+  int32_t rc = feed_init(h);
+  if (rc != AIR_OK) return rc;
+  // the pass that last read this slot must have converted it (an event that was never recorded is complete)
+  AIR_CUDA(cudaStreamWaitEvent(h->feed_stream, h->feed_consumed[slot], 0));
+  AIR_CUDA(cudaMemcpyAsync(h->feed_buf[slot], img_u8_host, (size_t)h->cfg.B * h->P, cudaMemcpyHostToDevice,
+                           h->feed_stream));
+  AIR_CUDA(cudaEventRecord(h->feed_fed[slot], h->feed_stream));
+  h->feed_pending[slot] = true;
+  return AIR_OK;
+}
+
+int32_t air_forward_fed_u8_rng(air_handle* h, const float* params, int32_t slot, uint64_t seed, const air_prior* prior,
+                               const air_outputs* outs, float* scalars_host, float* loss_per_sample_host, void* stream) {
+  if (!h || !params || slot < 0 || slot > 1) return fail(AIR_ERR_ARG, "air_forward_fed_u8_rng: bad argument");
+  if (!h->feed_stream || !h->feed_pending[slot])
+    return fail(AIR_ERR_ARG, "air_forward_fed_u8_rng: nothing was fed into this slot (call air_feed_host_u8 first)");
+  int32_t rc = check_outs(outs, prior != nullptr);
+  if (rc != AIR_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const air_config& c = h->cfg;
+  if ((rc = draw_noise_impl(h, seed, h->st_eps_where, h->st_eps_what, h->st_u, st)) != AIR_OK) return rc;
+  AIR_CUDA(cudaStreamWaitEvent(st, h->feed_fed[slot], 0));
+  const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
+  AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
+                         (const uint8_t*)h->feed_buf[slot], h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr,
+                         h->x.plane(), h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
+  ++h->launches;
+  AIR_CUDA(cudaEventRecord(h->feed_consumed[slot], st));
+  h->feed_pending[slot] = false;
+  rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
+                    nullptr, nullptr, nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
+  if (rc != AIR_OK) return rc;
+  if (prior && scalars_host)
+    AIR_CUDA(cudaMemcpyAsync(scalars_host, outs->scalars, sizeof(float) * AIR_N_SCALARS, cudaMemcpyDeviceToHost, st));
+  if (prior && loss_per_sample_host)
+    AIR_CUDA(cudaMemcpyAsync(loss_per_sample_host, outs->loss_per_sample, sizeof(float) * c.B, cudaMemcpyDeviceToHost,
+                             st));
+  AIR_CUDA(cudaEventRecord(h->feed_done[slot], st));
+  return AIR_OK;
+}
+
+int32_t air_feed_wait(air_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot > 1) return fail(AIR_ERR_ARG, "air_feed_wait: bad argument");
+  if (!h->feed_stream) return fail(AIR_ERR_ARG, "air_feed_wait: the feed was never used on this handle");
+  AIR_CUDA(cudaEventSynchronize(h->feed_done[slot]));
   return AIR_OK;
 }
 

@@ -341,6 +341,53 @@ class Engine:
                                                    current_stream_ptr()), "air_forward_host_u8_rng")
         return scalars_host, loss_per_sample_host
 
+    # ---- double-buffered host feed: the copy of batch i+1 overlaps the pass over batch i (data.py:121-158's input queue) ----
+    def feed_host_u8(self, slot: int, img_u8_host):
+        """Enqueue the host->device copy of one pinned uint8 batch [B,H,W] into staging slot 0/1; returns at once."""
+        assert img_u8_host.dtype == torch.uint8 and not img_u8_host.is_cuda and img_u8_host.is_contiguous()
+        assert img_u8_host.numel() == self.B * self.cfg.H * self.cfg.W, "feed_host_u8: wrong batch shape"
+        with torch.cuda.device(self.device):
+            check(self.lib.air_feed_host_u8(self._handle, int(slot), ptr(img_u8_host)), "air_feed_host_u8")
+
+    def forward_fed_u8_rng(self, params, slot: int, seed: int, prior: air_prior, scalars_host, loss_per_sample_host):
+        """forward_host_u8_rng on the batch fed into ``slot``; does NOT synchronise: call feed_wait(slot) before reading the
+        host buffers (which must stay alive, and be distinct per slot, until then)."""
+        self._chk(params, (self.n_params,), "params")
+        for t, n in ((scalars_host, _lib.AIR_N_SCALARS), (loss_per_sample_host, self.B)):
+            assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n)
+        with torch.cuda.device(self.device):
+            check(self.lib.air_forward_fed_u8_rng(self._handle, ptr(params), int(slot), int(seed), C.byref(prior),
+                                                  C.byref(self._c_out), ptr(scalars_host), ptr(loss_per_sample_host),
+                                                  current_stream_ptr()), "air_forward_fed_u8_rng")
+
+    def feed_wait(self, slot: int):
+        """Block until the results of the last forward_fed_u8_rng on ``slot`` are in host memory."""
+        check(self.lib.air_feed_wait(self._handle, int(slot)), "air_feed_wait")
+
+    def stream_host_u8(self, params, batches, prior: air_prior, seed0: int = 0):
+        """Run the forward + ELBO pass over an iterable of pinned uint8 host batches with the double-buffered feed and yield
+        (scalars [AIR_N_SCALARS], loss_per_sample [B]) host tensors per batch, in order (each pair is valid until the
+        next-but-one ``next()``).  Batch i uses noise seed ``seed0 + i``."""
+        scal = [torch.empty(_lib.AIR_N_SCALARS).pin_memory() for _ in range(2)]
+        lps = [torch.empty(self.B).pin_memory() for _ in range(2)]
+        it = iter(batches)
+        alive = [next(it, None), None]                   # a host batch must outlive its copy: one reference per slot
+        if alive[0] is None:
+            return
+        self.feed_host_u8(0, alive[0])
+        i = 0
+        while alive[i % 2] is not None:
+            alive[(i + 1) % 2] = next(it, None)
+            if alive[(i + 1) % 2] is not None:
+                self.feed_host_u8((i + 1) % 2, alive[(i + 1) % 2])
+            self.forward_fed_u8_rng(params, i % 2, seed0 + i, prior, scal[i % 2], lps[i % 2])
+            if i >= 1:
+                self.feed_wait((i - 1) % 2)
+                yield scal[(i - 1) % 2], lps[(i - 1) % 2]
+            i += 1
+        self.feed_wait((i - 1) % 2)
+        yield scal[(i - 1) % 2], lps[(i - 1) % 2]
+
     def forward_dataset_u8(self, params, dataset_u8, idx, eps_where, eps_what, u_pres, prior: Optional[air_prior] = None,
                            baseline=None, img_out=None):
         """forward() on the minibatch ``dataset_u8[idx]`` of a device-resident uint8 dataset [N,H,W]:

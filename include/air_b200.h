@@ -227,6 +227,22 @@ int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_
                                 const air_prior* prior, const air_outputs* outs, float* scalars_host,
                                 float* loss_per_sample_host, void* stream);
 
+/* Double-buffered host feed: the role of the reference's input queue (data.py:121-158, tf.train.slice_input_producer /
+ * tf.train.batch prefetching batch i+1 while sess.run works on batch i, multi_mnist.py:73,136).
+ *   air_feed_host_u8(h, slot, img)        enqueue the host->device copy of one uint8 batch [B,H,W] (pinned host memory)
+ *                                         into staging slot 0 or 1 on the handle's own copy stream; returns at once.  It
+ *                                         waits (on the device) until the last pass that read the slot has consumed it.
+ *   air_forward_fed_u8_rng(h, ..., slot)  air_forward_host_u8_rng on the batch fed into `slot`: `stream` waits for the
+ *                                         copy, runs the pass, enqueues the device->host copies of scalars /
+ *                                         loss_per_sample into the caller's (pinned) host buffers and returns WITHOUT
+ *                                         synchronising.
+ *   air_feed_wait(h, slot)                blocks the host until the results of the last pass on `slot` are in host memory.
+ * Every step still moves its own batch in and its own loss out; only the waiting is overlapped. */
+int32_t air_feed_host_u8(air_handle* h, int32_t slot, const uint8_t* img_u8_host);
+int32_t air_forward_fed_u8_rng(air_handle* h, const float* params, int32_t slot, uint64_t seed, const air_prior* prior,
+                               const air_outputs* outs, float* scalars_host, float* loss_per_sample_host, void* stream);
+int32_t air_feed_wait(air_handle* h, int32_t slot);
+
 /* Same with the whole DATASET resident on the device: dataset_u8 [n_dataset,H,W] uint8 as pickled by
  * data.py:35-107, idx [B] int32 = the minibatch indices tensors_from_data draws (data.py:121-158).  Gather, /255 and the
  * first layer's operand preparation run in one device pass; no host buffer is touched.  img_out [B,H,W] (optional)

@@ -580,6 +580,38 @@ def test_in_library_noise_is_reproducible_and_well_distributed():
 
 
 @pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT])
+def test_double_buffered_host_feed_equals_synchronous_calls(precision):
+    """air_feed_host_u8 / air_forward_fed_u8_rng / air_feed_wait (the copy of batch i+1 overlaps the pass over batch i):
+    every batch's scalars and per-sample loss are bit-identical to the synchronous air_forward_host_u8_rng call on the same
+    batch and seed -- seven distinct batches through two slots, plus the error paths."""
+    from attend_infer_repeat_b200.data import synthetic_multi_mnist_u8
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    B, T, n = 192, 3, 7
+    eng = air.Engine(U.cell_cfg(ocfg, precision), B, T, device=DEV)
+    params = O.flatten_params(ocfg, O.init_params(ocfg, 0)).to(DEV)
+    pr = U.prior_struct(O.PriorConfig(), 20000)
+    batches = [torch.from_numpy(synthetic_multi_mnist_u8(B, 50, 50, seed=10 + i)[0]).pin_memory() for i in range(n)]
+    sc, lps = torch.empty(16).pin_memory(), torch.empty(B).pin_memory()
+    with pytest.raises(air.AirError):
+        eng.feed_wait(0)                                      # the feed was never used
+    ref = []
+    for i, b in enumerate(batches):
+        eng.forward_host_u8_rng(params, b, 100 + i, pr, sc, lps)
+        ref.append((sc.clone(), lps.clone()))
+    assert not torch.equal(ref[0][1], ref[1][1])
+    got = [(s.clone(), l.clone()) for s, l in eng.stream_host_u8(params, batches, pr, seed0=100)]
+    assert len(got) == n
+    for (s0, l0), (s1, l1) in zip(ref, got):
+        assert torch.equal(s0, s1) and torch.equal(l0, l1)
+    assert list(eng.stream_host_u8(params, [], pr)) == []
+    with pytest.raises(air.AirError):
+        eng.forward_fed_u8_rng(params, 1, 0, pr, sc, lps)     # nothing pending in the slot
+    with pytest.raises(air.AirError):
+        eng.feed_host_u8(2, batches[0])                       # only slots 0 and 1 exist
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT])
 def test_iwae_bound_matches_oracle(precision):
     """BASELINE.json configs[4] shapes in small: K = 5 particles per canvas as consecutive rows of one forward pass;
     log w, the per-canvas bound log(1/K sum_k w_k) and its batch mean against the float64 oracle restatement (the
