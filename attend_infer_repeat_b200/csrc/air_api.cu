@@ -161,7 +161,8 @@ struct air_handle {
   float *g_gx = nullptr, *g_hrec = nullptr, *g_c = nullptr, *g_e = nullptr;   // [B,4nh], [B,nh], [B,nh], [B,n_enc]
   // tensor-core weight gradients (dW = X^T @ dY on the tcgen05 split engine): transposed hl operands, M contiguous
   bool tc_bwd = false;
-  __half *hl_xt = nullptr, *hl_yt = nullptr;
+  static constexpr int MAX_SIDE = 4;
+  __half *hl_xt[MAX_SIDE] = {}, *hl_yt[MAX_SIDE] = {};   // one pair of transposed-operand buffers per side stream
   size_t hl_xt_halves = 0, hl_yt_halves = 0;   // per plane
   // tensor-core input gradients (dX = dY @ W^T): dY row-major planes, W as stored ([in][out]) planes per layer
   __half *hl_dy2[2] = {nullptr, nullptr}, *wnt_arena = nullptr;   // dY planes, double buffered: a dX GEMM's epilogue
@@ -171,8 +172,12 @@ struct air_handle {
   std::map<int64_t, std::pair<size_t, int>> wnt_index;   // Layer::w_off -> (half offset of the hi plane, Npad)
   air::tc::RowsEntry* wnt_table = nullptr;               // device copy of the per-matrix table (prep_weights_rows_kernel)
   int wnt_entries = 0, wnt_blocks = 0;
-  // the weight-gradient work of a backward pass runs on a second stream, beside the dX / pointwise critical path
-  cudaStream_t side = nullptr;
+  // the weight-gradient work of a backward pass runs on side streams, beside the dX / pointwise critical path: the layers'
+  // weight gradients are independent of each other, so they are dealt round-robin to n_side streams (AIR_SIDE_STREAMS,
+  // default 2; each launch alone is too small to fill the machine)
+  cudaStream_t side[MAX_SIDE] = {};
+  int n_side = 0, side_next = 0;
+  int n_side_bufs = 1;             // operand buffer pairs carved into the training workspace
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   std::map<const float*, cudaEvent_t> dy_consumed;       // gradient buffer -> "the side stream has re-laid it out"
@@ -861,8 +866,10 @@ void carve_train(air_handle* h, Carver& cv) {
     visit(h->lstm_x, B);
     h->hl_xt_halves = xt;
     h->hl_yt_halves = yt;
-    h->hl_xt = cv.take<__half>(2 * xt);
-    h->hl_yt = cv.take<__half>(2 * yt);
+    for (int i = 0; i < h->n_side_bufs; ++i) {
+      h->hl_xt[i] = cv.take<__half>(2 * xt);
+      h->hl_yt[i] = cv.take<__half>(2 * yt);
+    }
     h->t_range_flag = cv.take<int>(1);
     // input gradients: the widest dY (rows padded to the 128-row tile) and one [round_up(K,64)][round_up(N,64)] pair
     // of planes per weight matrix
@@ -935,23 +942,28 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
   // fork: everything below runs on the side stream once X and dY are complete on the main stream; the main stream goes on
   // with the input gradient of this layer (its own row-major copy of dY) and the layers below
   cudaStream_t st = main_st;
-  if (h->side) {
+  int lane = 0;                    // which side stream / operand buffer pair this layer uses
+  if (h->n_side) {
+    lane = h->side_next;
+    h->side_next = (h->side_next + 1) % h->n_side;
     cudaEvent_t ready = next_event(h);
     AIR_CUDA(cudaEventRecord(ready, main_st));
-    AIR_CUDA(cudaStreamWaitEvent(h->side, ready, 0));
-    st = h->side;
+    AIR_CUDA(cudaStreamWaitEvent(h->side[lane], ready, 0));
+    st = h->side[lane];
     dx_follows = false;
   }
+  __half* const hl_xt = h->hl_xt[lane];
+  __half* const hl_yt = h->hl_yt[lane];
   const int mp = round_up(M, 64), KA = round_up(l.K, 128), NA = round_up(l.N, 64);
   const int np = NA, MA = round_up(M, 128);
   if ((size_t)KA * mp > h->hl_xt_halves || (size_t)NA * mp > h->hl_yt_halves || (size_t)MA * np > h->hl_dy_halves)
     return fail(AIR_ERR_ARG, "internal: transposed operand does not fit the training workspace");
   AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((l.K + 31) / 32, (mp + tc::ST_M - 1) / tc::ST_M), dim3(256), 0, st, X, ldx, M, l.K,
-                         1.0f, h->hl_xt, (size_t)KA * mp, mp, h->t_range_flag, 1, (__half*)nullptr, (size_t)0, 0,
+                         1.0f, hl_xt, (size_t)KA * mp, mp, h->t_range_flag, 1, (__half*)nullptr, (size_t)0, 0,
                          (float*)nullptr));
   // one read of dY: transposed planes (this GEMM), the bias gradient, and the row-major planes of the dX GEMM that follows
   AIR_CUDA(air::launch_k(tc::split_transpose_kernel, dim3((dx_follows ? np : l.N + 31) / 32, (mp + tc::ST_M - 1) / tc::ST_M), dim3(256), 0,
-                         st, dY, ldy, M, l.N, 1.0f, h->hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1,
+                         st, dY, ldy, M, l.N, 1.0f, hl_yt, (size_t)NA * mp, mp, h->t_range_flag, 1,
                          dx_follows ? h->hl_dy2[0] : (__half*)nullptr, (size_t)MA * np, np,
                          l.b_off >= 0 ? grad + l.b_off : (float*)nullptr));
   if (dx_follows) {
@@ -960,15 +972,17 @@ int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const f
     h->dy_ready_n = l.N;
     h->dy_ready_buf = 0;
   }
-  if (h->side) {   // dY (and X, which nobody overwrites within a pass) have been read
+  if (h->n_side) {   // dY (and X, which nobody overwrites within a pass) have been read
+    auto prev = h->dy_consumed.find(dY);   // an earlier reader of the same buffer on another side stream: chain the events
+    if (prev != h->dy_consumed.end()) AIR_CUDA(cudaStreamWaitEvent(st, prev->second, 0));
     cudaEvent_t done = next_event(h);
     AIR_CUDA(cudaEventRecord(done, st));
     h->dy_consumed[dY] = done;
   }
   const CUtensorMap *tm_a = nullptr, *tm_b = nullptr;
-  int32_t rc = get_tmap2(h, h->hl_xt, mp, 2LL * KA, tc::BM, &tm_a);
+  int32_t rc = get_tmap2(h, hl_xt, mp, 2LL * KA, tc::BM, &tm_a);
   if (rc != AIR_OK) return rc;
-  if ((rc = get_tmap2(h, h->hl_yt, mp, 2LL * NA, 64, &tm_b)) != AIR_OK) return rc;
+  if ((rc = get_tmap2(h, hl_yt, mp, 2LL * NA, 64, &tm_b)) != AIR_OK) return rc;
   tc::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.out_f32 = grad + l.w_off;
@@ -1263,12 +1277,13 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
       return rc;
   }
   // join: the weight gradients of the side stream are part of this call's result
-  if (h->side) {
+  for (int i = 0; i < h->n_side; ++i) {
     cudaEvent_t done = next_event(h);
-    AIR_CUDA(cudaEventRecord(done, h->side));
+    AIR_CUDA(cudaEventRecord(done, h->side[i]));
     AIR_CUDA(cudaStreamWaitEvent(st, done, 0));
-    h->dy_consumed.clear();
   }
+  h->dy_consumed.clear();
+  h->side_next = 0;
   // l2_weight * sum of tf.nn.l2_loss over the 2-D variables (model.py:345-350): weights and the [1,nh] initial state
   if (l2_weight > 0.f) {
     for (const ParamEntry& e : h->entries) {
@@ -1473,7 +1488,7 @@ int32_t air_destroy(air_handle* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->tws) cudaFree(h->tws);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-  if (h->side) cudaStreamDestroy(h->side);
+  for (int i = 0; i < h->n_side; ++i) cudaStreamDestroy(h->side[i]);
   if (h->trace) cudaFree(h->trace);
   if (h->feed_stream) {
     cudaStreamSynchronize(h->feed_stream);
@@ -1551,6 +1566,11 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
     return fail(AIR_ERR_ARG, "air_train_enable: the backward pass covers discrete_steps = 1 (the script configuration)");
   if (on && !h->tws) {
     h->tc_bwd = getenv("AIR_NO_TC_BWD") == nullptr && air::tc::get_encode_fn() != nullptr;
+    // side streams for the weight-gradient work: AIR_SIDE_STREAMS=n (1..MAX_SIDE, default 2), AIR_NO_SIDE_STREAM=1 for none
+    int want_side = 2;
+    if (const char* v = getenv("AIR_SIDE_STREAMS")) want_side = std::max(0, std::min(atoi(v), (int)air_handle::MAX_SIDE));
+    if (getenv("AIR_NO_SIDE_STREAM") != nullptr || !h->tc_bwd) want_side = 0;
+    h->n_side_bufs = std::max(1, want_side);
     Carver sizing(nullptr);
     carve_train(h, sizing);
     cudaError_t e = cudaMalloc(&h->tws, sizing.off);
@@ -1562,9 +1582,12 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
     if (h->tc_bwd) {
       const int32_t rc = upload_backward_weight_table(h);
       if (rc != AIR_OK) return rc;
-      if (getenv("AIR_NO_SIDE_STREAM") == nullptr) {
-        AIR_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-        h->ev_pool.resize(96);
+      for (int i = 0; i < want_side; ++i) {
+        AIR_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+        h->n_side = i + 1;
+      }
+      if (h->n_side) {
+        h->ev_pool.resize(128);
         for (cudaEvent_t& e : h->ev_pool) AIR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       }
     }

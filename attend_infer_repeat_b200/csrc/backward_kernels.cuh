@@ -630,7 +630,11 @@ __global__ void rmsprop_centered_kernel(float* __restrict__ theta, const float* 
   const float g = grad[i] * grad_scale;
   const float mgi = mg[i] + (1.0f - rho) * (g - mg[i]);
   const float msi = ms[i] + (1.0f - rho) * (g * g - ms[i]);
-  const float mo = mu * mom[i] + lr * g / sqrtf(msi - mgi * mgi + eps);
+  // ms - mg^2 is a variance estimate, but in fp32 it rounds below zero once the gradient of an element stops changing
+  // (ms -> g^2, mg -> g; seen after ~140 steps on a fixed batch): TF's kernel then takes the square root of a negative
+  // number and the parameter is NaN for good.  Clamping the variance at 0 changes nothing wherever TF's result is finite
+  // and the estimate non-negative.
+  const float mo = mu * mom[i] + lr * g / sqrtf(fmaxf(msi - mgi * mgi, 0.0f) + eps);
   mg[i] = mgi;
   ms[i] = msi;
   mom[i] = mo;

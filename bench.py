@@ -153,8 +153,9 @@ def workload_config(args, n):
                   f"images) + {args.batch * 3 * 11.6e3 / 1e6:.0f} MB of outputs written per step > 126 MB L2"}
 
 
-def cpu_baseline(args):
-    """Oracle port timed on the host cores of the GPU box, bounded to ~10-30 s."""
+def cpu_baseline(args, device=None, precision=None):
+    """Oracle port timed on the host cores of the GPU box, bounded to ~10-30 s.  With `device`, the same sample also goes
+    through the CUDA engine once and the line gets the second half of BASELINE.json's metric, "ELBO delta vs ref"."""
     from oracle import air_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -165,15 +166,48 @@ def cpu_baseline(args):
     img, _ = O.synthetic_multi_mnist(B, ocfg.H, ocfg.W, seed=1)
     noise = O.make_noise(ocfg, B, 1)
     with torch.no_grad():
-        O.forward(ocfg, pc, params, img, *noise, global_step=20000)
+        ref = O.forward(ocfg, pc, params, img, *noise, global_step=20000)
         n, t0 = 0, time.perf_counter()
         while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
             O.forward(ocfg, pc, params, img, *noise, global_step=20000)
             n += 1
         dt = time.perf_counter() - t0
-    return {"value": B * ocfg.T * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    base = {"value": B * ocfg.T * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle/air_oracle.py (torch-CPU fp32 restatement of the TF1 path; TF1 cannot run here), "
                       f"{B} canvases x {n} steps in {dt:.1f} s"}
+    delta = None
+    if device is not None:
+        delta = _elbo_delta(O, ocfg, pc, params, img, noise, ref, B, device, precision)
+    return base, delta
+
+
+def _elbo_delta(O, ocfg, pc, params, img, noise, ref, B, device, precision):
+    """CUDA engine vs the oracle on the cpu_baseline sample (the checker's own leg: the oracle is not on the timed path)."""
+    import attend_infer_repeat_b200 as air
+    eng = None
+    try:
+        eng = air.Engine(air.CellConfig(precision=precision), B, ocfg.T, device=device)
+        pr = air.make_prior(dict(loc=pc.what_loc, scale=pc.what_scale),
+                            dict(loc=pc.where_scale_loc, scale=pc.where_scale_scale),
+                            dict(loc=pc.where_shift_loc, scale=pc.where_shift_scale),
+                            float(O.steps_prior_success_prob(pc, 20000)), True)
+        out = eng.forward(O.flatten_params(ocfg, params).to(device), img.to(device).contiguous(),
+                          *(t.to(device).contiguous() for t in noise), pr)
+        torch.cuda.synchronize()
+        elbo, elbo_ref = -float(out["scalars"][air._lib.SCALAR_INDEX["loss"]]), float(ref["elbo"])
+        lps, lps_ref = out["loss_per_sample"].cpu().double(), ref["loss_per_sample"].double()
+        canvas, canvas_ref = out["canvas"].cpu().reshape(-1), ref["canvas"].reshape(-1)
+        pres_equal = bool(torch.equal(out["presence"].reshape(-1).cpu(), ref["outs"]["presence"].reshape(-1)))
+        return {"elbo_cuda": elbo, "elbo_oracle": elbo_ref, "rel": abs(elbo - elbo_ref) / abs(elbo_ref),
+                "per_sample_max_rel": float(((lps - lps_ref).abs() / lps_ref.abs().clamp_min(1.0)).max()),
+                "canvas_max_abs": float((canvas - canvas_ref).abs().max()),
+                "presence_bit_exact": pres_equal, "tolerance": 1e-4,
+                "sample": f"the {B} canvases of cpu_baseline, same weights / images / noise on both sides"}
+    except Exception as e:                      # never lose the bench line over the accuracy report
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        if eng is not None:
+            eng.close()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -427,8 +461,10 @@ def run_native(args, rank, local_rank, world):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "train_step": train, "cpu_baseline": cpu_baseline(args) if world == 1 else None,
+                "roofline": roofline, "train_step": train, "cpu_baseline": None, "elbo_delta_vs_oracle": None,
                 "elbo": -float(eng.scalar("loss")) / world}
+        if world == 1:
+            line["cpu_baseline"], line["elbo_delta_vs_oracle"] = cpu_baseline(args, dev, prec)
         emit(line)
     if dist is not None:
         dist.barrier()

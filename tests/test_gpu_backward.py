@@ -212,6 +212,30 @@ def test_centered_rmsprop_matches_oracle():
     eng.close()
 
 
+def test_centered_rmsprop_stays_finite_on_a_nearly_constant_gradient():
+    """ms - mg^2 rounds below zero in fp32 once an element's gradient all but stops changing (a fixed batch: NaN parameters
+    after ~140 steps with the formula taken literally); the kernel clamps the variance estimate at 0."""
+    n = 20000
+    g = torch.Generator().manual_seed(5)
+    g0 = torch.randn(n, generator=g) * torch.logspace(-6, 1, n)
+    theta, mg, ms, mom = torch.zeros(n).cuda(), torch.zeros(n).cuda(), torch.ones(n).cuda(), torch.zeros(n).cuda()
+    mg_r, ms_r, negative = torch.zeros(n), torch.ones(n), 0
+    ocfg = U.oracle_cfg(**U.TINY)
+    eng = air.Engine(U.cell_cfg(ocfg), 2, ocfg.T, device="cuda")
+    for step in range(300):
+        grad = g0 * (1.0 + 1e-4 * torch.randn(n, generator=g))
+        eng.rmsprop_step(theta, grad.cuda(), mg, ms, mom, 1e-5)
+        # the literal formula on the same sequence (otherwise this test checks nothing)
+        mg_r = mg_r + (1.0 - 0.9) * (grad - mg_r)
+        ms_r = ms_r + (1.0 - 0.9) * (grad * grad - ms_r)
+        negative += int(((ms_r - mg_r * mg_r + 1e-10) < 0).sum())
+    torch.cuda.synchronize()
+    assert negative > 0
+    for t in (theta, mg, ms, mom):
+        assert bool(torch.isfinite(t).all())
+    eng.close()
+
+
 def test_training_loop_matches_oracle_loop():
     """Three full training steps (forward + ELBO, backward, centered RMSProp) on the engine against the same loop on the
     oracle (autograd + the restated ApplyCenteredRMSProp): losses and the final parameters agree."""

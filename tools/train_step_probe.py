@@ -1,6 +1,7 @@
 """One B=4096 training step (forward with saved activations + backward + RMSProp) for ncu launch lists / profiles."""
 import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import attend_infer_repeat_b200 as air
 from attend_infer_repeat_b200.cell import _init_flat
@@ -32,3 +33,22 @@ for i in range(steps):
         eng.check_range()
 torch.cuda.synchronize()
 print("loss", float(eng.scalar("loss")))
+if os.environ.get("AIR_PROBE_TIME"):      # device time per training step (CUDA events on the launching stream)
+    n_t = int(os.environ["AIR_PROBE_TIME"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    first_bad = torch.full((), -1, device=dev, dtype=torch.int64)      # first step with a non-finite gradient (no host sync)
+    track = os.environ.get("AIR_PROBE_NANTRACK") is not None
+    e0.record()
+    for i in range(n_t):
+        eng.forward(params, img, ew, ea, u, prior)
+        eng.backward(params, img, ew, ea, prior, grad)
+        if track:
+            bad = ~torch.isfinite(grad).all()
+            first_bad = torch.where(bad & (first_bad < 0), torch.full_like(first_bad, i), first_bad)
+        eng.rmsprop_step(params, grad, mg, ms, mom, 1e-5)
+    e1.record()
+    if track:
+        print("first step with a non-finite gradient:", int(first_bad), "max|g|", float(grad.abs().max()))
+    torch.cuda.synchronize()
+    print(f"train step: {e0.elapsed_time(e1) / n_t:.4f} ms over {n_t} steps, AIR_SIDE_STREAMS={os.environ.get('AIR_SIDE_STREAMS', 'default')}, "
+          f"loss {float(eng.scalar('loss')):.4f}, grad nan {int(torch.isnan(grad).sum())}")
