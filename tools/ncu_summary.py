@@ -3,6 +3,7 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv  > profiles/rNN_launches.md
     python tools/ncu_summary.py full     gpurun_out/prof.ncu-rep  > profiles/rNN_full.md
+    python tools/ncu_summary.py train    gpurun_out/train_launches.csv > profiles/rNN_train_launches.md
 
 `launches` reads the CSV log of `ncu --metrics gpu__time_duration.sum --clock-control none --csv` (one row per launch)
 and prints every launch of ONE forward pass plus the per-kernel share of the step.  `full` reads a `--set full`
@@ -47,6 +48,36 @@ def launches(path, per_step=None):
         print(f"| {k} | {n} | {t:.2f} | {100 * t / total:.1f}% |")
 
 
+def train(path):
+    """Launch list of ONE training step (tools/train_step_probe.py): from one rmsprop_centered_kernel (exclusive) to the next
+    (inclusive), split at the forward's elbo_scalars_kernel."""
+    rows = list(csv.reader(l for l in open(path, errors="replace") if l.startswith('"')))
+    hdr = rows[0]
+    ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    seq = [(short(r[ki]), float(r[vi].replace(",", "")) / 1e3, r[gi], r[bi]) for r in rows[1:]]
+    ends = [i for i, s in enumerate(seq) if s[0].startswith("rmsprop_centered")]
+    step = seq[ends[-2] + 1: ends[-1] + 1] if len(ends) >= 2 else seq
+    cut = max(i for i, s in enumerate(step) if s[0].startswith("elbo_scalars")) + 1
+    total = sum(s[1] for s in step)
+    fwd, bwd = sum(s[1] for s in step[:cut]), sum(s[1] for s in step[cut:])
+    print(f"# ncu launch list: one TRAINING step at B=4096 (tools/train_step_probe.py; AIR_PREC_TC_SPLIT handle in training "
+          f"mode)\n\n{len(step)} launches, {total:.1f} us serialised (cold-cache, --clock-control none; ncu serialises the "
+          f"streams, the real step overlaps the weight-gradient work with the critical path): forward {fwd:.1f} us, backward + "
+          f"optimiser {bwd:.1f} us.\n")
+    for title, part in (("forward (activations kept)", step[:cut]), ("backward + centered RMSProp", step[cut:])):
+        agg = OrderedDict()
+        for k, us, _, _ in part:
+            n, t = agg.get(k, (0, 0.0))
+            agg[k] = (n + 1, t + us)
+        print(f"## {title}\n\n| kernel | launches | us | share of step |\n|---|---|---|---|")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"| {k} | {n} | {t:.1f} | {100 * t / total:.1f}% |")
+        print()
+    print("## every launch\n\n| # | kernel | grid | block | us |\n|---|---|---|---|---|")
+    for i, (k, us, g, b) in enumerate(step):
+        print(f"| {i} | {k} | {g} | {b} | {us:.2f} |")
+
+
 WANT = [
     ("gpu__time_duration.sum", "us"),
     ("dram__bytes_read.sum", "DRAM rd"),
@@ -75,4 +106,4 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "train": train}[sys.argv[1]](sys.argv[2])
