@@ -283,10 +283,14 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
     const float* wh = a.where + ((size_t)t * B + b) * 4;
     float* o = a.dwhere_paint + ((size_t)t * B + b) * 4;
     // x_g - S_w = (U S_w - tx S_w) / sx  ->  d x_g / d sx = -(x_g - S_w) / sx,  d x_g / d tx = -S_w / sx
-    o[0] = -s[0] / wh[0];
-    o[1] = -S_w * s[1] / wh[0];
-    o[2] = -s[2] / wh[2];
-    o[3] = -S_h * s[3] / wh[2];
+    // A sampled scale can be exactly 0 (loc + scale * eps cancels in fp32: ~2e-8 per draw, i.e. once every few hundred
+    // steps at B = 4096) or too small for 1 / s to be finite.  The glimpse then covers no canvas pixel, the sums are
+    // exactly 0 and the gradient through the painted canvas is 0 -- not the 0 / 0 the formula gives (which turned every
+    // parameter upstream of `where` into NaN; the reference's graph divides by the same determinant).
+    o[0] = s[0] == 0.f ? 0.f : -s[0] / wh[0];
+    o[1] = s[1] == 0.f ? 0.f : -S_w * s[1] / wh[0];
+    o[2] = s[2] == 0.f ? 0.f : -s[2] / wh[2];
+    o[3] = s[3] == 0.f ? 0.f : -S_h * s[3] / wh[2];
   }
 }
 
@@ -631,8 +635,8 @@ __global__ void rmsprop_centered_kernel(float* __restrict__ theta, const float* 
   const float mgi = mg[i] + (1.0f - rho) * (g - mg[i]);
   const float msi = ms[i] + (1.0f - rho) * (g * g - ms[i]);
   // ms - mg^2 is a variance estimate, but in fp32 it rounds below zero once the gradient of an element stops changing
-  // (ms -> g^2, mg -> g; seen after ~140 steps on a fixed batch): TF's kernel then takes the square root of a negative
-  // number and the parameter is NaN for good.  Clamping the variance at 0 changes nothing wherever TF's result is finite
+  // (ms -> g^2, mg -> g; reproduced on the host after ~140 steps of a gradient with 1e-4 relative jitter): the literal
+  // formula then takes the square root of a negative number and the parameter is NaN for good.  Clamping the variance at 0 changes nothing wherever TF's result is finite
   // and the estimate non-negative.
   const float mo = mu * mom[i] + lr * g / sqrtf(fmaxf(msi - mgi * mgi, 0.0f) + eps);
   mg[i] = mgi;
