@@ -41,10 +41,21 @@ PARITY PINNING STATUS
     this container over a torch-backed stand-in for the TF primitives
     (tools/make_golden.py -> tests/golden/*.npz): step-count algebra, _anneal_weight,
     _prior_loss, _reinforce.
-  * everything else (LSTM, MLPs, STN read/paint, canvas, rec-loss): PARITY UNPINNED by
-    the reference (test/cell_test.py asserts nothing, no golden files).  Independent
-    cross-checks in tests/test_oracle_blocks.py: F.affine_grid + F.grid_sample
-    (align_corners=True, zeros), torch.nn.LSTMCell with gate permutation,
+  * pinned by running the reference's own cell.py / modules.py / neural.py / model.py /
+    mnist_model.py source over tools/snt_stub.py + tools/tf_stub.py (make_golden.py:
+    cell_vectors -> tests/golden/reference_cell_*.npz): AIRCell._build x T through
+    dynamic_rnn, the post-processing of model.py:83-104 and the reconstruction loss --
+    i.e. every decision those files make (parameter order (sx, tx, sy, ty), biases,
+    explore-eps mix, presence product, LSTM wiring, canvas accumulation, output
+    multiplier, variable inventory): script configuration through AIRonMNIST, a
+    non-square canvas with odd widths, and the non-discrete mode; agreement <= 1.2e-5.
+  * PARITY UNPINNED by the reference: the arithmetic INSIDE the Sonnet / TF modules
+    (snt.Linear, snt.LSTM, AffineGridWarper, resampler, the distributions) -- those
+    packages are absent, test/cell_test.py asserts nothing and there are no golden
+    files; the stand-ins restate their documented semantics, with the warper and the
+    resampler implemented through torch's affine_grid / grid_sample, independently of
+    this file's hand-written gather.  Further cross-checks in
+    tests/test_oracle_blocks.py: torch.nn.LSTMCell with gate permutation,
     torch.distributions Normal / kl_divergence.
 
 Everything is written with differentiable torch ops so that autograd on this oracle is

@@ -84,3 +84,37 @@ def test_fused_elbo_kernel_vs_reference_prior_loss_and_reinforce(i):
     eng_like(D32(g["baseline"]).reshape(-1))
     s = bufs["scalars"].cpu().numpy()
     assert np.isclose(s[idx["reinforce_loss"]], g["reinforce_baseline"], rtol=2e-5, atol=2e-4)   # [B,B] broadcast mean
+
+
+@pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT])
+@pytest.mark.parametrize("case", ["script", "odd", "soft"])
+def test_unrolled_forward_vs_reference_cell_vectors(case, precision):
+    """air_forward against the vectors the reference's own AIRCell / AIRModel / AIRonMNIST source produced
+    (tools/make_golden.py: cell_vectors): 1e-4 absolute + 1e-4 relative on every tensor model.py:86-104 exposes, exact
+    presence / step counts away from ties, 1e-4 of the batch's mean magnitude on the reconstruction loss."""
+    from oracle import air_oracle as O
+    from tests import util as U
+    ocfg, params, img, noise, ref = U.load_cell_golden(case)
+    T, B = ocfg.T, img.shape[0]
+    out = U.run_cuda(ocfg, params, img, noise, O.PriorConfig(), 0, precision=precision, device=DEV)
+    for k in ("what", "what_loc", "what_scale", "where", "where_loc", "where_scale", "presence_prob"):
+        U.assert_close(out[k].reshape(ref[k].shape), ref[k], atol=1e-4, rtol=1e-4, name=k)
+    if ocfg.discrete_steps:
+        bad, unsafe = U.presence_mismatches(out["presence"], ref["presence_prob"].reshape(T, B), noise[2].reshape(T, B))
+        assert bad == 0, f"{bad} presence mismatches away from ties"
+        same = (out["presence"].reshape(T, B) == ref["presence"].reshape(T, B)).all(0)
+        assert bool(same.any())
+        assert torch.equal(out["num_step_per_sample"].reshape(-1)[same], ref["num_step_per_sample"].reshape(-1)[same])
+    else:
+        U.assert_close(out["presence"].reshape(ref["presence"].shape), ref["presence"], atol=1e-4, name="presence")
+        same = torch.ones(B, dtype=torch.bool)
+    U.assert_close(out["canvas"].reshape(T, B, -1)[:, same], ref["canvas"].reshape(T, B, -1)[:, same], atol=1e-4,
+                   rtol=1e-4, name="canvas")
+    U.assert_close(out["glimpse_viz"].reshape(T, B, -1)[:, same], ref["glimpse"].reshape(T, B, -1)[:, same], atol=1e-4,
+                   name="glimpse")
+    U.assert_close(out["final_h"], ref["final_h"], atol=1e-4, name="final_h")
+    U.assert_close(out["final_c"], ref["final_c"], atol=1e-4, name="final_c")
+    U.assert_close(out["num_steps_posterior"], ref["num_steps_posterior"], atol=1e-5, rtol=1e-4, name="q(n)")
+    scale = max(1.0, float(ref["rec_loss_per_sample"].abs().mean()))
+    U.assert_close(out["rec_loss_per_sample"][same], ref["rec_loss_per_sample"][same], atol=1e-4 * scale, rtol=1e-4,
+                   name="rec_loss_per_sample")

@@ -96,3 +96,36 @@ def test_prior_loss_and_reinforce(i):
     r1, iw1, _, _ = O.reinforce(post["num_steps_posterior"], post["num_step_per_sample"], iw, T32(g["baseline"]))
     assert tuple(iw1.shape) == (B, B) == g["imp_weight_baseline"].shape
     assert close(iw1.numpy(), g["imp_weight_baseline"]) and close(float(r1), g["reinforce_baseline"], 1e-5)
+
+
+# ---- the cell and the unroll: golden vectors from the reference's own cell.py / modules.py / neural.py / model.py /
+# mnist_model.py, executed over tools/snt_stub.py + tools/tf_stub.py (tools/make_golden.py: cell_vectors) -------------------
+CELL_KEYS = ("what", "what_loc", "what_scale", "where", "where_loc", "where_scale", "presence_prob")
+
+
+@pytest.mark.parametrize("case", ["script", "odd", "soft"])
+def test_cell_and_unroll_match_the_reference_source(case):
+    """AIRCell._build x T through dynamic_rnn + the post-processing of model.py:83-104 + the reconstruction loss of
+    model.py:319-321, as the reference's source computes them on seeded weights / images / draws: the script
+    configuration through AIRonMNIST, a non-square canvas + glimpse with odd widths, and the non-discrete mode.  Pins the
+    oracle's glue -- (sx, tx, sy, ty) order, biases, explore-eps mix, presence product, LSTM wiring, canvas accumulation."""
+    from tests import util as U
+    ocfg, params, img, noise, ref = U.load_cell_golden(case)
+    with torch.no_grad():
+        res = O.forward(ocfg, O.PriorConfig(), params, img, *noise, global_step=0)
+    for k in CELL_KEYS:
+        U.assert_close(res["outs"][k].reshape(ref[k].shape), ref[k], atol=2e-5, rtol=1e-5, name=k)
+    if ocfg.discrete_steps:
+        assert torch.equal(res["outs"]["presence"].reshape(ref["presence"].shape), ref["presence"])
+        assert torch.equal(res["num_step_per_sample"].reshape(-1), ref["num_step_per_sample"].reshape(-1))
+    else:
+        U.assert_close(res["outs"]["presence"].reshape(ref["presence"].shape), ref["presence"], atol=1e-6, name="presence")
+        U.assert_close(res["num_step_per_sample"], ref["num_step_per_sample"], atol=1e-5, name="num_step_per_sample")
+    for k in ("canvas", "glimpse", "final_canvas", "final_h", "final_c"):
+        U.assert_close(res[k].reshape(ref[k].shape), ref[k], atol=5e-5, rtol=1e-5, name=k)
+    U.assert_close(res["num_steps_posterior"], ref["num_steps_posterior"], atol=1e-6, rtol=1e-5, name="q(n)")
+    U.assert_close(res["rec_loss_per_sample"], ref["rec_loss_per_sample"], atol=0, rtol=1e-5, name="rec_loss_per_sample")
+    # the vectors are not degenerate: something was painted, and (discrete cases) both outcomes of the step draw occur
+    assert float(ref["canvas"].abs().max()) > 0.1
+    if ocfg.discrete_steps:
+        assert 0.0 < float(ref["presence"].mean()) < 1.0

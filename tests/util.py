@@ -86,3 +86,32 @@ def presence_mismatches(pres_cuda, p_oracle, u, margin=1e-5):
     safe = torch.cumprod(safe_step.float(), 0).bool()
     mism = (pres_cuda.reshape(T, -1) != pres_o.reshape(T, -1)) & safe.reshape(T, -1)
     return int(mism.sum()), int((~safe).sum())
+
+
+# ---- golden vectors of the reference's own AIRCell / AIRModel source (tools/make_golden.py: cell_vectors) ------------------
+CELL_GOLDEN_CASES = ("script", "odd", "soft")
+
+
+def load_cell_golden(case):
+    """-> (oracle config, params dict, img, noise tuple, dict of the reference's outputs as torch tensors)."""
+    import json
+    import os
+    import numpy as np
+    from tests.golden_recipe import golden_tensor
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cell_%s.npz" % case))
+    c = json.loads(str(g["cfg_json"]))
+    ocfg = O.AirConfig(H=c["H"], W=c["W"], h=c["h"], w=c["w"], T=c["T"], na=c["na"], nh=c["nh"],
+                       enc_hidden=tuple(c["enc"]), glenc_hidden=tuple(c["glenc"]), dec_hidden=tuple(c["dec"]),
+                       where_hidden=tuple(c["where"]), steps_hidden=tuple(c["steps"]), output_std=c["output_std"],
+                       output_multiplier=c["output_multiplier"], explore_eps=c["explore_eps"],
+                       scale_bias=c["transform_var_bias"], step_bias=c["step_bias"], discrete_steps=c["discrete_steps"])
+    spec = O.param_spec(ocfg)
+    # the variables the reference's graph created are exactly the entries of the flat parameter buffer
+    created = {str(n): tuple(int(x) for x in s) for n, s in zip(g["param_names"], g["param_shapes"])}
+    two_d = lambda s: (1, int(s[0])) if len(s) == 1 else (int(s[0]), int(s[1]))      # biases / h0 / c0 are rows
+    assert created == {n: two_d(s) for n, s in spec}, (created, spec)
+    params = {n: torch.from_numpy(golden_tensor(n, two_d(s), c["seed"])).reshape(tuple(s)) for n, s in spec}
+    noise = tuple(torch.from_numpy(g[k]) for k in ("eps_where", "eps_what", "u_pres"))
+    ref = {k: torch.from_numpy(np.asarray(g[k])) for k in g.files
+           if k not in ("cfg_json", "param_names", "param_shapes", "img", "eps_where", "eps_what", "u_pres")}
+    return ocfg, params, torch.from_numpy(g["img"]), noise, ref

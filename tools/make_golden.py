@@ -1,16 +1,24 @@
 #!/usr/bin/env python
 """Generate tests/golden/reference_*.npz by executing the REFERENCE'S OWN source files
-(/root/reference/attend_infer_repeat/{prior,ops,model}.py) in this container.
+(/root/reference/attend_infer_repeat/{prior,ops,model,cell,modules,neural,mnist_model}.py) in this container.
 
 TensorFlow 1.1 / Sonnet are not installable here, so the reference's TF primitives are served by tools/tf_stub.py
-(an eager, torch-backed restatement of the documented semantics of ~50 TF ops); everything ABOVE the primitives --
-geometric_prior, _cumprod, bernoulli_to_modified_geometric, masked_apply, tabular_kl, sample_from_tensor,
-NumStepsDistribution, Loss, clip_preserve, AIRModel._anneal_weight, AIRModel._prior_loss, AIRModel._reinforce -- is
-the reference's code, byte for byte.  The vectors pin the oracle (tests/test_oracle_golden.py) and, through it and
-directly, the CUDA library (tests/test_gpu_golden.py).  /root/reference is only needed to RE-generate; the committed
-.npz files travel.
+(an eager, torch-backed restatement of the documented semantics of ~60 TF ops) and the ten Sonnet classes it uses by
+tools/snt_stub.py; everything ABOVE them is the reference's code, byte for byte (one exception, spelt out in
+load_reference_modules_py: the Python-2 integer division of modules.py:60):
 
-    python tools/make_golden.py            # writes tests/golden/reference_prior.npz, reference_loss.npz
+  reference_prior.npz, reference_loss.npz   geometric_prior, _cumprod, bernoulli_to_modified_geometric, masked_apply,
+                                            tabular_kl, sample_from_tensor, NumStepsDistribution, Loss, clip_preserve,
+                                            AIRModel._anneal_weight, AIRModel._prior_loss, AIRModel._reinforce
+  reference_cell_<case>.npz                 AIRonMNIST.__init__ / AIRModel.__init__ + _build (AIRCell.initial_state,
+                                            AIRCell._build x T through dynamic_rnn, post-processing, model.py:83-104)
+                                            with the Encoder / Decoder / StochasticTransformParam / StepsPredictor /
+                                            ParametrisedGaussian / SpatialTransformer / MLP / Affine modules
+
+The vectors pin the oracle (tests/test_oracle_golden.py) and, through it and directly, the CUDA library
+(tests/test_gpu_golden.py).  /root/reference is only needed to RE-generate; the committed .npz files travel.
+
+    python tools/make_golden.py            # writes tests/golden/reference_{prior,loss,cell_script,cell_odd,cell_soft}.npz
 """
 import os
 import sys
@@ -46,6 +54,128 @@ def np_(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 
 
+def load_reference_modules_py():
+    """modules.py:60 is `n_params = self._n_param / 2` followed by a slice: Python-2 integer division.  The file is
+    executed from where it lies with that one operator spelt `//`; nothing else is touched."""
+    import types
+    path = os.path.join(REF, "modules.py")
+    src = open(path).read()
+    assert src.count("n_params = self._n_param / 2") == 1
+    src = src.replace("n_params = self._n_param / 2", "n_params = self._n_param // 2")
+    mod = types.ModuleType("modules")
+    mod.__file__ = path
+    sys.modules["modules"] = mod
+    exec(compile(src, path, "exec"), mod.__dict__)
+
+
+CELL_CASES = {
+    # the script configuration (scripts/multi_mnist.py:55-59,82-94) through AIRonMNIST
+    "script": dict(B=6, H=50, W=50, h=20, w=20, T=3, na=50, nh=256, enc=[256, 256], glenc=[256, 256], dec=[256, 256],
+                   where=[256, 256], steps=[128, 64], output_std=.3, output_multiplier=.5, explore_eps=1e-3,
+                   step_bias=.75, transform_var_bias=.5, discrete_steps=True, seed=11),
+    # odd widths, a NON-square canvas and glimpse (x / y order), through AIRModel directly
+    "odd": dict(B=5, H=9, W=14, h=4, w=6, T=4, na=7, nh=12, enc=[10], glenc=[9, 8], dec=[11], where=[13], steps=[6],
+                output_std=.5, output_multiplier=1., explore_eps=None, step_bias=0., transform_var_bias=-1.,
+                discrete_steps=True, seed=12),
+    # all steps taken and weighted by the step probability (cell.py:150-151)
+    "soft": dict(B=4, H=12, W=12, h=5, w=5, T=3, na=6, nh=10, enc=[8], glenc=[8], dec=[8], where=[8], steps=[5],
+                 output_std=.3, output_multiplier=.5, explore_eps=1e-2, step_bias=.5, transform_var_bias=.5,
+                 discrete_steps=False, seed=13),
+}
+
+
+def canonical_name(path, cfg):
+    """Sonnet variable path of the stub (-> snt_stub.py) -> the flat-buffer name of include/air_b200.h."""
+    parts = path.strip("/").split("/")
+    if parts[0] == "lstm":
+        return {"w_gates": "lstm.w", "b_gates": "lstm.b", "initial_state_0": "lstm.h0", "initial_state_1": "lstm.c0"}[parts[1]]
+    assert parts[0] == "AIRCell", path
+    if parts[1] == "ParametrisedGaussian":
+        assert parts[2] == "linear"
+        return "what." + parts[3]
+    prefix, hidden, has_out = {"Encoder": ("input_encoder", cfg["enc"], False),
+                               "Encoder_1": ("glimpse_encoder", cfg["glenc"], False),
+                               "StochasticTransformParam": ("transform_estimator", cfg["where"], True),
+                               "StepsPredictor": ("steps_predictor", cfg["steps"], True),
+                               "Decoder": ("glimpse_decoder", cfg["dec"], True)}[parts[1]]
+    assert parts[2] == "MLP" and parts[3].startswith("linear"), path
+    i = 0 if parts[3] == "linear" else int(parts[3].split("_")[1])
+    assert i < len(hidden) + int(has_out), path
+    return "%s.%s.%s" % (prefix, "out" if i == len(hidden) else i, parts[4])
+
+
+def cell_vectors(out_dir):
+    """tests/golden/reference_cell_<case>.npz: the reference's AIRonMNIST / AIRModel / AIRCell source run on seeded
+    weights (tests/golden_recipe.py), images and noise; every tensor model.py:86-104 exposes, plus the reconstruction
+    loss of model.py:319-321."""
+    import functools
+    import snt_stub
+    sys.path.insert(0, ROOT)
+    from tests.golden_recipe import golden_tensor
+    import mnist_model as ref_mnist     # noqa: E402  reference source
+    import model as ref_model           # noqa: E402
+    import modules as ref_modules       # noqa: E402  (the patched load above)
+
+    for case, cfg in CELL_CASES.items():
+        snt_stub.reset()
+        requested = {}
+
+        def source(path, shape, cfg=cfg, requested=requested):
+            name = canonical_name(path, cfg)
+            shape2 = (1, shape[0]) if len(shape) == 1 else shape
+            requested[name] = shape2
+            return torch.from_numpy(golden_tensor(name, shape2, cfg["seed"])).reshape(shape)
+
+        snt_stub.VARIABLE_SOURCE = source
+        B, H, W, T = cfg["B"], cfg["H"], cfg["W"], cfg["T"]
+        rs = np.random.RandomState(cfg["seed"])
+        img = (rs.rand(B, H, W) * (rs.rand(B, H, W) > 0.7)).astype(np.float32)
+        eps_where = rs.standard_normal((T, B, 4)).astype(np.float32)
+        eps_what = rs.standard_normal((T, B, cfg["na"])).astype(np.float32)
+        u = rs.rand(T, B, 1).astype(np.float32)
+        nums = np.zeros((3, B, 1), np.float32)
+        # draws in the order cell.py makes them within a step: where (:133), presence (:147, discrete only), what (:156)
+        tf_stub.NOISE_NORMAL[:] = [torch.from_numpy(x[t]) for t in range(T) for x in (eps_where, eps_what)]
+        tf_stub.NOISE_UNIFORM[:] = [torch.from_numpy(u[t]) for t in range(T)] if cfg["discrete_steps"] else []
+        obs, nums_t = torch.from_numpy(img), torch.from_numpy(nums)
+        if case == "script":
+            m = ref_mnist.AIRonMNIST(obs, nums_t, glimpse_size=(cfg["h"], cfg["w"]), max_steps=T,
+                                     inpt_encoder_hidden=cfg["enc"], glimpse_encoder_hidden=cfg["glenc"],
+                                     glimpse_decoder_hidden=cfg["dec"], transform_estimator_hidden=cfg["where"],
+                                     steps_pred_hidden=cfg["steps"], baseline_hidden=[256, 128],
+                                     transform_var_bias=cfg["transform_var_bias"], step_bias=cfg["step_bias"],
+                                     output_multiplier=cfg["output_multiplier"], discrete_steps=cfg["discrete_steps"],
+                                     explore_eps=cfg["explore_eps"])
+            assert abs(m.output_std - cfg["output_std"]) < 1e-12 and m.n_appearance == cfg["na"]
+        else:
+            import sonnet as snt
+            P = functools.partial
+            m = ref_model.AIRModel(obs, nums_t, T, (cfg["h"], cfg["w"]), cfg["na"], snt.LSTM(cfg["nh"]),
+                                   P(ref_modules.Encoder, cfg["enc"]), P(ref_modules.Encoder, cfg["glenc"]),
+                                   P(ref_modules.Decoder, cfg["dec"]),
+                                   P(ref_modules.StochasticTransformParam, cfg["where"],
+                                     scale_bias=cfg["transform_var_bias"]),
+                                   P(ref_modules.StepsPredictor, cfg["steps"], cfg["step_bias"]),
+                                   output_std=cfg["output_std"], discrete_steps=cfg["discrete_steps"],
+                                   output_multiplier=cfg["output_multiplier"], explore_eps=cfg["explore_eps"])
+        assert not tf_stub.NOISE_NORMAL and not tf_stub.NOISE_UNIFORM, "the cell did not consume every queued draw"
+        # model.py:319-321
+        rec_ps = tf_stub.reduce_sum(-m.output_distrib.log_prob(m.obs), axis=(1, 2))
+        G = {"cfg_json": np.array(__import__("json").dumps(cfg)), "img": img, "eps_where": eps_where,
+             "eps_what": eps_what, "u_pres": u,
+             "param_names": np.array(sorted(requested)),
+             "param_shapes": np.array([requested[k] for k in sorted(requested)], dtype=np.int64)}
+        for name in ("what", "what_loc", "what_scale", "where", "where_loc", "where_scale", "presence_prob", "presence",
+                     "canvas", "glimpse", "final_canvas", "num_step_per_sample"):
+            G[name] = np_(getattr(m, name))
+        G["final_h"], G["final_c"] = np_(m.final_state[0]), np_(m.final_state[1])
+        G["num_steps_posterior"] = np_(m.num_steps_distrib.prob())
+        G["rec_loss_per_sample"] = np_(rec_ps)
+        np.savez_compressed(os.path.join(out_dir, "reference_cell_%s.npz" % case), **G)
+        print("cell case", case, {k: tuple(v.shape) for k, v in G.items() if k in ("canvas", "glimpse", "what", "presence")},
+              "params", len(requested), "num_step", float(m.num_step))
+
+
 def main():
     tf_stub.install()
     # TF rebinding semantics for augmented assignment (`expr *= weight`, `importance_weight -= baseline`)
@@ -56,6 +186,7 @@ def main():
         setattr(torch.Tensor, name, fn)
     torch.Tensor.get_shape = lambda self: TensorShape(self.shape)
     sys.path.insert(0, REF)
+    load_reference_modules_py()
     import model as ref_model      # noqa: E402  reference source
     import ops as ref_ops          # noqa: E402
     import prior as ref_prior      # noqa: E402
@@ -153,6 +284,7 @@ def main():
                 case_id += 1
     L["n_cases"] = np.array(case_id)
     np.savez_compressed(os.path.join(out_dir, "reference_loss.npz"), **L)
+    cell_vectors(out_dir)
     for name, fn in saved.items():
         setattr(torch.Tensor, name, fn)
     print("wrote", sorted(os.listdir(out_dir)), "cases:", case_id)

@@ -21,6 +21,9 @@ float32, float64, int32, int64, bool_ = torch.float32, torch.float64, torch.int3
 Tensor = torch.Tensor
 
 
+builtins_range = range      # tf.range shadows the builtin further down
+
+
 def convert_to_tensor(x, dtype=None):
     if isinstance(x, torch.Tensor):
         return x if dtype is None else x.to(dtype)
@@ -92,8 +95,27 @@ def split(value, num, axis=0):
     return list(torch.chunk(convert_to_tensor(value), int(num), dim=int(axis)))
 
 
-def zeros(shp, dtype=float32):
-    return torch.zeros(tuple(shp), dtype=dtype)
+def zeros(shp, dtype=float32, name=None):
+    return torch.zeros(tuple(int(i) for i in shp), dtype=dtype)
+
+
+def ones(shp, dtype=float32, name=None):
+    return torch.ones(tuple(int(i) for i in shp), dtype=dtype)
+
+
+def tile(x, multiples):
+    return convert_to_tensor(x).repeat(*[int(m) for m in multiples])
+
+
+newaxis = None
+
+
+def Variable(initial_value, trainable=True, dtype=None, name=None):   # noqa: N802  (tf.Variable: eager, its value)
+    return convert_to_tensor(initial_value, dtype)
+
+
+def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True):
+    return convert_to_tensor(initializer, dtype)
 
 
 def zeros_like(x):
@@ -249,6 +271,17 @@ class _NN:
         var = ((x - x.mean(dim=axes, keepdim=True)) ** 2).mean(dim=axes)
         return mean, var
 
+    @staticmethod
+    def dynamic_rnn(cell, inputs, initial_state=None, time_major=False, **_):
+        """Unrolls `cell` over the leading (time) axis and stacks every output over time  [upstream, time_major=True]."""
+        assert time_major
+        state, per_step = initial_state, []
+        for t in builtins_range(int(inputs.shape[0])):
+            out, state = cell(inputs[t], state)
+            per_step.append(out)
+        outputs = [torch.stack([o[i] for o in per_step], 0) for i in builtins_range(len(per_step[0]))]
+        return outputs, state
+
     elu = staticmethod(torch.nn.functional.elu)
     sigmoid = staticmethod(torch.sigmoid)
     tanh = staticmethod(torch.tanh)
@@ -296,6 +329,9 @@ def uniform_unit_scaling_initializer(*a, **k):
 # ------------------------------------------------------------------------------------------------------------------
 # tf.contrib.distributions  [upstream TF 1.1]
 # ------------------------------------------------------------------------------------------------------------------
+NOISE_NORMAL, NOISE_UNIFORM = [], []      # queued draws (tools/make_golden.py)
+
+
 class Normal:
     def __init__(self, loc, scale, validate_args=False, allow_nan_stats=True, name=None):
         loc, scale = _binary_args(loc, scale)
@@ -305,6 +341,13 @@ class Normal:
     def log_prob(self, x):
         z = (convert_to_tensor(x) - self.loc) / self.scale
         return -0.5 * z * z - (0.5 * math.log(2.0 * math.pi) + torch.log(self.scale))
+
+    def sample(self):
+        """sampled * scale + loc with sampled ~ N(0, 1)  [upstream Normal._sample_n]; the draws come from NOISE_NORMAL
+        (first in, first out) when the generator queued any, so that the vectors can store them."""
+        eps = NOISE_NORMAL.pop(0) if NOISE_NORMAL else torch.randn(self.loc.shape)
+        assert tuple(eps.shape) == tuple(self.loc.shape), (tuple(eps.shape), tuple(self.loc.shape))
+        return eps * self.scale + self.loc
 
 
 def kl(a, b):
@@ -330,8 +373,11 @@ class Bernoulli:
         self.dtype = dtype
 
     def sample(self, n=None):
+        """cast(uniform < probs)  [upstream Bernoulli._sample_n]; uniforms from NOISE_UNIFORM when queued."""
         shp = tuple(self.probs.shape) if n is None else (int(n),) + tuple(self.probs.shape)
-        return (torch.rand(shp) < self.probs).to(self.dtype)
+        u = NOISE_UNIFORM.pop(0) if NOISE_UNIFORM else torch.rand(shp)
+        assert tuple(u.shape) == shp, (tuple(u.shape), shp)
+        return (u < self.probs).to(self.dtype)
 
 
 class NormalWithSoftplusScale(Normal):
@@ -365,14 +411,8 @@ def install():
     sys.modules["tensorflow.python.training"].moving_averages = sys.modules["tensorflow.python.training.moving_averages"]
     sys.modules["tensorflow.python.util"].nest = sys.modules["tensorflow.python.util.nest"]
     sys.modules["tensorflow.python.util.nest"].flatten = lambda x: list(x) if isinstance(x, (list, tuple)) else [x]
-    snt = types.ModuleType("sonnet")                      # base classes only: no Sonnet arithmetic is emulated
-
-    class _Base:
-        def __init__(self, *a, **k):
-            pass
-
-    snt.AbstractModule = snt.RNNCore = snt.Linear = _Base
-    sys.modules["sonnet"] = snt
+    import snt_stub                                       # the Sonnet modules cell.py / modules.py / neural.py use
+    sys.modules["sonnet"] = snt_stub.module()
     ev = types.ModuleType("evaluation")                  # evaluation.py is Python-2 syntax; model.py only imports a name
     ev.gradient_summaries = lambda *a, **k: None
     sys.modules["evaluation"] = ev
