@@ -48,7 +48,11 @@ PARITY PINNING STATUS
     i.e. every decision those files make (parameter order (sx, tx, sy, ty), biases,
     explore-eps mix, presence product, LSTM wiring, canvas accumulation, output
     multiplier, variable inventory): script configuration through AIRonMNIST, a
-    non-square canvas with odd widths, and the non-discrete mode; agreement <= 1.2e-5.
+    non-square canvas with odd widths, and the non-discrete mode; agreement <= 8e-6.
+  * pinned likewise: AIRModel.train_step (model.py:261-376) run from the reference's
+    source with compute_gradients = autograd through its own loss assembly -- every loss
+    term and d opt_loss / d (every model variable), plus BaselineMLP output / loss /
+    gradient through AIRonMNIST; autograd on this oracle agrees to <= 3.4e-5 of max |g|.
   * PARITY UNPINNED by the reference: the arithmetic INSIDE the Sonnet / TF modules
     (snt.Linear, snt.LSTM, AffineGridWarper, resampler, the distributions) -- those
     packages are absent, test/cell_test.py asserts nothing and there are no golden

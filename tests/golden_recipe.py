@@ -15,3 +15,13 @@ def golden_tensor(name, shape, seed):
     if name.endswith(".w"):
         return (x / np.sqrt(rows)).astype(np.float32)        # fan-in scaling like the effective reference init (App. C2)
     return (0.1 * x).astype(np.float32)                      # biases and the trainable initial state: small, non-zero
+
+
+def golden_subset(name, numel, n=1024):
+    """Flat indices at which a large gradient tensor is stored in the vectors (all of them for small tensors): a fixed
+    pseudo-random subset per tensor name.  The vectors also hold every tensor's L2 norm and maximum magnitude."""
+    numel = int(numel)
+    if numel <= 4 * n:
+        return np.arange(numel)
+    rs = np.random.RandomState(zlib.crc32(("subset:" + name).encode()) % (2 ** 31 - 1))
+    return np.sort(rs.choice(numel, size=n, replace=False))

@@ -129,3 +129,50 @@ def test_cell_and_unroll_match_the_reference_source(case):
     assert float(ref["canvas"].abs().max()) > 0.1
     if ocfg.discrete_steps:
         assert 0.0 < float(ref["presence"].mean()) < 1.0
+
+
+@pytest.mark.parametrize("case", ["script", "odd", "soft"])
+def test_train_step_losses_and_gradients_match_the_reference_source(case):
+    """AIRModel.train_step (model.py:261-376) executed from the reference's source on the model of the forward vectors, with
+    compute_gradients = autograd through its own loss assembly: every loss term, and d opt_loss / d (every model variable)
+    against autograd on the oracle -- which pins the gradient oracle of the backward kernels (stop_gradient placement,
+    REINFORCE, the straight-through clip, L2 on the 2-D variables only).  The script case goes through AIRonMNIST, so the
+    BaselineMLP's input order (modules.py:125-143), its [B]-[B,1] broadcast and its own gradient are covered too."""
+    from tests import util as U
+    ocfg, params, img, noise, ref = U.load_cell_golden(case)
+    pc, gstep, l2, g = U.load_train_golden(case)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    baseline, pb = None, None
+    if "baseline_out" in g.files:
+        seed = __import__("json").loads(str(g["cfg_json"]))["seed"]
+        pb = {k: v.clone().requires_grad_(True) for k, v in U.golden_baseline_params(g, seed).items()}
+        T, B = ocfg.T, img.shape[0]
+        b_in = {k: ref[k].reshape(T, B, -1) for k in ("what", "where", "presence")}
+        baseline = O.baseline_mlp(pb, 2, img, b_in["what"], b_in["where"], b_in["presence"], ref["final_h"], ref["final_c"])
+        U.assert_close(baseline.detach(), T32(g["baseline_out"]), atol=1e-5, rtol=1e-5, name="baseline")
+    res = O.forward(ocfg, pc, p, img, *noise, global_step=gstep,
+                    baseline=None if baseline is None else baseline.detach())
+    for k in ("loss", "rec_loss", "prior_loss", "kl_num_steps", "kl_what", "kl_where", "reinforce_loss"):
+        U.assert_close(res[k].detach().float(), T32(g["train:" + k]), atol=1e-5, rtol=2e-5, name=k)
+    U.assert_close(res["loss_per_sample"].detach(), T32(g["train:loss_per_sample"]), atol=1e-4, rtol=1e-5, name="loss_ps")
+    U.assert_close(res["prior_loss_per_sample"].detach(), T32(g["train:prior_loss_per_sample"]), atol=1e-5, rtol=1e-5,
+                   name="prior_ps")
+    U.assert_close(res["importance_weight"].detach().reshape(-1), T32(g["train:importance_weight"]).reshape(-1),
+                   atol=1e-3, rtol=1e-5, name="importance_weight")
+    assert float(res["steps_prior_success_prob"]) == pytest.approx(float(g["train:steps_prior_success_prob"]), rel=1e-12)
+    loss = res["opt_loss"]
+    if l2 > 0:      # model.py:345-350: the 2-D variables (weights and the [1, nh] trainable initial state)
+        loss = loss + l2 * sum(0.5 * (v ** 2).sum() for k, v in p.items() if k.endswith(".w") or k in ("lstm.h0", "lstm.c0"))
+    U.assert_close(loss.detach().float(), T32(g["train:opt_loss"]), atol=1e-5, rtol=2e-5, name="opt_loss")
+    loss.backward()
+    for name, _ in O.param_spec(ocfg):
+        grad = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        U.compare_with_golden_gradient("grad:", name, grad, g)
+    if baseline is not None:
+        # model.py:253-259 with the [B] - [B,1] broadcast
+        target = res["rec_loss_per_sample"].detach()
+        b_loss = 0.5 * ((target[None, :] - baseline) ** 2).mean()
+        U.assert_close(b_loss.detach(), T32(g["train:baseline_loss"]), atol=0, rtol=2e-5, name="baseline_loss")
+        b_loss.backward()
+        for name in pb:
+            U.compare_with_golden_gradient("bgrad:", name, pb[name].grad, g)

@@ -112,6 +112,45 @@ def load_cell_golden(case):
     assert created == {n: two_d(s) for n, s in spec}, (created, spec)
     params = {n: torch.from_numpy(golden_tensor(n, two_d(s), c["seed"])).reshape(tuple(s)) for n, s in spec}
     noise = tuple(torch.from_numpy(g[k]) for k in ("eps_where", "eps_what", "u_pres"))
-    ref = {k: torch.from_numpy(np.asarray(g[k])) for k in g.files
-           if k not in ("cfg_json", "param_names", "param_shapes", "img", "eps_where", "eps_what", "u_pres")}
+    forward_keys = ("what", "what_loc", "what_scale", "where", "where_loc", "where_scale", "presence_prob", "presence",
+                    "canvas", "glimpse", "final_canvas", "num_step_per_sample", "final_h", "final_c",
+                    "num_steps_posterior", "rec_loss_per_sample")
+    ref = {k: torch.from_numpy(np.asarray(g[k])) for k in forward_keys}
     return ocfg, params, torch.from_numpy(g["img"]), noise, ref
+
+
+def load_train_golden(case):
+    """The AIRModel.train_step part of the vectors: (PriorConfig, global_step, l2_weight, g) with g the raw npz."""
+    import json
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cell_%s.npz" % case))
+    tc = json.loads(str(g["train_cfg_json"]))
+    pc = O.PriorConfig(analytic=tc["analytic"], where_shift_loc=0.0 if tc["shift_has_loc"] else None,
+                       where_shift_scale=1.0 if tc["shift_has_loc"] else 0.8)
+    return pc, tc["global_step"], tc["l2_weight"], g
+
+
+def golden_baseline_params(g, seed):
+    """BaselineMLP parameters of the script case (re-drawn from the recipe), keyed 'baseline.<i|out>.<w|b>'."""
+    from tests.golden_recipe import golden_tensor
+    out = {}
+    for n, s in zip(g["baseline_param_names"], g["baseline_param_shapes"]):
+        t = torch.from_numpy(golden_tensor(str(n), (int(s[0]), int(s[1])), seed))
+        out[str(n)] = t.reshape(-1) if str(n).endswith(".b") else t
+    return out
+
+
+def compare_with_golden_gradient(prefix, name, got, g, rel=2e-4):
+    """`got`: full gradient tensor; the vectors hold its entries at golden_subset(name), its L2 norm and max magnitude."""
+    import numpy as np
+    from tests.golden_recipe import golden_subset
+    flat = got.detach().reshape(-1).double().cpu().numpy()
+    ref = g[prefix + name].astype(np.float64)
+    norm, gmax = (float(x) for x in g[prefix + "stats:" + name])
+    idx = golden_subset(name, flat.size)
+    err = float(np.abs(flat[idx] - ref).max()) if ref.size else 0.0
+    tol = rel * gmax + 1e-7
+    assert err <= tol, f"{name}: max |g - g_ref| {err:.3e} > {tol:.3e} (max |g_ref| {gmax:.3e})"
+    got_norm = float(np.sqrt((flat ** 2).sum()))
+    assert abs(got_norm - norm) <= 5 * rel * norm + 1e-7, f"{name}: |g| {got_norm:.6e} vs {norm:.6e}"

@@ -72,7 +72,7 @@ CELL_CASES = {
     # the script configuration (scripts/multi_mnist.py:55-59,82-94) through AIRonMNIST
     "script": dict(B=6, H=50, W=50, h=20, w=20, T=3, na=50, nh=256, enc=[256, 256], glenc=[256, 256], dec=[256, 256],
                    where=[256, 256], steps=[128, 64], output_std=.3, output_multiplier=.5, explore_eps=1e-3,
-                   step_bias=.75, transform_var_bias=.5, discrete_steps=True, seed=11),
+                   step_bias=.75, transform_var_bias=.5, discrete_steps=True, baseline=[256, 128], seed=11),
     # odd widths, a NON-square canvas and glimpse (x / y order), through AIRModel directly
     "odd": dict(B=5, H=9, W=14, h=4, w=6, T=4, na=7, nh=12, enc=[10], glenc=[9, 8], dec=[11], where=[13], steps=[6],
                 output_std=.5, output_multiplier=1., explore_eps=None, step_bias=0., transform_var_bias=-1.,
@@ -89,6 +89,10 @@ def canonical_name(path, cfg):
     parts = path.strip("/").split("/")
     if parts[0] == "lstm":
         return {"w_gates": "lstm.w", "b_gates": "lstm.b", "initial_state_0": "lstm.h0", "initial_state_1": "lstm.c0"}[parts[1]]
+    if parts[0] == "BaselineMLP":                         # modules.py:125-143, baseline_hidden of mnist_model.py:18
+        assert parts[1] == "MLP" and parts[2].startswith("linear"), path
+        i = 0 if parts[2] == "linear" else int(parts[2].split("_")[1])
+        return "baseline.%s.%s" % ("out" if i == len(cfg["baseline"]) else i, parts[3])
     assert parts[0] == "AIRCell", path
     if parts[1] == "ParametrisedGaussian":
         assert parts[2] == "linear"
@@ -104,51 +108,127 @@ def canonical_name(path, cfg):
     return "%s.%s.%s" % (prefix, "out" if i == len(hidden) else i, parts[4])
 
 
+class GoldenOptimizer:
+    """Stands where tf.train.RMSPropOptimizer stands in AIRModel.train_step (model.py:265,355-360): compute_gradients is
+    tf.gradients(opt_loss, model_vars) -- autograd through the reference's own loss assembly -- and nothing is applied."""
+    captured = None
+    captured_baseline = None
+
+    def __init__(self, learning_rate, **kwargs):
+        pass
+
+    def compute_gradients(self, loss, var_list=None):
+        var_list = list(var_list)
+        grads = torch.autograd.grad(loss, var_list, allow_unused=True, retain_graph=True)
+        GoldenOptimizer.captured = list(zip(grads, var_list))
+        return GoldenOptimizer.captured
+
+    def apply_gradients(self, gvs, global_step=None):
+        return None
+
+    def minimize(self, loss, var_list=None):
+        """model.py:253-259: the baseline's own train step; the gradient of baseline_loss w.r.t. the baseline variables."""
+        var_list = list(var_list)
+        GoldenOptimizer.captured_baseline = list(zip(torch.autograd.grad(loss, var_list, retain_graph=True), var_list))
+        return None
+
+
+TRAIN_CASES = {   # global_step, l2_weight, prior variants.  "script" goes through AIRonMNIST, whose BaselineMLP
+    # (mnist_model.py:26) _reinforce builds and subtracts ([B] - [B,1] -> [B,B], model.py:224-231); AIRModel alone has none
+    "script": dict(global_step=20000, l2_weight=0., analytic=True, shift_has_loc=True),
+    "odd": dict(global_step=3000, l2_weight=1e-3, analytic=False, shift_has_loc=False),
+    "soft": dict(global_step=60000, l2_weight=0., analytic=True, shift_has_loc=True),
+}
+
+
+def train_vectors(m, cfg, case, G, requested, requested_baseline):
+    """AIRModel.train_step on the model the forward vectors came from (no new draws): the loss terms of
+    model.py:319-343 and d opt_loss / d (every model variable) as compute_gradients sees it."""
+    import snt_stub
+    from tests.golden_recipe import golden_subset
+    tc = TRAIN_CASES[case]
+    tf_stub.train.get_or_create_global_step = staticmethod(lambda: torch.tensor(tc["global_step"], dtype=torch.int64))
+    nsp = AttrDict(anneal='exp', init=1. - 1e-15, final=1e-7, steps_div=1e4, steps=1e5, hold_init=1e3,
+                   analytic=tc["analytic"])
+    shift = AttrDict(loc=0., scale=1.) if tc["shift_has_loc"] else AttrDict(scale=.8)
+    GoldenOptimizer.captured = GoldenOptimizer.captured_baseline = None
+    m.train_step(1e-5, l2_weight=tc["l2_weight"], what_prior=AttrDict(loc=0., scale=1.),
+                 where_scale_prior=AttrDict(loc=0., scale=1.), where_shift_prior=shift, num_steps_prior=nsp,
+                 use_prior=True, use_reinforce=True, optimizer=GoldenOptimizer, opt_kwargs=dict(momentum=.9, centered=True))
+    name_of = {id(v): canonical_name(p, cfg) for p, v in snt_stub.VARIABLES.items()}
+    assert len(GoldenOptimizer.captured) == len(requested), "compute_gradients did not see every model variable"
+    def store(prefix, name, g):
+        """A gradient tensor: its entries at golden_subset(name) (all of them when small), L2 norm, maximum magnitude."""
+        flat = np_(g).reshape(-1).astype(np.float32)
+        G[prefix + name] = flat[golden_subset(name, flat.size)]
+        G[prefix + "stats:" + name] = np.array([np.sqrt((flat.astype(np.float64) ** 2).sum()), np.abs(flat).max()])
+
+    for g, v in GoldenOptimizer.captured:
+        store("grad:", name_of[id(v)], torch.zeros_like(v) if g is None else g)
+    if requested_baseline:      # AIRonMNIST: the BaselineMLP of mnist_model.py:26 (built by _reinforce, model.py:224-229)
+        assert len(GoldenOptimizer.captured_baseline) == len(requested_baseline)
+        G["baseline_param_names"] = np.array(sorted(requested_baseline))
+        G["baseline_param_shapes"] = np.array([requested_baseline[k] for k in sorted(requested_baseline)], dtype=np.int64)
+        G["baseline_out"] = np_(m.baseline)
+        G["train:baseline_loss"] = np_(m.baseline_loss)
+        for g, v in GoldenOptimizer.captured_baseline:
+            store("bgrad:", name_of[id(v)], g)
+    G["train_cfg_json"] = np.array(__import__("json").dumps(tc))
+    for name, val in (("loss", m.loss.value), ("loss_per_sample", m.loss.per_sample), ("opt_loss", m.opt_loss),
+                      ("rec_loss", m.rec_loss), ("prior_loss", m.prior_loss.value),
+                      ("prior_loss_per_sample", m.prior_loss.per_sample), ("kl_num_steps", m.kl_num_steps),
+                      ("kl_what", m.kl_what), ("kl_where", m.kl_where), ("reinforce_loss", m.reinforce_loss),
+                      ("importance_weight", m.importance_weight),
+                      ("steps_prior_success_prob", m.steps_prior_success_prob)):
+        G["train:" + name] = np_(val)
+
+
 def cell_vectors(out_dir):
     """tests/golden/reference_cell_<case>.npz: the reference's AIRonMNIST / AIRModel / AIRCell source run on seeded
-    weights (tests/golden_recipe.py), images and noise; every tensor model.py:86-104 exposes, plus the reconstruction
-    loss of model.py:319-321."""
+    weights (tests/golden_recipe.py), images and noise; every tensor model.py:86-104 exposes, the reconstruction loss of
+    model.py:319-321, and the losses / gradients of AIRModel.train_step (train_vectors)."""
     import functools
+    import json
     import snt_stub
     sys.path.insert(0, ROOT)
     from tests.golden_recipe import golden_tensor
     import mnist_model as ref_mnist     # noqa: E402  reference source
     import model as ref_model           # noqa: E402
     import modules as ref_modules       # noqa: E402  (the patched load above)
+    import sonnet as snt                # noqa: E402  (tools/snt_stub.py)
 
-    for case, cfg in CELL_CASES.items():
+    def build(case, cfg):
+        """Run the reference's model constructor (-> AIRCell x T) on the inputs seeded by cfg['seed']."""
         snt_stub.reset()
-        requested = {}
+        requested, requested_baseline = {}, {}
 
-        def source(path, shape, cfg=cfg, requested=requested):
+        def source(path, shape):
             name = canonical_name(path, cfg)
             shape2 = (1, shape[0]) if len(shape) == 1 else shape
-            requested[name] = shape2
-            return torch.from_numpy(golden_tensor(name, shape2, cfg["seed"])).reshape(shape)
+            (requested_baseline if name.startswith("baseline.") else requested)[name] = shape2
+            return torch.from_numpy(golden_tensor(name, shape2, cfg["seed"])).reshape(shape).requires_grad_(True)
 
         snt_stub.VARIABLE_SOURCE = source
         B, H, W, T = cfg["B"], cfg["H"], cfg["W"], cfg["T"]
         rs = np.random.RandomState(cfg["seed"])
-        img = (rs.rand(B, H, W) * (rs.rand(B, H, W) > 0.7)).astype(np.float32)
-        eps_where = rs.standard_normal((T, B, 4)).astype(np.float32)
-        eps_what = rs.standard_normal((T, B, cfg["na"])).astype(np.float32)
-        u = rs.rand(T, B, 1).astype(np.float32)
-        nums = np.zeros((3, B, 1), np.float32)
+        inp = {"img": (rs.rand(B, H, W) * (rs.rand(B, H, W) > 0.7)).astype(np.float32),
+               "eps_where": rs.standard_normal((T, B, 4)).astype(np.float32),
+               "eps_what": rs.standard_normal((T, B, cfg["na"])).astype(np.float32),
+               "u_pres": rs.rand(T, B, 1).astype(np.float32)}
         # draws in the order cell.py makes them within a step: where (:133), presence (:147, discrete only), what (:156)
-        tf_stub.NOISE_NORMAL[:] = [torch.from_numpy(x[t]) for t in range(T) for x in (eps_where, eps_what)]
-        tf_stub.NOISE_UNIFORM[:] = [torch.from_numpy(u[t]) for t in range(T)] if cfg["discrete_steps"] else []
-        obs, nums_t = torch.from_numpy(img), torch.from_numpy(nums)
+        tf_stub.NOISE_NORMAL[:] = [torch.from_numpy(inp[k][t]) for t in range(T) for k in ("eps_where", "eps_what")]
+        tf_stub.NOISE_UNIFORM[:] = [torch.from_numpy(inp["u_pres"][t]) for t in range(T)] if cfg["discrete_steps"] else []
+        obs, nums_t = torch.from_numpy(inp["img"]), torch.zeros(3, B, 1)
         if case == "script":
             m = ref_mnist.AIRonMNIST(obs, nums_t, glimpse_size=(cfg["h"], cfg["w"]), max_steps=T,
                                      inpt_encoder_hidden=cfg["enc"], glimpse_encoder_hidden=cfg["glenc"],
                                      glimpse_decoder_hidden=cfg["dec"], transform_estimator_hidden=cfg["where"],
-                                     steps_pred_hidden=cfg["steps"], baseline_hidden=[256, 128],
+                                     steps_pred_hidden=cfg["steps"], baseline_hidden=cfg["baseline"],
                                      transform_var_bias=cfg["transform_var_bias"], step_bias=cfg["step_bias"],
                                      output_multiplier=cfg["output_multiplier"], discrete_steps=cfg["discrete_steps"],
                                      explore_eps=cfg["explore_eps"])
             assert abs(m.output_std - cfg["output_std"]) < 1e-12 and m.n_appearance == cfg["na"]
         else:
-            import sonnet as snt
             P = functools.partial
             m = ref_model.AIRModel(obs, nums_t, T, (cfg["h"], cfg["w"]), cfg["na"], snt.LSTM(cfg["nh"]),
                                    P(ref_modules.Encoder, cfg["enc"]), P(ref_modules.Encoder, cfg["glenc"]),
@@ -159,21 +239,45 @@ def cell_vectors(out_dir):
                                    output_std=cfg["output_std"], discrete_steps=cfg["discrete_steps"],
                                    output_multiplier=cfg["output_multiplier"], explore_eps=cfg["explore_eps"])
         assert not tf_stub.NOISE_NORMAL and not tf_stub.NOISE_UNIFORM, "the cell did not consume every queued draw"
+        return m, inp, requested, requested_baseline
+
+    def well_conditioned(m, cfg, u):
+        """Seeds are chosen so that the vectors are not dominated by fp32 noise: every glimpse that is painted has
+        |sx|, |sy| >= 0.2 (1 / s amplifies rounding in the inverse transformer), no step draw is within 1e-3 of a tie, and
+        the discrete cases hold both taken and skipped steps."""
+        wh, pres = np_(m.where), np_(m.presence)[..., 0]
+        painted = pres > 0
+        if cfg["discrete_steps"]:
+            if np.abs(u[..., 0] - np_(m.presence_prob)[..., 0]).min() < 1e-3 or painted.sum() < 3 or painted.all():
+                return False
+        s = np.minimum(np.abs(wh[..., 0]), np.abs(wh[..., 2]))[painted]
+        return s.size > 0 and s.min() >= 0.2
+
+    for case, base_cfg in CELL_CASES.items():
+        for seed in range(base_cfg["seed"], base_cfg["seed"] + 5000, 10):
+            cfg = dict(base_cfg, seed=seed)
+            m, inp, requested, requested_baseline = build(case, cfg)
+            if well_conditioned(m, cfg, inp["u_pres"]):
+                break
+        else:
+            raise RuntimeError("no well-conditioned seed found for case " + case)
         # model.py:319-321
         rec_ps = tf_stub.reduce_sum(-m.output_distrib.log_prob(m.obs), axis=(1, 2))
-        G = {"cfg_json": np.array(__import__("json").dumps(cfg)), "img": img, "eps_where": eps_where,
-             "eps_what": eps_what, "u_pres": u,
-             "param_names": np.array(sorted(requested)),
-             "param_shapes": np.array([requested[k] for k in sorted(requested)], dtype=np.int64)}
+        G = dict(inp)
+        G.update({"cfg_json": np.array(json.dumps(cfg)), "param_names": np.array(sorted(requested)),
+                  "param_shapes": np.array([requested[k] for k in sorted(requested)], dtype=np.int64)})
         for name in ("what", "what_loc", "what_scale", "where", "where_loc", "where_scale", "presence_prob", "presence",
                      "canvas", "glimpse", "final_canvas", "num_step_per_sample"):
             G[name] = np_(getattr(m, name))
         G["final_h"], G["final_c"] = np_(m.final_state[0]), np_(m.final_state[1])
         G["num_steps_posterior"] = np_(m.num_steps_distrib.prob())
         G["rec_loss_per_sample"] = np_(rec_ps)
+        train_vectors(m, cfg, case, G, requested, requested_baseline)
         np.savez_compressed(os.path.join(out_dir, "reference_cell_%s.npz" % case), **G)
-        print("cell case", case, {k: tuple(v.shape) for k, v in G.items() if k in ("canvas", "glimpse", "what", "presence")},
-              "params", len(requested), "num_step", float(m.num_step))
+        wh = G["where"]
+        print("cell case", case, "seed", cfg["seed"], {k: tuple(G[k].shape) for k in ("canvas", "glimpse", "what")},
+              "params", len(requested), "num_step", float(m.num_step.detach()),
+              "min |s| painted", float(np.minimum(np.abs(wh[..., 0]), np.abs(wh[..., 2]))[G["presence"][..., 0] > 0].min()))
 
 
 def main():
@@ -185,6 +289,7 @@ def main():
         saved[name] = getattr(torch.Tensor, name)
         setattr(torch.Tensor, name, fn)
     torch.Tensor.get_shape = lambda self: TensorShape(self.shape)
+    torch.Tensor.assign = lambda self, value: value          # tf.Variable.assign builds an op; nothing runs it here
     sys.path.insert(0, REF)
     load_reference_modules_py()
     import model as ref_model      # noqa: E402  reference source

@@ -63,6 +63,10 @@ class AbstractModule:
         parent.counters[base] = idx + 1
         self._scope = parent.path + "/" + base + ("" if idx == 0 else "_%d" % idx)
 
+    @property
+    def variable_scope(self):
+        return types.SimpleNamespace(name=self._scope)
+
     @contextlib.contextmanager
     def _enter_variable_scope(self):
         _STACK.append(_Frame(self._scope))

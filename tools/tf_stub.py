@@ -231,10 +231,32 @@ def variable_scope(*a, **k):
     yield
 
 
+control_dependencies = variable_scope
+
+
+def group(*a, **k):
+    return None
+
+
+def square(x):
+    x = convert_to_tensor(x)
+    return x * x
+
+
+def trainable_variables():
+    """Every variable the Sonnet stand-in created, in creation order (nothing else in the reference is trainable)."""
+    import snt_stub
+    return list(snt_stub.VARIABLES.values())
+
+
 name_scope = variable_scope
 
 
-def get_collection(*a, **k):
+def get_collection(key=None, scope=None):
+    """Only tf.get_collection(TRAINABLE_VARIABLES, scope=<module scope>) returns anything (model.py:228-229)."""
+    if key == GraphKeys.TRAINABLE_VARIABLES and scope:
+        import snt_stub
+        return [v for path, v in snt_stub.VARIABLES.items() if path == scope or path.startswith(scope + "/")]
     return []
 
 
@@ -281,6 +303,10 @@ class _NN:
             per_step.append(out)
         outputs = [torch.stack([o[i] for o in per_step], 0) for i in builtins_range(len(per_step[0]))]
         return outputs, state
+
+    @staticmethod
+    def l2_loss(t):
+        return 0.5 * (convert_to_tensor(t) ** 2).sum()
 
     elu = staticmethod(torch.nn.functional.elu)
     sigmoid = staticmethod(torch.sigmoid)
