@@ -86,8 +86,12 @@ def test_fused_elbo_kernel_vs_reference_prior_loss_and_reinforce(i):
     assert np.isclose(s[idx["reinforce_loss"]], g["reinforce_baseline"], rtol=2e-5, atol=2e-4)   # [B,B] broadcast mean
 
 
-@pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT])
-@pytest.mark.parametrize("case", ["script", "odd", "soft"])
+# the tensor-core engine on the script configuration (what it is built for); the fp32 engine on every case
+CELL_RUNS = [("script", air.AIR_PREC_FP32), ("script", air.AIR_PREC_TC_SPLIT), ("odd", air.AIR_PREC_FP32),
+             ("soft", air.AIR_PREC_FP32)]
+
+
+@pytest.mark.parametrize("case,precision", CELL_RUNS)
 def test_unrolled_forward_vs_reference_cell_vectors(case, precision):
     """air_forward against the vectors the reference's own AIRCell / AIRModel / AIRonMNIST source produced
     (tools/make_golden.py: cell_vectors): 1e-4 absolute + 1e-4 relative on every tensor model.py:86-104 exposes, exact
@@ -120,8 +124,7 @@ def test_unrolled_forward_vs_reference_cell_vectors(case, precision):
                    name="rec_loss_per_sample")
 
 
-@pytest.mark.parametrize("precision", [air.AIR_PREC_FP32, air.AIR_PREC_TC_SPLIT])
-@pytest.mark.parametrize("case", ["script", "odd"])
+@pytest.mark.parametrize("case,precision", [r for r in CELL_RUNS if r[0] != "soft"])     # the backward pass is discrete-only
 def test_backward_vs_reference_train_step_vectors(case, precision):
     """air_backward against d opt_loss / d (model variables) as the reference's own AIRModel.train_step computes it
     (tools/make_golden.py: train_vectors; autograd through the reference's loss assembly): 5e-4 of each tensor's max |g| on
