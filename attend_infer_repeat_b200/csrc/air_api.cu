@@ -140,7 +140,7 @@ struct air_handle {
   int prep_tiles = 0;
   int* range_flag = nullptr;
   std::map<std::pair<const void*, int>, CUtensorMap> tmap_cache;
-  // training (air_train_enable / air_backward; AIR_PREC_FP32 engine): saved activations + gradient scratch, one cudaMalloc
+  // training (air_train_enable / air_backward; either engine): saved activations + gradient scratch, one cudaMalloc
   // inference: the prepared fp16-split weight arena is reused while the caller vouches that `params` is unchanged
   bool cache_weights = false;
   const float* weights_ready = nullptr;
@@ -180,7 +180,7 @@ struct air_handle {
   int n_side_bufs = 1;             // operand buffer pairs carved into the training workspace
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
-  std::map<const float*, cudaEvent_t> dy_consumed;       // gradient buffer -> "the side stream has re-laid it out"
+  std::map<const float*, cudaEvent_t> dy_consumed;       // gradient buffer -> "its last reader on a side stream has re-laid it out"
   const float* dy_ready = nullptr;                       // dY whose row-major planes currently sit in hl_dy2[dy_ready_buf]
   int dy_ready_m = 0, dy_ready_n = 0;                    // ... with these dimensions
   int* t_range_flag = nullptr;
@@ -926,7 +926,7 @@ cudaEvent_t next_event(air_handle* h) {
   h->ev_next = (h->ev_next + 1) % h->ev_pool.size();
   return e;
 }
-// before the main stream overwrites a gradient buffer: wait until the side stream has finished reading it
+// before the main stream overwrites a gradient buffer: wait until the side streams have finished reading it
 int32_t wait_consumed(air_handle* h, const float* buf, cudaStream_t st) {
   auto it = h->dy_consumed.find(buf);
   if (it != h->dy_consumed.end()) {
@@ -939,7 +939,7 @@ int32_t wait_consumed(air_handle* h, const float* buf, cudaStream_t st) {
 int32_t layer_weight_grad_tc(air_handle* h, float* grad, const Layer& l, const float* X, int ldx, const float* dY, int ldy,
                              int M, bool dx_follows, cudaStream_t main_st) {
   namespace tc = air::tc;
-  // fork: everything below runs on the side stream once X and dY are complete on the main stream; the main stream goes on
+  // fork: everything below runs on a side stream once X and dY are complete on the main stream; the main stream goes on
   // with the input gradient of this layer (its own row-major copy of dY) and the layers below
   cudaStream_t st = main_st;
   int lane = 0;                    // which side stream / operand buffer pair this layer uses
@@ -1276,7 +1276,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
         AIR_OK)
       return rc;
   }
-  // join: the weight gradients of the side stream are part of this call's result
+  // join: the weight gradients of the side streams are part of this call's result
   for (int i = 0; i < h->n_side; ++i) {
     cudaEvent_t done = next_event(h);
     AIR_CUDA(cudaEventRecord(done, h->side[i]));

@@ -430,7 +430,7 @@ def run_native(args, rank, local_rank, world):
     roofline["paint_elbo_gbs"] = paint_bytes / (acc["paint_elbo"] * 1e-3) / 1e9
 
     # ---- full training step (BASELINE.json configs[2] per GPU): forward + ELBO with saved activations, backward,
-    # one all-reduce of the flat gradient buffer (N > 1), centered RMSProp -- AIR_PREC_FP32 engine
+    # one all-reduce of the flat gradient buffer (N > 1), centered RMSProp -- same engine as the forward arm
     train = None
     if not args.no_train:
         teng = air.Engine(air.CellConfig(precision=prec), B, T, device=dev)

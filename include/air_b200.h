@@ -274,9 +274,10 @@ int32_t air_iwae_bound(int32_t n_canvases, int32_t K, int32_t T, int32_t na, con
 
 /* ---- training step: opt.compute_gradients(opt_loss, model_vars) + opt.apply_gradients of
  *      AIRModel.train_step (model.py:261-265,335-360) ------------------------------------------------------- */
-/* Switch a handle (AIR_PREC_FP32 engine, discrete_steps = 1) to training mode: allocates the second workspace
- * (saved activations + gradient scratch, air_train_workspace_bytes) once; from then on air_forward with a prior keeps
- * every activation the backward pass needs. */
+/* Switch a handle (either engine, discrete_steps = 1) to training mode: allocates the second workspace (saved
+ * activations + gradient scratch, air_train_workspace_bytes) once; from then on air_forward with a prior keeps every
+ * activation the backward pass needs.  air_backward runs its weight-gradient work on side streams owned by the handle
+ * (AIR_SIDE_STREAMS = 0..4, default 2) and joins them on the caller's stream before it returns. */
 int32_t air_train_enable(air_handle* h, int32_t on);
 int64_t air_train_workspace_bytes(const air_handle* h);
 /* Gradient of opt_loss = loss.value + reinforce_loss (+ l2) with respect to the flat parameter buffer, for the batch the
