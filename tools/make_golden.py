@@ -16,7 +16,7 @@ load_reference_modules_py: the Python-2 integer division of modules.py:60):
                                             ParametrisedGaussian / SpatialTransformer / MLP / Affine modules
 
 The vectors pin the oracle (tests/test_oracle_golden.py) and, through it and directly, the CUDA library
-(tests/test_gpu_golden.py).  /root/reference is only needed to RE-generate; the committed .npz files travel.
+(tests/test_gpu_golden.py, tests/test_gpu_zz_reference_vectors.py).  /root/reference is only needed to RE-generate; the committed .npz files travel.
 
     python tools/make_golden.py            # writes tests/golden/reference_{prior,loss,cell_script,cell_odd,cell_soft}.npz
 """
