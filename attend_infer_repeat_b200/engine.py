@@ -366,8 +366,9 @@ class Engine:
 
     def stream_host_u8(self, params, batches, prior: air_prior, seed0: int = 0):
         """Run the forward + ELBO pass over an iterable of pinned uint8 host batches with the double-buffered feed and yield
-        (scalars [AIR_N_SCALARS], loss_per_sample [B]) host tensors per batch, in order (each pair is valid until the
-        next-but-one ``next()``).  Batch i uses noise seed ``seed0 + i``."""
+        (scalars [AIR_N_SCALARS], loss_per_sample [B]) host tensors per batch, in order.  The two tensors are the slot's
+        pinned buffers: read (or clone) them before the next ``next()``, which enqueues the pass that overwrites them.
+        Batch i uses noise seed ``seed0 + i``."""
         scal = [torch.empty(_lib.AIR_N_SCALARS).pin_memory() for _ in range(2)]
         lps = [torch.empty(self.B).pin_memory() for _ in range(2)]
         it = iter(batches)
