@@ -88,6 +88,7 @@ SYMBOLS = {
     "air_param_entry": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "air_workspace_bytes": (C.c_int64, [_P]),
+    "air_row_schedule_check": (C.c_int32, [C.POINTER(air_config), C.c_char_p, C.c_int32]),
     "air_launch_count": (C.c_int64, [_P]),
     "air_profile_enable": (C.c_int32, [_P, C.c_int32]),
     "air_profile_read": (C.c_int32, [_P, _P, C.c_int32]),

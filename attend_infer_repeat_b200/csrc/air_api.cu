@@ -36,6 +36,7 @@
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
 #include "lstm_tc.cuh"
+#include "row_tc.cuh"
 
 namespace {
 
@@ -96,6 +97,7 @@ struct TcWeight {
   int split_n = 0, split_off = 0;   // what head only: scale half starts at row split_off
   int n_box = 0, n_pass = 0;
   CUtensorMap tm_chain;
+  CUtensorMap tm_row;                    // row_tc.cuh view: boxes of 128 rows x 64 K
   int64_t bias_src = -1, bias_off = 0;   // bias in params; zero-padded copy in the bias arena (floats)
   int perm_nh = 0;                       // lstm_tc.cuh column regrouping
 };
@@ -114,6 +116,7 @@ struct air_handle {
   Layer what_lin, lstm_x, lstm_h;
   Layer what_chain;                // what_lin with the loc / scale halves on 16-row boundaries (chain_tc.cuh)
   bool chain_ok = false;           // the fused-chain kernels cover this configuration
+  bool row_ok = false;             // the fused row kernel (row_tc.cuh) covers this configuration
   int na_off = 0;
   bool lstm_ok = false;            // the cluster LSTM kernel (lstm_tc.cuh) covers this configuration
   int lstm_x_perm = -1, lstm_h_perm = -1;   // tcw indices of the regrouped W[:n_enc] / W[n_enc:]
@@ -423,6 +426,179 @@ int32_t launch_chain_traced(air_handle* h, air::chain::Params& cp, cudaStream_t 
 
 air::chain::HlIn chain_in(const Buf& b) { return air::chain::HlIn{b.hlt, b.plane_t(), b.nsl}; }
 
+// ---- fused row kernel (row_tc.cuh) ---------------------------------------------------------------------------------
+// The layer list of the row path from the configuration alone (dimensions only; no device state): where MLP, steps MLP,
+// glimpse Encoder, what head, Decoder.
+std::vector<air::row::LayerDesc> row_layer_dims(const air_config& c, int which) {
+  using namespace air::row;
+  std::vector<LayerDesc> v;
+  const int na_off = round_up(c.na, 16);
+  auto mlp = [&](int n_in, const int32_t* hidden, int n_hidden, int n_out, int a_src) {
+    int d = n_in;
+    for (int i = 0; i < n_hidden; ++i) {
+      LayerDesc L;
+      L.K = d;
+      L.N = hidden[i];
+      L.epi = T_ELU;
+      L.a_src = (i == 0) ? a_src : 0;
+      v.push_back(L);
+      d = hidden[i];
+    }
+    if (n_out > 0) {
+      LayerDesc L;
+      L.K = d;
+      L.N = n_out;
+      L.epi = T_OUT;
+      L.a_src = (n_hidden == 0) ? a_src : 0;
+      v.push_back(L);
+    }
+  };
+  if (which == 0) {   // heads: h_t -> where MLP -> where code ; h_t -> steps MLP -> logit
+    mlp(c.nh, c.where_hidden, c.n_where_hidden, 8, 1);
+    v.back().out_kind = OUT_M_SMEM;
+    v.back().where_after = true;
+    mlp(c.nh, c.steps_hidden, c.n_steps_hidden, 1, 1);
+  } else {            // glimpse VAE: crop -> glimpse Encoder -> what head -> Decoder
+    mlp(c.h * c.w, c.glenc_hidden, c.n_glenc_hidden, 0, 1);
+    LayerDesc L;
+    L.K = c.glenc_hidden[c.n_glenc_hidden - 1];
+    L.N = 2 * na_off;
+    L.epi = T_WHAT;
+    v.push_back(L);
+    mlp(c.na, c.dec_hidden, c.n_dec_hidden, c.h * c.w, 0);
+  }
+  return v;
+}
+
+// "" when the row kernel covers the configuration and its schedule replays cleanly on the host
+std::string row_schedule_check(const air_config& c) {
+  if (2 * round_up(c.na, 16) > 128) return "what head wider than 128 columns";
+  if (c.nh > 256) return "hidden state wider than the 256-K operand";
+  for (const int32_t* hv : {c.where_hidden, c.steps_hidden, c.glenc_hidden, c.dec_hidden})
+    for (int i = 0; i < AIR_MAX_HIDDEN; ++i)
+      if (hv[i] > 256) return "a hidden layer is wider than 256";
+  for (int which = 0; which < 2; ++which) {
+    std::vector<air::row::LayerDesc> layers = row_layer_dims(c, which);
+    if ((int)layers.size() > air::row::MAXTM) return "too many layers";
+    air::row::Schedule sch;
+    if (!air::row::build_schedule(layers, sch)) return sch.error;
+    if (getenv("AIR_ROW_DUMP") && getenv("AIR_ROW_DUMP")[0]) {   // debug: the three programs, one line per unit / task
+      for (size_t i = 0; i < sch.units.size(); ++i) {
+        const air::row::Unit& u = sch.units[i];
+        fprintf(stderr, "unit %3zu  layer %2d  n_row %3d  kb0 %2d  nkb %d  nsl %d  N %3d  A%d D%d  fill %2d use %2d %s%s%s%s%s\n", i,
+                u.tm, u.n_row, u.kb0, u.nkb, u.nsl, u.n16 * 16, u.a_half, u.d_idx, u.fill, u.use,
+                (u.flags & air::row::U_WAIT_A) ? " WAIT_A" : "", (u.flags & air::row::U_WAIT_D) ? " WAIT_D" : "",
+                (u.flags & air::row::U_ACC0) ? " ACC0" : "", (u.flags & air::row::U_COMMIT_D) ? " COMMIT_D" : "",
+                (u.flags & air::row::U_COMMIT_A) ? " COMMIT_A" : "");
+      }
+      static const char* tn[] = {"LOAD_HL", "LOAD_CROP", "ELU", "OUT", "WHAT", "WHERE"};
+      for (size_t i = 0; i < sch.tasks.size(); ++i) {
+        const air::row::Task& t = sch.tasks[i];
+        fprintf(stderr, "task %3zu  %-9s  D%d use %2d  A%d fill %2d  s0 %3d nsl %d n_valid %3d\n", i, tn[t.type], t.d_idx, t.use,
+                t.a_half, t.fill, t.s0, t.nsl, t.n_valid);
+      }
+    }
+    const std::string r = air::row::simulate(sch);
+    if (!r.empty()) return r;
+  }
+  return "";
+}
+
+// which = 0: heads (where MLP + where sampling, steps MLP); which = 1: glimpse VAE (crop -> what -> decoded glimpse)
+int32_t launch_row_path(air_handle* h, int which, const float* eps_where, const float* eps_what, const air_outputs* o,
+                        int T_run, cudaStream_t st) {
+  using namespace air::row;
+  const air_config& c = h->cfg;
+  std::vector<LayerDesc> layers = row_layer_dims(c, which);
+  // bind weights / biases / outputs, in the order row_layer_dims() lists the layers
+  std::vector<const Layer*> src;
+  if (which == 0) {
+    for (const Mlp* m : {&h->where_mlp, &h->steps_mlp})
+      for (const Layer& l : m->layers) src.push_back(&l);
+  } else {
+    for (const Layer& l : h->glenc.layers) src.push_back(&l);
+    src.push_back(&h->what_chain);
+    for (const Layer& l : h->dec.layers) src.push_back(&l);
+  }
+  if (src.size() != layers.size()) return fail(AIR_ERR_ARG, "internal: row layer list mismatch");
+  static thread_local air::row::Params p;   // 17 KB: kept off the stack
+  memset(&p, 0, sizeof(p));
+  for (size_t i = 0; i < layers.size(); ++i) {
+    const TcWeight& w = h->tcw[src[i]->tc];
+    layers[i].tm = (int)i;
+    layers[i].lo_row = w.N_alloc;
+    layers[i].box_rows = air::row::row_box_rows(w.N_alloc);
+    layers[i].bias = h->bias_arena + w.bias_off;
+    p.tm[i] = w.tm_row;
+  }
+  if (which == 0) {
+    layers.back().out = h->logit;
+    layers.back().ldo = 1;
+  } else {
+    layers.back().out = o->glimpse;
+    layers.back().ldo = h->G;
+  }
+  Schedule sch;
+  if (!build_schedule(layers, sch)) return fail(AIR_ERR_ARG, "internal: row schedule: " + sch.error);
+  p.n_units = (int)sch.units.size();
+  p.n_tasks = (int)sch.tasks.size();
+  p.n_tm = (int)layers.size();
+  memcpy(p.unit, sch.units.data(), sizeof(Unit) * sch.units.size());
+  memcpy(p.task, sch.tasks.data(), sizeof(Task) * sch.tasks.size());
+  p.M = T_run * c.B;
+  p.B = c.B;
+  p.in[0] = chain_in(which == 0 ? h->hs : h->crop);
+  p.eps_where = eps_where;
+  p.where = o->where;
+  p.where_loc = o->where_loc;
+  p.where_scale = o->where_scale;
+  p.max_crop = c.max_crop_size;
+  p.scale_bias = c.scale_bias;
+  p.eps_what = eps_what;
+  p.what = o->what;
+  p.what_loc = o->what_loc;
+  p.what_scale = o->what_scale;
+  p.na = c.na;
+  p.na_off = h->na_off;
+  p.what_offset = c.what_scale_offset;
+  p.range_flag = h->range_flag;
+  {   // the noise prefetch parks in the staging tile until the what head: legal iff no T_OUT task runs before it
+    bool seen_what = false, out_before = false;
+    for (const Task& t : sch.tasks) {
+      if (t.type == T_WHAT) seen_what = true;
+      if (t.type == T_OUT && !seen_what) out_before = true;
+    }
+    p.prefetch_eps = (seen_what && !out_before) ? 1 : 0;
+  }
+  // debug: AIR_ROW_TRACE=<prefix> dumps the per-unit / per-task SM-clock stamps of every launch to <prefix>.<seq>.bin
+  static const char* trace_prefix = getenv("AIR_ROW_TRACE");
+  if (trace_prefix) {
+    const size_t n = (size_t)((p.M + air::tc::BM - 1) / air::tc::BM) * (MAXU + MAXTASK) * 4;
+    if (!h->trace) AIR_CUDA(cudaMalloc(&h->trace, sizeof(long long) * 1024 * (MAXU + MAXTASK) * 4));
+    if (n > (size_t)1024 * (MAXU + MAXTASK) * 4) return fail(AIR_ERR_ARG, "AIR_ROW_TRACE: too many tiles");
+    AIR_CUDA(cudaMemsetAsync(h->trace, 0, sizeof(long long) * n, st));
+    p.trace = h->trace;
+    AIR_CUDA(launch_row(p, st));
+    std::vector<long long> host(n);
+    AIR_CUDA(cudaMemcpyAsync(host.data(), h->trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    AIR_CUDA(cudaStreamSynchronize(st));
+    const std::string path = std::string(trace_prefix) + "." + std::to_string(h->trace_seq++) + ".bin";
+    if (FILE* f = fopen(path.c_str(), "wb")) {
+      const int hdr[4] = {p.n_units, p.n_tasks, MAXU, MAXTASK};
+      fwrite(hdr, sizeof(int), 4, f);
+      fwrite(p.unit, sizeof(Unit), p.n_units, f);
+      for (int i = 0; i < p.n_tasks; ++i) fwrite(&p.task[i].type, 1, 1, f);
+      fwrite(host.data(), sizeof(long long), n, f);
+      fclose(f);
+    }
+    ++h->launches;
+    return AIR_OK;
+  }
+  AIR_CUDA(launch_row(p, st));
+  ++h->launches;
+  return AIR_OK;
+}
+
 // The shared body of air_forward / air_cell_step: T_run steps starting from explicit or initial state.
 int32_t forward_impl(air_handle* h, const float* params, const float* img, const float* eps_where,
                      const float* eps_what, const float* u_pres, const float* baseline, const air_prior* prior,
@@ -558,6 +734,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                                cudaMemcpyDeviceToDevice, st));
   }
 
+  // 4.-7. row kernel (row_tc.cuh), two launches around the glimpse read: heads + where sampling, then the glimpse VAE
+  static const bool no_row = getenv("AIR_NO_ROW") != nullptr;
+  const bool rowk = chain && h->row_ok && !train && !no_row;
   // 4. heads over all T*B hidden states at once
   mark(h, AIR_ST_WHERE_MLP, st);
   Buf m;
@@ -566,7 +745,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   Buf logit;
   logit.f32 = h->logit;
   logit.ld = 1;
-  if (chain) {
+  if (rowk) {
+    if ((rc = launch_row_path(h, 0, eps_where, eps_what, o, T_run, st)) != AIR_OK) return rc;
+    mark(h, AIR_ST_STEPS, st);
+  } else if (chain) {
     // both heads of every (t, canvas) row in ONE launch: hs -> where MLP -> m ; hs -> steps MLP -> logit
     air::chain::Params cp;
     memset(&cp, 0, sizeof(cp));
@@ -598,9 +780,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   pa.discrete = c.discrete_steps;
   mark(h, AIR_ST_READ, st);
 
-  // 5. where sampling + glimpse read   (cell.py:129-135)
+  // 5. where sampling + glimpse read   (cell.py:129-135); the heads launch of the row kernel has sampled `where` already
   AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(256), air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
-                         h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
+                         rowk ? (const float*)nullptr : (const float*)h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
                          (tc && !train) ? nullptr : h->crop.f32,
                          tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
                          c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
@@ -609,7 +791,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
   // 6. glimpse encoder -> what   (cell.py:153-156)   7. decoder   (cell.py:158)
-  if (chain) {
+  if (rowk) {
+    if ((rc = launch_row_path(h, 1, eps_where, eps_what, o, T_run, st)) != AIR_OK) return rc;
+    mark(h, AIR_ST_DECODER, st);
+  } else if (chain) {
     // crop -> glimpse Encoder -> what head (sample) -> Decoder -> glimpse, one launch, activations resident in TMEM
     air::chain::Params cp;
     memset(&cp, 0, sizeof(cp));
@@ -1439,7 +1624,7 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
     e = cudaMemset(h->ws, 0, h->ws_bytes);
     std::vector<air::tc::PrepEntry> table;
     int tiles = 0;
-    bool ok = e == cudaSuccess;
+    bool ok = e == cudaSuccess, row_tm_ok = true;
     for (TcWeight& w : h->tcw) {
       air::tc::PrepEntry pe;
       pe.src_off = w.src_off;
@@ -1466,7 +1651,9 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
         else
           ok = ok && air::chain::make_weight_tmap(&w.tm_chain, h->arena + w.arena_off, w.Kpad, w.N_alloc, w.n_box);
       }
+      row_tm_ok = row_tm_ok && air::row::make_row_weight_tmap(&w.tm_row, h->arena + w.arena_off, w.Kpad, w.N_alloc);
     }
+    h->row_ok = h->chain_ok && row_tm_ok && row_schedule_check(c).empty();
     h->prep_tiles = tiles;
     if (ok)
       ok = cudaMemcpy(h->prep_table, table.data(), sizeof(air::tc::PrepEntry) * table.size(),
@@ -1502,6 +1689,16 @@ int32_t air_destroy(air_handle* h) {
   }
   delete h;
   return AIR_OK;
+}
+
+int32_t air_row_schedule_check(const air_config* cfg, char* msg, int32_t msg_len) {
+  if (!cfg) return fail(AIR_ERR_ARG, "air_row_schedule_check: NULL config");
+  const std::string r = row_schedule_check(*cfg);
+  if (msg && msg_len > 0) {
+    strncpy(msg, r.c_str(), (size_t)msg_len - 1);
+    msg[msg_len - 1] = 0;
+  }
+  return r.empty() ? AIR_OK : fail(AIR_ERR_ARG, "row schedule: " + r);
 }
 
 int64_t air_param_count(const air_handle* h) { return h ? h->n_params : 0; }

@@ -207,19 +207,24 @@ struct PresenceArgs {
   float step_bias, explore_eps;
   int discrete;
 };
+// one step of the scan: presence probability p_t and the carried presence (cell.py:137-151)
+__device__ __forceinline__ void presence_step(const PresenceArgs& pa, size_t i, float& pres, float& p) {
+  p = sigmoid_f(pa.logit[i] + pa.step_bias);
+  if (pa.explore_eps >= 0.f) p = __fadd_rn(pa.explore_eps / 2.0f, __fmul_rn(1.0f - pa.explore_eps, p));
+  if (pa.discrete) {
+    const float z = (pa.u_pres[i] < p) ? 1.0f : 0.0f;
+    pres *= z;
+  } else {
+    pres = p;
+  }
+}
 __device__ __forceinline__ void presence_scan(const PresenceArgs& pa, int b, int T, int B) {
   float pres = pa.presence_in ? pa.presence_in[b] : 1.0f;
   for (int t = 0; t < T; ++t) {
     const size_t i = (size_t)t * B + b;
-    float p = sigmoid_f(pa.logit[i] + pa.step_bias);
-    if (pa.explore_eps >= 0.f) p = __fadd_rn(pa.explore_eps / 2.0f, __fmul_rn(1.0f - pa.explore_eps, p));
+    float p;
+    presence_step(pa, i, pres, p);
     pa.presence_prob[i] = p;
-    if (pa.discrete) {
-      const float z = (pa.u_pres[i] < p) ? 1.0f : 0.0f;
-      pres *= z;
-    } else {
-      pres = p;
-    }
     pa.presence[i] = pres;
   }
 }
@@ -251,14 +256,18 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   if (threadIdx.x < 4 * T) {
     const int t = threadIdx.x >> 2, k = threadIdx.x & 3;
     const size_t row = (size_t)t * B + b;
-    const float mk = m[row * 8 + k];
-    const float loc = (k & 1) ? tanhf(mk) : __fmul_rn(max_crop, sigmoid_f(mk));
-    const float sc = softplus_f(m[row * 8 + 4 + k] + scale_bias);
-    const float wv = __fadd_rn(__fmul_rn(eps_where[row * 4 + k], sc), loc);
-    where_loc[row * 4 + k] = loc;
-    where_scale[row * 4 + k] = sc;
-    where[row * 4 + k] = wv;
-    s_where[t][k] = wv;
+    if (m) {
+      const float mk = m[row * 8 + k];
+      const float loc = (k & 1) ? tanhf(mk) : __fmul_rn(max_crop, sigmoid_f(mk));
+      const float sc = softplus_f(m[row * 8 + 4 + k] + scale_bias);
+      const float wv = __fadd_rn(__fmul_rn(eps_where[row * 4 + k], sc), loc);
+      where_loc[row * 4 + k] = loc;
+      where_scale[row * 4 + k] = sc;
+      where[row * 4 + k] = wv;
+      s_where[t][k] = wv;
+    } else {   // m == null: the where code has been sampled by the row kernel's heads launch (row_tc.cuh)
+      s_where[t][k] = where[row * 4 + k];
+    }
   }
   if (pa.logit && threadIdx.x == 64) presence_scan(pa, b, T, B);   // StepsPredictor + Bernoulli draw (cell.py:137-151)
   if (!bulk)
@@ -413,6 +422,9 @@ struct ElboArgs {
   int do_elbo;
   float* prior_part;           // [B] scratch: prior_weight * prior_per_sample (prior CTAs -> elbo_scalars_kernel)
   int n_prior_ctas;            // leading CTAs of the paint grid that compute the prior terms (launch_paint_elbo)
+  PresenceArgs scan;           // scan.logit != null: presence / presence_prob are not inputs -- this grid runs the presence scan
+                               // itself (the fused row kernel has no per-canvas CTA to do it): the paint CTA of a canvas
+                               // writes the two outputs, the prior warp of the canvas recomputes the same values locally
   air_prior prior;
   double steps_prior[AIR_MAX_STEPS + 1];   // geometric_prior(success_prob, T) (prior.py:26-32): the same table for
                                            // every canvas, computed once on the host (air_api.cu:steps_prior_table)
@@ -471,13 +483,34 @@ __device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int f
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const air_prior& pr = a.prior;
+  float pp[T], pz[T];   // presence_prob / presence of this canvas
+  if (a.scan.logit) {
+    float carry = a.scan.presence_in ? a.scan.presence_in[b] : 1.0f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      presence_step(a.scan, (size_t)t * B + b, carry, pp[t]);
+      pz[t] = carry;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      pp[t] = a.presence_prob[(size_t)t * B + b];
+      pz[t] = a.presence[(size_t)t * B + b];
+    }
+  }
   // step-count posterior q(n): lane k owns n = k (float64 island)
   const int k = lane;
   double pi = 0.0;
   if (k <= T) {
     double cum = 1.0;
-    for (int j = 0; j < k && j < T; ++j) cum *= (double)a.presence_prob[(size_t)j * B + b];
-    pi = (k < T) ? (1.0 - (double)a.presence_prob[(size_t)k * B + b]) * cum : cum;
+#pragma unroll
+    for (int j = 0; j < T; ++j)
+      if (j < k) cum *= (double)pp[j];
+    double pk = 0.0;
+#pragma unroll
+    for (int j = 0; j < T; ++j)
+      if (j == k) pk = (double)pp[j];
+    pi = (k < T) ? (1.0 - pk) * cum : cum;
   }
   double sum = pi;
 #pragma unroll
@@ -507,7 +540,7 @@ __device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int f
     klw[t] = warp_sum(v);
   }
   // KL(where) per step (model.py:188-214): lane t owns step t; (sx, sy) vs scale prior, (tx, ty) vs shift prior
-  float klwh_l = 0.f, pres_l = 0.f;
+  float klwh_l = 0.f;
   if (lane < T) {
     const float* wlp = a.where_loc + ((size_t)lane * B + b) * 4;
     const float* wsp = a.where_scale + ((size_t)lane * B + b) * 4;
@@ -518,13 +551,12 @@ __device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int f
     const float k_tx = normal_kl(wl.y, ws.y, pr.where_shift_has_loc ? pr.where_shift_loc : wl.y, pr.where_shift_scale);
     const float k_ty = normal_kl(wl.w, ws.w, pr.where_shift_has_loc ? pr.where_shift_loc : wl.w, pr.where_shift_scale);
     klwh_l = __fadd_rn(__fadd_rn(k_sx, k_tx), __fadd_rn(k_sy, k_ty));
-    pres_l = a.presence[(size_t)lane * B + b];
   }
   float klwh[T], pres[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     klwh[t] = __shfl_sync(0xffffffffu, klwh_l, t);
-    pres[t] = __shfl_sync(0xffffffffu, pres_l, t);
+    pres[t] = pz[t];
   }
   if (lane != 0) return;
   a.kl_num_steps_per_sample[b] = kl_n;
@@ -732,7 +764,18 @@ __global__ void __launch_bounds__(256, 8) paint_elbo_kernel(ElboArgs a) {
     float4 iv;   // (a', d', -tx', -ty')
     inv_params(wh[0], wh[1], wh[2], wh[3], iv.x, iv.y, iv.z, iv.w);
     s_inv[threadIdx.x] = iv;
-    s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
+    if (!a.scan.logit) s_pres[threadIdx.x] = a.presence[(size_t)threadIdx.x * B + b];
+  }
+  if (a.scan.logit && threadIdx.x == 32) {   // presence scan of this canvas (cell.py:137-151)
+    float carry = a.scan.presence_in ? a.scan.presence_in[b] : 1.0f;
+    for (int t = 0; t < T; ++t) {
+      const size_t i = (size_t)t * B + b;
+      float p;
+      presence_step(a.scan, i, carry, p);
+      a.scan.presence_prob[i] = p;
+      a.scan.presence[i] = carry;
+      s_pres[t] = carry;
+    }
   }
   __syncthreads();
   // inverse-warp tap tables while the copy is in flight: glimpse-space taps of every canvas column / row

@@ -137,6 +137,37 @@ def make_prior(what_prior=None, where_scale_prior=None, where_shift_prior=None, 
     return p
 
 
+def c_config(cfg: CellConfig, B: int, T: int) -> air_config:
+    """The C struct of a configuration (include/air_b200.h: air_config)."""
+    c = air_config()
+    c.B, c.H, c.W, c.h, c.w, c.T, c.na, c.nh = int(B), cfg.H, cfg.W, cfg.h, cfg.w, int(T), cfg.na, cfg.nh
+    c.n_enc_hidden = _fill_hidden(c.enc_hidden, cfg.enc_hidden)
+    c.n_glenc_hidden = _fill_hidden(c.glenc_hidden, cfg.glenc_hidden)
+    c.n_dec_hidden = _fill_hidden(c.dec_hidden, cfg.dec_hidden)
+    c.n_where_hidden = _fill_hidden(c.where_hidden, cfg.where_hidden)
+    c.n_steps_hidden = _fill_hidden(c.steps_hidden, cfg.steps_hidden)
+    c.output_std = float(cfg.output_std)
+    c.output_multiplier = float(cfg.output_multiplier)
+    c.explore_eps = -1.0 if cfg.explore_eps is None else float(cfg.explore_eps)
+    c.scale_bias = float(cfg.scale_bias)
+    c.step_bias = float(cfg.step_bias)
+    c.what_scale_offset = float(cfg.what_scale_offset)
+    c.forget_bias = float(cfg.forget_bias)
+    c.max_crop_size = float(cfg.max_crop_size)
+    c.discrete_steps = int(bool(cfg.discrete_steps))
+    c.precision = int(cfg.precision)
+    return c
+
+
+def row_schedule_check(cfg: CellConfig, B: int = 64, T: int = 3) -> str:
+    """Host-only replay of the fused row kernel's schedule for `cfg` (air_row_schedule_check): "" when the row kernel
+    covers the configuration, else the reason it does not.  Needs no GPU."""
+    c = c_config(cfg, B, T)
+    msg = C.create_string_buffer(256)
+    _lib.lib().air_row_schedule_check(C.byref(c), msg, 256)
+    return msg.value.decode()
+
+
 class Engine:
     """Owns an air_handle for (cfg, B, T) on one device and the output tensors of the fused call."""
 
@@ -148,23 +179,7 @@ class Engine:
         self.cfg, self.B, self.T = cfg, int(B), int(T)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.lib = _lib.lib()
-        c = air_config()
-        c.B, c.H, c.W, c.h, c.w, c.T, c.na, c.nh = self.B, cfg.H, cfg.W, cfg.h, cfg.w, self.T, cfg.na, cfg.nh
-        c.n_enc_hidden = _fill_hidden(c.enc_hidden, cfg.enc_hidden)
-        c.n_glenc_hidden = _fill_hidden(c.glenc_hidden, cfg.glenc_hidden)
-        c.n_dec_hidden = _fill_hidden(c.dec_hidden, cfg.dec_hidden)
-        c.n_where_hidden = _fill_hidden(c.where_hidden, cfg.where_hidden)
-        c.n_steps_hidden = _fill_hidden(c.steps_hidden, cfg.steps_hidden)
-        c.output_std = float(cfg.output_std)
-        c.output_multiplier = float(cfg.output_multiplier)
-        c.explore_eps = -1.0 if cfg.explore_eps is None else float(cfg.explore_eps)
-        c.scale_bias = float(cfg.scale_bias)
-        c.step_bias = float(cfg.step_bias)
-        c.what_scale_offset = float(cfg.what_scale_offset)
-        c.forget_bias = float(cfg.forget_bias)
-        c.max_crop_size = float(cfg.max_crop_size)
-        c.discrete_steps = int(bool(cfg.discrete_steps))
-        c.precision = int(cfg.precision)
+        c = c_config(cfg, self.B, self.T)
         self._c_cfg = c
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -161,6 +161,11 @@ int32_t air_param_entries(const air_handle* h);
 int32_t air_param_entry(const air_handle* h, int32_t i, const char** name, int64_t* offset,
                         int32_t* rows, int32_t* cols);
 int64_t air_workspace_bytes(const air_handle* h);
+/* Host-only self-check of the fused row kernel's schedule (csrc/row_tc.cuh) for a configuration: builds the unit / task
+ * programs of the producer, MMA and epilogue roles for the row path of cell.py:129-158 and replays them against the
+ * mbarrier protocol.  AIR_OK when the configuration is covered and the replay is deadlock- and hazard-free; otherwise
+ * AIR_ERR_ARG with the reason in `msg` (the engine then uses the per-stage kernels).  Needs no GPU. */
+int32_t air_row_schedule_check(const air_config* cfg, char* msg, int32_t msg_len);
 
 /* ---- instrumentation (bench.py): kernels launched so far through this handle, and per-stage device
  *      time of the LAST air_forward measured with CUDA events on the caller's stream. */
