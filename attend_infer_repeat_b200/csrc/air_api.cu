@@ -35,6 +35,7 @@
 #include "gemm_simt.cuh"
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
+#include "enc_tc.cuh"
 #include "lstm_tc.cuh"
 #include "row_tc.cuh"
 
@@ -117,6 +118,7 @@ struct air_handle {
   Layer what_chain;                // what_lin with the loc / scale halves on 16-row boundaries (chain_tc.cuh)
   bool chain_ok = false;           // the fused-chain kernels cover this configuration
   bool row_ok = false;             // the fused row kernel (row_tc.cuh) covers this configuration
+  bool enc1_ok = false;            // the split-K first encoder layer (enc_tc.cuh) covers this configuration
   int na_off = 0;
   bool lstm_ok = false;            // the cluster LSTM kernel (lstm_tc.cuh) covers this configuration
   int lstm_x_perm = -1, lstm_h_perm = -1;   // tcw indices of the regrouped W[:n_enc] / W[n_enc:]
@@ -314,10 +316,17 @@ int32_t dense(air_handle* h, const float* params, const Buf& in, int row0, const
 
 // neural.MLP (neural.py:63-102): ELU hidden layers, linear output layer.  Hidden activations ping-pong between the two
 // workspace buffers (fp32 rows or hl planes depending on the engine); the last layer writes `out`.
+int32_t run_mlp_from(air_handle* h, const float* params, const Mlp& mlp, const Buf& in, int M, const Buf& out,
+                     bool out_f32, bool out_hl, cudaStream_t st, const std::vector<float*>* saves, bool first_to_ping);
 int32_t run_mlp(air_handle* h, const float* params, const Mlp& mlp, const Buf& in, int M, const Buf& out,
                 bool out_f32, bool out_hl, cudaStream_t st, const std::vector<float*>* saves = nullptr) {
+  return run_mlp_from(h, params, mlp, in, M, out, out_f32, out_hl, st, saves, true);
+}
+// first_to_ping = false: `in` already sits in the ping buffer (the split-K first encoder layer wrote it there)
+int32_t run_mlp_from(air_handle* h, const float* params, const Mlp& mlp, const Buf& in, int M, const Buf& out,
+                     bool out_f32, bool out_hl, cudaStream_t st, const std::vector<float*>* saves, bool first_to_ping) {
   Buf cur = in;
-  bool to_ping = true;
+  bool to_ping = first_to_ping;
   const int nl = (int)mlp.layers.size();
   for (int i = 0; i < nl; ++i) {
     const Layer& l = mlp.layers[i];
@@ -422,6 +431,12 @@ int32_t launch_chain_traced(air_handle* h, air::chain::Params& cp, cudaStream_t 
     fclose(f);
   }
   return AIR_OK;
+}
+
+// the split-K first encoder layer reads fp32 images itself: no operand planes of the image are needed
+bool enc1_active(const air_handle* h) {
+  static const bool off = getenv("AIR_NO_ENC1") != nullptr;
+  return h->use_tc && h->enc1_ok && !off;
 }
 
 air::chain::HlIn chain_in(const Buf& b) { return air::chain::HlIn{b.hlt, b.plane_t(), b.nsl}; }
@@ -631,7 +646,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     ++h->launches;
     h->weights_ready = params;
   }
-  if (tc) {
+  const bool enc1 = enc1_active(h);
+  if (tc && !enc1) {
     if (!x_hl_ready) {
       const size_t n4 = (size_t)B * ((P + 3) / 4);
       AIR_CUDA(air::launch_k(air::tc::split_rows_kernel, dim3((unsigned)((n4 + thr - 1) / thr)), dim3(thr), 0, st, img,
@@ -642,8 +658,44 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
   const bool lstm_fused = tc && h->lstm_ok && !(train && layerwise);
-  if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
-                    train ? &h->sv_enc : nullptr)) != AIR_OK)
+  if (enc1) {
+    // first layer: split-K cluster kernel straight from the fp32 image (enc_tc.cuh); the remaining layers as before
+    const Layer& l0 = h->enc.layers[0];
+    const TcWeight& w0 = h->tcw[l0.tc];
+    const bool only = h->enc.layers.size() == 1;
+    Buf dst = only ? h->e : h->ping;
+    dst.kpad = round_up(l0.N, air::tc::BK);
+    air::enc::Params ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.tm_w = w0.tm_chain;
+    ep.img = img;
+    ep.bias = params + l0.b_off;
+    ep.B = B;
+    ep.P = P;
+    ep.nkb_total = w0.Kpad / air::tc::BK;
+    ep.nkb_per_cta = (ep.nkb_total + air::enc::KSPLIT - 1) / air::enc::KSPLIT;
+    ep.w_lo_row = w0.N_alloc;
+    const bool want_hl = only ? (tc && !lstm_fused) : true;
+    const bool want_f32 = only ? (lstm_fused || train) : train;
+    ep.out_hl = want_hl ? dst.hl : nullptr;
+    ep.hl_plane = dst.plane();
+    ep.ld_hl = dst.kpad;
+    ep.out_f32 = want_f32 ? (only ? h->e.f32 : h->sv_enc[0]) : nullptr;
+    ep.range_flag = h->range_flag;
+    AIR_CUDA(air::enc::launch_enc1(ep, st));
+    ++h->launches;
+    if (!only) {
+      Mlp rest;
+      rest.layers.assign(h->enc.layers.begin() + 1, h->enc.layers.end());
+      rest.n_hidden = h->enc.n_hidden - 1;
+      std::vector<float*> rest_saves;
+      if (train) rest_saves.assign(h->sv_enc.begin() + 1, h->sv_enc.end());
+      if ((rc = run_mlp_from(h, params, rest, dst, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
+                             train ? &rest_saves : nullptr, /*first_to_ping=*/false)) != AIR_OK)
+        return rc;
+    }
+  } else if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
+                           train ? &h->sv_enc : nullptr)) != AIR_OK)
     return rc;
   mark(h, AIR_ST_LSTM, st);
 
@@ -737,6 +789,12 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   // 4.-7. row kernel (row_tc.cuh), two launches around the glimpse read: heads + where sampling, then the glimpse VAE
   static const bool no_row = getenv("AIR_NO_ROW") != nullptr;
   const bool rowk = chain && h->row_ok && !train && !no_row;
+  // The heads keep chain_kernel by default: the where code is the one quantity the canvas amplifies (1 / s_x in the
+  // inverse transformer), and chain_kernel's sweep order -- every cross term of a layer before any main term -- leaves
+  // about half the accumulator-truncation bias of the row kernel's per-unit sweeps (measured on the ill-conditioned
+  // canvases of test_forward_tc_trained_like_weights); the heads are 4 us of the pass.  AIR_ROW_HEADS=1 selects the row kernel.
+  static const bool row_heads_env = getenv("AIR_ROW_HEADS") != nullptr;
+  const bool row_heads = rowk && row_heads_env;
   // 4. heads over all T*B hidden states at once
   mark(h, AIR_ST_WHERE_MLP, st);
   Buf m;
@@ -745,7 +803,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   Buf logit;
   logit.f32 = h->logit;
   logit.ld = 1;
-  if (rowk) {
+  if (row_heads) {
     if ((rc = launch_row_path(h, 0, eps_where, eps_what, o, T_run, st)) != AIR_OK) return rc;
     mark(h, AIR_ST_STEPS, st);
   } else if (chain) {
@@ -781,8 +839,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   mark(h, AIR_ST_READ, st);
 
   // 5. where sampling + glimpse read   (cell.py:129-135); the heads launch of the row kernel has sampled `where` already
-  AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(256), air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
-                         rowk ? (const float*)nullptr : (const float*)h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
+  static const int read_threads = getenv("AIR_READ_THREADS") ? atoi(getenv("AIR_READ_THREADS")) : air::WHERE_READ_THREADS;
+  AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(read_threads),
+                         air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
+                         row_heads ? (const float*)nullptr : (const float*)h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
                          (tc && !train) ? nullptr : h->crop.f32,
                          tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
                          c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
@@ -1654,6 +1714,7 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
       row_tm_ok = row_tm_ok && air::row::make_row_weight_tmap(&w.tm_row, h->arena + w.arena_off, w.Kpad, w.N_alloc);
     }
     h->row_ok = h->chain_ok && row_tm_ok && row_schedule_check(c).empty();
+    h->enc1_ok = h->chain_ok && h->enc.layers[0].N == air::enc::N1 && (h->P % 4) == 0;
     h->prep_tiles = tiles;
     if (ok)
       ok = cudaMemcpy(h->prep_table, table.data(), sizeof(air::tc::PrepEntry) * table.size(),
@@ -1911,7 +1972,7 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
   // uint8 -> float32 / 255 (data.py:116) on the device, fused with the first layer's operand split
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
-                         (const uint8_t*)h->st_img_u8, h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(),
+                         (const uint8_t*)h->st_img_u8, h->st_img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(),
                          h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
   ++h->launches;
   rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
@@ -1960,7 +2021,7 @@ int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_
   if ((rc = draw_noise_impl(h, seed, h->st_eps_where, h->st_eps_what, h->st_u, st)) != AIR_OK) return rc;
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
-                         (const uint8_t*)h->st_img_u8, h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(),
+                         (const uint8_t*)h->st_img_u8, h->st_img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(),
                          h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
   ++h->launches;
   rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
@@ -2025,7 +2086,7 @@ int32_t air_forward_fed_u8_rng(air_handle* h, const float* params, int32_t slot,
   AIR_CUDA(cudaStreamWaitEvent(st, h->feed_fed[slot], 0));
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
-                         (const uint8_t*)h->feed_buf[slot], h->st_img, h->use_tc ? h->x.hl : (__half*)nullptr,
+                         (const uint8_t*)h->feed_buf[slot], h->st_img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr,
                          h->x.plane(), h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
   ++h->launches;
   AIR_CUDA(cudaEventRecord(h->feed_consumed[slot], st));
@@ -2064,7 +2125,7 @@ int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t
   // gather + uint8 -> float32 / 255 (data.py:116,131-132) + the first layer's operand split, one pass, all on the device
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dataset_u8,
-                         img, h->use_tc ? h->x.hl : (__half*)nullptr, h->x.plane(), h->x.kpad, c.B, h->P, idx));
+                         img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(), h->x.kpad, c.B, h->P, idx));
   ++h->launches;
   return forward_impl(h, params, img, eps_where, eps_what, u_pres, baseline, prior, outs, c.T, nullptr, nullptr, nullptr,
                       nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);

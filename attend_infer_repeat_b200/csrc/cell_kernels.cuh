@@ -193,6 +193,9 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, const flo
 //   crop[t,b] = resampler(img[b], AffineGridWarper(where))                  (modules.py:104-109, cell.py:135)
 // dynamic smem: H*W floats (image) + T*(w+h) taps.
 // ---------------------------------------------------------------------------------------------------
+// 128 threads, 16 CTAs per SM: the kernel is a chain of dependent latencies (where code -> taps -> image copy -> crop), so
+// more, smaller CTAs in flight hide more of it than 8 of 256 did (measured at B = 4096: 35 -> see profiles/r02)
+constexpr int WHERE_READ_THREADS = 128;
 __host__ __device__ inline size_t where_read_smem(int T, int H, int W, int h, int w) {
   return sizeof(float) * ((size_t)H * W + 4) / 16 * 16 + 16 + sizeof(Tap) * (size_t)T * (w + h);
 }
@@ -229,7 +232,7 @@ __device__ __forceinline__ void presence_scan(const PresenceArgs& pa, int b, int
   }
 }
 
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(WHERE_READ_THREADS, 2048 / WHERE_READ_THREADS)
 where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_where, const float* __restrict__ img,
                   float* __restrict__ where, float* __restrict__ where_loc, float* __restrict__ where_scale,
                   float* __restrict__ crop, HlOut crop_hl, int T, int B, int H, int W, int h, int w, float max_crop,
@@ -819,7 +822,8 @@ inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStrea
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  return launch_k(paint_elbo_kernel<T>, dim3(a.B + a.n_prior_ctas), dim3(256), smem, st, a);
+  static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
+  return launch_k(paint_elbo_kernel<T>, dim3(a.B + a.n_prior_ctas), dim3(nt), smem, st, a);
 }
 // host-side constants of ElboArgs (float64 maths on the host, exactly what the device code computed per tap before)
 inline void fill_elbo_consts(ElboArgs& a) {
@@ -830,7 +834,9 @@ inline void fill_elbo_consts(ElboArgs& a) {
 // prior terms (when a prior is given) followed by paint + reconstruction term
 inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
   fill_elbo_consts(a);
-  a.n_prior_ctas = a.do_elbo ? (a.B + 7) / 8 : 0;   // 8 warps per CTA, one canvas per warp
+  static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
+  const int wpc = nt / 32;                          // warps per CTA, one canvas per warp
+  a.n_prior_ctas = a.do_elbo ? (a.B + wpc - 1) / wpc : 0;
   const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);
   switch (a.T) {
     case 1: return launch_paint_elbo_t<1>(a, smem, st);

@@ -163,3 +163,17 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "configs[1]" in d["config"]["workload"]
+
+
+def test_row_kernel_schedule_replays_cleanly_on_the_host():
+    """air_row_schedule_check (no GPU): the producer / MMA / epilogue programs of the row kernel (csrc/row_tc.cuh) for the
+    script configuration, BASELINE configs[3] and an odd-shaped one are deadlock- and hazard-free under the mbarrier
+    protocol; configurations the kernel does not cover are refused with a reason (the engine then uses chain_kernel)."""
+    import attend_infer_repeat_b200 as air
+    assert air.row_schedule_check(air.CellConfig(precision=air.AIR_PREC_TC_SPLIT)) == ""
+    assert air.row_schedule_check(air.CellConfig(H=100, W=100, h=28, w=28, precision=air.AIR_PREC_TC_SPLIT), T=5) == ""
+    odd = air.CellConfig(H=9, W=14, h=4, w=6, na=7, nh=256, enc_hidden=(40,), glenc_hidden=(24, 200), dec_hidden=(30,),
+                         where_hidden=(20,), steps_hidden=(10,), precision=air.AIR_PREC_TC_SPLIT)
+    assert air.row_schedule_check(odd, T=4) == ""
+    assert "wider than 256" in air.row_schedule_check(air.CellConfig(glenc_hidden=(300,), precision=air.AIR_PREC_TC_SPLIT))
+    assert "what head" in air.row_schedule_check(air.CellConfig(na=80, precision=air.AIR_PREC_TC_SPLIT))
