@@ -119,6 +119,7 @@ SYMBOLS = {
     "air_gather_u8": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "air_linear_backward": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "air_baseline_grad": (C.c_int32, [_P, _P, C.c_float, C.c_float, _P, C.c_int32, _P]),
+    "air_baseline_grad_dev": (C.c_int32, [_P, _P, C.c_float, _P, C.c_int32, _P]),
     "air_elbo_scalars": (C.c_int32, [_P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_elbo_scalars_raw": (C.c_int32, [C.c_int32, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_prior_terms": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior),

@@ -1445,6 +1445,11 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   a.explore_eps = c.explore_eps;
   a.inv_batch = inv_batch > 0.f ? inv_batch : 1.0f / (float)B;
   a.baseline_mean = baseline_mean;
+  // NaN: the mean is whatever scalars[AIR_S_MEAN_BASELINE] holds on the device when the kernel runs (the last
+  // air_forward / air_elbo_scalars with a baseline, or the all-reduced block under sharding) -- no host round trip
+  a.baseline_mean_dev = (baseline_mean != baseline_mean && o && o->scalars) ? o->scalars + AIR_S_MEAN_BASELINE : nullptr;
+  if (baseline_mean != baseline_mean && !a.baseline_mean_dev)
+    return fail(AIR_ERR_ARG, "air_backward: baseline_mean = NaN needs outs->scalars");
   a.step_W = c.W > 1 ? 2.0 / (double)(c.W - 1) : 0.0;
   a.step_H = c.H > 1 ? 2.0 / (double)(c.H - 1) : 0.0;
   a.step_w = c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0;
@@ -1823,6 +1828,13 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
   if (on && !h->cfg.discrete_steps)
     return fail(AIR_ERR_ARG, "air_train_enable: the backward pass covers discrete_steps = 1 (the script configuration)");
   if (on && !h->tws) {
+    // (checked before anything is allocated: a failed enable must leave the handle exactly as it was, so that a retry
+    // runs the whole initialisation again instead of finding a half-built workspace)
+    const size_t smem = air::paint_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
+    const size_t smem_r = air::read_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
+    if (smem > 200 * 1024 || smem_r > 200 * 1024)
+      return fail(AIR_ERR_ARG, "air_train_enable: image / glimpse tile does not fit in shared memory");
+    const int32_t rc_init = [&]() -> int32_t {
     h->tc_bwd = getenv("AIR_NO_TC_BWD") == nullptr && air::tc::get_encode_fn() != nullptr;
     // side streams for the weight-gradient work: AIR_SIDE_STREAMS=n (1..MAX_SIDE, default 2), AIR_NO_SIDE_STREAM=1 for none
     int want_side = 2;
@@ -1845,14 +1857,24 @@ int32_t air_train_enable(air_handle* h, int32_t on) {
         h->n_side = i + 1;
       }
       if (h->n_side) {
-        h->ev_pool.resize(128);
+        h->ev_pool.assign(128, nullptr);
         for (cudaEvent_t& e : h->ev_pool) AIR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       }
     }
-    const size_t smem = air::paint_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
-    const size_t smem_r = air::read_bwd_smem(h->cfg.T, h->cfg.H, h->cfg.W, h->cfg.h, h->cfg.w);
-    if (smem > 200 * 1024 || smem_r > 200 * 1024)
-      return fail(AIR_ERR_ARG, "air_train_enable: image / glimpse tile does not fit in shared memory");
+    return AIR_OK;
+    }();
+    if (rc_init != AIR_OK) {   // undo: streams, events, workspace
+      for (int i = 0; i < h->n_side; ++i) cudaStreamDestroy(h->side[i]);
+      h->n_side = 0;
+      for (cudaEvent_t e : h->ev_pool)
+        if (e) cudaEventDestroy(e);
+      h->ev_pool.clear();
+      if (h->tws) cudaFree(h->tws);
+      h->tws = nullptr;
+      h->tws_bytes = 0;
+      h->train = false;
+      return rc_init;
+    }
   }
   h->train = on != 0;
   h->fwd_saved = false;
@@ -1913,8 +1935,18 @@ int32_t air_linear_backward(const float* X, const float* W, const float* dY, con
 int32_t air_baseline_grad(const float* target, const float* baseline, float target_mean, float inv_batch, float* d_baseline,
                           int32_t B, void* stream) {
   if (!target || !baseline || !d_baseline || B < 1) return fail(AIR_ERR_ARG, "air_baseline_grad: bad argument");
+  (void)target;
   air::baseline_grad_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(baseline, target_mean, inv_batch,
-                                                                                d_baseline, B);
+                                                                                d_baseline, B, nullptr);
+  AIR_CUDA(cudaGetLastError());
+  return AIR_OK;
+}
+
+int32_t air_baseline_grad_dev(const float* baseline, const float* target_mean_dev, float inv_batch, float* d_baseline,
+                              int32_t B, void* stream) {
+  if (!baseline || !target_mean_dev || !d_baseline || B < 1) return fail(AIR_ERR_ARG, "air_baseline_grad_dev: bad argument");
+  air::baseline_grad_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(baseline, 0.f, inv_batch, d_baseline, B,
+                                                                                target_mean_dev);
   AIR_CUDA(cudaGetLastError());
   return AIR_OK;
 }
@@ -1973,7 +2005,7 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
                          (const uint8_t*)h->st_img_u8, h->st_img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(),
-                         h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
+                         h->x.kpad, c.B, h->P, (const int32_t*)nullptr, 0LL));
   ++h->launches;
   rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
                     nullptr, nullptr, nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
@@ -2022,7 +2054,7 @@ int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
                          (const uint8_t*)h->st_img_u8, h->st_img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(),
-                         h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
+                         h->x.kpad, c.B, h->P, (const int32_t*)nullptr, 0LL));
   ++h->launches;
   rc = forward_impl(h, params, h->st_img, h->st_eps_where, h->st_eps_what, h->st_u, nullptr, prior, outs, c.T, nullptr,
                     nullptr, nullptr, nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);
@@ -2087,7 +2119,7 @@ int32_t air_forward_fed_u8_rng(air_handle* h, const float* params, int32_t slot,
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
                          (const uint8_t*)h->feed_buf[slot], h->st_img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr,
-                         h->x.plane(), h->x.kpad, c.B, h->P, (const int32_t*)nullptr));
+                         h->x.plane(), h->x.kpad, c.B, h->P, (const int32_t*)nullptr, 0LL));
   ++h->launches;
   AIR_CUDA(cudaEventRecord(h->feed_consumed[slot], st));
   h->feed_pending[slot] = false;
@@ -2125,7 +2157,8 @@ int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t
   // gather + uint8 -> float32 / 255 (data.py:116,131-132) + the first layer's operand split, one pass, all on the device
   const size_t n4 = (size_t)c.B * ((h->P + 3) / 4);
   AIR_CUDA(air::launch_k(air::tc::u8_to_f32_hl_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, dataset_u8,
-                         img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(), h->x.kpad, c.B, h->P, idx));
+                         img, (h->use_tc && !enc1_active(h)) ? h->x.hl : (__half*)nullptr, h->x.plane(), h->x.kpad, c.B, h->P, idx,
+                         (long long)n_dataset));   // indices are clamped to [0, n_dataset)
   ++h->launches;
   return forward_impl(h, params, img, eps_where, eps_what, u_pres, baseline, prior, outs, c.T, nullptr, nullptr, nullptr,
                       nullptr, nullptr, c.output_multiplier, st, /*x_hl_ready=*/h->use_tc);

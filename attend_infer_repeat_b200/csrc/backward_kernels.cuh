@@ -86,6 +86,7 @@ struct BwdArgs {
   float output_std, output_multiplier, max_crop, explore_eps;
   float inv_batch;             // 1 / (global batch): every per-sample term enters the loss through a batch mean
   float baseline_mean;         // mean over the global batch of the REINFORCE baseline (0 without one)
+  const float* baseline_mean_dev;   // non-null: read the mean from device memory instead (scalars[AIR_S_MEAN_BASELINE])
   double step_W, step_H, step_w, step_h;   // np.linspace steps (host, float64) as in the forward
   air_prior prior;
   double steps_prior[AIR_MAX_STEPS + 1];
@@ -297,12 +298,8 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
 template <int T>
 inline cudaError_t launch_paint_bwd_t(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = paint_bwd_smem(a.T, a.H, a.W, a.h, a.w);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(paint_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  cudaError_t e = ensure_dynamic_smem(paint_bwd_kernel<T>, smem);
+  if (e != cudaSuccess) return e;
   return launch_k(paint_bwd_kernel<T>, dim3(a.B), dim3(256), smem, st, a);
 }
 inline cudaError_t launch_paint_bwd(const BwdArgs& a, cudaStream_t st) {
@@ -387,12 +384,8 @@ __global__ void __launch_bounds__(256) read_bwd_kernel(BwdArgs a) {
 }
 inline cudaError_t launch_read_bwd(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = read_bwd_smem(a.T, a.H, a.W, a.h, a.w);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(read_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  cudaError_t e = ensure_dynamic_smem(read_bwd_kernel, smem);
+  if (e != cudaSuccess) return e;
   return launch_k(read_bwd_kernel, dim3(a.B), dim3(256), smem, st, a);
 }
 
@@ -500,7 +493,8 @@ __global__ void __launch_bounds__(128) latent_bwd_kernel(BwdArgs a) {
       iw = __fadd_rn(iw, __fadd_rn(__fadd_rn(__fmul_rn(a.kl_n_ps[b], pr.steps_weight), a.kl_what_ps[b]), a.kl_where_ps[b]));
     const double nv_scale = pr.nvil_scale != 0.f ? (double)pr.nvil_scale : 1.0;
     const double nv_shift = pr.nvil_scale != 0.f ? (double)pr.nvil_shift : 0.0;
-    cq = (double)a.inv_batch * ((double)iw - (double)a.baseline_mean - nv_shift) * nv_scale;
+    const double bmean = a.baseline_mean_dev ? (double)__ldg(a.baseline_mean_dev) : (double)a.baseline_mean;
+    cq = (double)a.inv_batch * ((double)iw - bmean - nv_shift) * nv_scale;
   }
   double dsw_run = 0.0;   // sum_{t < k} dL/dw_t
 #pragma unroll
@@ -615,9 +609,10 @@ __global__ void l2_grad_kernel(const float* __restrict__ w, float* __restrict__ 
 // baseline_loss = .5 * mean((stop_gradient(iw) - baseline)^2) with iw [B] and baseline [B,1] broadcasting to [B,B]
 // (model.py:253-259): d / d baseline_i = -(mean_j iw_j - baseline_i) / B
 __global__ void baseline_grad_kernel(const float* __restrict__ baseline, float target_mean, float inv_batch,
-                                     float* __restrict__ d_baseline, int B) {
+                                     float* __restrict__ d_baseline, int B, const float* __restrict__ target_mean_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) d_baseline[i] = -inv_batch * (target_mean - baseline[i]);
+  const float tm = target_mean_dev ? __ldg(target_mean_dev) : target_mean;
+  if (i < B) d_baseline[i] = -inv_batch * (tm - baseline[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -250,11 +250,15 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   if (threadIdx.x == 0 && bulk) {
     mbar_init(&bar, 1);
     fence_mbar_init();
+  }
+  griddep_launch();
+  griddep_wait();   // m / eps / where come from earlier kernels of the chain -- and so may the image (the uint8 entry
+                    // points convert it on this stream; every kernel in between releases its dependents early, so the
+                    // prologue is NOT transitively ordered after that producer): the copy starts after the wait
+  if (threadIdx.x == 0 && bulk) {
     mbar_expect_tx(&bar, (uint32_t)P * 4u);
     bulk_g2s(s_img, src, (uint32_t)P * 4u, &bar);
   }
-  griddep_launch();
-  griddep_wait();   // the image is an external input; m / eps come from earlier kernels of the chain
   // the T where codes of this canvas (4 components each) while the image is in flight
   if (threadIdx.x < 4 * T) {
     const int t = threadIdx.x >> 2, k = threadIdx.x & 3;
@@ -816,12 +820,8 @@ __global__ void __launch_bounds__(256, 8) paint_elbo_kernel(ElboArgs a) {
 
 template <int T>
 inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStream_t st) {
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(paint_elbo_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  cudaError_t e = ensure_dynamic_smem(paint_elbo_kernel<T>, smem);
+  if (e != cudaSuccess) return e;
   static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
   return launch_k(paint_elbo_kernel<T>, dim3(a.B + a.n_prior_ctas), dim3(nt), smem, st, a);
 }

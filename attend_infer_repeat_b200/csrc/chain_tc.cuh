@@ -426,12 +426,8 @@ inline bool make_weight_tmap(CUtensorMap* tm, const __half* base, int kpad, int 
 }
 
 inline cudaError_t launch_chain(const Params& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = ensure_dynamic_smem(chain_kernel, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   return launch_k(chain_kernel, dim3((p.M + BM - 1) / BM), dim3(NUM_THREADS), SMEM_BYTES, st, p);
 }
 

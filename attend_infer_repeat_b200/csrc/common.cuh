@@ -6,6 +6,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace air {
 
 constexpr int ACT_NONE = 0;
@@ -79,6 +83,26 @@ inline bool pdl_enabled() {
 }
 
 #ifdef __CUDACC__
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: the opt-in is remembered per (device, kernel),
+// not per process, so a second handle on another GPU of the same process gets it too.
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t bytes) {
+  // keyed by (device, kernel ADDRESS): instantiations of one kernel template share a function-pointer type
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> configured;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kernel));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = configured.find(key);
+  if (it != configured.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) configured[key] = bytes;
+  return e;
+}
+
 // <<<>>> replacement that sets the PDL attribute (or not)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

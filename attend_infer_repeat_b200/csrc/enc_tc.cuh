@@ -281,7 +281,7 @@ __global__ void __cluster_dims__(KSPLIT, 1, 1) __launch_bounds__(ENC_THREADS, 1)
 }
 
 inline cudaError_t launch_enc1(const Params& p, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(enc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM_BYTES);
+  cudaError_t e = ensure_dynamic_smem(enc1_kernel, ENC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   return launch_k(enc1_kernel, dim3(KSPLIT, (p.B + BM - 1) / BM), dim3(ENC_THREADS), ENC_SMEM_BYTES, st, p);
 }

@@ -589,14 +589,17 @@ __global__ void split_rows_bf16_kernel(const float* __restrict__ src, int ld, in
 // gather != null: row r of the batch is row gather[r] of a device-resident uint8 dataset (the minibatch indices of
 // tensors_from_data, data.py:121-158), so the host never touches the pixels.
 __global__ void u8_to_f32_hl_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, __half* __restrict__ hl,
-                                    size_t plane, int ld_hl, int M, int K, const int32_t* __restrict__ gather) {
+                                    size_t plane, int ld_hl, int M, int K, const int32_t* __restrict__ gather,
+                                    long long n_src = 0) {
   griddep_launch();
   griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 pixels
   const int kq = (K + 3) / 4;
   if (idx >= (size_t)M * kq) return;
   const int row = (int)(idx / kq), k = (int)(idx % kq) * 4;
-  const uint8_t* s = src + (size_t)(gather ? gather[row] : row) * K + k;
+  long long srow = gather ? (long long)gather[row] : (long long)row;
+  if (gather && n_src > 0) srow = srow < 0 ? 0 : (srow >= n_src ? n_src - 1 : srow);   // a bad index must not read out of bounds
+  const uint8_t* s = src + (size_t)srow * K + k;
   float f[4] = {0.f, 0.f, 0.f, 0.f};
   const bool vec = (k + 3 < K) && ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
   if (vec) {
@@ -728,13 +731,8 @@ template <int BN, int STAGES>
 inline cudaError_t launch_gemm_cfg(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p, int n_alloc,
                                    cudaStream_t st) {
   using L = Smem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = ensure_dynamic_smem(linear_tc_kernel<BN, STAGES>, L::TOTAL);
+  if (e != cudaSuccess) return e;
   const int nz = p.kb_per_z > 0 ? (p.num_k_blocks + p.kb_per_z - 1) / p.kb_per_z : 1;
   dim3 grid(n_alloc / BN, (p.M + BM - 1) / BM, nz);
   return launch_k(linear_tc_kernel<BN, STAGES>, grid, dim3(num_threads(BN)), L::TOTAL, st, tm_a, tm_b, p);

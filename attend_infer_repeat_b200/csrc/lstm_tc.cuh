@@ -384,12 +384,8 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
 }
 
 inline cudaError_t launch_lstm(const Params& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = ensure_dynamic_smem(lstm_cluster_kernel, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   return launch_k(lstm_cluster_kernel, dim3(CLUSTER, (p.B + BM - 1) / BM), dim3(NUM_THREADS), SMEM_BYTES, st, p);
 }
 

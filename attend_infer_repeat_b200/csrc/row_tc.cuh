@@ -842,7 +842,7 @@ inline bool make_row_weight_tmap(CUtensorMap* tm, const __half* base, int kpad, 
 }
 
 inline cudaError_t launch_row(const Params& p, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROW_SMEM_BYTES);
+  cudaError_t e = ensure_dynamic_smem(row_kernel, ROW_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   return launch_k(row_kernel, dim3((p.M + BM - 1) / BM), dim3(ROW_THREADS), ROW_SMEM_BYTES, st, p);
 }

@@ -305,7 +305,8 @@ class Engine:
 
     # -- training step -----------------------------------------------------------------
     def train_enable(self, on: bool = True):
-        """Keep the activations of every following forward() for backward() (fp32 engine only)."""
+        """Keep the activations of every following forward() for backward() (either engine: on an AIR_PREC_TC_SPLIT
+        handle the training forward and the gradient GEMMs run on the tensor cores)."""
         with torch.cuda.device(self.device):
             check(self.lib.air_train_enable(self._handle, int(on)), "air_train_enable")
 

@@ -65,6 +65,18 @@ def baseline_grad(target, baseline, target_mean, inv_batch):
     return out
 
 
+def baseline_grad_dev(baseline, target_mean_dev, inv_batch):
+    """baseline_grad with the target mean read from a 1-element device tensor when the kernel runs (no host sync)."""
+    baseline = _cuda_f32(baseline.reshape(-1), "baseline")
+    assert target_mean_dev.is_cuda and target_mean_dev.dtype == torch.float32 and target_mean_dev.numel() >= 1
+    B = baseline.numel()
+    out = torch.empty(B, 1, device=baseline.device, dtype=torch.float32)
+    with torch.cuda.device(baseline.device):
+        check(_lib.lib().air_baseline_grad_dev(ptr(baseline), ptr(target_mean_dev), float(inv_batch), ptr(out), B,
+                                               current_stream_ptr()), "air_baseline_grad_dev")
+    return out
+
+
 def lstm_step(x, h, c, w, b, forget_bias=1.0):
     """snt.LSTM step; returns new (h, c).  Gate order i, j, f, o; w is [nx + nh, 4 nh]."""
     x, w, b = _cuda_f32(x, "x"), _cuda_f32(w, "w"), _cuda_f32(b, "b")

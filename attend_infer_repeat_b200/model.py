@@ -15,6 +15,7 @@ from . import _lib
 from . import functional as F
 from .cell import AIRCell
 from .engine import make_prior
+from ._lib import SCALAR_INDEX
 from .ops import Loss
 from .prior import NumStepsDistribution, geometric_prior
 
@@ -171,17 +172,29 @@ class AIRModel:
                 b = self.baseline_module(self.obs, self.what, self.where, self.presence, self.final_state)
                 self.baseline = b                                                 # [B,1]
                 eng.elbo_scalars(b.reshape(-1), self._prior_struct)               # REINFORCE with the baseline mean
-                # [B] - [B,1] broadcasts to [B,B] in the reference; exposed as written, lazily
-                self.importance_weight = self.reinforce_imp_weight - b
-                # .5 * mean over the [B,B] broadcast of (iw_j - b_i)^2, without materialising it a second time
-                iw, bb = self.reinforce_imp_weight.double(), b.reshape(-1).double()
-                self.baseline_loss = (.5 * ((iw * iw).mean() - 2. * iw.mean() * bb.mean() + (bb * bb).mean())).float()
-            else:
-                self.importance_weight = self.reinforce_imp_weight
+                # [B] - [B,1] broadcasts to [B,B] in the reference (67 MB at B = 4096, 4.3 GB at 32768).
+                # Nothing on the path needs the matrix -- the `importance_weight` property forms it on request.
+                # .5 * mean over that broadcast of (iw_j - b_i)^2 = .5 (E iw^2 - 2 E iw E b + E b^2): four batch means the
+                # scalars kernel has just written (device arithmetic on 4 numbers, float64, no host round trip)
+                sc = eng.out["scalars"].double()
+                m_iw, m_iw2 = sc[SCALAR_INDEX["mean_iw"]], sc[SCALAR_INDEX["mean_iw2"]]
+                m_b, m_b2 = sc[SCALAR_INDEX["mean_baseline"]], sc[SCALAR_INDEX["mean_baseline2"]]
+                self.baseline_loss = (.5 * (m_iw2 - 2. * m_iw * m_b + m_b2)).float()
             self.reinforce_loss = eng.scalar("reinforce_loss")
         self.opt_loss = eng.scalar("opt_loss")
         if self.nums is not None:
             self.num_step_accuracy = (self.gt_num_steps == self.num_step_per_sample).to(torch.float32).mean()
+
+    @property
+    def importance_weight(self):
+        """model.py:231: stop_gradient(iw) - baseline.  With a BaselineMLP that is [B] - [B,1] = a [B,B] matrix in the
+        reference; it is formed here only when somebody reads the attribute."""
+        iw = getattr(self, "reinforce_imp_weight", None)
+        if iw is None:
+            raise AttributeError("importance_weight exists after train_step() (model.py:224-231)")
+        b = self.baseline if (self._train_cfg and self._train_cfg["use_reinforce"] and self.baseline_module is not None) \
+            else None
+        return iw if b is None else iw - b
 
     def train_step(self, learning_rate, l2_weight=0., what_prior=None, where_scale_prior=None,
                    where_shift_prior=None,
@@ -245,27 +258,28 @@ class AIRModel:
         eng, pr = self.engine, self._prior_struct
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         B = self.batch_size
-        bmean = 0.0
-        if self._train_cfg["use_reinforce"] and self.baseline_module is not None:
-            b = self.baseline.reshape(-1)
-            bmean = float(sharding.global_baseline_mean(b, B)) if world > 1 else float(b.mean())
+        has_baseline = self._train_cfg["use_reinforce"] and self.baseline_module is not None
+        if world > 1:
+            # 16 floats: after this the scalar block holds the means of the WHOLE batch on every rank -- among them the
+            # baseline mean and the importance-weight mean the two backward passes read from device memory below
+            sharding.combine_scalars(out["scalars"], B, pr.steps_weight, bool(pr.use_prior), bool(pr.use_reinforce),
+                                     nvil_shift=pr.nvil_shift, nvil_scale=pr.nvil_scale)
         eps_where, eps_what, _ = self._last_noise
-        eng.backward(self.cell.params, self.obs, eps_where, eps_what, pr, self._grad, baseline_mean=bmean,
+        # baseline_mean = NaN: air_backward reads scalars[mean_baseline] on the device (no host synchronisation in the step)
+        eng.backward(self.cell.params, self.obs, eps_where, eps_what, pr, self._grad,
+                     baseline_mean=float("nan") if has_baseline else 0.0,
                      inv_batch=1.0 / (world * B), l2_weight=float(self.l2_weight) / world)
         if world > 1:
             dist.all_reduce(self._grad)          # the ONE data-path collective: sum of the per-shard partial gradients
-            sharding.combine_scalars(out["scalars"], B, pr.steps_weight, bool(pr.use_prior), bool(pr.use_reinforce),
-                                     nvil_shift=pr.nvil_shift, nvil_scale=pr.nvil_scale)
         o = self._opt
         eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
                          float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
         # the baseline's own train step at 10x the learning rate (model.py:362-367, _make_baseline_train_step :253-259)
-        if self._train_cfg["use_reinforce"] and self.baseline_module is not None:
+        if has_baseline:
             bm = self.baseline_module
             target = self.reinforce_imp_weight
-            tmean = None
-            if world > 1:
-                tmean = float(sharding.global_baseline_mean(target.reshape(-1), B))
+            # the (global) importance-weight mean sits in the scalar block: read on the device by the gradient kernel
+            tmean = out["scalars"][SCALAR_INDEX["mean_iw"]:SCALAR_INDEX["mean_iw"] + 1]
             g = bm.backward(target, self.baseline, tmean, 1.0 / (world * B))
             if world > 1:
                 dist.all_reduce(g)

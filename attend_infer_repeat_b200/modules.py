@@ -162,8 +162,12 @@ class BaselineMLP:
         call; left in ``self.grad`` (flat).  ``target_mean`` / ``inv_batch`` are the global-batch values under sharding."""
         from . import functional as F
         B = baseline.shape[0]
-        tm = float(target.mean()) if target_mean is None else float(target_mean)
-        d_out = F.baseline_grad(target, baseline, tm, 1.0 / B if inv_batch is None else inv_batch)
+        ib = 1.0 / B if inv_batch is None else inv_batch
+        if isinstance(target_mean, torch.Tensor):      # a device scalar (e.g. scalars[mean_iw]): no host round trip
+            d_out = F.baseline_grad_dev(baseline, target_mean, ib)
+        else:
+            tm = float(target.mean()) if target_mean is None else float(target_mean)
+            d_out = F.baseline_grad(target, baseline, tm, ib)
         self.grad.zero_()
         self.mlp.backward(d_out, self.grad_views)
         return self.grad

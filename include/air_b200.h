@@ -295,6 +295,8 @@ int64_t air_train_workspace_bytes(const air_handle* h);
  *                  gradient buffers are SUMMED by one all-reduce
  *   l2_weight      model.py:345-350 (2-D variables only)
  *   grad_params    [air_param_count] overwritten */
+/*   (baseline_mean = NaN: the mean is read on the device from outs->scalars[AIR_S_MEAN_BASELINE] when the kernel runs --
+ *    the value air_forward / air_elbo_scalars left there, or the all-reduced block under sharding; no host round trip) */
 int32_t air_backward(air_handle* h, const float* params, const float* img, const float* eps_where,
                      const float* eps_what, const air_prior* prior, const air_outputs* outs, float baseline_mean,
                      float inv_batch, float l2_weight, float* grad_params, void* stream);
@@ -317,6 +319,10 @@ int32_t air_linear_backward(const float* X, const float* W, const float* dY, con
  * baseline [B,1] broadcasting to [B,B] (model.py:253-259): -(target_mean - baseline_i) * inv_batch. */
 int32_t air_baseline_grad(const float* target, const float* baseline, float target_mean, float inv_batch,
                           float* d_baseline, int32_t B, void* stream);
+/* The same with the target mean read from device memory when the kernel runs (e.g. outs->scalars + AIR_S_MEAN_IW after
+ * air_elbo_scalars, or its all-reduced value under sharding): the training step needs no host round trip for it. */
+int32_t air_baseline_grad_dev(const float* baseline, const float* target_mean_dev, float inv_batch, float* d_baseline,
+                              int32_t B, void* stream);
 
 /* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
  * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be

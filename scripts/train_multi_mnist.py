@@ -24,12 +24,16 @@ import attend_infer_repeat_b200 as air                                   # noqa:
 from attend_infer_repeat_b200.data import ResidentDataset, synthetic_multi_mnist_u8   # noqa: E402
 
 
-def main():
+def B_valid(args):
+    return args.batch_size
+
+
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--data-path", default=None, help="directory with mnist_train.pickle / mnist_validation.pickle")
     ap.add_argument("--batch-size", type=int, default=64, help="per GPU (multi_mnist.py:26)")
     ap.add_argument("--iters", type=int, default=300000, help="multi_mnist.py:131")
-    ap.add_argument("--learning-rate", type=float, default=1e-5)
+    ap.add_argument("--learning-rate", type=float, default=1e-4, help="multi_mnist.py:24 (the baseline trains at 10x)")
     ap.add_argument("--l2-weight", type=float, default=0.0)
     ap.add_argument("--log-every", type=int, default=10000)
     ap.add_argument("--save-every", type=int, default=5000)
@@ -37,7 +41,9 @@ def main():
     ap.add_argument("--resume", default=None)
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--seed", type=int, default=0)
-    args = ap.parse_args()
+    ap.add_argument("--n-synthetic", type=int, default=20000, help="synthetic canvases when no --data-path is given")
+    ap.add_argument("--log-json", default=None, help="append one JSON line per log point to this file")
+    args = ap.parse_args(argv)
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -45,14 +51,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+    # every rank draws its own where / what / presence noise (AIRCell.draw_noise uses torch's CUDA generator)
+    torch.cuda.manual_seed(args.seed * 1000003 + rank)
 
     if args.data_path:
         train = ResidentDataset.from_pickle("mnist_train.pickle", args.data_path, device=dev, seed=args.seed + rank)
         valid = ResidentDataset.from_pickle("mnist_validation.pickle", args.data_path, device=dev, seed=1)
     else:
-        train = ResidentDataset(*synthetic_multi_mnist_u8(20000, 50, 50, seed=0), device=dev, seed=args.seed + rank)
-        valid = ResidentDataset(*synthetic_multi_mnist_u8(2000, 50, 50, seed=1), device=dev, seed=1)
+        train = ResidentDataset(*synthetic_multi_mnist_u8(args.n_synthetic, 50, 50, seed=0), device=dev,
+                                seed=args.seed + rank)
+        valid = ResidentDataset(*synthetic_multi_mnist_u8(max(B_valid(args), args.n_synthetic // 10), 50, 50, seed=1),
+                                device=dev, seed=1)
 
     B = args.batch_size
     idx = train.next_indices(B)
@@ -78,6 +89,10 @@ def main():
             for k in ("mg", "ms", "mom"):
                 model.baseline_module.slots[k].copy_(ck["baseline"]["slots"][k])
         model.global_step = int(ck["global_step"])
+        if "rng" in ck:     # noise stream, minibatch stream and validation stream continue where the checkpoint left them
+            torch.cuda.set_rng_state(ck["rng"]["cuda"].cpu(), dev)
+            train._gen.set_state(ck["rng"]["train"].cpu())
+            valid._gen.set_state(ck["rng"]["valid"].cpu())
 
     def scalars():
         names = ["loss", "rec_loss", "num_step_acc", "num_step", "prior_loss", "kl_num_steps", "kl_what", "kl_where",
@@ -94,6 +109,11 @@ def main():
         if rank == 0:
             for k, v in out.items():
                 print(f"Step {itr}, Data {k} " + ", ".join(f"{n} = {x:.4f}" for n, x in v.items()), flush=True)
+            if args.log_json:
+                import json
+                with open(args.log_json, "a") as f:
+                    f.write(json.dumps(dict(step=itr, **out)) + "\n")
+        return out
 
     def save(itr):
         if rank != 0:
@@ -101,7 +121,9 @@ def main():
         os.makedirs(args.checkpoint_dir, exist_ok=True)
         bm = model.baseline_module
         torch.save(dict(params=model.params, slots=model._slots, global_step=itr,
-                        baseline=None if bm is None or bm.params is None else dict(params=bm.params, slots=bm.slots)),
+                        baseline=None if bm is None or bm.params is None else dict(params=bm.params, slots=bm.slots),
+                        rng=dict(cuda=torch.cuda.get_rng_state(dev), train=train._gen.get_state(),
+                                 valid=valid._gen.get_state())),
                    os.path.join(args.checkpoint_dir, f"model-{itr}.pt"))
 
     itr = global_step()
@@ -122,6 +144,7 @@ def main():
         if itr % args.save_every == 0:
             save(itr)
     save(itr)
+    return model
 
 
 if __name__ == "__main__":
