@@ -120,6 +120,11 @@ SYMBOLS = {
     "air_linear_backward": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "air_baseline_grad": (C.c_int32, [_P, _P, C.c_float, C.c_float, _P, C.c_int32, _P]),
     "air_baseline_grad_dev": (C.c_int32, [_P, _P, C.c_float, _P, C.c_int32, _P]),
+    "air_baseline_attach": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "air_baseline_param_count": (C.c_int64, [_P]),
+    "air_baseline_input_width": (C.c_int32, [_P]),
+    "air_baseline_forward": (C.c_int32, [_P, _P, _P, C.POINTER(air_outputs), _P, _P]),
+    "air_baseline_backward": (C.c_int32, [_P, _P, _P, _P, _P]),
     "air_elbo_scalars": (C.c_int32, [_P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_elbo_scalars_raw": (C.c_int32, [C.c_int32, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_prior_terms": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior),

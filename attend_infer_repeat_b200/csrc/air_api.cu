@@ -190,6 +190,20 @@ struct air_handle {
   int dy_ready_m = 0, dy_ready_n = 0;                    // ... with these dimensions
   int* t_range_flag = nullptr;
   std::map<std::tuple<const void*, int, long long, int>, CUtensorMap> tmap_cache2;
+  // BaselineMLP on the engine (air_baseline_attach / _forward / _backward; modules.py:125-143, model.py:253-259)
+  struct Baseline {
+    bool attached = false;
+    int n_in = 0;
+    Mlp mlp;                         // offsets into the caller's flat baseline parameter / gradient buffers
+    int64_t n_params = 0;
+    char* ws = nullptr;
+    Buf x;                           // gathered input rows: fp32 [B, n_in] (+ hl planes for the tensor-core first layer)
+    std::vector<float*> act;         // hidden activations [B, N_i] fp32
+    float* g[2] = {nullptr, nullptr};   // gradient ping-pong [B, widest layer]
+    __half* w_arena = nullptr;       // prepared first-layer weight (hl planes)
+    air::tc::PrepEntry* prep_table = nullptr;
+    int prep_tiles = 0;
+  } bl;
   // instrumentation: kernel-launch counter and optional per-stage CUDA-event timing (air_profile_*)
   uint64_t launches = 0;
   bool profile = false;
@@ -1109,6 +1123,8 @@ void carve_train(air_handle* h, Carver& cv) {
     visit(h->what_lin, TB);
     visit(h->lstm_h, TB);
     visit(h->lstm_x, B);
+    if (h->bl.attached)
+      for (const Layer& l : h->bl.mlp.layers) visit(l, B);
     h->hl_xt_halves = xt;
     h->hl_yt_halves = yt;
     for (int i = 0; i < h->n_side_bufs; ++i) {
@@ -1131,6 +1147,8 @@ void carve_train(air_handle* h, Carver& cv) {
     visit2(h->what_lin, TB);
     visit2(h->lstm_h, TB);
     visit2(h->lstm_x, B);
+    if (h->bl.attached)   // (only the dY plane size matters for the baseline: its input gradients run on the SIMT GEMMs)
+      for (const Layer& l : h->bl.mlp.layers) dy = std::max(dy, (size_t)round_up((int)B, 128) * round_up(l.N, 64));
     h->hl_dy_halves = dy;
     h->hl_dy2[0] = cv.take<__half>(2 * dy);
     h->hl_dy2[1] = cv.take<__half>(2 * dy);
@@ -1397,6 +1415,17 @@ int32_t mlp_backward(air_handle* h, const float* params, float* grad, const Mlp&
   return AIR_OK;
 }
 
+int32_t join_side_streams(air_handle* h, cudaStream_t st) {
+  for (int i = 0; i < h->n_side; ++i) {
+    cudaEvent_t done = next_event(h);
+    AIR_CUDA(cudaEventRecord(done, h->side[i]));
+    AIR_CUDA(cudaStreamWaitEvent(st, done, 0));
+  }
+  h->dy_consumed.clear();
+  h->side_next = 0;
+  return AIR_OK;
+}
+
 int32_t backward_impl(air_handle* h, const float* params, const float* img, const float* eps_where,
                       const float* eps_what, const air_prior* prior, const air_outputs* o, float baseline_mean,
                       float inv_batch, float l2_weight, float* grad, cudaStream_t st) {
@@ -1527,13 +1556,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
       return rc;
   }
   // join: the weight gradients of the side streams are part of this call's result
-  for (int i = 0; i < h->n_side; ++i) {
-    cudaEvent_t done = next_event(h);
-    AIR_CUDA(cudaEventRecord(done, h->side[i]));
-    AIR_CUDA(cudaStreamWaitEvent(st, done, 0));
-  }
-  h->dy_consumed.clear();
-  h->side_next = 0;
+  if ((rc = join_side_streams(h, st)) != AIR_OK) return rc;
   // l2_weight * sum of tf.nn.l2_loss over the 2-D variables (model.py:345-350): weights and the [1,nh] initial state
   if (l2_weight > 0.f) {
     for (const ParamEntry& e : h->entries) {
@@ -1740,6 +1763,7 @@ int32_t air_destroy(air_handle* h) {
     if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
   if (h->tws) cudaFree(h->tws);
+  if (h->bl.ws) cudaFree(h->bl.ws);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < h->n_side; ++i) cudaStreamDestroy(h->side[i]);
   if (h->trace) cudaFree(h->trace);
@@ -1949,6 +1973,159 @@ int32_t air_baseline_grad_dev(const float* baseline, const float* target_mean_de
                                                                                 target_mean_dev);
   AIR_CUDA(cudaGetLastError());
   return AIR_OK;
+}
+
+// ---- BaselineMLP on the engine ------------------------------------------------------------------------------------
+int32_t air_baseline_attach(air_handle* h, int32_t n_hidden, const int32_t* hidden) {
+  if (!h || !hidden || n_hidden < 1 || n_hidden > AIR_MAX_HIDDEN) return fail(AIR_ERR_ARG, "air_baseline_attach: bad argument");
+  if (h->bl.attached) return fail(AIR_ERR_ARG, "air_baseline_attach: already attached");
+  if (h->tws) return fail(AIR_ERR_ARG, "air_baseline_attach: attach before air_train_enable (the training workspace is sized "
+                                       "for the widest layer)");
+  const air_config& c = h->cfg;
+  air_handle::Baseline& bl = h->bl;
+  bl.n_in = h->P + c.T * (c.na + 4 + 1) + 2 * c.nh;   // concat[img, what, where, presence, h, c] (modules.py:131-141)
+  int d = bl.n_in;
+  int64_t off = 0;
+  int wmax = 1;
+  for (int i = 0; i <= n_hidden; ++i) {
+    Layer l;
+    l.K = d;
+    l.N = i < n_hidden ? hidden[i] : 1;
+    if (l.N < 1) return fail(AIR_ERR_ARG, "air_baseline_attach: hidden widths must be positive");
+    l.w_off = off;
+    off += (int64_t)l.K * l.N;
+    l.b_off = off;
+    off += l.N;
+    bl.mlp.layers.push_back(l);
+    d = l.N;
+    wmax = std::max(wmax, l.N);
+  }
+  bl.mlp.n_hidden = n_hidden;
+  bl.n_params = off;
+  const int B = c.B, B_alloc = round_up(B, air::tc::BM);
+  Layer& l0 = bl.mlp.layers[0];
+  const int Kpad = round_up(l0.K, air::tc::BK), N_alloc = round_up(l0.N, 64);
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass == 0 ? nullptr : bl.ws);
+    bl.x.f32 = cv.take<float>((size_t)B * bl.n_in);
+    bl.x.ld = bl.n_in;
+    bl.act.clear();
+    for (int i = 0; i < n_hidden; ++i) bl.act.push_back(cv.take<float>((size_t)B * bl.mlp.layers[i].N));
+    bl.g[0] = cv.take<float>((size_t)B * wmax);
+    bl.g[1] = cv.take<float>((size_t)B * wmax);
+    if (h->use_tc) {
+      bl.x.rows_alloc = B_alloc;
+      bl.x.kpad = Kpad;
+      bl.x.hl = cv.take<__half>(2 * (size_t)B_alloc * Kpad);
+      bl.w_arena = cv.take<__half>(2 * (size_t)N_alloc * Kpad);
+      bl.prep_table = cv.take<air::tc::PrepEntry>(1);
+    }
+    if (pass == 0) {
+      AIR_CUDA(cudaMalloc(&bl.ws, cv.off));
+      AIR_CUDA(cudaMemset(bl.ws, 0, cv.off));   // K / N padding of the operand planes stays zero
+    }
+  }
+  if (h->use_tc) {
+    TcWeight w;
+    w.src_off = l0.w_off;
+    w.K = l0.K;
+    w.N = l0.N;
+    w.Kpad = Kpad;
+    w.BN = 64;
+    w.N_alloc = N_alloc;
+    w.bias_src = -1;
+    if (!air::tc::make_tmap(&w.tm, bl.w_arena, Kpad, 2 * (int64_t)N_alloc, 64))
+      return fail(AIR_ERR_CUDA, "air_baseline_attach: cuTensorMapEncodeTiled failed");
+    air::tc::PrepEntry pe;
+    memset(&pe, 0, sizeof(pe));
+    pe.src_off = l0.w_off;
+    pe.dst_off = 0;
+    pe.plane = (int64_t)N_alloc * Kpad;
+    pe.K = l0.K;
+    pe.N = l0.N;
+    pe.Kpad = Kpad;
+    pe.tile_begin = 0;
+    pe.tiles_n = (l0.N + 31) / 32;
+    pe.bias_src = -1;
+    bl.prep_tiles = pe.tiles_n * ((l0.K + 31) / 32);
+    AIR_CUDA(cudaMemcpy(bl.prep_table, &pe, sizeof(pe), cudaMemcpyHostToDevice));
+    l0.tc = (int)h->tcw.size();
+    h->tcw.push_back(w);
+  }
+  bl.attached = true;
+  return AIR_OK;
+}
+
+int64_t air_baseline_param_count(const air_handle* h) { return (h && h->bl.attached) ? h->bl.n_params : 0; }
+int32_t air_baseline_input_width(const air_handle* h) { return (h && h->bl.attached) ? h->bl.n_in : 0; }
+
+int32_t air_baseline_forward(air_handle* h, const float* bparams, const float* img, const air_outputs* o, float* baseline,
+                             void* stream) {
+  if (!h || !bparams || !img || !o || !baseline) return fail(AIR_ERR_ARG, "air_baseline_forward: NULL argument");
+  if (!h->bl.attached) return fail(AIR_ERR_ARG, "air_baseline_forward: air_baseline_attach first");
+  if (!o->what || !o->where || !o->presence || !o->final_h || !o->final_c)
+    return fail(AIR_ERR_ARG, "air_baseline_forward: outs needs what / where / presence / final_h / final_c");
+  cudaStream_t st = (cudaStream_t)stream;
+  const air_config& c = h->cfg;
+  air_handle::Baseline& bl = h->bl;
+  const int B = c.B;
+  const size_t n = (size_t)B * bl.n_in;
+  AIR_CUDA(air::launch_k(air::baseline_gather_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img,
+                         (const float*)o->what, (const float*)o->where, (const float*)o->presence, (const float*)o->final_h,
+                         (const float*)o->final_c, bl.x.f32, bl.x.hl, bl.x.plane(), bl.x.kpad, B, c.T, h->P, c.na, c.nh, bl.n_in));
+  ++h->launches;
+  const int nl = (int)bl.mlp.layers.size();
+  for (int i = 0; i < nl; ++i) {
+    const Layer& l = bl.mlp.layers[i];
+    const bool last = i == nl - 1;
+    float* dst = last ? baseline : bl.act[i];
+    const int act = last ? air::ACT_NONE : air::ACT_ELU;
+    if (i == 0 && h->use_tc) {
+      AIR_CUDA(air::launch_k(air::tc::prep_weights_kernel, dim3(bl.prep_tiles), dim3(256), 0, st, bparams, bl.w_arena,
+                             bl.prep_table, 1, h->range_flag, (float*)nullptr));
+      ++h->launches;
+      Buf out;
+      out.f32 = dst;
+      out.ld = l.N;
+      const int32_t rc = dense(h, bparams, bl.x, 0, l, true, nullptr, 0, out, true, false, B, act, st);
+      if (rc != AIR_OK) return rc;
+    } else {
+      const float* A = i == 0 ? bl.x.f32 : bl.act[i - 1];
+      AIR_CUDA(air::launch_linear_simt(A, l.K, bparams + l.w_off, l.N, bparams + l.b_off, nullptr, 0, dst, l.N, B, l.N, l.K,
+                                       act, st));
+      ++h->launches;
+    }
+  }
+  return AIR_OK;
+}
+
+int32_t air_baseline_backward(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad, void* stream) {
+  if (!h || !bparams || !d_baseline || !bgrad) return fail(AIR_ERR_ARG, "air_baseline_backward: NULL argument");
+  if (!h->bl.attached) return fail(AIR_ERR_ARG, "air_baseline_backward: air_baseline_attach first");
+  cudaStream_t st = (cudaStream_t)stream;
+  air_handle::Baseline& bl = h->bl;
+  const int B = h->cfg.B;
+  AIR_CUDA(cudaMemsetAsync(bgrad, 0, sizeof(float) * (size_t)bl.n_params, st));
+  const int nl = (int)bl.mlp.layers.size();
+  const float* cur = d_baseline;
+  int ld_cur = 1;
+  int32_t rc;
+  for (int i = nl - 1; i >= 0; --i) {
+    const Layer& l = bl.mlp.layers[i];
+    const float* X = i == 0 ? bl.x.f32 : bl.act[i - 1];
+    // dW += X^T dY, db += colsum(dY): the tensor-core split-K GEMM on a side stream when the handle trains on it
+    if ((rc = layer_param_grads(h, bgrad, l, X, l.K, cur, ld_cur, B, st)) != AIR_OK) return rc;
+    if (i > 0) {
+      float* dst = (cur == bl.g[0]) ? bl.g[1] : bl.g[0];
+      if ((rc = wait_consumed(h, dst, st)) != AIR_OK) return rc;
+      AIR_CUDA(air::launch_gemm_simt(false, true, cur, ld_cur, bparams + l.w_off, l.N, dst, l.K, B, l.K, l.N, false, X, l.K, 1,
+                                     st));   // (X is the ELU output of the layer below: the mask is elu'(X))
+      ++h->launches;
+      cur = dst;
+      ld_cur = l.K;
+    }
+  }
+  return join_side_streams(h, st);
 }
 
 int32_t air_forward(air_handle* h, const float* params, const float* img, const float* eps_where,

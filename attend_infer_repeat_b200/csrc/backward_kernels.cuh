@@ -608,6 +608,44 @@ __global__ void l2_grad_kernel(const float* __restrict__ w, float* __restrict__ 
 
 // baseline_loss = .5 * mean((stop_gradient(iw) - baseline)^2) with iw [B] and baseline [B,1] broadcasting to [B,B]
 // (model.py:253-259): d / d baseline_i = -(mean_j iw_j - baseline_i) / B
+// BaselineMLP input rows (modules.py:131-141): x[b] = concat[img[b] (P), what[:, b] (T * na), where[:, b] (T * 4),
+// presence[:, b] (T), h[b] (nh), c[b] (nh)] -- the time-major cell outputs transposed to batch-major exactly as
+// tf.transpose(t, (1, 0, 2)) + reshape does.  One pass: fp32 rows and (tensor-core engine) the fp16 hi/lo operand planes.
+__global__ void baseline_gather_kernel(const float* __restrict__ img, const float* __restrict__ what,
+                                       const float* __restrict__ where, const float* __restrict__ presence,
+                                       const float* __restrict__ hfin, const float* __restrict__ cfin, float* __restrict__ x,
+                                       __half* __restrict__ hl, size_t plane, int ld_hl, int B, int T, int P, int na, int nh,
+                                       int n_in) {
+  griddep_launch();
+  griddep_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * n_in) return;
+  const int b = (int)(idx / n_in);
+  int k = (int)(idx % n_in);
+  const int col = k;
+  float v;
+  if (k < P) {
+    v = img[(size_t)b * P + k];
+  } else if ((k -= P) < T * na) {
+    v = what[((size_t)(k / na) * B + b) * na + k % na];
+  } else if ((k -= T * na) < T * 4) {
+    v = where[((size_t)(k / 4) * B + b) * 4 + k % 4];
+  } else if ((k -= T * 4) < T) {
+    v = presence[(size_t)k * B + b];
+  } else if ((k -= T) < nh) {
+    v = hfin[(size_t)b * nh + k];
+  } else {
+    v = cfin[(size_t)b * nh + (k - nh)];
+  }
+  x[idx] = v;
+  if (hl) {
+    __half hi, lo;
+    split_f16(v, hi, lo);
+    hl[(size_t)b * ld_hl + col] = hi;
+    hl[plane + (size_t)b * ld_hl + col] = lo;
+  }
+}
+
 __global__ void baseline_grad_kernel(const float* __restrict__ baseline, float target_mean, float inv_batch,
                                      float* __restrict__ d_baseline, int B, const float* __restrict__ target_mean_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -649,6 +649,9 @@ __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) 
   return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H);
 }
 
+#ifndef PAINT_MIN_CTAS
+#define PAINT_MIN_CTAS 8
+#endif
 template <int T, int CPT>
 __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const float* __restrict__ s_gl,
                                             const Tap* __restrict__ s_tx, const Tap* __restrict__ s_ty,
@@ -731,7 +734,7 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const floa
 }
 
 template <int T>
-__global__ void __launch_bounds__(256, 8) paint_elbo_kernel(ElboArgs a) {
+__global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_pres[AIR_MAX_STEPS], s_red[32];

@@ -326,6 +326,31 @@ class Engine:
                                         float(l2_weight), ptr(grad), current_stream_ptr()), "air_backward")
         return grad
 
+    # ---- BaselineMLP on the engine (modules.py:125-143; air_baseline_*) ------------------------------------------
+    def baseline_attach(self, hidden: Sequence[int]):
+        """Register a BaselineMLP(hidden) with this handle (before train_enable).  Returns (n_in, n_params)."""
+        arr = (C.c_int32 * len(hidden))(*[int(v) for v in hidden])
+        with torch.cuda.device(self.device):
+            check(self.lib.air_baseline_attach(self._handle, len(hidden), arr), "air_baseline_attach")
+        return int(self.lib.air_baseline_input_width(self._handle)), int(self.lib.air_baseline_param_count(self._handle))
+
+    def baseline_forward(self, bparams, img, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """baseline [B,1] for the batch of the LAST forward(): input rows gathered from `img` and this engine's cell outputs,
+        first layer on the engine's GEMM path."""
+        if out is None:
+            out = torch.empty(self.B, 1, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.air_baseline_forward(self._handle, ptr(bparams), ptr(img), C.byref(self._c_out), ptr(out),
+                                                current_stream_ptr()), "air_baseline_forward")
+        return out
+
+    def baseline_backward(self, bparams, d_baseline, bgrad) -> torch.Tensor:
+        """d baseline_loss / d baseline parameters for the last baseline_forward(), into bgrad (flat)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.air_baseline_backward(self._handle, ptr(bparams), ptr(d_baseline), ptr(bgrad),
+                                                 current_stream_ptr()), "air_baseline_backward")
+        return bgrad
+
     def rmsprop_step(self, params, grad, mg, ms, mom, learning_rate, decay=0.9, momentum=0.9, epsilon=1e-10,
                      grad_scale=1.0):
         """Centered RMSProp with momentum, TF semantics (model.py:265,355-360), in place on the flat buffers."""

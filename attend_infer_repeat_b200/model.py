@@ -238,6 +238,8 @@ class AIRModel:
         # the training engine (same arithmetic mode as the model, activations kept) replaces the inference engine
         self.engine = self.cell.engine(self.batch_size, self.max_steps, materialise_canvas=True,
                                        materialise_viz=self._materialise_canvas)
+        if self.baseline_module is not None and hasattr(self.baseline_module, "attach") and use_reinforce:
+            self.baseline_module.attach(self.engine)     # BaselineMLP on the engine (before the training workspace is sized)
         self.engine.train_enable(True)
         n = self.engine.n_params
         dev = self.obs.device

@@ -156,6 +156,16 @@ class BaselineMLP:
         self.slots = dict(mg=torch.zeros_like(self.params), ms=torch.ones_like(self.params),
                           mom=torch.zeros_like(self.params))
 
+    def attach(self, engine):
+        """Run on `engine` (Engine.baseline_attach, before train_enable): the input rows are gathered from the engine's own
+        cell outputs in one pass and the big first layer and its weight gradient run on the engine's GEMM path."""
+        n_in, n_params = engine.baseline_attach(self._n_hidden)
+        if self.params is None:
+            self._build_params(n_in, engine.device)
+        assert self.params.numel() == n_params, (self.params.numel(), n_params)
+        self._engine = engine
+        return self
+
     def backward(self, target, baseline, target_mean=None, inv_batch=None):
         """Gradient of baseline_loss = .5 * mean((stop_gradient(target) - baseline)^2) (model.py:253-259; target [B],
         baseline [B,1] -> [B,B] broadcast) with respect to the baseline's parameters, for the LAST
@@ -168,11 +178,16 @@ class BaselineMLP:
         else:
             tm = float(target.mean()) if target_mean is None else float(target_mean)
             d_out = F.baseline_grad(target, baseline, tm, ib)
+        if getattr(self, "_engine", None) is not None:
+            return self._engine.baseline_backward(self.params, d_out, self.grad)
         self.grad.zero_()
         self.mlp.backward(d_out, self.grad_views)
         return self.grad
 
     def __call__(self, img, what, where, presence_prob, state=None):
+        if getattr(self, "_engine", None) is not None:
+            # (what / where / presence / state are the engine's own output buffers of the last forward)
+            return self._engine.baseline_forward(self.params, img.reshape(img.shape[0], -1))
         B = img.shape[0]
         parts = [t.transpose(0, 1).reshape(B, -1) for t in (what, where, presence_prob)]
         if state is not None:

@@ -324,6 +324,24 @@ int32_t air_baseline_grad(const float* target, const float* baseline, float targ
 int32_t air_baseline_grad_dev(const float* baseline, const float* target_mean_dev, float inv_batch, float* d_baseline,
                               int32_t B, void* stream);
 
+/* BaselineMLP of modules.py:125-143 ON THE ENGINE: concat[img, what, where, presence, h, c] (batch-major) -> MLP(hidden, 1).
+ *   air_baseline_attach    once per handle, BEFORE air_train_enable (the training workspace is sized for the widest
+ *                          layer); the flat parameter / gradient layout is (w_0 [n_in, h_0], b_0 [h_0], ..., w_out
+ *                          [h_last, 1], b_out [1]) -- air_baseline_param_count floats, air_baseline_input_width = n_in
+ *   air_baseline_forward   gathers the input rows from `img` and the cell outputs in `outs` (what, where, presence,
+ *                          final_h, final_c of the last air_forward) in one pass, runs the first (n_in x h_0) layer on
+ *                          the handle's engine (tcgen05 split GEMM on an AIR_PREC_TC_SPLIT handle) and the small layers
+ *                          on the fp32 GEMMs; baseline [B]
+ *   air_baseline_backward  d baseline_loss / d parameters for the last air_baseline_forward given d loss / d baseline [B]
+ *                          (air_baseline_grad / air_baseline_grad_dev); bgrad is overwritten.  The n_in x h_0 weight
+ *                          gradient runs on the tensor-core split-K GEMM of the training workspace when that exists. */
+int32_t air_baseline_attach(air_handle* h, int32_t n_hidden, const int32_t* hidden);
+int64_t air_baseline_param_count(const air_handle* h);
+int32_t air_baseline_input_width(const air_handle* h);
+int32_t air_baseline_forward(air_handle* h, const float* bparams, const float* img, const air_outputs* outs, float* baseline,
+                             void* stream);
+int32_t air_baseline_backward(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad, void* stream);
+
 /* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
  * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be
  * known after the forward pass): AIRModel._reinforce, model.py:218-251. */
