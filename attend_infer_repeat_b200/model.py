@@ -271,18 +271,25 @@ class AIRModel:
         eng.backward(self.cell.params, self.obs, eps_where, eps_what, pr, self._grad,
                      baseline_mean=float("nan") if has_baseline else 0.0,
                      inv_batch=1.0 / (world * B), l2_weight=float(self.l2_weight) / world)
+        grad_work = None
         if world > 1:
-            dist.all_reduce(self._grad)          # the ONE data-path collective: sum of the per-shard partial gradients
+            # the ONE data-path collective: sum of the per-shard partial gradients.  Issued on NCCL's stream; the baseline's
+            # backward pass below runs beside it, the optimiser waits for it.
+            grad_work = dist.all_reduce(self._grad, async_op=True)
         o = self._opt
+        g_base = None
+        if has_baseline:
+            # the baseline's gradient (model.py:253-259): needs only this step's forward results, so it overlaps the all-reduce
+            bm = self.baseline_module
+            tmean = out["scalars"][SCALAR_INDEX["mean_iw"]:SCALAR_INDEX["mean_iw"] + 1]
+            g_base = bm.backward(self.reinforce_imp_weight, self.baseline, tmean, 1.0 / (world * B))
+        if grad_work is not None:
+            grad_work.wait()
         eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
                          float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
         # the baseline's own train step at 10x the learning rate (model.py:362-367, _make_baseline_train_step :253-259)
         if has_baseline:
-            bm = self.baseline_module
-            target = self.reinforce_imp_weight
-            # the (global) importance-weight mean sits in the scalar block: read on the device by the gradient kernel
-            tmean = out["scalars"][SCALAR_INDEX["mean_iw"]:SCALAR_INDEX["mean_iw"] + 1]
-            g = bm.backward(target, self.baseline, tmean, 1.0 / (world * B))
+            bm, g = self.baseline_module, g_base
             if world > 1:
                 dist.all_reduce(g)
             eng.rmsprop_step(bm.params, g, bm.slots["mg"], bm.slots["ms"], bm.slots["mom"],

@@ -47,28 +47,39 @@ def combine_scalars(scalars: torch.Tensor, n_local: int, steps_weight: float = 1
     means exactly as the single-device kernel forms them."""
     import torch.distributed as dist
     assert scalars.numel() == AIR_N_SCALARS
-    buf = torch.zeros(AIR_N_SCALARS, dtype=torch.float64, device=scalars.device)
-    for name in _MEAN_SLOTS:
-        buf[SCALAR_INDEX[name]] = scalars[SCALAR_INDEX[name]].double() * n_local
+    dev = scalars.device
+    # a handful of vector operations (this runs every training step between the forward and the backward pass: one tiny
+    # launch per scalar would cost more than the all-reduce)
+    mean_idx = _index_tensor(tuple(SCALAR_INDEX[n] for n in _MEAN_SLOTS), dev)
+    wire = torch.float32 if dev.type == "cuda" else torch.float64          # NCCL path: fp32 on the wire (16 floats)
+    buf = torch.zeros(AIR_N_SCALARS, dtype=wire, device=dev)
+    buf[mean_idx] = (scalars[mean_idx].double() * float(n_local)).to(wire)
     buf[AIR_N_SCALARS - 1] = float(n_local)
-    if scalars.device.type == "cuda":
-        buf = buf.float()          # NCCL path: fp32 on the wire (16 floats)
     dist.all_reduce(buf, group=group)
-    n = buf[AIR_N_SCALARS - 1]
-    m = {name: buf[SCALAR_INDEX[name]] / n for name in _MEAN_SLOTS}
-    prior_loss = m["kl_num_steps"] * steps_weight + m["kl_what"] + m["kl_where"]
-    loss = m["rec_loss"] + prior_loss * (1.0 if use_prior else 0.0)
+    m = buf / buf[AIR_N_SCALARS - 1]                                       # global means at the mean slots
+    I = SCALAR_INDEX
+    prior_loss = m[I["kl_num_steps"]] * steps_weight + m[I["kl_what"]] + m[I["kl_where"]]
+    loss = m[I["rec_loss"]] + prior_loss * (1.0 if use_prior else 0.0)
     nv_scale, nv_shift = (nvil_scale, nvil_shift) if nvil_scale != 0.0 else (1.0, 0.0)
-    reinforce = (nv_scale * (m["mean_iw_logq"] - (m["mean_baseline"] + nv_shift) * m["mean_logq"])
+    reinforce = (nv_scale * (m[I["mean_iw_logq"]] - (m[I["mean_baseline"]] + nv_shift) * m[I["mean_logq"]])
                  if use_reinforce else torch.zeros_like(loss))
-    scalars.zero_()
-    for name in _MEAN_SLOTS:
-        scalars[SCALAR_INDEX[name]] = m[name].to(scalars.dtype)
-    scalars[SCALAR_INDEX["prior_loss"]] = prior_loss.to(scalars.dtype)
-    scalars[SCALAR_INDEX["loss"]] = loss.to(scalars.dtype)
-    scalars[SCALAR_INDEX["reinforce_loss"]] = reinforce.to(scalars.dtype)
-    scalars[SCALAR_INDEX["opt_loss"]] = (loss + reinforce).to(scalars.dtype)
+    out = torch.zeros(AIR_N_SCALARS, dtype=m.dtype, device=dev)
+    out[mean_idx] = m[mean_idx]
+    derived = torch.stack([prior_loss, loss, reinforce, loss + reinforce])
+    out[_index_tensor((I["prior_loss"], I["loss"], I["reinforce_loss"], I["opt_loss"]), dev)] = derived
+    scalars.copy_(out.to(scalars.dtype))
     return scalars
+
+
+_INDEX_CACHE = {}
+
+
+def _index_tensor(idx: tuple, device) -> torch.Tensor:
+    key = (idx, str(device))
+    t = _INDEX_CACHE.get(key)
+    if t is None:
+        t = _INDEX_CACHE[key] = torch.tensor(idx, dtype=torch.long, device=device)
+    return t
 
 
 def allreduce_gradient(flat_grad: torch.Tensor, n_local: int, n_global: Optional[int] = None, group=None,
