@@ -5,7 +5,7 @@ Everything numerical runs in libair_b200.so (hand-written CUDA behind a C ABI, i
 device memory, streams and torch.distributed.  There is no CPU or library fallback: importing works anywhere (so the
 host logic can be tested), but any compute call without the CUDA library and a B200 raises.
 """
-from . import functional, ops, prior  # noqa: F401
+from . import evaluation, functional, ops, prior  # noqa: F401
 from ._lib import AIR_PREC_FP32, AIR_PREC_TC_SPLIT, AirError, build  # noqa: F401
 from .cell import AIRCell  # noqa: F401
 from .data import ResidentDataset, load_data, save_data, tensors_from_data  # noqa: F401

@@ -162,6 +162,7 @@ struct air_handle {
   float *g_glimpse = nullptr, *g_crop = nullptr;   // [T*B, G]
   float *g_what = nullptr, *g_r = nullptr;         // [T*B, na], [T*B, 2na]
   float *g_wh_paint = nullptr, *g_wh_read = nullptr, *g_m = nullptr, *g_logit = nullptr;   // [T*B,4] x2, [T*B,8], [T*B]
+  float* g_pres = nullptr;         // [T*B] d rec / d presence (non-discrete steps)
   float *g_h = nullptr, *g_gates = nullptr;        // [T*B, nh], [T*B, 4nh]
   float *g_gx = nullptr, *g_hrec = nullptr, *g_c = nullptr, *g_e = nullptr;   // [B,4nh], [B,nh], [B,nh], [B,n_enc]
   // tensor-core weight gradients (dW = X^T @ dY on the tcgen05 split engine): transposed hl operands, M contiguous
@@ -1103,6 +1104,7 @@ void carve_train(air_handle* h, Carver& cv) {
   h->g_wh_read = cv.take<float>(TB * 4);
   h->g_m = cv.take<float>(TB * 8);
   h->g_logit = cv.take<float>(TB);
+  h->g_pres = cv.take<float>(TB);
   h->g_h = cv.take<float>(TB * c.nh);
   h->g_gates = cv.take<float>(TB * 4 * c.nh);
   h->g_gx = cv.take<float>(B * 4 * c.nh);
@@ -1467,6 +1469,8 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   a.dr = h->g_r;
   a.dm = h->g_m;
   a.dlogit = h->g_logit;
+  a.discrete = c.discrete_steps;
+  a.dpresence = c.discrete_steps ? nullptr : h->g_pres;   // non-discrete steps: the painted canvas depends on presence = p
   a.T = T; a.B = B; a.H = c.H; a.W = c.W; a.h = c.h; a.w = c.w; a.na = na;
   a.output_std = c.output_std;
   a.output_multiplier = c.output_multiplier;
@@ -1849,8 +1853,6 @@ int32_t air_check_range(air_handle* h, void* stream) {
 
 int32_t air_train_enable(air_handle* h, int32_t on) {
   if (!h) return fail(AIR_ERR_ARG, "air_train_enable: NULL handle");
-  if (on && !h->cfg.discrete_steps)
-    return fail(AIR_ERR_ARG, "air_train_enable: the backward pass covers discrete_steps = 1 (the script configuration)");
   if (on && !h->tws) {
     // (checked before anything is allocated: a failed enable must leave the handle exactly as it was, so that a retry
     // runs the whole initialisation again instead of finding a half-built workspace)

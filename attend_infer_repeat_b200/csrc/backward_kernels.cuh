@@ -82,6 +82,8 @@ struct BwdArgs {
   float* dr;                   // [T,B,2na]
   float* dm;                   // [T,B,8]
   float* dlogit;               // [T,B]
+  float* dpresence;            // [T,B] non-discrete steps only (cell.py:150-151: presence = presence_prob): d rec / d presence_t
+  int discrete;                // cfg.discrete_steps
   int T, B, H, W, h, w, na;
   float output_std, output_multiplier, max_crop, explore_eps;
   float inv_batch;             // 1 / (global batch): every per-sample term enters the loss through a batch mean
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   __shared__ float4 s_inv[AIR_MAX_STEPS];
   __shared__ float s_pres[AIR_MAX_STEPS];
   __shared__ float s_red[8][4 * T];
+  __shared__ float s_redp[8][T];
   __shared__ int s_rect[T][4];   // canvas rectangle inside glimpse t's footprint: c_lo, c_hi, r_lo, r_hi
   const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
   const int P = H * W, G = h * w;
@@ -216,15 +219,17 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
 
   const float S_w = ((float)w - 1.0f) * 0.5f, S_h = ((float)h - 1.0f) * 0.5f;
   float acc[T][4];   // per step: sum gx * (xg - S_w), sum gx, sum gy * (yg - S_h), sum gy
+  float dp_acc[T];   // per step: sum_g glimpse_t[g] * (sum_p w(p, g) dC[p]) = d rec / d presence_t (non-discrete steps)
 #pragma unroll
-  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = dp_acc[t] = 0.f;
   const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float pres = s_pres[t];
     const int c_lo = s_rect[t][0], c_hi = s_rect[t][1], r_lo = s_rect[t][2], r_hi = s_rect[t][3];
     float* dgl = a.dglimpse + ((size_t)t * B + b) * G;
-    if (pres == 0.f || c_hi < c_lo || r_hi < r_lo) {   // CTA-uniform: this glimpse never reached the canvas
+    // (a presence of exactly 0 still has a gradient when presence is the continuous probability)
+    if ((a.discrete && pres == 0.f) || c_hi < c_lo || r_hi < r_lo) {   // CTA-uniform: this glimpse never reached the canvas
       for (int g = threadIdx.x; g < G; g += blockDim.x) dgl[g] = 0.f;
       continue;
     }
@@ -264,6 +269,7 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
       float sum = 0.f;
       for (int r = lo; r <= hi; ++r) sum = fmaf(btap_weight(s_ty[t * H + r], j * w), s_U[(r - r_lo) * w + i], sum);
       dgl[g] = pres * sum;
+      dp_acc[t] = fmaf(sum, D[g], dp_acc[t]);
     }
     __syncthreads();   // s_U is reused by the next step
   }
@@ -275,6 +281,13 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
       const float v = warp_sum(acc[t][k]);
       if (lane == 0) s_red[wid][t * 4 + k] = v;
     }
+  if (a.dpresence) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float v = warp_sum(dp_acc[t]);
+      if (lane == 0) s_redp[wid][t] = v;
+    }
+  }
   __syncthreads();
   if (threadIdx.x < T) {
     const int t = threadIdx.x;
@@ -292,6 +305,11 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
     o[1] = s[1] == 0.f ? 0.f : -S_w * s[1] / wh[0];
     o[2] = s[2] == 0.f ? 0.f : -s[2] / wh[2];
     o[3] = s[3] == 0.f ? 0.f : -S_h * s[3] / wh[2];
+    if (a.dpresence) {
+      float dp = 0.f;
+      for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) dp += s_redp[wi][t];
+      a.dpresence[(size_t)t * B + b] = dp;
+    }
   }
 }
 
@@ -536,6 +554,13 @@ __global__ void __launch_bounds__(128) latent_bwd_kernel(BwdArgs a) {
       for (int i = 0; i < k; ++i)
         if (i != j) prod *= p[i];
       g += dpi[k] * ((k < T) ? (1.0 - p[k]) * prod : prod);
+    }
+    if (!a.discrete) {
+      // cell.py:150-151: presence_t IS presence_prob_t -- the painted canvas (d rec / d presence_t from paint_bwd) and,
+      // with sampled-style step weights (analytic = False, model.py:163: the weights are the presence), both KL terms
+      // depend on p_t directly
+      if (a.dpresence) g += (double)a.dpresence[(size_t)j * B + b];
+      if (!pr.analytic) g += (double)coef * ((double)klw[j] + (double)klwh[j]);
     }
     double s = p[j], scale = 1.0;   // p = eps/2 + (1 - eps) * sigmoid(.)   (cell.py:140-141)
     if (ee >= 0.f) {

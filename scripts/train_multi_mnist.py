@@ -143,6 +143,8 @@ def main(argv=None):
             log(itr)
         if itr % args.save_every == 0:
             save(itr)
+            if rank == 0:     # progress figure next to the checkpoint (evaluation.py:31-65; multi_mnist.py:145-146)
+                air.evaluation.make_fig(model, args.checkpoint_dir, itr)
     save(itr)
     return model
 

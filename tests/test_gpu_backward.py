@@ -179,7 +179,7 @@ def test_backward_small_batch_on_the_tensor_core_engine():
     compare(ocfg, g, g_ref)
 
 
-def test_backward_requires_training_mode_and_discrete_steps():
+def test_backward_requires_training_mode():
     ocfg = U.oracle_cfg(**U.TINY)
     eng = air.Engine(U.cell_cfg(ocfg, air.AIR_PREC_FP32), 4, ocfg.T, device="cuda")
     flat = torch.zeros(eng.n_params, device="cuda")
@@ -187,11 +187,28 @@ def test_backward_requires_training_mode_and_discrete_steps():
     with pytest.raises(air.AirError):
         eng.backward(flat, z(4, 3, 3), z(3, 4, 4), z(3, 4, 10), U.prior_struct(O.PriorConfig(), 0))
     eng.close()
-    ocfg = U.oracle_cfg(**U.SCRIPT, discrete_steps=False)
-    eng = air.Engine(U.cell_cfg(ocfg), 4, 3, device="cuda")
-    with pytest.raises(air.AirError):       # the backward pass covers sampled (discrete) presence only
-        eng.train_enable(True)
-    eng.close()
+
+
+@pytest.mark.parametrize("case", ["default", "sampled_step_weights", "no_reinforce"])
+@pytest.mark.parametrize("shape,precision", [("tiny", air.AIR_PREC_FP32), ("script", air.AIR_PREC_FP32),
+                                             ("script", air.AIR_PREC_TC_SPLIT)])
+def test_backward_non_discrete_steps(shape, precision, case):
+    """discrete_steps = False (cell.py:150-151): presence_t = presence_prob_t, so the painted canvas -- and with
+    analytic = False the KL weights -- are differentiable functions of the steps predictor.  Autograd on the oracle is the
+    reference (float64 at the script sizes, where it is what both fp32 implementations approximate)."""
+    kw, B = (U.TINY, 12) if shape == "tiny" else (U.SCRIPT, 64 if precision == air.AIR_PREC_TC_SPLIT else 16)
+    ocfg = U.oracle_cfg(**kw, discrete_steps=False)
+    pc = O.PriorConfig(**CASES[case])
+    params, img, nums, noise = U.make_problem(ocfg, B, seed=15)
+    if shape == "script":
+        noise, _ = well_conditioned(ocfg, pc, params, img, noise)
+    dt = torch.float64 if shape == "script" else torch.float32
+    res_o, g_ref = oracle_grads(ocfg, pc, params, img, noise, 20000, dtype=dt)
+    res_c, g = cuda_grads(ocfg, pc, params, img, noise, 20000, precision=precision)
+    U.assert_close(res_c["presence"], res_o["outs"]["presence"].detach().float(), atol=1e-5, name="presence")
+    worst = compare(ocfg, g, g_ref)
+    # the steps predictor must receive the canvas's gradient: its output weights' gradient is not what the discrete path gives
+    print(f"non-discrete {shape}/{case}: worst {worst[1]} ({worst[0]:.2f} of tolerance)")
 
 
 def test_centered_rmsprop_matches_oracle():

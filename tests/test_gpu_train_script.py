@@ -60,3 +60,41 @@ def test_train_script_checkpoint_resume_is_bit_identical(tmp_path, monkeypatch):
     ck_a, ck_b = torch.load(tmp_path / "a" / "model-20.pt"), torch.load(tmp_path / "b" / "model-20.pt")
     for k in ("mg", "ms", "mom"):
         assert torch.equal(ck_a["slots"][k], ck_b["slots"][k]), k
+
+
+def test_progress_figure_data_and_logger(tmp_path):
+    """evaluation.py:31-108 on the device: make_fig's arrays / rectangles for the current batch and make_logger's scalar set."""
+    import numpy as np
+    import attend_infer_repeat_b200 as air
+    from attend_infer_repeat_b200.data import ResidentDataset, synthetic_multi_mnist_u8
+    from attend_infer_repeat_b200.evaluation import make_fig, make_logger, rect_stn_bbox
+    dev = torch.device("cuda", 0)
+    ds = ResidentDataset(*synthetic_multi_mnist_u8(256, 50, 50, seed=0), device=dev, seed=0)
+    B = 16
+    imgs, nums = ds.gather(ds.next_indices(B))
+    model = air.AIRonMNIST(imgs, nums, max_steps=3, explore_eps=1e-3, inpt_encoder_hidden=[256, 256],
+                           glimpse_encoder_hidden=[256, 256], glimpse_decoder_hidden=[256, 256],
+                           transform_estimator_hidden=[256, 256], steps_pred_hidden=[128, 64], baseline_hidden=[256, 128],
+                           transform_var_bias=.5, step_bias=.75, output_multiplier=.5, precision=air.AIR_PREC_TC_SPLIT)
+    pr = dict(loc=0., scale=1.)
+    nsp = dict(anneal='exp', init=1. - 1e-15, final=1e-7, steps_div=1e4, steps=1e5, hold_init=1e3, analytic=True)
+    train_op, _ = model.train_step(1e-4, 0., pr, pr, pr, nsp)
+    train_op()
+    d = make_fig(model, str(tmp_path), 1, n_samples=10)
+    assert os.path.exists(tmp_path / "progress_fig_1.npz")
+    assert d["obs"].shape == (10, 50, 50) and d["canvas"].shape == (3, 10, 50, 50) and d["glimpse"].shape == (3, 10, 20, 20)
+    assert d["prob"].shape == (10, 3) and d["bbox"].shape == (3, 10, 4)
+    pres, where = model.presence[:, :10, 0].cpu().numpy(), model.where[:, :10].cpu().numpy()
+    for i in range(3):
+        for j in range(10):
+            if pres[i, j] > .5:
+                np.testing.assert_allclose(d["bbox"][i, j], rect_stn_bbox(50, 50, where[i, j]), rtol=1e-6)
+            else:
+                assert np.isnan(d["bbox"][i, j]).all()
+    lines = []
+    log = make_logger(model, lambda: ds.gather(ds.next_indices(B)), 2, lambda: ds.gather(ds.next_indices(B)), 2, out=lines.append)
+    res = log(7)
+    assert len(lines) == 2 and lines[0].startswith("Step 7, Data train loss = ") and "Data test" in lines[1]
+    assert set(res["train"]) == {"loss", "rec_loss", "num_step_acc", "num_step", "prior_loss", "kl_num_steps", "kl_what",
+                                 "kl_where", "baseline_loss", "reinforce_loss", "imp_weight"}
+    assert all(v == v for v in res["test"].values())

@@ -177,3 +177,11 @@ def test_row_kernel_schedule_replays_cleanly_on_the_host():
     assert air.row_schedule_check(odd, T=4) == ""
     assert "wider than 256" in air.row_schedule_check(air.CellConfig(glenc_hidden=(300,), precision=air.AIR_PREC_TC_SPLIT))
     assert "what head" in air.row_schedule_check(air.CellConfig(na=80, precision=air.AIR_PREC_TC_SPLIT))
+
+
+def test_rect_stn_bbox_matches_the_reference_formula():
+    """evaluation.py:23-28: x = W (1 - sx + tx) / 2, y = H (1 - sy + ty) / 2, bbox = [y - .5, x - .5, H sy, W sx]."""
+    from attend_infer_repeat_b200.evaluation import rect_stn_bbox
+    assert rect_stn_bbox(50, 50, (1., 0., 1., 0.)) == [-.5, -.5, 50., 50.]           # identity: the whole image
+    b = rect_stn_bbox(50, 40, (.5, .2, .25, -.4))
+    assert b == [40 * (1 - .25 - .4) / 2 - .5, 50 * (1 - .5 + .2) / 2 - .5, 40 * .25, 50 * .5]
