@@ -52,7 +52,7 @@ def test_unrolled_forward_vs_reference_cell_vectors(case, precision):
                    name="rec_loss_per_sample")
 
 
-@pytest.mark.parametrize("case,precision", [r for r in CELL_RUNS if r[0] != "soft"])     # the backward pass is discrete-only
+@pytest.mark.parametrize("case,precision", CELL_RUNS)     # "soft" = discrete_steps False (cell.py:150-151)
 def test_backward_vs_reference_train_step_vectors(case, precision):
     """air_backward against d opt_loss / d (model variables) as the reference's own AIRModel.train_step computes it
     (tools/make_golden.py: train_vectors; autograd through the reference's loss assembly): 5e-4 of each tensor's max |g| on
