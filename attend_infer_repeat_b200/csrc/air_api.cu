@@ -690,8 +690,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     ep.nkb_total = w0.Kpad / air::tc::BK;
     ep.nkb_per_cta = (ep.nkb_total + air::enc::KSPLIT - 1) / air::enc::KSPLIT;
     ep.w_lo_row = w0.N_alloc;
-    const bool want_hl = only ? (tc && !lstm_fused) : true;
-    const bool want_f32 = only ? (lstm_fused || train) : train;
+    const bool want_hl = true;
+    const bool want_f32 = train;
     ep.out_hl = want_hl ? dst.hl : nullptr;
     ep.hl_plane = dst.plane();
     ep.ld_hl = dst.kpad;
@@ -705,11 +705,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
       rest.n_hidden = h->enc.n_hidden - 1;
       std::vector<float*> rest_saves;
       if (train) rest_saves.assign(h->sv_enc.begin() + 1, h->sv_enc.end());
-      if ((rc = run_mlp_from(h, params, rest, dst, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
+      if ((rc = run_mlp_from(h, params, rest, dst, B, h->e, !tc || train, tc, st,
                              train ? &rest_saves : nullptr, /*first_to_ping=*/false)) != AIR_OK)
         return rc;
     }
-  } else if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || lstm_fused || train, tc && !lstm_fused, st,
+  } else if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || train, tc, st,
                            train ? &h->sv_enc : nullptr)) != AIR_OK)
     return rc;
   mark(h, AIR_ST_LSTM, st);
@@ -748,6 +748,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     lp.tm_h = h->tcw[h->lstm_h_perm].tm_chain;
     lp.bias = h->bias_arena + h->tcw[h->lstm_x_perm].bias_off;
     lp.e = h->e.f32;
+    lp.e_hl = h->e.hl;            // the encoder's last layer wrote hl planes (tensor-core engine)
+    lp.e_plane = h->e.plane();
+    lp.e_ld = h->e.kpad;
+    lp.hs_last_only = train ? 0 : 1;
     lp.n_enc = h->n_enc;
     const bool rows = h_in || train;   // explicit per-canvas state (air_cell_step) or the tiled copy kept for the backward
     lp.h_init = rows ? h->h_init.f32 : params + h->lstm_h0;   // cell.py:103: (h0, c0) [1,nh] tiled to the batch
@@ -766,7 +770,24 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     lp.T = T_run;
     lp.forget_bias = c.forget_bias;
     lp.range_flag = h->range_flag;
-    AIR_CUDA(air::lstm::launch_lstm(lp, st));
+    static const char* lstm_trace = getenv("AIR_LSTM_TRACE");
+    if (lstm_trace) {   // debug: per-phase SM-clock stamps of every CTA -> <AIR_LSTM_TRACE>.<seq>.bin
+      const size_t n = (size_t)((B + air::tc::BM - 1) / air::tc::BM) * air::lstm::CLUSTER * 64;
+      if (!h->trace) AIR_CUDA(cudaMalloc(&h->trace, sizeof(long long) * 1024 * (air::row::MAXU + air::row::MAXTASK) * 4));
+      AIR_CUDA(cudaMemsetAsync(h->trace, 0, sizeof(long long) * n, st));
+      lp.trace = h->trace;
+      AIR_CUDA(air::lstm::launch_lstm(lp, st));
+      std::vector<long long> host(n);
+      AIR_CUDA(cudaMemcpyAsync(host.data(), h->trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+      AIR_CUDA(cudaStreamSynchronize(st));
+      const std::string path = std::string(lstm_trace) + "." + std::to_string(h->trace_seq++) + ".bin";
+      if (FILE* f = fopen(path.c_str(), "wb")) {
+        fwrite(host.data(), sizeof(long long), n, f);
+        fclose(f);
+      }
+    } else {
+      AIR_CUDA(air::lstm::launch_lstm(lp, st));
+    }
     ++h->launches;
   }
   for (int t = 0; t < (lstm_fused ? 0 : T_run); ++t) {

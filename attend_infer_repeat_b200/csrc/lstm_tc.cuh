@@ -25,6 +25,10 @@ struct Params {
   CUtensorMap tm_h;       // prepared W[n_enc:]^T, same permutation
   const float* bias;      // lstm.b permuted the same way (bias arena), [4 * NH]
   const float* e;         // [B, n_enc] fp32: input-encoder output
+  const __half* e_hl;     // the same as row-major hl planes [2][rows_alloc][e_ld] (preferred: 16-byte loads, no staging), or null
+  size_t e_plane;
+  int e_ld;
+  int hs_last_only;       // inference: only the last step's fp32 h rows are needed (final_h); the heads read the hl copy
   int n_enc;
   const float* h_init;    // [B, NH] fp32 (row pitch h_init_ld; 0 = one [NH] vector broadcast to every canvas)
   int h_init_ld;
@@ -41,7 +45,12 @@ struct Params {
   int B, T;
   float forget_bias;
   int* range_flag;
+  long long* trace;       // debug (AIR_LSTM_TRACE): [CTA][64] SM-clock stamps, or null
 };
+#define LSTM_TRACE(slot)                                                                                              \
+  do {                                                                                                                \
+    if (p.trace) p.trace[((size_t)(blockIdx.y * CLUSTER + blockIdx.x)) * 64 + (slot)] = clock64();                   \
+  } while (0)
 
 __device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, float (&v)[4]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -187,6 +196,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
         const int nsl = (K + 15) / 16, nkb = (nsl + 3) / 4;
         mbar_wait(a_ready, g & 1);
         tc_fence_after();
+        LSTM_TRACE(32 + 2 * g);
         for (int kb = 0; kb < nkb; ++kb) {
           const int hs = kb & 3, ls = 4 + (kb & 1);
           mbar_wait(&full_bar[hs], (par >> hs) & 1);
@@ -220,6 +230,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
           umma_commit(&empty_bar[hs]);
         }
         umma_commit(d_full);
+        LSTM_TRACE(33 + 2 * g);
       }
     }
     __syncwarp();
@@ -234,30 +245,61 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     const int u0 = (int)rank * UPC + cq * 16;   // first hidden unit of this thread
     const int my_slice = (int)rank * 4 + cq;    // == u0 / 16
     uint32_t ovf = 0;
+    const bool tr = threadIdx.x == 64;
+    if (tr) LSTM_TRACE(0);
+    // With the 227 KB shared-memory carve-out the L1 is a few KB and every first touch is an L2 round trip; the bias and
+    // initial-state lines this thread needs in the gx epilogue are pulled in now, behind the operand load and the gx GEMM
+    // (measured: the gx epilogue was a chain of eight exposed L2 latencies, 13 k of the kernel's 96 k clocks).
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + (size_t)rank * NH + gate * UPC + cq * 16));
+    if (p.h_init_ld == 0) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.h_init + (cq + 4 * s) * 16));
+    }
 
     // --- operand of the gx GEMM: e rows, fp32 -> hi/lo -> TMEM (each thread: slices cq, cq + 4, ...) ---
     {
       const int nsl = (p.n_enc + 15) / 16;
-      for (int s = cq; s < nsl; s += 4) {
-        float v[16];
-        tile_load(stage, lane, v, p.e, p.n_enc, row_w, s * 16, p.n_enc, p.B);
-        uint32_t hi[8], lo[8];
-        split_pack16(v, hi, lo, ovf);
-        tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
-        tmem_st_32x8(t_lane + A_LO_COL + s * 8, lo);
+      if (p.e_hl) {
+        // the encoder's last layer wrote e as hl planes: the packed words are read as they are (four 16-byte loads per
+        // slice, all in flight together; the staged fp32 path below cost 11 k clocks of a 96 k kernel)
+        const __half* src = p.e_hl + (size_t)row * p.e_ld;
+#pragma unroll 4
+        for (int s = cq; s < nsl; s += 4) {
+          const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(src + s * 16)), h1 = __ldg(reinterpret_cast<const uint4*>(src + s * 16) + 1);
+          const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(src + p.e_plane + s * 16));
+          const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(src + p.e_plane + s * 16) + 1);
+          const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
+          tmem_st_32x8(t_lane + A_LO_COL + s * 8, lo);
+        }
+      } else {
+        for (int s = cq; s < nsl; s += 4) {
+          float v[16];
+          tile_load(stage, lane, v, p.e, p.n_enc, row_w, s * 16, p.n_enc, p.B);
+          uint32_t hi[8], lo[8];
+          split_pack16(v, hi, lo, ovf);
+          tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
+          tmem_st_32x8(t_lane + A_LO_COL + s * 8, lo);
+        }
       }
     }
     // cell state of this thread's 16 units, in registers for the whole recurrence
     float c_reg[16];
-    tile_load(stage, lane, c_reg, p.c_in, p.c_in_ld, row_w, u0, NH, p.B);
+    if (p.c_in_ld == 0) load16(p.c_in + u0, c_reg);   // one trainable vector for every canvas (cell.py:103)
+    else tile_load(stage, lane, c_reg, p.c_in, p.c_in_ld, row_w, u0, NH, p.B);
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(a_ready);
+    if (tr) LSTM_TRACE(1);
 
     // --- gx: D + bias -> scratch, in this thread's own read-back order: [gate * 4 + k4][row][4 floats] ---
     float* gx_mine = p.gx_scr + ((((size_t)tile * CLUSTER + rank) * 4 + cq) * 16 * BM + rit) * 4;
     mbar_wait(d_full, 0);
     tc_fence_after();
+    if (tr) LSTM_TRACE(2);
 #pragma unroll
     for (int gate = 0; gate < 4; ++gate) {
       float v[16], b[16];
@@ -273,7 +315,8 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     // --- operand of step 1: h_init rows ---
     for (int s = cq; s < NH / 16; s += 4) {
       float v[16];
-      tile_load(stage, lane, v, p.h_init, p.h_init_ld, row_w, s * 16, NH, p.B);
+      if (p.h_init_ld == 0) load16(p.h_init + s * 16, v);   // the broadcast trainable initial state: same 64 bytes in every lane
+      else tile_load(stage, lane, v, p.h_init, p.h_init_ld, row_w, s * 16, NH, p.B);
       uint32_t hi[8], lo[8];
       split_pack16(v, hi, lo, ovf);
       tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
@@ -282,10 +325,12 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(a_ready);
+    if (tr) LSTM_TRACE(3);
 
     for (int t = 0; t < p.T; ++t) {
       mbar_wait(d_full, (t + 1) & 1);
       tc_fence_after();
+      if (tr) LSTM_TRACE(4 + 5 * t);
       // ---- gate math of 16 units, four at a time ----
       float h_new[16];
 #pragma unroll
@@ -322,10 +367,11 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
                                                                 fmaf(go[2], W_UNSCALE, ao[2]), fmaf(go[3], W_UNSCALE, ao[3]));
         }
       }
+      if (tr) LSTM_TRACE(5 + 5 * t);
       if (p.c_save) tile_store(stage, lane, c_reg, p.c_save + (size_t)t * p.B * NH, NH, row_w, u0, NH, p.B);
       // ---- h_t: fp32 rows (output + final state), hl copy for the heads chain, own slice straight into TMEM, and the
       //      exchange buffer for the other three CTAs ----
-      tile_store(stage, lane, h_new, p.hs + (size_t)t * p.B * NH, NH, row_w, u0, NH, p.B);
+      if (!p.hs_last_only || t + 1 == p.T) tile_store(stage, lane, h_new, p.hs + (size_t)t * p.B * NH, NH, row_w, u0, NH, p.B);
       uint32_t hi[8], lo[8];
       split_pack16(h_new, hi, lo, ovf);
       if (p.hs_hlt.p && row < p.B) {
@@ -341,8 +387,14 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
       }
       tmem_st_32x8(t_lane + A_HI_COL + my_slice * 8, hi);
       tmem_st_32x8(t_lane + A_LO_COL + my_slice * 8, lo);
-      __half* xb = p.hx + (size_t)(t & 1) * 2 * p.hx_plane + ((size_t)tile * 16 * BM) * 16;   // this tile, this parity
-      {
+      // The h slabs reach the other three CTAs through L2.  When the canvas tile is also a tile of the heads' operand
+      // (B a multiple of 128: row t * B + m0 starts a 128-row tile) the slice-major hl copy just written IS the exchange
+      // buffer -- same [slice][128 rows][16] layout -- and nothing is stored twice; otherwise a private double buffer.
+      const bool via_hlt = p.hs_hlt.p && (p.B % BM) == 0;
+      __half* xb = via_hlt ? p.hs_hlt.p + ((((size_t)t * p.B + m0) >> 7) * (size_t)p.hs_hlt.nsl) * BM * 16
+                           : p.hx + (size_t)(t & 1) * 2 * p.hx_plane + ((size_t)tile * 16 * BM) * 16;
+      const size_t xplane = via_hlt ? p.hs_hlt.plane : p.hx_plane;
+      if (!via_hlt) {
         __half* d = xb + ((size_t)my_slice * BM + rit) * 16;
         *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(d + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -350,18 +402,20 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
         *reinterpret_cast<uint4*>(d + p.hx_plane + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       }
       __syncwarp();
+      if (tr) LSTM_TRACE(6 + 5 * t);
       if (lane == 0) {
 #pragma unroll
         for (uint32_t r = 0; r < CLUSTER; ++r) mbar_arrive_remote(x_bar, r);
       }
       mbar_wait_cluster(x_bar, t & 1);
+      if (tr) LSTM_TRACE(7 + 5 * t);
       // ---- the other CTAs' slabs: slices 4 r' + cq, r' != rank ----
 #pragma unroll
       for (int rr = 1; rr < CLUSTER; ++rr) {
         const int s = ((int)((rank + rr) & 3)) * 4 + cq;
         const __half* src = xb + ((size_t)s * BM + rit) * 16;
         const uint4 h0 = ld_cg_u4(src), h1 = ld_cg_u4(src + 8);
-        const uint4 l0 = ld_cg_u4(src + p.hx_plane), l1 = ld_cg_u4(src + p.hx_plane + 8);
+        const uint4 l0 = ld_cg_u4(src + xplane), l1 = ld_cg_u4(src + xplane + 8);
         const uint32_t whi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const uint32_t wlo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         tmem_st_32x8(t_lane + A_HI_COL + s * 8, whi);
@@ -370,7 +424,9 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(a_ready);
+      if (tr) LSTM_TRACE(8 + 5 * t);
     }
+    if (tr) LSTM_TRACE(30);
     if ((ovf & 0x80008000u) && p.range_flag) atomicOr(p.range_flag, 1);
   }
 
