@@ -144,9 +144,43 @@ class AIRModel:
         return o
 
     # ------------------------------------------------------------------------------------------------------
+    # attributes created by train_step / _prior_loss / _reinforce in the reference (model.py:143-372).  The reference's are graph
+    # tensors, evaluated only when somebody fetches them; here they are materialised on first access after each forward
+    # (the training step itself needs none of them: at B = 4096 building them eagerly cost 0.3 ms of host time per step,
+    # and the step is host-bound -- tools/train_op_host_probe.py)
+    _LAZY_LOSS_ATTRS = ("rec_loss_per_sample", "rec_loss", "kl_num_steps_per_sample", "kl_num_steps", "kl_what", "kl_where",
+                        "prior_step_weight", "prior_loss", "prior_weight", "loss", "baseline_loss", "reinforce_loss",
+                        "opt_loss", "num_step_accuracy")
+
+    def __getattr__(self, name):
+        # (only reached when normal lookup fails)
+        if name in AIRModel._LAZY_LOSS_ATTRS and self.__dict__.get("_loss_outputs") is not None:
+            self._materialise_losses()
+            if name in self.__dict__:
+                return self.__dict__[name]
+        raise AttributeError(name)
+
     def _expose_losses(self, o):
-        """Attributes created by train_step / _prior_loss / _reinforce in the reference (model.py:143-372)."""
+        """The part of the loss assembly the training step needs right away: the REINFORCE importance weight, the baseline
+        (BaselineMLP forward on the engine) and the scalar block re-formed with the baseline mean.  Everything else is lazy."""
         eng = self.engine
+        for k in AIRModel._LAZY_LOSS_ATTRS:
+            self.__dict__.pop(k, None)
+        self._loss_outputs = o
+        tc = self._train_cfg
+        self.reinforce_imp_weight = o["rec_loss_per_sample"]
+        if tc["use_reinforce"]:
+            if not _get(tc["num_steps_prior"], "analytic", True):
+                sw = float(_get(tc["num_steps_prior"], "weight", 1.))
+                self.reinforce_imp_weight = (o["rec_loss_per_sample"] + o["kl_num_steps_per_sample"] * sw +
+                                             o["kl_what_per_sample"] + o["kl_where_per_sample"])
+            if self.baseline_module is not None:
+                b = self.baseline_module(self.obs, self.what, self.where, self.presence, self.final_state)
+                self.baseline = b                                                 # [B,1]
+                eng.elbo_scalars(b.reshape(-1), self._prior_struct)               # REINFORCE with the baseline mean
+
+    def _materialise_losses(self):
+        o, eng = self._loss_outputs, self.engine
         self.rec_loss_per_sample = o["rec_loss_per_sample"]
         self.rec_loss = eng.scalar("rec_loss")
         self.kl_num_steps_per_sample = o["kl_num_steps_per_sample"]
@@ -164,18 +198,12 @@ class AIRModel:
         loss = Loss()
         loss._value, loss._per_sample = eng.scalar("loss"), o["loss_per_sample"]
         self.loss = loss
-        self.reinforce_imp_weight = self.rec_loss_per_sample
         if tc["use_reinforce"]:
-            if not _get(tc["num_steps_prior"], "analytic", True):
-                self.reinforce_imp_weight = self.rec_loss_per_sample + self.prior_loss.per_sample
             if self.baseline_module is not None:
-                b = self.baseline_module(self.obs, self.what, self.where, self.presence, self.final_state)
-                self.baseline = b                                                 # [B,1]
-                eng.elbo_scalars(b.reshape(-1), self._prior_struct)               # REINFORCE with the baseline mean
                 # [B] - [B,1] broadcasts to [B,B] in the reference (67 MB at B = 4096, 4.3 GB at 32768).
                 # Nothing on the path needs the matrix -- the `importance_weight` property forms it on request.
                 # .5 * mean over that broadcast of (iw_j - b_i)^2 = .5 (E iw^2 - 2 E iw E b + E b^2): four batch means the
-                # scalars kernel has just written (device arithmetic on 4 numbers, float64, no host round trip)
+                # scalars kernel has written (device arithmetic on 4 numbers, float64, no host round trip)
                 sc = eng.out["scalars"].double()
                 m_iw, m_iw2 = sc[SCALAR_INDEX["mean_iw"]], sc[SCALAR_INDEX["mean_iw2"]]
                 m_b, m_b2 = sc[SCALAR_INDEX["mean_baseline"]], sc[SCALAR_INDEX["mean_baseline2"]]
@@ -267,33 +295,35 @@ class AIRModel:
             sharding.combine_scalars(out["scalars"], B, pr.steps_weight, bool(pr.use_prior), bool(pr.use_reinforce),
                                      nvil_shift=pr.nvil_shift, nvil_scale=pr.nvil_scale)
         eps_where, eps_what, _ = self._last_noise
+        o = self._opt
+        # The baseline's own gradient (model.py:253-259) needs only this step's forward results: it goes FIRST, so that under
+        # sharding its all-reduce hides behind the main backward pass, and the main gradient's all-reduce behind the baseline's
+        # optimiser step -- every collective is issued on NCCL's stream (async_op) and joined where its result is consumed.
+        base_work = None
+        if has_baseline:
+            bm = self.baseline_module
+            # the (global) importance-weight mean sits in the scalar block: read on the device by the gradient kernel
+            tmean = out["scalars"][SCALAR_INDEX["mean_iw"]:SCALAR_INDEX["mean_iw"] + 1]
+            g_base = bm.backward(self.reinforce_imp_weight, self.baseline, tmean, 1.0 / (world * B))
+            if world > 1:
+                base_work = dist.all_reduce(g_base, async_op=True)
         # baseline_mean = NaN: air_backward reads scalars[mean_baseline] on the device (no host synchronisation in the step)
         eng.backward(self.cell.params, self.obs, eps_where, eps_what, pr, self._grad,
                      baseline_mean=float("nan") if has_baseline else 0.0,
                      inv_batch=1.0 / (world * B), l2_weight=float(self.l2_weight) / world)
         grad_work = None
         if world > 1:
-            # the ONE data-path collective: sum of the per-shard partial gradients.  Issued on NCCL's stream; the baseline's
-            # backward pass below runs beside it, the optimiser waits for it.
-            grad_work = dist.all_reduce(self._grad, async_op=True)
-        o = self._opt
-        g_base = None
+            grad_work = dist.all_reduce(self._grad, async_op=True)   # the ONE data-path collective of the cell's parameters
+        # the baseline's train step at 10x the learning rate (model.py:362-367, _make_baseline_train_step :253-259)
         if has_baseline:
-            # the baseline's gradient (model.py:253-259): needs only this step's forward results, so it overlaps the all-reduce
-            bm = self.baseline_module
-            tmean = out["scalars"][SCALAR_INDEX["mean_iw"]:SCALAR_INDEX["mean_iw"] + 1]
-            g_base = bm.backward(self.reinforce_imp_weight, self.baseline, tmean, 1.0 / (world * B))
+            if base_work is not None:
+                base_work.wait()
+            eng.rmsprop_step(bm.params, g_base, bm.slots["mg"], bm.slots["ms"], bm.slots["mom"],
+                             10.0 * float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
         if grad_work is not None:
             grad_work.wait()
         eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
                          float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
-        # the baseline's own train step at 10x the learning rate (model.py:362-367, _make_baseline_train_step :253-259)
-        if has_baseline:
-            bm, g = self.baseline_module, g_base
-            if world > 1:
-                dist.all_reduce(g)
-            eng.rmsprop_step(bm.params, g, bm.slots["mg"], bm.slots["ms"], bm.slots["mom"],
-                             10.0 * float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
         # UPDATE_OPS (model.py:357-360): the moving moments of the importance weight absorb this batch AFTER the gradient
         # was taken with their previous values (TF leaves the order of the read and the assign unspecified)
         if self.decay_rate is not None and self._train_cfg["use_reinforce"]:
