@@ -9,7 +9,7 @@ from . import evaluation, functional, ops, prior  # noqa: F401
 from ._lib import AIR_PREC_FP32, AIR_PREC_TC_SPLIT, AirError, build  # noqa: F401
 from .cell import AIRCell  # noqa: F401
 from .data import ResidentDataset, load_data, save_data, tensors_from_data  # noqa: F401
-from .engine import CellConfig, Engine, c_config, make_prior, param_count, param_spec, row_schedule_check  # noqa: F401
+from .engine import CellConfig, Engine, EnginePool, c_config, make_prior, param_count, param_spec, row_schedule_check  # noqa: F401
 from .mnist_model import AIRonMNIST  # noqa: F401
 from .model import AIRModel  # noqa: F401
 from .modules import (LSTM, BaselineMLP, Decoder, Encoder, ParametrisedGaussian, SpatialTransformer,  # noqa: F401

@@ -990,7 +990,30 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   }
   a.lp_const = (float)(0.5 * 1.8378770664093453 /* log(2 pi) */ + std::log((double)c.output_std));
   a.prior_part = h->prior_part;
-  AIR_CUDA(air::launch_paint_elbo(a, st));   // paint CTAs + (when a prior is given) the prior-term CTAs, one grid
+  a.trace = nullptr;
+  // debug: AIR_PAINT_TRACE=<prefix> dumps 8 stamps per CTA of the paint grid (globaltimer ns, SM id) to <prefix>.<seq>.bin
+  static const char* paint_trace = getenv("AIR_PAINT_TRACE");
+  if (paint_trace) {
+    const size_t n = (size_t)(B + (B + 7) / 8 + 8) * 8;
+    long long* dbuf = nullptr;
+    AIR_CUDA(cudaMalloc(&dbuf, sizeof(long long) * n));
+    AIR_CUDA(cudaMemsetAsync(dbuf, 0, sizeof(long long) * n, st));
+    a.trace = dbuf;
+    AIR_CUDA(air::launch_paint_elbo(a, st));
+    std::vector<long long> host(n);
+    AIR_CUDA(cudaMemcpyAsync(host.data(), dbuf, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    AIR_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dbuf);
+    const std::string path = std::string(paint_trace) + "." + std::to_string(h->trace_seq++) + ".bin";
+    if (FILE* f = fopen(path.c_str(), "wb")) {
+      const int hdr[4] = {B, a.n_prior_ctas, 8, 0};
+      fwrite(hdr, sizeof(int), 4, f);
+      fwrite(host.data(), sizeof(long long), n, f);
+      fclose(f);
+    }
+  } else {
+    AIR_CUDA(air::launch_paint_elbo(a, st));   // paint CTAs + (when a prior is given) the prior-term CTAs, one grid
+  }
   ++h->launches;
 
   if (prior) {

@@ -43,6 +43,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool bulk_ok(const void* src, int n_floats) {
   return ((n_floats & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
 }
@@ -429,6 +434,8 @@ struct ElboArgs {
   int do_elbo;
   float* prior_part;           // [B] scratch: prior_weight * prior_per_sample (prior CTAs -> elbo_scalars_kernel)
   int n_prior_ctas;            // leading CTAs of the paint grid that compute the prior terms (launch_paint_elbo)
+  long long t_stride;          // B * H * W: elements between the canvases of consecutive steps (host)
+  long long* trace;            // debug (AIR_PAINT_TRACE): 8 stamps per CTA (globaltimer ns at the phase boundaries, SM id)
   PresenceArgs scan;           // scan.logit != null: presence / presence_prob are not inputs -- this grid runs the presence scan
                                // itself (the fused row kernel has no per-canvas CTA to do it): the paint CTA of a canvas
                                // writes the two outputs, the prior warp of the canvas recomputes the same values locally
@@ -639,25 +646,68 @@ inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStrea
 //   rec[b]   = sum_px 0.5 ((x - mu)/sigma)^2 + log sigma + 0.5 log 2 pi, mu = multiplier * canvas_T (model.py:319-321)
 //   (loss_per_sample[b] = rec[b] + prior part is completed by elbo_scalars_kernel)
 // The canvas is never read back from HBM: it accumulates in registers across the T steps and is written once per step.
-// Thread mapping: a thread owns a fixed column (a column PAIR when W is even: 8-byte stores) and walks down the rows, so
-// "is this column inside glimpse t's footprint" is a loop-invariant bit mask, the row test is one broadcast shared-memory
-// load, and a (row, step) whose footprint misses costs a handful of instructions.  In pass k the CTA's threads cover one
-// contiguous run of W * rows_per_pass pixels: every store instruction is fully coalesced.
-// dynamic smem: T*G floats (glimpses) + T*(W+H) taps.
+// The bilinear resampler is separable -- canvas[r][c] = sum_i wy[r][i] (sum_j wx[c][j] glimpse[i][j]) with two non-zero
+// taps per axis -- and the kernel was issue-bound (ncu r02a: 310 warp instructions per 32 pixel pairs, 68 % issue
+// utilisation, 30 % of DRAM), so it runs in two passes over shared memory:
+//   columns: s_col[t][i][c] = presence_t * (wx_f glimpse[i][j_f] + wx_c glimpse[i][j_c])     T*h*W values, 2 taps each
+//   rows:    canvas_t[r][c] += wy_f s_col[t][i_f][c] + wy_c s_col[t][i_c][c]                  T*H*W values, 2 taps each
+// The row pass touches no tap table of the columns and no mask: a canvas pixel costs two 8-byte shared loads and four
+// FMAs per step.  (Association differs from the four-product form of the stand-alone resampler by a few ulp.)
+// Thread mapping of the row pass: a thread owns a fixed column (a column PAIR when W is even: 8-byte stores) and walks
+// down the rows; in pass k the CTA's threads cover one contiguous run of W * rows_per_pass pixels, so every store
+// instruction is fully coalesced.
+// dynamic smem: T*G floats (glimpses) + T*(W+H) taps + T*h*W floats (column pass).
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) {
-  return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H);
+  return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H) +
+         sizeof(float) * (size_t)T * h * W;
 }
 
 #ifndef PAINT_MIN_CTAS
 #define PAINT_MIN_CTAS 8
 #endif
+// column pass: s_col[t][i][c] for every glimpse row i and canvas column c (zero outside the footprint / absent steps)
+template <int T>
+__device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __restrict__ s_gl,
+                                              const Tap* __restrict__ s_tx, const float* __restrict__ s_pres,
+                                              float* __restrict__ s_col) {
+  const int W = a.W, h = a.h, w = a.w;
+  const int NT = blockDim.x;
+  const int CP = W < NT ? W : NT;               // columns resident in one sweep
+  const int RG = NT / CP;                       // glimpse rows per sweep
+  const int cslot = (int)threadIdx.x % CP, islot = (int)threadIdx.x / CP;
+  if (islot >= RG) return;
+  for (int c = cslot; c < W; c += CP) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float pres = s_pres[t];
+      if (pres == 0.f) continue;                // the row pass skips absent steps as well
+      const Tap tx = s_tx[t * W + c];
+      const float wf = __fmul_rn(pres, tx.wf), wc = __fmul_rn(pres, tx.wc);
+      const float* g = s_gl + t * h * w;
+      float* dst = s_col + (size_t)t * h * W + c;
+      for (int i = islot; i < h; i += RG)
+        dst[i * W] = fmaf(wc, g[i * w + tx.i_c], __fmul_rn(wf, g[i * w + tx.i_f]));
+    }
+  }
+}
+
+// row pass.  s_ty is laid out [H][T] (the T taps of a canvas row are adjacent: one base pointer, immediate offsets) and its
+// indices are shared-window BYTE ADDRESSES of s_col rows, the step's slab included; i_f < 0 marks a (row, step) that paints
+// nothing (outside the footprint, or the step is absent).  Every address in the loop is a pointer induction variable.
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 template <int T, int CPT>
-__device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const float* __restrict__ s_gl,
-                                            const Tap* __restrict__ s_tx, const Tap* __restrict__ s_ty,
-                                            const float* __restrict__ s_pres) {
-  const int B = a.B, H = a.H, W = a.W;
-  const int P = H * W, G = a.h * a.w;
+__device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap* __restrict__ s_ty) {
+  const int H = a.H, W = a.W;
   const int NT = blockDim.x;
   const int TPR = W / CPT;                      // threads per row
   const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
@@ -665,69 +715,60 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const floa
   const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
   const float mult = a.output_multiplier;
   const bool do_elbo = a.do_elbo != 0;
-  float pres[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) pres[t] = s_pres[t];
-  const float* cin = a.canvas_in ? a.canvas_in + (size_t)b * P : nullptr;
-  const float* obs = a.img + (size_t)b * P;
-  float* cbase = a.canvas ? a.canvas + (size_t)b * P : nullptr;
-  const size_t tstride = (size_t)B * P;
+  const bool has_cin = a.canvas_in != nullptr, has_dst = a.canvas != nullptr;
+  const long long tstride = a.t_stride;
+  const size_t base = (size_t)b * H * W;
+  const int dp = RPP * W;
   float rec = 0.f;
   if (rslot >= RPP) return rec;
   for (int c = cslot * CPT; c < W; c += TPRB * CPT) {
-    // loop-invariant: which (step, column) pairs lie inside the glimpse footprint (and are present at all)
-    uint32_t colmask = 0;
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (pres[t] != 0.f) {
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-          const Tap tx = s_tx[t * W + c + j];
-          if ((tx.wf != 0.f) | (tx.wc != 0.f)) colmask |= 1u << (t * CPT + j);
-        }
-      }
-    }
+    const uint32_t c4 = (uint32_t)c * 4u;
+    const Tap* typ = s_ty + rslot * T;
+    const size_t off = base + rslot * W + c;
+    const float* obs = a.img + off;
+    const float* cin = a.canvas_in + off;        // only dereferenced when has_cin / has_dst
+    float* dst = a.canvas + off;
     for (int r = rslot; r < H; r += RPP) {
-      const int p = r * W + c;
       float acc[CPT], xo[CPT];
       if (CPT == 2) {
-        const float2 ci = cin ? *reinterpret_cast<const float2*>(cin + p) : make_float2(0.f, 0.f);
-        const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs + p) : make_float2(0.f, 0.f);
+        const float2 ci = has_cin ? *reinterpret_cast<const float2*>(cin) : make_float2(0.f, 0.f);
+        const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs) : make_float2(0.f, 0.f);
         acc[0] = ci.x; acc[CPT - 1] = ci.y;
         xo[0] = xv.x; xo[CPT - 1] = xv.y;
       } else {
-        acc[0] = cin ? cin[p] : 0.f;
-        xo[0] = do_elbo ? obs[p] : 0.f;
+        acc[0] = has_cin ? cin[0] : 0.f;
+        xo[0] = do_elbo ? obs[0] : 0.f;
       }
+      float* d = dst;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const uint32_t cm = (colmask >> (t * CPT)) & ((1u << CPT) - 1u);
-        if (cm) {
-          const Tap ty = s_ty[t * H + r];
-          if ((ty.wf != 0.f) | (ty.wc != 0.f)) {
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-              if (cm & (1u << j)) {
-                const Tap tx = s_tx[t * W + c + j];
-                const float v = bilinear_pre(s_gl + t * G, tx, ty);
-                acc[j] = __fadd_rn(acc[j], __fmul_rn(pres[t], v));
-              }
-            }
+        const Tap ty = typ[t];
+        if (ty.i_f >= 0) {
+          if (CPT == 2) {
+            const float2 u = lds_f2((uint32_t)ty.i_f + c4), v = lds_f2((uint32_t)ty.i_c + c4);
+            acc[0] = __fadd_rn(acc[0], fmaf(ty.wc, v.x, __fmul_rn(ty.wf, u.x)));
+            acc[CPT - 1] = __fadd_rn(acc[CPT - 1], fmaf(ty.wc, v.y, __fmul_rn(ty.wf, u.y)));
+          } else {
+            acc[0] = __fadd_rn(acc[0], fmaf(ty.wc, lds_f1((uint32_t)ty.i_c + c4), __fmul_rn(ty.wf, lds_f1((uint32_t)ty.i_f + c4))));
           }
         }
-        if (cbase) {
-          float* dst = cbase + (size_t)t * tstride + p;
-          if (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(__fmul_rn(acc[0], mult), __fmul_rn(acc[CPT - 1], mult));
-          else          dst[0] = __fmul_rn(acc[0], mult);
+        if (has_dst) {
+          if (CPT == 2) *reinterpret_cast<float2*>(d) = make_float2(__fmul_rn(acc[0], mult), __fmul_rn(acc[CPT - 1], mult));
+          else          d[0] = __fmul_rn(acc[0], mult);
+          d += tstride;
         }
       }
       if (do_elbo) {   // sum of squared residuals; the constants of Normal.log_prob are applied once per canvas
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-          const float d = xo[j] - __fmul_rn(acc[j], mult);
-          rec = fmaf(d, d, rec);
+          const float dd = xo[j] - __fmul_rn(acc[j], mult);
+          rec = fmaf(dd, dd, rec);
         }
       }
+      obs += dp;
+      cin += dp;
+      dst += dp;
+      typ += RPP * T;
     }
   }
   return rec;
@@ -743,14 +784,19 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   const int G = h * w;
   float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
   Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);         // [T][W]
-  Tap* s_ty = s_tx + (size_t)T * W;                                                                      // [T][H]
+  Tap* s_ty = s_tx + (size_t)T * W;                                                                      // [H][T]
+  float* s_col = reinterpret_cast<float*>(s_ty + (size_t)T * H);                                         // [T][h][W]
 
   griddep_launch();
   griddep_wait();
+  long long* tr = a.trace ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
+#define PAINT_STAMP(i) do { if (tr && threadIdx.x == 0) tr[i] = (long long)globaltimer_ns(); } while (0)
+  PAINT_STAMP(0);
   // The first n_prior_ctas CTAs of the grid compute the prior terms (one warp per canvas) while the others paint: the
   // latency-bound float64 / log chains hide behind the bandwidth-bound paint CTAs instead of costing a launch.
   if ((int)blockIdx.x < a.n_prior_ctas) {
     prior_terms_warp<T>(a, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), 0);
+    PAINT_STAMP(6);
     return;
   }
   const int b = blockIdx.x - a.n_prior_ctas;
@@ -788,17 +834,28 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
     }
   }
   __syncthreads();
+  PAINT_STAMP(1);
   // inverse-warp tap tables while the copy is in flight: glimpse-space taps of every canvas column / row
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float4 iv = s_inv[t];
     for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
       if (j < W) s_tx[t * W + j] = make_tap(inv_coord_s(iv.x, iv.z, j, a.step_W, w), w, 1);
-      else       s_ty[t * H + (j - W)] = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, w);
+      else {
+        Tap tp = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, W);
+        const bool live = (s_pres[t] != 0.f) & ((tp.wf != 0.f) | (tp.wc != 0.f));
+        const int col0 = (int)smem_u32(s_col) + t * h * W * 4;   // shared-window address of step t's slab
+        tp.i_f = live ? col0 + tp.i_f * 4 : -1;
+        tp.i_c = col0 + tp.i_c * 4;
+        s_ty[(j - W) * T + t] = tp;
+      }
     }
   }
   __syncthreads();
+  PAINT_STAMP(2);
   if (bulk) mbar_wait(&bar, 0);
+  PAINT_STAMP(3);
+  paint_columns<T>(a, s_gl, s_tx, s_pres, s_col);
 
   // optional visualisation output: presence * sigmoid(glimpse)   (model.py:90)
   if (a.glimpse_viz) {
@@ -813,9 +870,18 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   // column pairs need an even row pitch and 8-byte aligned rows
   const bool pair = ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.canvas) & 7) == 0) &&
                     ((reinterpret_cast<uintptr_t>(a.canvas_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.img) & 7) == 0);
-  float rec = pair ? paint_rows<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
+  __syncthreads();
+  PAINT_STAMP(4);
+  float rec = pair ? paint_rows<T, 2>(a, b, s_ty) : paint_rows<T, 1>(a, b, s_ty);
+  PAINT_STAMP(5);
   if (!a.do_elbo) return;
   rec = block_sum(rec, s_red);
+  PAINT_STAMP(6);
+  if (tr && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[7] = smid;
+  }
   // sum_px 0.5 ((x - mu) / sigma)^2 + (log sigma + 0.5 log 2 pi); elbo_scalars_kernel adds the prior part
   if (threadIdx.x == 0)
     a.rec_loss_per_sample[b] = fmaf(__fmul_rn(0.5f * a.inv_sigma, a.inv_sigma), rec, __fmul_rn((float)(H * W), a.lp_const));
@@ -833,6 +899,7 @@ inline void fill_elbo_consts(ElboArgs& a) {
   a.inv_sigma = 1.0f / a.output_std;
   a.step_W = a.W > 1 ? 2.0 / (double)(a.W - 1) : 0.0;
   a.step_H = a.H > 1 ? 2.0 / (double)(a.H - 1) : 0.0;
+  a.t_stride = (long long)a.B * a.H * a.W;
 }
 // prior terms (when a prior is given) followed by paint + reconstruction term
 inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {

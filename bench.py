@@ -200,6 +200,10 @@ def workload_config(args, n):
             "max_steps": sh["T"], "particles": K,
             "outputs": "all 10 AIRCell outputs materialised [T,B,.] fp32 + per-sample ELBO terms",
             "parallelism": f"dp{n}", "precision": args.precision,
+            "streams": (args.streams if conf["mode"] != "train" else 1),
+            "batches_in_flight": (f"{args.streams} independent batches of {args.batch} canvases, one per CUDA stream / handle "
+                                  "(EnginePool); every step is one full pass over one batch"
+                                  if conf["mode"] != "train" and args.streams > 1 else "one batch at a time"),
             "weights": ("updated every step (the tensor-core operand arena is rebuilt from the fp32 parameters each pass)"
                         if conf["mode"] == "train" else
                         "constant over the timed loop; tensor-core operand arena prepared once (air_cache_weights)"),
@@ -345,13 +349,17 @@ def run_native(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n_steps):
-        """exactly n_steps timed calls of fn(i): device time by CUDA events on the launching stream, max over ranks."""
+    def timed(fn, n_steps, join=None):
+        """exactly n_steps timed calls of fn(i): device time by CUDA events on the launching stream, max over ranks.
+        ``join`` makes the launching stream wait for the side streams the steps ran on (EnginePool) before the closing event;
+        every such stream starts by waiting for the launching stream, i.e. for the opening event."""
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(n_steps):
             fn(i)
+        if join is not None:
+            join()
         ev1.record()
         barrier()
         return _max_over_ranks(ev0.elapsed_time(ev1), dist, dev)
@@ -368,59 +376,74 @@ def run_native(args, rank, local_rank, world):
 
     # =====================================================================================================
     if mode in ("forward", "iwae"):
-        eng = air.Engine(cfg, R, T, device=dev)
-        eng.cache_weights(True)    # forward-only loop with constant parameters: the fp16-split weight arena is built once
+        # Independent batches are enqueued round-robin on args.streams engines / CUDA streams (EnginePool): every step is
+        # still one full pass over one batch of R rows, but kernels of neighbouring batches may co-run.  --streams 1 is the
+        # one-batch-at-a-time latency figure, also measured below and reported as "single_stream".
+        pool = air.EnginePool(cfg, R, T, n_streams=args.streams, device=dev)
+        pool.cache_weights(True)   # forward-only loop with constant parameters: the fp16-split weight arena is built once
+        eng = pool.engines[0]
         params, _ = _init_flat(air.param_spec(cfg), dev, seed=0)
         pending = [None]
 
         def step(i):
             img, ew, ea, u = sets[i % len(sets)]
-            out = eng.forward(params, img, ew, ea, u, prior)
-            if K > 1:
-                eng.iwae_bound(K, prior)
-            if dist is not None:
-                # the only cross-rank exchange of forward+ELBO: 16 floats.  Issued on NCCL's stream from a copy of the
-                # block and joined one step late, so its ~30 us latency never sits between two kernels of the pass.
-                if pending[0] is not None:
-                    pending[0][0].wait()
-                buf = out["scalars"].clone()
-                pending[0] = (dist.all_reduce(buf, async_op=True), buf)
+            with pool.next() as e:
+                out = e.forward(params, img, ew, ea, u, prior)
+                if K > 1:
+                    e.iwae_bound(K, prior)
+                if dist is not None:
+                    # the only cross-rank exchange of forward+ELBO: 16 floats.  Issued on NCCL's stream from a copy of the
+                    # block and joined one step late, so its ~30 us latency never sits between two kernels of the pass.
+                    if pending[0] is not None:
+                        pending[0][0].wait()
+                    buf = out["scalars"].clone()
+                    pending[0] = (dist.all_reduce(buf, async_op=True), buf)
             return out
 
-        for i in range(max(args.warmup, 3)):
+        def step_single(i):
+            img, ew, ea, u = sets[i % len(sets)]
+            eng.forward(params, img, ew, ea, u, prior)
+            if K > 1:
+                eng.iwae_bound(K, prior)
+
+        for i in range(max(args.warmup, 3) * len(pool)):
             step(i)
+        pool.join()
         barrier()
-        launches0 = eng.launch_count
+        launches0 = sum(e.launch_count for e in pool.engines)
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
         t_wall0 = time.time()
-        ms = timed(step, args.steps)
+        ms = timed(step, args.steps, join=pool.join)
         if pending[0] is not None:
             pending[0][0].wait()
         t_wall1 = time.time()
-        launches = eng.launch_count - launches0
+        launches = sum(e.launch_count for e in pool.engines) - launches0
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
         value = world * R * T * args.steps / (ms * 1e-3)
         elbo = -float(eng.scalar("loss"))
+        if len(pool) > 1:
+            n1 = max(50, args.steps // 4)
+            for i in range(3):
+                step_single(i)
+            ms1 = timed(step_single, n1)
+            extra["single_stream"] = {"ms_per_step": ms1 / n1, "value": world * R * T * n1 / (ms1 * 1e-3), "steps": n1,
+                                      "note": "one batch at a time on one stream (latency of a pass); the headline value "
+                                              f"keeps {len(pool)} independent batches in flight on {len(pool)} streams"}
 
         # ---- end to end through the C ABI with HOST buffers (uint8 images in, loss out, every step) ----------
         scal2 = [torch.empty(air._lib.AIR_N_SCALARS).pin_memory() for _ in range(2)]
         lps2 = [torch.empty(R).pin_memory() for _ in range(2)]
         if K == 1:
             def run_fed(n):
-                acc_ = 0.0
-                eng.feed_host_u8(0, host_u8[0])
-                for i in range(n):
-                    if i + 1 < n:
-                        eng.feed_host_u8((i + 1) % 2, host_u8[(i + 1) % len(host_u8)])
-                    eng.forward_fed_u8_rng(params, i % 2, 1000 + i, prior, scal2[i % 2], lps2[i % 2])
-                    if i >= 1:
-                        eng.feed_wait((i - 1) % 2)
-                        acc_ += float(scal2[(i - 1) % 2][0])          # the host reads every step's loss
-                eng.feed_wait((n - 1) % 2)
-                return acc_ + float(scal2[(n - 1) % 2][0])
-            run_fed(4)
+                acc_, n_out = 0.0, 0
+                for scal_h, lps_h in pool.stream_host_u8(params, (host_u8[i % len(host_u8)] for i in range(n)), prior, 1000):
+                    acc_ += float(scal_h[0])                          # the host reads every step's loss
+                    n_out += 1
+                assert n_out == n
+                return acc_
+            run_fed(4 * len(pool))
             barrier()
             t0 = time.perf_counter()
             run_fed(args.steps)
@@ -440,9 +463,10 @@ def run_native(args, rank, local_rank, world):
             d2h = (scal2[0].numel() + lps2[0].numel()) * 4
             e2e = {"value": world * R * T * args.steps / (fed_ms * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": host_u8[0].numel(), "d2h_bytes_per_step": d2h, "ms_per_step": fed_ms / args.steps,
-                   "api": "air_feed_host_u8 + air_forward_fed_u8_rng + air_feed_wait (double-buffered feed: pinned host uint8 "
-                          "images in on a copy stream while the previous batch is processed, in-library Philox noise, loss "
-                          "scalars + per-sample loss out and read on the host every step; host wall clock)",
+                   "api": "EnginePool.stream_host_u8 = air_feed_host_u8 + air_forward_fed_u8_rng + air_feed_wait per batch, "
+                          f"round-robin over {len(pool)} handles / streams (double-buffered feed per handle: pinned host uint8 "
+                          "images in on a copy stream while earlier batches are processed, in-library Philox noise, loss "
+                          "scalars + per-sample loss out and read on the host every step, in order; host wall clock)",
                    "synchronous": {"value": world * R * T * args.steps / (sync_ms * 1e-3), "ms_per_step": sync_ms / args.steps,
                                    "h2d_bytes_per_step": host_u8[0].numel(),
                                    "api": "air_forward_host_u8_rng (copy in, pass, copy out, host synchronisation, one call "
@@ -527,7 +551,7 @@ def run_native(args, rank, local_rank, world):
         if mode == "forward" and not args.no_train:
             extra["train_step"] = kernel_train_loop(air, cfg, prec, R, T, dev, sets, params, prior, world, dist, barrier,
                                                     max(20, args.steps // 5))
-        eng.close()
+        pool.close()
 
     # =====================================================================================================
     else:   # mode == "train": the reference's train step through the public API
@@ -686,6 +710,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="canvases per GPU (default: the configuration's)")
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc"])
     ap.add_argument("--input-sets", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=3,
+                    help="forward / IWAE configs: independent batches in flight (EnginePool); 1 = one pass at a time")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
     if args.batch is None:

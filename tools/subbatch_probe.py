@@ -12,8 +12,9 @@ cfg = air.CellConfig(precision=air.AIR_PREC_TC_SPLIT)
 T, Btot = 3, 4096
 params, _ = _init_flat(air.param_spec(cfg), dev, seed=0)
 prior = air.make_prior(dict(loc=0., scale=1.), dict(loc=0., scale=1.), dict(loc=0., scale=1.), 0.5, True)
-for S in (1, 2, 4):
-    B = Btot // S
+full = len(sys.argv) > 1 and sys.argv[1] == "full"     # full: S engines of 4096 canvases each (two batches in flight)
+for S in ((1, 2, 3, 4, 6, 8) if full else (1, 2, 4)):
+    B = Btot if full else Btot // S
     engs = [air.Engine(cfg, B, T, device=dev) for _ in range(S)]
     for e in engs:
         e.cache_weights(True)
@@ -38,6 +39,13 @@ for S in (1, 2, 4):
         torch.cuda.current_stream().wait_stream(st)
     ev1.record()
     torch.cuda.synchronize()
-    print(f"S={S} x B={B}: {ev0.elapsed_time(ev1) / n:.4f} ms per 4096 canvases")
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    host = (time.perf_counter() - t0) / n / (S if full else 1)
+    torch.cuda.synchronize()
+    print(f"S={S} x B={B}: {ev0.elapsed_time(ev1) / n / (S if full else 1):.4f} ms per 4096 canvases (host enqueue {host * 1e3:.4f} ms)")
     for e in engs:
         e.close()
