@@ -484,18 +484,28 @@ __device__ __forceinline__ float tabular_kl_entry(float p, double q, double zero
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Per-canvas prior terms (model.py:126-216, prior.py:62-90,148-151).  One WARP per canvas, no shared memory:
+// Per-canvas prior terms (model.py:126-216, prior.py:62-90,148-151).  A group of L = 8 lanes per canvas (four canvases
+// per warp), no shared memory:
 //   q(n) (float64 island, lane k owns n = k), KL(q(n) || prior), log q(n_b), the per-step weights,
-//   KL(what) (lanes over the na latents, one warp reduction per step), KL(where).
+//   KL(what) (lanes over the na latents, one group reduction per step), KL(where) (lane t owns step t).
+// (Round 1 used a whole warp per canvas; most of the work is scalar per canvas, so 31 lanes replayed it: 1560 warp
+// instructions per canvas, 15 % of the paint grid's issue slots.  One THREAD per canvas needs the fewest instructions
+// but its dependent chain -- 150 KL terms with two IEEE divisions and a log each -- runs for 100 us.)
 // Runs inside the paint grid (its leading CTAs) and leaves prior_weight * prior_per_sample in prior_part[b];
 // elbo_scalars_kernel adds the reconstruction term on top (Loss.add, ops.py:12-29).  `finalize` != 0 (air_prior_terms,
 // stand-alone kernel): there is no canvas, the reconstruction term is exactly 0 and loss_per_sample is complete.
 // ---------------------------------------------------------------------------------------------------
+// lanes of a warp that share one canvas: T + 1 <= L (lane k owns n = k)
 template <int T>
-__device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int finalize) {
+struct PriorGroup { static constexpr int L = (T + 1 <= 8) ? 8 : 16; };
+
+template <int T>
+__device__ __forceinline__ void prior_terms_group(const ElboArgs& a, int b_in, int finalize) {
+  constexpr int L = PriorGroup<T>::L;
   const int B = a.B;
-  const int lane = threadIdx.x & 31;
-  if (b >= B) return;
+  const int lane = threadIdx.x & (L - 1);
+  const bool valid = b_in < B;             // every lane of the warp takes part in the shuffles; only valid groups store
+  const int b = valid ? b_in : B - 1;
   const air_prior& pr = a.prior;
   float pp[T], pz[T];   // presence_prob / presence of this canvas
   if (a.scan.logit) {
@@ -528,20 +538,20 @@ __device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int f
   }
   double sum = pi;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   float q = 0.f, kl = 0.f;
   if (k <= T) {
     q = (float)(pi / sum);
     kl = tabular_kl_entry(q, a.steps_prior[k], 0.0);
-    a.num_steps_posterior[(size_t)b * (T + 1) + k] = q;
+    if (valid) a.num_steps_posterior[(size_t)b * (T + 1) + k] = q;
   }
   float kl_n = 0.f;   // fp32 sum over n in index order (model.py:149)
   float qs[T + 1];
 #pragma unroll
   for (int j = 0; j <= T; ++j) {
-    const float v = __shfl_sync(0xffffffffu, kl, j);
+    const float v = __shfl_sync(0xffffffffu, kl, j, L);
     kl_n = (j == 0) ? v : __fadd_rn(kl_n, v);
-    qs[j] = __shfl_sync(0xffffffffu, q, j);
+    qs[j] = __shfl_sync(0xffffffffu, q, j, L);
   }
   // KL(what) per step (model.py:174-186): lanes over the latents
   float klw[T];
@@ -549,9 +559,11 @@ __device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int f
   for (int t = 0; t < T; ++t) {
     float v = 0.f;
     const size_t base = ((size_t)t * B + b) * a.na;
-    for (int i = lane; i < a.na; i += 32)
+    for (int i = lane; i < a.na; i += L)
       v += normal_kl(a.what_loc[base + i], a.what_scale[base + i], pr.what_loc, pr.what_scale);
-    klw[t] = warp_sum(v);
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    klw[t] = v;
   }
   // KL(where) per step (model.py:188-214): lane t owns step t; (sx, sy) vs scale prior, (tx, ty) vs shift prior
   float klwh_l = 0.f;
@@ -569,10 +581,10 @@ __device__ __forceinline__ void prior_terms_warp(const ElboArgs& a, int b, int f
   float klwh[T], pres[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    klwh[t] = __shfl_sync(0xffffffffu, klwh_l, t);
+    klwh[t] = __shfl_sync(0xffffffffu, klwh_l, t, L);
     pres[t] = pz[t];
   }
-  if (lane != 0) return;
+  if (lane != 0 || !valid) return;
   a.kl_num_steps_per_sample[b] = kl_n;
   float n = 0.f;
 #pragma unroll
@@ -622,11 +634,12 @@ template <int T>
 __global__ void __launch_bounds__(128) prior_terms_kernel(ElboArgs a, int finalize) {
   griddep_launch();
   griddep_wait();
-  prior_terms_warp<T>(a, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), finalize);
+  prior_terms_group<T>(a, (int)((blockIdx.x * blockDim.x + threadIdx.x) / PriorGroup<T>::L), finalize);
 }
 
 inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStream_t st) {
-  const dim3 grid((a.B + 3) / 4), block(128);
+  const int L = (a.T + 1 <= 8) ? 8 : 16;       // PriorGroup<T>::L
+  const dim3 grid((a.B * L + 127) / 128), block(128);
   switch (a.T) {
     case 1: return launch_k(prior_terms_kernel<1>, grid, block, 0, st, a, finalize);
     case 2: return launch_k(prior_terms_kernel<2>, grid, block, 0, st, a, finalize);
@@ -666,6 +679,13 @@ __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) 
 #ifndef PAINT_MIN_CTAS
 #define PAINT_MIN_CTAS 8
 #endif
+// q = n / d, r = n % d for 0 <= n < 2048, 1 <= d <= 2048 without the ~25-instruction integer division: (n + 0.5) / d is at
+// least 0.5 / d away from an integer, far more than the rounding of the float product
+__device__ __forceinline__ void small_divmod(int n, int d, int& q, int& r) {
+  q = (int)(((float)n + 0.5f) * __frcp_rn((float)d));
+  r = n - q * d;
+}
+
 // column pass: s_col[t][i][c] for every glimpse row i and canvas column c (zero outside the footprint / absent steps)
 template <int T>
 __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __restrict__ s_gl,
@@ -675,7 +695,8 @@ __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __
   const int NT = blockDim.x;
   const int CP = W < NT ? W : NT;               // columns resident in one sweep
   const int RG = NT / CP;                       // glimpse rows per sweep
-  const int cslot = (int)threadIdx.x % CP, islot = (int)threadIdx.x / CP;
+  int cslot, islot;
+  small_divmod((int)threadIdx.x, CP, islot, cslot);
   if (islot >= RG) return;
   for (int c = cslot; c < W; c += CP) {
 #pragma unroll
@@ -683,7 +704,8 @@ __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __
       const float pres = s_pres[t];
       if (pres == 0.f) continue;                // the row pass skips absent steps as well
       const Tap tx = s_tx[t * W + c];
-      const float wf = __fmul_rn(pres, tx.wf), wc = __fmul_rn(pres, tx.wc);
+      const float pm = __fmul_rn(pres, a.output_multiplier);   // the row pass accumulates multiplier * canvas
+      const float wf = __fmul_rn(pm, tx.wf), wc = __fmul_rn(pm, tx.wc);
       const float* g = s_gl + t * h * w;
       float* dst = s_col + (size_t)t * h * W + c;
       for (int i = islot; i < h; i += RG)
@@ -712,7 +734,8 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
   const int TPR = W / CPT;                      // threads per row
   const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
   const int RPP = NT / TPRB;                    // rows per pass
-  const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
+  int cslot, rslot;
+  small_divmod((int)threadIdx.x, TPRB, rslot, cslot);
   const float mult = a.output_multiplier;
   const bool do_elbo = a.do_elbo != 0;
   const bool has_cin = a.canvas_in != nullptr, has_dst = a.canvas != nullptr;
@@ -733,10 +756,10 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
       if (CPT == 2) {
         const float2 ci = has_cin ? *reinterpret_cast<const float2*>(cin) : make_float2(0.f, 0.f);
         const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs) : make_float2(0.f, 0.f);
-        acc[0] = ci.x; acc[CPT - 1] = ci.y;
+        acc[0] = __fmul_rn(ci.x, mult); acc[CPT - 1] = __fmul_rn(ci.y, mult);
         xo[0] = xv.x; xo[CPT - 1] = xv.y;
       } else {
-        acc[0] = has_cin ? cin[0] : 0.f;
+        acc[0] = has_cin ? __fmul_rn(cin[0], mult) : 0.f;
         xo[0] = do_elbo ? obs[0] : 0.f;
       }
       float* d = dst;
@@ -753,15 +776,15 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
           }
         }
         if (has_dst) {
-          if (CPT == 2) *reinterpret_cast<float2*>(d) = make_float2(__fmul_rn(acc[0], mult), __fmul_rn(acc[CPT - 1], mult));
-          else          d[0] = __fmul_rn(acc[0], mult);
+          if (CPT == 2) *reinterpret_cast<float2*>(d) = make_float2(acc[0], acc[CPT - 1]);
+          else          d[0] = acc[0];
           d += tstride;
         }
       }
       if (do_elbo) {   // sum of squared residuals; the constants of Normal.log_prob are applied once per canvas
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-          const float dd = xo[j] - __fmul_rn(acc[j], mult);
+          const float dd = xo[j] - acc[j];
           rec = fmaf(dd, dd, rec);
         }
       }
@@ -792,10 +815,10 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   long long* tr = a.trace ? a.trace + (size_t)blockIdx.x * 8 : nullptr;
 #define PAINT_STAMP(i) do { if (tr && threadIdx.x == 0) tr[i] = (long long)globaltimer_ns(); } while (0)
   PAINT_STAMP(0);
-  // The first n_prior_ctas CTAs of the grid compute the prior terms (one warp per canvas) while the others paint: the
-  // latency-bound float64 / log chains hide behind the bandwidth-bound paint CTAs instead of costing a launch.
+  // The first n_prior_ctas CTAs of the grid compute the prior terms (8 lanes per canvas) while the others paint: the
+  // latency-bound float64 / log chains hide behind the paint CTAs instead of costing a launch.
   if ((int)blockIdx.x < a.n_prior_ctas) {
-    prior_terms_warp<T>(a, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), 0);
+    prior_terms_group<T>(a, (int)((blockIdx.x * blockDim.x + threadIdx.x) / PriorGroup<T>::L), 0);
     PAINT_STAMP(6);
     return;
   }
@@ -859,11 +882,24 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
 
   // optional visualisation output: presence * sigmoid(glimpse)   (model.py:90)
   if (a.glimpse_viz) {
+    if (((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.glimpse_viz) & 15) == 0) && T * (G >> 2) < 2048) {
+      const int G4 = G >> 2;                       // 16-byte pieces, all T glimpses in one flat loop
+      for (int i = threadIdx.x; i < T * G4; i += blockDim.x) {
+        int t, g;
+        small_divmod(i, G4, t, g);
+        const float pres_t = s_pres[t];
+        float4 v = reinterpret_cast<const float4*>(s_gl)[i];
+        v.x = __fmul_rn(pres_t, sigmoid_fast(v.x)); v.y = __fmul_rn(pres_t, sigmoid_fast(v.y));
+        v.z = __fmul_rn(pres_t, sigmoid_fast(v.z)); v.w = __fmul_rn(pres_t, sigmoid_fast(v.w));
+        reinterpret_cast<float4*>(a.glimpse_viz + ((size_t)t * B + b) * G)[g] = v;
+      }
+    } else {
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      float* dst = a.glimpse_viz + ((size_t)t * B + b) * G;
-      const float pres_t = s_pres[t];
-      for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = __fmul_rn(pres_t, sigmoid_fast(s_gl[t * G + g]));
+      for (int t = 0; t < T; ++t) {
+        float* dst = a.glimpse_viz + ((size_t)t * B + b) * G;
+        const float pres_t = s_pres[t];
+        for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = __fmul_rn(pres_t, sigmoid_fast(s_gl[t * G + g]));
+      }
     }
   }
 
@@ -905,8 +941,8 @@ inline void fill_elbo_consts(ElboArgs& a) {
 inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
   fill_elbo_consts(a);
   static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
-  const int wpc = nt / 32;                          // warps per CTA, one canvas per warp
-  a.n_prior_ctas = a.do_elbo ? (a.B + wpc - 1) / wpc : 0;
+  const int cpc = nt / ((a.T + 1 <= 8) ? 8 : 16);   // canvases per prior CTA (PriorGroup<T>::L lanes each)
+  a.n_prior_ctas = a.do_elbo ? (a.B + cpc - 1) / cpc : 0;
   const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);
   switch (a.T) {
     case 1: return launch_paint_elbo_t<1>(a, smem, st);
