@@ -435,6 +435,8 @@ struct ElboArgs {
   float* prior_part;           // [B] scratch: prior_weight * prior_per_sample (prior CTAs -> elbo_scalars_kernel)
   int n_prior_ctas;            // leading CTAs of the paint grid that compute the prior terms (launch_paint_elbo)
   long long t_stride;          // B * H * W: elements between the canvases of consecutive steps (host)
+  int col_cp, col_rg;          // column pass: columns resident in one sweep min(W, threads), glimpse rows per sweep (host)
+  int row_tprb, row_rpp;       // row pass: threads per canvas row resident in one pass, rows per pass (host)
   long long* trace;            // debug (AIR_PAINT_TRACE): 8 stamps per CTA (globaltimer ns at the phase boundaries, SM id)
   PresenceArgs scan;           // scan.logit != null: presence / presence_prob are not inputs -- this grid runs the presence scan
                                // itself (the fused row kernel has no per-canvas CTA to do it): the paint CTA of a canvas
@@ -686,18 +688,24 @@ __device__ __forceinline__ void small_divmod(int n, int d, int& q, int& r) {
   r = n - q * d;
 }
 
+// column pairs in the row pass need an even row pitch and 8-byte aligned rows
+__host__ __device__ inline bool paint_pairs(const ElboArgs& a) {
+  return ((a.W & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.canvas) & 7) == 0) &&
+         ((reinterpret_cast<uintptr_t>(a.canvas_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.img) & 7) == 0);
+}
+
 // column pass: s_col[t][i][c] for every glimpse row i and canvas column c (zero outside the footprint / absent steps)
 template <int T>
 __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __restrict__ s_gl,
                                               const Tap* __restrict__ s_tx, const float* __restrict__ s_pres,
                                               float* __restrict__ s_col) {
   const int W = a.W, h = a.h, w = a.w;
-  const int NT = blockDim.x;
-  const int CP = W < NT ? W : NT;               // columns resident in one sweep
-  const int RG = NT / CP;                       // glimpse rows per sweep
+  const int CP = a.col_cp;                      // columns resident in one sweep
+  const int RG = a.col_rg;                      // glimpse rows per sweep
   int cslot, islot;
   small_divmod((int)threadIdx.x, CP, islot, cslot);
   if (islot >= RG) return;
+#pragma unroll 1
   for (int c = cslot; c < W; c += CP) {
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -708,6 +716,7 @@ __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __
       const float wf = __fmul_rn(pm, tx.wf), wc = __fmul_rn(pm, tx.wc);
       const float* g = s_gl + t * h * w;
       float* dst = s_col + (size_t)t * h * W + c;
+#pragma unroll 1
       for (int i = islot; i < h; i += RG)
         dst[i * W] = fmaf(wc, g[i * w + tx.i_c], __fmul_rn(wf, g[i * w + tx.i_f]));
     }
@@ -730,10 +739,8 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 template <int T, int CPT>
 __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap* __restrict__ s_ty) {
   const int H = a.H, W = a.W;
-  const int NT = blockDim.x;
-  const int TPR = W / CPT;                      // threads per row
-  const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
-  const int RPP = NT / TPRB;                    // rows per pass
+  const int TPRB = a.row_tprb;                  // threads per row (W / CPT) resident in one pass
+  const int RPP = a.row_rpp;                    // rows per pass
   int cslot, rslot;
   small_divmod((int)threadIdx.x, TPRB, rslot, cslot);
   const float mult = a.output_multiplier;
@@ -744,6 +751,7 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
   const int dp = RPP * W;
   float rec = 0.f;
   if (rslot >= RPP) return rec;
+#pragma unroll 1
   for (int c = cslot * CPT; c < W; c += TPRB * CPT) {
     const uint32_t c4 = (uint32_t)c * 4u;
     const Tap* typ = s_ty + rslot * T;
@@ -751,16 +759,33 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
     const float* obs = a.img + off;
     const float* cin = a.canvas_in + off;        // only dereferenced when has_cin / has_dst
     float* dst = a.canvas + off;
+    // the observation of the NEXT row is fetched one iteration ahead (its latency would otherwise sit in front of the
+    // residual at the end of every iteration)
+    float xn[CPT];
+    if (CPT == 2) {
+      const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs) : make_float2(0.f, 0.f);
+      xn[0] = xv.x; xn[CPT - 1] = xv.y;
+    } else {
+      xn[0] = do_elbo ? obs[0] : 0.f;
+    }
+#pragma unroll 1
     for (int r = rslot; r < H; r += RPP) {
       float acc[CPT], xo[CPT];
+      xo[0] = xn[0]; xo[CPT - 1] = xn[CPT - 1];
+      obs += dp;
+      if (do_elbo && r + RPP < H) {
+        if (CPT == 2) {
+          const float2 xv = *reinterpret_cast<const float2*>(obs);
+          xn[0] = xv.x; xn[CPT - 1] = xv.y;
+        } else {
+          xn[0] = obs[0];
+        }
+      }
       if (CPT == 2) {
         const float2 ci = has_cin ? *reinterpret_cast<const float2*>(cin) : make_float2(0.f, 0.f);
-        const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs) : make_float2(0.f, 0.f);
         acc[0] = __fmul_rn(ci.x, mult); acc[CPT - 1] = __fmul_rn(ci.y, mult);
-        xo[0] = xv.x; xo[CPT - 1] = xv.y;
       } else {
         acc[0] = has_cin ? __fmul_rn(cin[0], mult) : 0.f;
-        xo[0] = do_elbo ? obs[0] : 0.f;
       }
       float* d = dst;
 #pragma unroll
@@ -788,7 +813,6 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
           rec = fmaf(dd, dd, rec);
         }
       }
-      obs += dp;
       cin += dp;
       dst += dp;
       typ += RPP * T;
@@ -889,8 +913,8 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
         small_divmod(i, G4, t, g);
         const float pres_t = s_pres[t];
         float4 v = reinterpret_cast<const float4*>(s_gl)[i];
-        v.x = __fmul_rn(pres_t, sigmoid_fast(v.x)); v.y = __fmul_rn(pres_t, sigmoid_fast(v.y));
-        v.z = __fmul_rn(pres_t, sigmoid_fast(v.z)); v.w = __fmul_rn(pres_t, sigmoid_fast(v.w));
+        v.x = __fmul_rn(pres_t, sigmoid_lean(v.x)); v.y = __fmul_rn(pres_t, sigmoid_lean(v.y));
+        v.z = __fmul_rn(pres_t, sigmoid_lean(v.z)); v.w = __fmul_rn(pres_t, sigmoid_lean(v.w));
         reinterpret_cast<float4*>(a.glimpse_viz + ((size_t)t * B + b) * G)[g] = v;
       }
     } else {
@@ -898,14 +922,12 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
       for (int t = 0; t < T; ++t) {
         float* dst = a.glimpse_viz + ((size_t)t * B + b) * G;
         const float pres_t = s_pres[t];
-        for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = __fmul_rn(pres_t, sigmoid_fast(s_gl[t * G + g]));
+        for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = __fmul_rn(pres_t, sigmoid_lean(s_gl[t * G + g]));
       }
     }
   }
 
-  // column pairs need an even row pitch and 8-byte aligned rows
-  const bool pair = ((W & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.canvas) & 7) == 0) &&
-                    ((reinterpret_cast<uintptr_t>(a.canvas_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.img) & 7) == 0);
+  const bool pair = paint_pairs(a);
   __syncthreads();
   PAINT_STAMP(4);
   float rec = pair ? paint_rows<T, 2>(a, b, s_ty) : paint_rows<T, 1>(a, b, s_ty);
@@ -941,6 +963,13 @@ inline void fill_elbo_consts(ElboArgs& a) {
 inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
   fill_elbo_consts(a);
   static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
+  // loop shapes of the two passes (integer divisions the kernel would otherwise do per thread)
+  const bool pair = paint_pairs(a);
+  const int tpr = pair ? a.W / 2 : a.W;
+  a.col_cp = a.W < nt ? a.W : nt;
+  a.col_rg = nt / a.col_cp;
+  a.row_tprb = tpr < nt ? tpr : nt;
+  a.row_rpp = nt / a.row_tprb;
   const int cpc = nt / ((a.T + 1 <= 8) ? 8 : 16);   // canvases per prior CTA (PriorGroup<T>::L lanes each)
   a.n_prior_ctas = a.do_elbo ? (a.B + cpc - 1) / cpc : 0;
   const size_t smem = paint_smem(a.T, a.H, a.W, a.h, a.w);

@@ -32,6 +32,14 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 
 // visualisation-only sigmoid (glimpse_viz, model.py:90): ex2.approx + fast division, ~2^-21 relative
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// four instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP; flush-to-zero so no range fix-ups): 1 / (1 + 2^(-x log2 e)), ~3e-7
+// relative; exact limits 0 and 1 at -inf / +inf.  For visualisation outputs.
+__device__ __forceinline__ float sigmoid_lean(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == ACT_ELU ? elu_f(v) : v; }
 
