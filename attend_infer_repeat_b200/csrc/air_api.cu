@@ -86,6 +86,7 @@ struct Buf {
   int nsl = 0;
   size_t plane_t() const { return (size_t)rows_alloc * nsl * 16; }
   air::HlOut hlt_out() const { return air::HlOut{hlt, plane_t(), 0, nsl}; }
+  bool hl_tiled = false;   // as the OUTPUT of dense(): write the hl result into hlt (slice-major tiles) instead of hl
 };
 
 // A weight matrix prepared for the tensor-core engine: W^T, fp16 split of (w * 2^8), [2][N_alloc][Kpad].
@@ -316,6 +317,11 @@ int32_t dense(air_handle* h, const float* params, const Buf& in, int row0, const
   p.out_hl = want_hl ? out.hl : nullptr;
   p.hl_plane = out.plane();
   p.ld_hl = out.kpad;
+  if (want_hl && out.hl_tiled) {   // slice-major tiles [row tile][slice][128][16]: the consumer reads whole 1 KB runs
+    p.out_hl = out.hlt;
+    p.hl_plane = out.plane_t();
+    p.hl_nsl = out.nsl;
+  }
   p.M = M;
   p.N = l.N;
   p.num_k_blocks = w.Kpad / air::tc::BK;
@@ -673,6 +679,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
 
   // 1. e = Encoder(img)   (modules.py:72-76; step-invariant, cell.py:125)
   const bool lstm_fused = tc && h->lstm_ok && !(train && layerwise);
+  // the cluster LSTM reads e as its A operand, thread <-> row: from row-major planes every lane touches its own sector
+  // (measured: 19 k of the kernel's 90 k clocks); the last encoder layer therefore writes slice-major tiles for it
+  const bool e_tiled = lstm_fused && h->e.hlt != nullptr && h->enc.layers.size() > 1;
+  Buf e_out = h->e;
+  e_out.hl_tiled = e_tiled;
   if (enc1) {
     // first layer: split-K cluster kernel straight from the fp32 image (enc_tc.cuh); the remaining layers as before
     const Layer& l0 = h->enc.layers[0];
@@ -705,11 +716,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
       rest.n_hidden = h->enc.n_hidden - 1;
       std::vector<float*> rest_saves;
       if (train) rest_saves.assign(h->sv_enc.begin() + 1, h->sv_enc.end());
-      if ((rc = run_mlp_from(h, params, rest, dst, B, h->e, !tc || train, tc, st,
+      if ((rc = run_mlp_from(h, params, rest, dst, B, e_out, !tc || train, tc, st,
                              train ? &rest_saves : nullptr, /*first_to_ping=*/false)) != AIR_OK)
         return rc;
     }
-  } else if ((rc = run_mlp(h, params, h->enc, x, B, h->e, !tc || train, tc, st,
+  } else if ((rc = run_mlp(h, params, h->enc, x, B, e_out, !tc || train, tc, st,
                            train ? &h->sv_enc : nullptr)) != AIR_OK)
     return rc;
   mark(h, AIR_ST_LSTM, st);
@@ -748,9 +759,10 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     lp.tm_h = h->tcw[h->lstm_h_perm].tm_chain;
     lp.bias = h->bias_arena + h->tcw[h->lstm_x_perm].bias_off;
     lp.e = h->e.f32;
-    lp.e_hl = h->e.hl;            // the encoder's last layer wrote hl planes (tensor-core engine)
-    lp.e_plane = h->e.plane();
+    lp.e_hl = e_tiled ? h->e.hlt : h->e.hl;   // the encoder's last layer wrote hl planes (tensor-core engine)
+    lp.e_plane = e_tiled ? h->e.plane_t() : h->e.plane();
     lp.e_ld = h->e.kpad;
+    lp.e_nsl = e_tiled ? h->e.nsl : 0;
     lp.hs_last_only = train ? 0 : 1;
     lp.n_enc = h->n_enc;
     const bool rows = h_in || train;   // explicit per-canvas state (air_cell_step) or the tiled copy kept for the backward
@@ -876,13 +888,32 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
 
   // 5. where sampling + glimpse read   (cell.py:129-135); the heads launch of the row kernel has sampled `where` already
   static const int read_threads = getenv("AIR_READ_THREADS") ? atoi(getenv("AIR_READ_THREADS")) : air::WHERE_READ_THREADS;
+  static const char* read_trace = getenv("AIR_READ_TRACE");   // debug: 8 stamps per CTA to <prefix>.<seq>.bin
+  long long* rtr = nullptr;
+  if (read_trace) {
+    AIR_CUDA(cudaMalloc(&rtr, sizeof(long long) * 8 * (size_t)B));
+    AIR_CUDA(cudaMemsetAsync(rtr, 0, sizeof(long long) * 8 * (size_t)B, st));
+  }
   AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(read_threads),
                          air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
                          row_heads ? (const float*)nullptr : (const float*)h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
                          (tc && !train) ? nullptr : h->crop.f32,
                          tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
                          c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
-                         c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0, pa));
+                         c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0, pa, rtr));
+  if (read_trace) {
+    std::vector<long long> host((size_t)B * 8);
+    AIR_CUDA(cudaMemcpyAsync(host.data(), rtr, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost, st));
+    AIR_CUDA(cudaStreamSynchronize(st));
+    cudaFree(rtr);
+    const std::string path = std::string(read_trace) + "." + std::to_string(h->trace_seq++) + ".bin";
+    if (FILE* f = fopen(path.c_str(), "wb")) {
+      const int hdr[4] = {B, 0, 8, 0};
+      fwrite(hdr, sizeof(int), 4, f);
+      fwrite(host.data(), sizeof(long long), host.size(), f);
+      fclose(f);
+    }
+  }
   ++h->launches;
   mark(h, AIR_ST_GLIMPSE_ENC, st);
 
@@ -1097,6 +1128,7 @@ void carve_workspace(air_handle* h, Carver& cv) {
     };
     hlt(h->hs, c.nh);
     hlt(h->crop, h->G);
+    if (h->lstm_ok) hlt(h->e, h->n_enc);
     if (h->lstm_ok) {
       h->gx_scr = cv.take<float>((size_t)B_alloc * 4 * c.nh);
       h->hx = cv.take<__half>(2 * 2 * (size_t)B_alloc * c.nh);

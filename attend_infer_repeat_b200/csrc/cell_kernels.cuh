@@ -190,6 +190,15 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, const flo
 // ---------------------------------------------------------------------------------------------------
 // (implemented by presence_scan() below: one thread of each canvas's where_read CTA)
 
+// q = n / d, r = n % d for 0 <= n < 2^20, 1 <= d without the ~25-instruction integer division: the float quotient of
+// (n + 0.5) / d is off by at most one, which the remainder check repairs
+__device__ __forceinline__ void small_divmod(int n, int d, int& q, int& r) {
+  q = (int)(((float)n + 0.5f) * __frcp_rn((float)d));
+  r = n - q * d;
+  if (r < 0) { --q; r += d; }
+  else if (r >= d) { ++q; r -= d; }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // where head + glimpse read.  One CTA per canvas b: the image is staged once in shared memory and all
 // T glimpses of that canvas are cropped from it (the T where-codes depend only on h_t, never on the crop).
@@ -202,7 +211,9 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gates, const flo
 // more, smaller CTAs in flight hide more of it than 8 of 256 did (measured at B = 4096: 35 -> see profiles/r02)
 constexpr int WHERE_READ_THREADS = 128;
 __host__ __device__ inline size_t where_read_smem(int T, int H, int W, int h, int w) {
-  return sizeof(float) * ((size_t)H * W + 4) / 16 * 16 + 16 + sizeof(Tap) * (size_t)T * (w + h);
+  // image + tap tables + (tensor-core engine) the fp16 hi / lo staging of the T glimpses
+  return sizeof(float) * ((size_t)H * W + 4) / 16 * 16 + 16 + sizeof(Tap) * (size_t)T * (w + h) +
+         2 * sizeof(__half) * (size_t)T * h * w;
 }
 
 // presence scan of one canvas, run by one thread of the canvas's where_read CTA
@@ -241,11 +252,13 @@ __global__ void __launch_bounds__(WHERE_READ_THREADS, 2048 / WHERE_READ_THREADS)
 where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_where, const float* __restrict__ img,
                   float* __restrict__ where, float* __restrict__ where_loc, float* __restrict__ where_scale,
                   float* __restrict__ crop, HlOut crop_hl, int T, int B, int H, int W, int h, int w, float max_crop,
-                  float scale_bias, double step_w, double step_h, PresenceArgs pa) {
+                  float scale_bias, double step_w, double step_h, PresenceArgs pa, long long* trace) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_where[AIR_MAX_STEPS][4];
   const int b = blockIdx.x;
+  long long* tr = trace ? trace + (size_t)blockIdx.x * 8 : nullptr;   // debug (AIR_READ_TRACE): phase stamps, ns
+#define READ_STAMP(i) do { if (tr && threadIdx.x == 0) tr[i] = (long long)globaltimer_ns(); } while (0)
   const int P = H * W, G = h * w;
   float* s_img = reinterpret_cast<float*>(smem_raw);
   Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * ((size_t)P + 4) / 16 * 16 + 16));   // [T][w]
@@ -260,6 +273,7 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   griddep_wait();   // m / eps / where come from earlier kernels of the chain -- and so may the image (the uint8 entry
                     // points convert it on this stream; every kernel in between releases its dependents early, so the
                     // prologue is NOT transitively ordered after that producer): the copy starts after the wait
+  READ_STAMP(0);
   if (threadIdx.x == 0 && bulk) {
     mbar_expect_tx(&bar, (uint32_t)P * 4u);
     bulk_g2s(s_img, src, (uint32_t)P * 4u, &bar);
@@ -285,40 +299,51 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   if (!bulk)
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_img[i] = src[i];
   __syncthreads();
+  READ_STAMP(1);
   for (int i = threadIdx.x; i < T * (w + h); i += blockDim.x) {
     const int t = i / (w + h), j = i - t * (w + h);
     if (j < w) s_tx[t * w + j] = make_tap(fwd_coord_s(s_where[t][0], s_where[t][1], j, step_w, W), W, 1);
     else       s_ty[t * h + (j - w)] = make_tap(fwd_coord_s(s_where[t][2], s_where[t][3], j - w, step_h, H), H, W);
   }
   __syncthreads();
+  READ_STAMP(2);
   if (bulk) mbar_wait(&bar, 0);
+  READ_STAMP(3);
   const int NT = blockDim.x;
   if (!crop && crop_hl.p && crop_hl.nsl > 0 && (G & 7) == 0) {
-    // tensor-core engine, fused-chain operand layout: a thread produces 8 consecutive glimpse pixels = one 16-byte
-    // store into the hi plane and one into the lo plane ([row tile of 128][K slice of 16][128 rows][16 fp16])
+    // tensor-core engine, fused-chain operand layout ([row tile of 128][K slice of 16][128 rows][16 fp16]): 16-byte
+    // stores of 8 consecutive glimpse pixels into the hi plane and into the lo plane.  The gather runs with lane <->
+    // glimpse pixel (neighbouring lanes read neighbouring image pixels: few bank conflicts, taps of a row broadcast) and
+    // stages the split halves in shared memory; a second sweep with thread <-> 8-pixel chunk does the global stores.
+    // (Round 1 gathered with thread <-> chunk: half of its shared-memory wavefronts were bank-conflict replays and the
+    // per-thread hi[8] / lo[8] arrays went through local memory.)
+    __half* s_hi = reinterpret_cast<__half*>(s_ty + (size_t)T * h);   // [T][G]
+    __half* s_lo = s_hi + (size_t)T * G;
+    const int TG = T * G;
+    for (int i = threadIdx.x; i < TG; i += NT) {
+      int t, g, r, c;
+      small_divmod(i, G, t, g);
+      small_divmod(g, w, r, c);
+      const Tap tx = s_tx[t * w + c], ty = s_ty[t * h + r];
+      float v = 0.f;
+      if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear_pre(s_img, tx, ty);
+      __half hi, lo;
+      split_f16(v, hi, lo);
+      s_hi[i] = hi;
+      s_lo[i] = lo;
+    }
+    __syncthreads();
     const int chunks = G >> 3;
     for (int i = threadIdx.x; i < T * chunks; i += NT) {
-      const int t = i / chunks, g0 = (i - t * chunks) << 3;
+      int t, ch;
+      small_divmod(i, chunks, t, ch);
+      const int g0 = ch << 3;
       const size_t row = (size_t)t * B + b;
-      const Tap* txs = s_tx + t * w;
-      const Tap* tys = s_ty + t * h;
-      int r = g0 / w, c = g0 - r * w;
-      __align__(16) __half hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const Tap tx = txs[c], ty = tys[r];
-        float v = 0.f;
-        if (((tx.wf != 0.f) | (tx.wc != 0.f)) & ((ty.wf != 0.f) | (ty.wc != 0.f))) v = bilinear_pre(s_img, tx, ty);
-        split_f16(v, hi[j], lo[j]);
-        if (++c == w) {
-          c = 0;
-          ++r;
-        }
-      }
       __half* dst = crop_hl.p + (((row >> 7) * (size_t)crop_hl.nsl + (size_t)(g0 >> 4)) * 128 + (row & 127)) * 16 + (g0 & 15);
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(dst + crop_hl.plane) = *reinterpret_cast<const uint4*>(lo);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(s_hi + t * G + g0);
+      *reinterpret_cast<uint4*>(dst + crop_hl.plane) = *reinterpret_cast<const uint4*>(s_lo + t * G + g0);
     }
+    READ_STAMP(4);
     return;
   }
   const int dr = NT / w, dc = NT - dr * w;
@@ -681,13 +706,6 @@ __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) 
 #ifndef PAINT_MIN_CTAS
 #define PAINT_MIN_CTAS 8
 #endif
-// q = n / d, r = n % d for 0 <= n < 2048, 1 <= d <= 2048 without the ~25-instruction integer division: (n + 0.5) / d is at
-// least 0.5 / d away from an integer, far more than the rounding of the float product
-__device__ __forceinline__ void small_divmod(int n, int d, int& q, int& r) {
-  q = (int)(((float)n + 0.5f) * __frcp_rn((float)d));
-  r = n - q * d;
-}
-
 // column pairs in the row pass need an even row pitch and 8-byte aligned rows
 __host__ __device__ inline bool paint_pairs(const ElboArgs& a) {
   return ((a.W & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.canvas) & 7) == 0) &&

@@ -142,6 +142,7 @@ struct GemmParams {
   __half* out_hl;        // hl buffer of the consumer: hi plane at out_hl, lo plane at out_hl + hl_plane; or null
   size_t hl_plane;       // elements between the hi and the lo plane (rows_alloc * ld_hl)
   int ld_hl;             // Kpad of the consumer
+  int hl_nsl;            // > 0: out_hl is slice-major tiled, [row / 128][hl_nsl slices][128 rows][16] per plane (chain_tc.cuh)
   int M, N;
   int num_k_blocks;      // Kpad / 64
   int a_lo_row;          // row coordinate of the lo plane in the A tensor map (= rows_alloc of A)
@@ -371,7 +372,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               if (n0 + c0 + j < p.N) dst[j] = v[j];
           }
         }
-        if (p.out_hl && n0 + c0 < p.ld_hl) {
+        if (p.out_hl && n0 + c0 < (p.hl_nsl ? p.hl_nsl * 16 : p.ld_hl)) {
           __align__(16) __half hi[16], lo[16];
           if (p.hl_bf16) {
 #pragma unroll
@@ -388,7 +389,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               amax = fmax_nan(amax, fabsf(v[j]));
             }
           }
-          __half* dh = p.out_hl + (size_t)row * p.ld_hl + n0 + c0;
+          __half* dh = p.hl_nsl ? p.out_hl + ((((size_t)row >> 7) * p.hl_nsl + ((n0 + c0) >> 4)) * 128 + (row & 127)) * 16
+                                : p.out_hl + (size_t)row * p.ld_hl + n0 + c0;
           __half* dl = dh + p.hl_plane;
 #pragma unroll
           for (int j = 0; j < 16; j += 8) {

@@ -28,6 +28,7 @@ struct Params {
   const __half* e_hl;     // the same as row-major hl planes [2][rows_alloc][e_ld] (preferred: 16-byte loads, no staging), or null
   size_t e_plane;
   int e_ld;
+  int e_nsl;              // > 0: e_hl is slice-major tiled, [row tile][e_nsl][128 rows][16] per plane (coalesced 1 KB runs)
   int hs_last_only;       // inference: only the last step's fp32 h rows are needed (final_h); the heads read the hl copy
   int n_enc;
   const float* h_init;    // [B, NH] fp32 (row pitch h_init_ld; 0 = one [NH] vector broadcast to every canvas)
@@ -264,12 +265,15 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
       if (p.e_hl) {
         // the encoder's last layer wrote e as hl planes: the packed words are read as they are (four 16-byte loads per
         // slice, all in flight together; the staged fp32 path below cost 11 k clocks of a 96 k kernel)
-        const __half* src = p.e_hl + (size_t)row * p.e_ld;
+        const __half* src = p.e_nsl ? p.e_hl + ((size_t)tile * p.e_nsl * BM + rit) * 16 : p.e_hl + (size_t)row * p.e_ld;
+        const size_t sstride = p.e_nsl ? (size_t)BM * 16 : 16;   // halves between consecutive slices of this row
 #pragma unroll 4
         for (int s = cq; s < nsl; s += 4) {
-          const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(src + s * 16)), h1 = __ldg(reinterpret_cast<const uint4*>(src + s * 16) + 1);
-          const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(src + p.e_plane + s * 16));
-          const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(src + p.e_plane + s * 16) + 1);
+          const uint4* sp = reinterpret_cast<const uint4*>(src + s * sstride);
+          const uint4* lp = reinterpret_cast<const uint4*>(src + p.e_plane + s * sstride);
+          const uint4 h0 = __ldg(sp), h1 = __ldg(sp + 1);
+          const uint4 l0 = __ldg(lp);
+          const uint4 l1 = __ldg(lp + 1);
           const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
           tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);

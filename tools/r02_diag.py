@@ -15,6 +15,7 @@ if trace:
     os.environ["AIR_ROW_TRACE"] = os.path.join(out_dir, "rtrace")
     os.environ["AIR_LSTM_TRACE"] = os.path.join(out_dir, "ltrace")
     os.environ["AIR_PAINT_TRACE"] = os.path.join(out_dir, "ptrace")
+    os.environ["AIR_READ_TRACE"] = os.path.join(out_dir, "wtrace")
 
 import torch  # noqa: E402
 import attend_infer_repeat_b200 as air  # noqa: E402
