@@ -2658,7 +2658,7 @@ int32_t air_stn_paint(const float* glimpse, const float* where, float* out, int3
                       int32_t w, void* stream) {
   if (!glimpse || !where || !out || B < 1 || H < 1 || W < 1 || h < 1 || w < 1)
     return fail(AIR_ERR_ARG, "air_stn_paint: bad argument");
-  const size_t smem = air::paint_smem(1, H, W, h, w);
+  const size_t smem = air::paint_smem_direct(1, H, W, h, w);
   if (smem > 200 * 1024) return fail(AIR_ERR_ARG, "air_stn_paint: glimpse does not fit in shared memory");
   if (smem > 48 * 1024)
     AIR_CUDA(cudaFuncSetAttribute(air::stn_paint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -460,6 +460,7 @@ struct ElboArgs {
   float* prior_part;           // [B] scratch: prior_weight * prior_per_sample (prior CTAs -> elbo_scalars_kernel)
   int n_prior_ctas;            // leading CTAs of the paint grid that compute the prior terms (launch_paint_elbo)
   long long t_stride;          // B * H * W: elements between the canvases of consecutive steps (host)
+  int separable;               // paint_use_separable(T, H, W, h, w) (host)
   int col_cp, col_rg;          // column pass: columns resident in one sweep min(W, threads), glimpse rows per sweep (host)
   int row_tprb, row_rpp;       // row pass: threads per canvas row resident in one pass, rows per pass (host)
   long long* trace;            // debug (AIR_PAINT_TRACE): 8 stamps per CTA (globaltimer ns at the phase boundaries, SM id)
@@ -698,9 +699,22 @@ inline cudaError_t launch_prior_terms(const ElboArgs& a, int finalize, cudaStrea
 // instruction is fully coalesced.
 // dynamic smem: T*G floats (glimpses) + T*(W+H) taps + T*h*W floats (column pass).
 // ---------------------------------------------------------------------------------------------------
+// direct form (large canvases): glimpses + tap tables
+__host__ __device__ inline size_t paint_smem_direct(int T, int H, int W, int h, int w) {
+  return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H);
+}
+// separable form: + the column pass's T*h*W floats
+__host__ __device__ inline size_t paint_smem_separable(int T, int H, int W, int h, int w) {
+  return paint_smem_direct(T, H, W, h, w) + sizeof(float) * (size_t)T * h * W;
+}
+// The separable form needs fewer instructions but T*h*W more floats of shared memory per CTA; it is used while at least six
+// CTAs still fit on an SM (50x50 / 20x20 / T = 3: 21.6 KB).  At 100x100 / 28x28 / T = 5 it would need 88 KB -- two CTAs per
+// SM, measured 191 us against 155 us for the direct form (four bilinear taps per pixel straight from the glimpse).
+__host__ __device__ inline bool paint_use_separable(int T, int H, int W, int h, int w) {
+  return paint_smem_separable(T, H, W, h, w) <= 36 * 1024;
+}
 __host__ __device__ inline size_t paint_smem(int T, int H, int W, int h, int w) {
-  return (sizeof(float) * (size_t)T * h * w + 15) / 16 * 16 + sizeof(Tap) * (size_t)T * (W + H) +
-         sizeof(float) * (size_t)T * h * W;
+  return paint_use_separable(T, H, W, h, w) ? paint_smem_separable(T, H, W, h, w) : paint_smem_direct(T, H, W, h, w);
 }
 
 #ifndef PAINT_MIN_CTAS
@@ -839,6 +853,89 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
   return rec;
 }
 
+// direct form of the row pass (round 1): four taps per pixel from the staged glimpse; s_tx [T][W], s_ty [T][H] with indices
+// pre-multiplied by the glimpse pitch w
+template <int T, int CPT>
+__device__ __forceinline__ float paint_rows_direct(const ElboArgs& a, int b, const float* __restrict__ s_gl,
+                                            const Tap* __restrict__ s_tx, const Tap* __restrict__ s_ty,
+                                            const float* __restrict__ s_pres) {
+  const int B = a.B, H = a.H, W = a.W;
+  const int P = H * W, G = a.h * a.w;
+  const int NT = blockDim.x;
+  const int TPR = W / CPT;                      // threads per row
+  const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
+  const int RPP = NT / TPRB;                    // rows per pass
+  const int cslot = (int)threadIdx.x % TPRB, rslot = (int)threadIdx.x / TPRB;
+  const float mult = a.output_multiplier;
+  const bool do_elbo = a.do_elbo != 0;
+  float pres[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) pres[t] = s_pres[t];
+  const float* cin = a.canvas_in ? a.canvas_in + (size_t)b * P : nullptr;
+  const float* obs = a.img + (size_t)b * P;
+  float* cbase = a.canvas ? a.canvas + (size_t)b * P : nullptr;
+  const size_t tstride = (size_t)B * P;
+  float rec = 0.f;
+  if (rslot >= RPP) return rec;
+  for (int c = cslot * CPT; c < W; c += TPRB * CPT) {
+    // loop-invariant: which (step, column) pairs lie inside the glimpse footprint (and are present at all)
+    uint32_t colmask = 0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (pres[t] != 0.f) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const Tap tx = s_tx[t * W + c + j];
+          if ((tx.wf != 0.f) | (tx.wc != 0.f)) colmask |= 1u << (t * CPT + j);
+        }
+      }
+    }
+    for (int r = rslot; r < H; r += RPP) {
+      const int p = r * W + c;
+      float acc[CPT], xo[CPT];
+      if (CPT == 2) {
+        const float2 ci = cin ? *reinterpret_cast<const float2*>(cin + p) : make_float2(0.f, 0.f);
+        const float2 xv = do_elbo ? *reinterpret_cast<const float2*>(obs + p) : make_float2(0.f, 0.f);
+        acc[0] = ci.x; acc[CPT - 1] = ci.y;
+        xo[0] = xv.x; xo[CPT - 1] = xv.y;
+      } else {
+        acc[0] = cin ? cin[p] : 0.f;
+        xo[0] = do_elbo ? obs[p] : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const uint32_t cm = (colmask >> (t * CPT)) & ((1u << CPT) - 1u);
+        if (cm) {
+          const Tap ty = s_ty[t * H + r];
+          if ((ty.wf != 0.f) | (ty.wc != 0.f)) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              if (cm & (1u << j)) {
+                const Tap tx = s_tx[t * W + c + j];
+                const float v = bilinear_pre(s_gl + t * G, tx, ty);
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(pres[t], v));
+              }
+            }
+          }
+        }
+        if (cbase) {
+          float* dst = cbase + (size_t)t * tstride + p;
+          if (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(__fmul_rn(acc[0], mult), __fmul_rn(acc[CPT - 1], mult));
+          else          dst[0] = __fmul_rn(acc[0], mult);
+        }
+      }
+      if (do_elbo) {   // sum of squared residuals; the constants of Normal.log_prob are applied once per canvas
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const float d = xo[j] - __fmul_rn(acc[j], mult);
+          rec = fmaf(d, d, rec);
+        }
+      }
+    }
+  }
+  return rec;
+}
+
 template <int T>
 __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -906,6 +1003,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
     const float4 iv = s_inv[t];
     for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
       if (j < W) s_tx[t * W + j] = make_tap(inv_coord_s(iv.x, iv.z, j, a.step_W, w), w, 1);
+      else if (!a.separable) s_ty[t * H + (j - W)] = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, w);
       else {
         Tap tp = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, W);
         const bool live = (s_pres[t] != 0.f) & ((tp.wf != 0.f) | (tp.wc != 0.f));
@@ -920,7 +1018,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   PAINT_STAMP(2);
   if (bulk) mbar_wait(&bar, 0);
   PAINT_STAMP(3);
-  paint_columns<T>(a, s_gl, s_tx, s_pres, s_col);
+  if (a.separable) paint_columns<T>(a, s_gl, s_tx, s_pres, s_col);
 
   // optional visualisation output: presence * sigmoid(glimpse)   (model.py:90)
   if (a.glimpse_viz) {
@@ -948,7 +1046,9 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   const bool pair = paint_pairs(a);
   __syncthreads();
   PAINT_STAMP(4);
-  float rec = pair ? paint_rows<T, 2>(a, b, s_ty) : paint_rows<T, 1>(a, b, s_ty);
+  float rec;
+  if (a.separable) rec = pair ? paint_rows<T, 2>(a, b, s_ty) : paint_rows<T, 1>(a, b, s_ty);
+  else rec = pair ? paint_rows_direct<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows_direct<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
   PAINT_STAMP(5);
   if (!a.do_elbo) return;
   rec = block_sum(rec, s_red);
@@ -982,6 +1082,7 @@ inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
   fill_elbo_consts(a);
   static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
   // loop shapes of the two passes (integer divisions the kernel would otherwise do per thread)
+  a.separable = paint_use_separable(a.T, a.H, a.W, a.h, a.w) ? 1 : 0;
   const bool pair = paint_pairs(a);
   const int tpr = pair ? a.W / 2 : a.W;
   a.col_cp = a.W < nt ? a.W : nt;

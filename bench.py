@@ -385,20 +385,47 @@ def run_native(args, rank, local_rank, world):
         params, _ = _init_flat(air.param_spec(cfg), dev, seed=0)
         pending = [None]
 
+        # The only cross-rank exchange of forward + ELBO is 16 floats per step.  The blocks of len(pool) consecutive steps are
+        # copied into one staging tensor and all-reduced together from a stream of their own, so neither the collective's ~30 us
+        # latency nor its join ever sits on a stream that runs passes (two staging tensors alternate; a staging tensor is
+        # rewritten only after the event that follows its previous all-reduce).
+        S_ = len(pool)
+        comm = torch.cuda.Stream(device=dev) if dist is not None else None
+        stage = [torch.zeros(S_, air._lib.AIR_N_SCALARS, device=dev) for _ in range(2)]
+        done = [None, None]          # event after the last all-reduce of each staging tensor
+        evs = []
+
         def step(i):
             img, ew, ea, u = sets[i % len(sets)]
+            j, g = i % S_, (i // S_) % 2
             with pool.next() as e:
                 out = e.forward(params, img, ew, ea, u, prior)
                 if K > 1:
                     e.iwae_bound(K, prior)
                 if dist is not None:
-                    # the only cross-rank exchange of forward+ELBO: 16 floats.  Issued on NCCL's stream from a copy of the
-                    # block and joined one step late, so its ~30 us latency never sits between two kernels of the pass.
+                    if done[g] is not None:
+                        torch.cuda.current_stream().wait_event(done[g])
+                    stage[g][j].copy_(out["scalars"])
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    evs.append(ev)
+            if dist is not None and j == S_ - 1:
+                for ev in evs:
+                    comm.wait_event(ev)
+                evs.clear()
+                with torch.cuda.stream(comm):
                     if pending[0] is not None:
-                        pending[0][0].wait()
-                    buf = out["scalars"].clone()
-                    pending[0] = (dist.all_reduce(buf, async_op=True), buf)
+                        pending[0].wait()
+                    pending[0] = dist.all_reduce(stage[g], async_op=True)
+                    pending[0].wait()                      # the COMM stream waits; the host and the pass streams do not
+                    done[g] = torch.cuda.Event()
+                    done[g].record()
             return out
+
+        def join_all():
+            pool.join()
+            if comm is not None:
+                torch.cuda.current_stream().wait_stream(comm)
 
         def step_single(i):
             img, ew, ea, u = sets[i % len(sets)]
@@ -408,16 +435,14 @@ def run_native(args, rank, local_rank, world):
 
         for i in range(max(args.warmup, 3) * len(pool)):
             step(i)
-        pool.join()
+        join_all()
         barrier()
         launches0 = sum(e.launch_count for e in pool.engines)
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
         t_wall0 = time.time()
-        ms = timed(step, args.steps, join=pool.join)
-        if pending[0] is not None:
-            pending[0][0].wait()
+        ms = timed(step, args.steps, join=join_all)
         t_wall1 = time.time()
         launches = sum(e.launch_count for e in pool.engines) - launches0
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
