@@ -461,6 +461,7 @@ struct ElboArgs {
   int n_prior_ctas;            // leading CTAs of the paint grid that compute the prior terms (launch_paint_elbo)
   long long t_stride;          // B * H * W: elements between the canvases of consecutive steps (host)
   int separable;               // paint_use_separable(T, H, W, h, w) (host)
+  int col_ni;                  // column pass: glimpse rows per thread, ceil(h / col_rg) (host)
   int col_cp, col_rg;          // column pass: columns resident in one sweep min(W, threads), glimpse rows per sweep (host)
   int row_tprb, row_rpp;       // row pass: threads per canvas row resident in one pass, rows per pass (host)
   long long* trace;            // debug (AIR_PAINT_TRACE): 8 stamps per CTA (globaltimer ns at the phase boundaries, SM id)
@@ -748,9 +749,14 @@ __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __
       const float wf = __fmul_rn(pm, tx.wf), wc = __fmul_rn(pm, tx.wc);
       const float* g = s_gl + t * h * w;
       float* dst = s_col + (size_t)t * h * W + c;
-#pragma unroll 1
-      for (int i = islot; i < h; i += RG)
-        dst[i * W] = fmaf(wc, g[i * w + tx.i_c], __fmul_rn(wf, g[i * w + tx.i_f]));
+      const float* gf = g + islot * w + tx.i_f;
+      const float* gc = g + islot * w + tx.i_c;
+      float* d = dst + islot * W;
+      const int n_i = a.col_ni, gstep = RG * w, dstep = RG * W;
+#pragma unroll 4
+      for (int k = 0; k < n_i; ++k) {
+        if (islot + k * RG < h) d[k * dstep] = fmaf(wc, gc[k * gstep], __fmul_rn(wf, gf[k * gstep]));
+      }
     }
   }
 }
@@ -768,7 +774,9 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
-template <int T, int CPT>
+// FAST: the hot configuration (canvases written, reconstruction term wanted, no initial canvas) with those three facts as
+// compile-time constants -- no predicates, no dead pointer arithmetic in the loop
+template <int T, int CPT, bool FAST>
 __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap* __restrict__ s_ty) {
   const int H = a.H, W = a.W;
   const int TPRB = a.row_tprb;                  // threads per row (W / CPT) resident in one pass
@@ -776,8 +784,8 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
   int cslot, rslot;
   small_divmod((int)threadIdx.x, TPRB, rslot, cslot);
   const float mult = a.output_multiplier;
-  const bool do_elbo = a.do_elbo != 0;
-  const bool has_cin = a.canvas_in != nullptr, has_dst = a.canvas != nullptr;
+  const bool do_elbo = FAST ? true : a.do_elbo != 0;
+  const bool has_cin = FAST ? false : a.canvas_in != nullptr, has_dst = FAST ? true : a.canvas != nullptr;
   const long long tstride = a.t_stride;
   const size_t base = (size_t)b * H * W;
   const int dp = RPP * W;
@@ -845,7 +853,7 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
           rec = fmaf(dd, dd, rec);
         }
       }
-      cin += dp;
+      if (!FAST) cin += dp;
       dst += dp;
       typ += RPP * T;
     }
@@ -1047,7 +1055,9 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   __syncthreads();
   PAINT_STAMP(4);
   float rec;
-  if (a.separable) rec = pair ? paint_rows<T, 2>(a, b, s_ty) : paint_rows<T, 1>(a, b, s_ty);
+  const bool fast = a.do_elbo && a.canvas && !a.canvas_in;
+  if (a.separable && pair && fast) rec = paint_rows<T, 2, true>(a, b, s_ty);
+  else if (a.separable) rec = pair ? paint_rows<T, 2, false>(a, b, s_ty) : paint_rows<T, 1, false>(a, b, s_ty);
   else rec = pair ? paint_rows_direct<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows_direct<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
   PAINT_STAMP(5);
   if (!a.do_elbo) return;
@@ -1087,6 +1097,7 @@ inline cudaError_t launch_paint_elbo(ElboArgs& a, cudaStream_t st) {
   const int tpr = pair ? a.W / 2 : a.W;
   a.col_cp = a.W < nt ? a.W : nt;
   a.col_rg = nt / a.col_cp;
+  a.col_ni = (a.h + a.col_rg - 1) / a.col_rg;
   a.row_tprb = tpr < nt ? tpr : nt;
   a.row_rpp = nt / a.row_tprb;
   const int cpc = nt / ((a.T + 1 <= 8) ? 8 : 16);   // canvases per prior CTA (PriorGroup<T>::L lanes each)
