@@ -145,6 +145,7 @@ struct air_handle {
   air::tc::PrepEntry* prep_table = nullptr;
   int prep_tiles = 0;
   int* range_flag = nullptr;
+  float* hw0 = nullptr;            // h0 @ W_h of the cluster LSTM (lstm_h0w_kernel), rebuilt with the weight arena
   std::map<std::pair<const void*, int>, CUtensorMap> tmap_cache;
   // training (air_train_enable / air_backward; either engine): saved activations + gradient scratch, one cudaMalloc
   // inference: the prepared fp16-split weight arena is reused while the caller vouches that `params` is unchanged
@@ -665,6 +666,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     AIR_CUDA(air::launch_k(air::tc::prep_weights_kernel, dim3(h->prep_tiles), dim3(256), 0, st, params, h->arena,
                            h->prep_table, (int)h->tcw.size(), h->range_flag, h->bias_arena));
     ++h->launches;
+    if (h->lstm_ok && h->hw0) {
+      AIR_CUDA(air::launch_k(air::lstm::lstm_h0w_kernel, dim3((4 * nh + 255) / 256), dim3(256), 0, st,
+                             params + h->lstm_h.w_off, params + h->lstm_h0, h->hw0, nh));
+      ++h->launches;
+    }
     h->weights_ready = params;
   }
   const bool enc1 = enc1_active(h);
@@ -768,6 +774,8 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     const bool rows = h_in || train;   // explicit per-canvas state (air_cell_step) or the tiled copy kept for the backward
     lp.h_init = rows ? h->h_init.f32 : params + h->lstm_h0;   // cell.py:103: (h0, c0) [1,nh] tiled to the batch
     lp.h_init_ld = rows ? nh : 0;
+    static const bool no_fold = getenv("AIR_LSTM_NO_FOLD") != nullptr;
+    lp.hw0 = (rows || no_fold) ? nullptr : h->hw0;   // broadcast initial state: step 1 needs no recurrent GEMM
     lp.c_in = rows ? (train ? h->c_all : h->cbuf) : params + h->lstm_c0;
     lp.c_in_ld = rows ? nh : 0;
     lp.c = h->cbuf;
@@ -1130,6 +1138,7 @@ void carve_workspace(air_handle* h, Carver& cv) {
     hlt(h->crop, h->G);
     if (h->lstm_ok) hlt(h->e, h->n_enc);
     if (h->lstm_ok) {
+      h->hw0 = cv.take<float>((size_t)4 * c.nh);
       h->gx_scr = cv.take<float>((size_t)B_alloc * 4 * c.nh);
       h->hx = cv.take<__half>(2 * 2 * (size_t)B_alloc * c.nh);
     }

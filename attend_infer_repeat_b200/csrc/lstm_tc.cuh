@@ -33,6 +33,8 @@ struct Params {
   int n_enc;
   const float* h_init;    // [B, NH] fp32 (row pitch h_init_ld; 0 = one [NH] vector broadcast to every canvas)
   int h_init_ld;
+  const float* hw0;       // broadcast initial state only: h0 @ W[n_enc:] as fp32, permuted like `bias` (lstm_h0w_kernel), or null.
+                          // Step 1 then needs no recurrent GEMM -- its gates are gx + hw0 -- and the gx epilogue IS step 1.
   const float* c_in;      // initial cell state, row pitch c_in_ld (0 = broadcast vector); the final state goes to `c`
   int c_in_ld;
   float* c;               // [B, NH] fp32: initial cell state in, final cell state out
@@ -142,7 +144,8 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
   const uint32_t rank = cluster_ctarank();
   const int tile = blockIdx.y;
   const int m0 = tile * BM;
-  const int n_groups = 1 + p.T;   // gx, then one GEMM per step
+  const bool fold0 = p.hw0 != nullptr;        // step 1's recurrent product is the constant hw0
+  const int n_groups = 1 + p.T - (fold0 ? 1 : 0);   // gx, then one GEMM per step (per step after the first when folded)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tm_x);
@@ -254,7 +257,11 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
 #pragma unroll
     for (int gate = 0; gate < 4; ++gate)
       asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + (size_t)rank * NH + gate * UPC + cq * 16));
-    if (p.h_init_ld == 0) {
+    if (fold0) {
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.hw0 + (size_t)rank * NH + gate * UPC + cq * 16));
+    } else if (p.h_init_ld == 0) {
 #pragma unroll
       for (int s = 0; s < 4; ++s) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.h_init + (cq + 4 * s) * 16));
     }
@@ -301,6 +308,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
 
     // --- gx: D + bias -> scratch, in this thread's own read-back order: [gate * 4 + k4][row][4 floats] ---
     float* gx_mine = p.gx_scr + ((((size_t)tile * CLUSTER + rank) * 4 + cq) * 16 * BM + rit) * 4;
+    if (!fold0) {
     mbar_wait(d_full, 0);
     tc_fence_after();
     if (tr) LSTM_TRACE(2);
@@ -330,9 +338,11 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     tc_fence_before();
     mbar_arrive(a_ready);
     if (tr) LSTM_TRACE(3);
+    }
 
     for (int t = 0; t < p.T; ++t) {
-      mbar_wait(d_full, (t + 1) & 1);
+      const bool first_folded = fold0 && t == 0;   // the accumulator holds gx: form gx + bias (kept for the later steps) and add hw0
+      mbar_wait(d_full, (fold0 ? t : t + 1) & 1);
       tc_fence_after();
       if (tr) LSTM_TRACE(4 + 5 * t);
       // ---- gate math of 16 units, four at a time ----
@@ -344,11 +354,43 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
         tmem_ld_32x4(t_lane + D_COL + 1 * UPC + cq * 16 + k4 * 4, gj);
         tmem_ld_32x4(t_lane + D_COL + 2 * UPC + cq * 16 + k4 * 4, gf);
         tmem_ld_32x4(t_lane + D_COL + 3 * UPC + cq * 16 + k4 * 4, go);
-        const float4 xi = *reinterpret_cast<const float4*>(gx_mine + (size_t)(0 * 4 + k4) * BM * 4);
-        const float4 xj = *reinterpret_cast<const float4*>(gx_mine + (size_t)(1 * 4 + k4) * BM * 4);
-        const float4 xf = *reinterpret_cast<const float4*>(gx_mine + (size_t)(2 * 4 + k4) * BM * 4);
-        const float4 xo = *reinterpret_cast<const float4*>(gx_mine + (size_t)(3 * 4 + k4) * BM * 4);
+        float4 xi, xj, xf, xo;
+        if (first_folded) {
+          const size_t bo = (size_t)rank * NH + cq * 16 + k4 * 4;
+          xi = *reinterpret_cast<const float4*>(p.bias + bo + 0 * UPC);
+          xj = *reinterpret_cast<const float4*>(p.bias + bo + 1 * UPC);
+          xf = *reinterpret_cast<const float4*>(p.bias + bo + 2 * UPC);
+          xo = *reinterpret_cast<const float4*>(p.bias + bo + 3 * UPC);
+        } else {
+          xi = *reinterpret_cast<const float4*>(gx_mine + (size_t)(0 * 4 + k4) * BM * 4);
+          xj = *reinterpret_cast<const float4*>(gx_mine + (size_t)(1 * 4 + k4) * BM * 4);
+          xf = *reinterpret_cast<const float4*>(gx_mine + (size_t)(2 * 4 + k4) * BM * 4);
+          xo = *reinterpret_cast<const float4*>(gx_mine + (size_t)(3 * 4 + k4) * BM * 4);
+        }
         tmem_ld_wait4(gi, gj, gf, go);
+        if (first_folded) {
+          // gx + bias of this thread's 4 x 4 values goes to the scratch the later steps re-read; the addend of THIS step
+          // becomes bias + hw0
+          if (p.T > 1) {
+            *reinterpret_cast<float4*>(gx_mine + (size_t)(0 * 4 + k4) * BM * 4) = make_float4(
+                fmaf(gi[0], W_UNSCALE, xi.x), fmaf(gi[1], W_UNSCALE, xi.y), fmaf(gi[2], W_UNSCALE, xi.z), fmaf(gi[3], W_UNSCALE, xi.w));
+            *reinterpret_cast<float4*>(gx_mine + (size_t)(1 * 4 + k4) * BM * 4) = make_float4(
+                fmaf(gj[0], W_UNSCALE, xj.x), fmaf(gj[1], W_UNSCALE, xj.y), fmaf(gj[2], W_UNSCALE, xj.z), fmaf(gj[3], W_UNSCALE, xj.w));
+            *reinterpret_cast<float4*>(gx_mine + (size_t)(2 * 4 + k4) * BM * 4) = make_float4(
+                fmaf(gf[0], W_UNSCALE, xf.x), fmaf(gf[1], W_UNSCALE, xf.y), fmaf(gf[2], W_UNSCALE, xf.z), fmaf(gf[3], W_UNSCALE, xf.w));
+            *reinterpret_cast<float4*>(gx_mine + (size_t)(3 * 4 + k4) * BM * 4) = make_float4(
+                fmaf(go[0], W_UNSCALE, xo.x), fmaf(go[1], W_UNSCALE, xo.y), fmaf(go[2], W_UNSCALE, xo.z), fmaf(go[3], W_UNSCALE, xo.w));
+          }
+          const size_t bo = (size_t)rank * NH + cq * 16 + k4 * 4;
+          const float4 hi4 = *reinterpret_cast<const float4*>(p.hw0 + bo + 0 * UPC);
+          const float4 hj4 = *reinterpret_cast<const float4*>(p.hw0 + bo + 1 * UPC);
+          const float4 hf4 = *reinterpret_cast<const float4*>(p.hw0 + bo + 2 * UPC);
+          const float4 ho4 = *reinterpret_cast<const float4*>(p.hw0 + bo + 3 * UPC);
+          xi = make_float4(xi.x + hi4.x, xi.y + hi4.y, xi.z + hi4.z, xi.w + hi4.w);
+          xj = make_float4(xj.x + hj4.x, xj.y + hj4.y, xj.z + hj4.z, xj.w + hj4.w);
+          xf = make_float4(xf.x + hf4.x, xf.y + hf4.y, xf.z + hf4.z, xf.w + hf4.w);
+          xo = make_float4(xo.x + ho4.x, xo.y + ho4.y, xo.z + ho4.z, xo.w + ho4.w);
+        }
         const float ai[4] = {xi.x, xi.y, xi.z, xi.w}, aj[4] = {xj.x, xj.y, xj.z, xj.w};
         const float af[4] = {xf.x, xf.y, xf.z, xf.w}, ao[4] = {xo.x, xo.y, xo.z, xo.w};
 #pragma unroll
@@ -441,6 +483,20 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+}
+
+// hw0[perm(n)] = sum_k h0[k] * W[n_enc + k][n] in fp32: the recurrent product of the broadcast trainable initial state
+// (cell.py:103), the same for every canvas; perm = the [cta][gate][unit] order of `bias` (linear_tc.cuh: prep_dst_row)
+__global__ void __launch_bounds__(256)
+lstm_h0w_kernel(const float* __restrict__ w_h, const float* __restrict__ h0, float* __restrict__ hw0, int nh) {
+  griddep_launch();
+  griddep_wait();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 4 * nh) return;
+  float acc = 0.f;
+  for (int k = 0; k < nh; ++k) acc = fmaf(h0[k], w_h[(size_t)k * 4 * nh + n], acc);
+  const int upc = nh >> 2, gate = n / nh, unit = n % nh;
+  hw0[(unit / upc) * nh + gate * upc + unit % upc] = acc;
 }
 
 inline cudaError_t launch_lstm(const Params& p, cudaStream_t st) {
