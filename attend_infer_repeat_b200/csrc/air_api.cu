@@ -688,13 +688,22 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   // the cluster LSTM reads e as its A operand, thread <-> row: from row-major planes every lane touches its own sector
   // (measured: 19 k of the kernel's 90 k clocks); the last encoder layer therefore writes slice-major tiles for it
   const bool e_tiled = lstm_fused && h->e.hlt != nullptr && h->enc.layers.size() > 1;
+  // inference with a two-layer input Encoder: the cluster LSTM can compute the second layer itself (lstm_tc.cuh, fuse_e2); the
+  // first layer's kernel then writes its activation straight into the LSTM's tiled operand buffer.  Opt-in
+  // (AIR_LSTM_FUSE_E2=1): measured at B = 4096 it shortens ONE pass (0.2679 -> 0.2652 ms: encoder 40.9 -> 32.2 us, LSTM
+  // 54.0 -> 60.6 us) but slows three batches in flight (0.223 -> 0.243 ms per batch) -- the small separate GEMM co-runs with
+  // the neighbouring batches' kernels, a longer 4-CTA-cluster kernel that needs whole SMs does not.
+  static const bool no_fuse_e2 = getenv("AIR_LSTM_FUSE_E2") == nullptr;
+  const bool fuse_e2 = e_tiled && !train && !no_fuse_e2 && enc1_active(h) && h->enc.layers.size() == 2 && h->enc.n_hidden == 2 &&
+                       h->enc.layers[0].N == h->n_enc && h->n_enc == air::lstm::NH &&
+                       h->tcw[h->enc.layers[1].tc].n_box == air::lstm::NH;
   Buf e_out = h->e;
   e_out.hl_tiled = e_tiled;
   if (enc1) {
     // first layer: split-K cluster kernel straight from the fp32 image (enc_tc.cuh); the remaining layers as before
     const Layer& l0 = h->enc.layers[0];
     const TcWeight& w0 = h->tcw[l0.tc];
-    const bool only = h->enc.layers.size() == 1;
+    const bool only = h->enc.layers.size() == 1 || fuse_e2;
     Buf dst = only ? h->e : h->ping;
     dst.kpad = round_up(l0.N, air::tc::BK);
     air::enc::Params ep;
@@ -712,6 +721,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     ep.out_hl = want_hl ? dst.hl : nullptr;
     ep.hl_plane = dst.plane();
     ep.ld_hl = dst.kpad;
+    if (fuse_e2) {
+      ep.out_hl = h->e.hlt;
+      ep.hl_plane = h->e.plane_t();
+      ep.hl_nsl = h->e.nsl;
+    }
     ep.out_f32 = want_f32 ? (only ? h->e.f32 : h->sv_enc[0]) : nullptr;
     ep.range_flag = h->range_flag;
     AIR_CUDA(air::enc::launch_enc1(ep, st));
@@ -769,6 +783,14 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     lp.e_plane = e_tiled ? h->e.plane_t() : h->e.plane();
     lp.e_ld = h->e.kpad;
     lp.e_nsl = e_tiled ? h->e.nsl : 0;
+    if (fuse_e2) {
+      const TcWeight& w2 = h->tcw[h->enc.layers[1].tc];
+      lp.fuse_e2 = 1;
+      lp.tm_e2 = w2.tm_chain;
+      lp.e2_lo_row = w2.N_alloc;
+      lp.n_e1 = h->enc.layers[0].N;
+      lp.bias_e2 = h->bias_arena + w2.bias_off;
+    }
     lp.hs_last_only = train ? 0 : 1;
     lp.n_enc = h->n_enc;
     const bool rows = h_in || train;   // explicit per-canvas state (air_cell_step) or the tiled copy kept for the backward

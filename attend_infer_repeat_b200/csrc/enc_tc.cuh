@@ -48,6 +48,7 @@ struct Params {
   __half* out_hl;          // e1 as hl planes [2][rows_alloc][ld_hl] (operand of the next layer), or null
   size_t hl_plane;
   int ld_hl;
+  int hl_nsl;              // > 0: out_hl is slice-major tiled, [row / 128][hl_nsl][128 rows][16] per plane (the cluster LSTM's operand)
   float* out_f32;          // e1 fp32 rows [B, N1] (training mode / fp32 consumers), or null
   int* range_flag;
 };
@@ -261,12 +262,27 @@ __global__ void __cluster_dims__(KSPLIT, 1, 1) __launch_bounds__(ENC_THREADS, 1)
           lo[j] = *reinterpret_cast<const uint32_t*>(&l);
           ovf |= (hi[j] & 0x7C007C00u) + 0x04000400u;
         }
+        if (p.hl_nsl > 0) {   // two 16-column slices of this row, each one 32-byte piece of its [128 rows][16] block
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            __half* d = p.out_hl + ((((size_t)row >> 7) * p.hl_nsl + (size_t)(cbase >> 4) + sl) * 128 + (row & 127)) * 16;
+            uint4* dh = reinterpret_cast<uint4*>(d);
+            uint4* dl = reinterpret_cast<uint4*>(d + p.hl_plane);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int q = sl * 2 + c;
+              dh[c] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+              dl[c] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+          }
+        } else {
         uint4* dh = reinterpret_cast<uint4*>(p.out_hl + (size_t)row * p.ld_hl + cbase);
         uint4* dl = reinterpret_cast<uint4*>(p.out_hl + p.hl_plane + (size_t)row * p.ld_hl + cbase);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
           dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        }
         }
         if ((ovf & 0x80008000u) && p.range_flag) atomicOr(p.range_flag, 1);
       }

@@ -33,6 +33,14 @@ struct Params {
   int n_enc;
   const float* h_init;    // [B, NH] fp32 (row pitch h_init_ld; 0 = one [NH] vector broadcast to every canvas)
   int h_init_ld;
+  // inference, input Encoder with >= 2 layers: the cluster computes the LAST encoder layer itself (e = ELU(e1 @ W2 + b2), every
+  // CTA all n_enc columns of its 128 rows) as an extra GEMM group in front of gx; `e_hl` then holds e1 (K = n_e1) and the
+  // activation never leaves tensor memory.  Saves a launch and the round trip of e through L2.
+  int fuse_e2;
+  CUtensorMap tm_e2;      // prepared W2^T [2][N_alloc][Kpad] (hi rows at 0, lo rows at e2_lo_row), box 256 x 64
+  int e2_lo_row;
+  int n_e1;               // K of the fused layer
+  const float* bias_e2;   // [n_enc]
   const float* hw0;       // broadcast initial state only: h0 @ W[n_enc:] as fp32, permuted like `bias` (lstm_h0w_kernel), or null.
                           // Step 1 then needs no recurrent GEMM -- its gates are gx + hw0 -- and the gx epilogue IS step 1.
   const float* c_in;      // initial cell state, row pitch c_in_ld (0 = broadcast vector); the final state goes to `c`
@@ -145,11 +153,13 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
   const int tile = blockIdx.y;
   const int m0 = tile * BM;
   const bool fold0 = p.hw0 != nullptr;        // step 1's recurrent product is the constant hw0
-  const int n_groups = 1 + p.T - (fold0 ? 1 : 0);   // gx, then one GEMM per step (per step after the first when folded)
+  const int gbase = p.fuse_e2 ? 1 : 0;        // index of the gx group
+  const int n_groups = gbase + 1 + p.T - (fold0 ? 1 : 0);   // [last encoder layer,] gx, then one GEMM per step (per step after the first when folded)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tm_x);
     prefetch_tmap(&p.tm_h);
+    if (p.fuse_e2) prefetch_tmap(&p.tm_e2);
     for (int s = 0; s < SLOTS; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -173,19 +183,21 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     if (elect_one()) {
       uint32_t par = 0;
       for (int g = 0; g < n_groups; ++g) {
-        const CUtensorMap* tm = g == 0 ? &p.tm_x : &p.tm_h;
-        const int K = g == 0 ? p.n_enc : NH;
+        const bool enc = p.fuse_e2 && g == 0;
+        const CUtensorMap* tm = enc ? &p.tm_e2 : (g == gbase ? &p.tm_x : &p.tm_h);
+        const int K = enc ? p.n_e1 : (g == gbase ? p.n_enc : NH);
+        const int row_hi = enc ? 0 : (int)rank * NH, row_lo = enc ? p.e2_lo_row : CLUSTER * NH + (int)rank * NH;
         const int nkb = ((K + 15) / 16 + 3) / 4;
         for (int kb = 0; kb < nkb; ++kb) {
           const int hs = kb & 3, ls = 4 + (kb & 1);
           mbar_wait(&empty_bar[hs], ((par >> hs) & 1) ^ 1);
           par ^= 1u << hs;
           mbar_expect_tx(&full_bar[hs], TILE_BYTES);
-          tma_load_2d(smem + hs * TILE_BYTES, tm, kb * BK, (int)rank * NH, &full_bar[hs]);
+          tma_load_2d(smem + hs * TILE_BYTES, tm, kb * BK, row_hi, &full_bar[hs]);
           mbar_wait(&empty_bar[ls], ((par >> ls) & 1) ^ 1);
           par ^= 1u << ls;
           mbar_expect_tx(&full_bar[ls], TILE_BYTES);
-          tma_load_2d(smem + ls * TILE_BYTES, tm, kb * BK, CLUSTER * NH + (int)rank * NH, &full_bar[ls]);
+          tma_load_2d(smem + ls * TILE_BYTES, tm, kb * BK, row_lo, &full_bar[ls]);
         }
       }
     }
@@ -196,7 +208,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
       uint32_t par = 0;
       constexpr uint32_t idesc = make_idesc_f16(BM, NH);
       for (int g = 0; g < n_groups; ++g) {
-        const int K = g == 0 ? p.n_enc : NH;
+        const int K = (p.fuse_e2 && g == 0) ? p.n_e1 : (g == gbase ? p.n_enc : NH);
         const int nsl = (K + 15) / 16, nkb = (nsl + 3) / 4;
         mbar_wait(a_ready, g & 1);
         tc_fence_after();
@@ -268,7 +280,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
 
     // --- operand of the gx GEMM: e rows, fp32 -> hi/lo -> TMEM (each thread: slices cq, cq + 4, ...) ---
     {
-      const int nsl = (p.n_enc + 15) / 16;
+      const int nsl = ((p.fuse_e2 ? p.n_e1 : p.n_enc) + 15) / 16;
       if (p.e_hl) {
         // the encoder's last layer wrote e as hl planes: the packed words are read as they are (four 16-byte loads per
         // slice, all in flight together; the staged fp32 path below cost 11 k clocks of a 96 k kernel)
@@ -306,10 +318,32 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
     mbar_arrive(a_ready);
     if (tr) LSTM_TRACE(1);
 
+    // --- fused last encoder layer: e = ELU(D + b2) -> fp16 hi/lo -> the A operand of the gx GEMM (slices cq, cq + 4, ...) ---
+    if (p.fuse_e2) {
+      mbar_wait(d_full, 0);
+      tc_fence_after();
+      const int nsl_e = (p.n_enc + 15) / 16;
+      for (int s = cq; s < nsl_e; s += 4) {
+        float v[16], b[16];
+        tmem_ld_32x16(t_lane + D_COL + s * 16, v);
+        load16(p.bias_e2 + s * 16, b);
+        tmem_ld_wait(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (s * 16 + j < p.n_enc) ? elu_fast(fmaf(v[j], W_UNSCALE, b[j])) : 0.f;
+        uint32_t hi[8], lo[8];
+        split_pack16(v, hi, lo, ovf);
+        tmem_st_32x8(t_lane + A_HI_COL + s * 8, hi);
+        tmem_st_32x8(t_lane + A_LO_COL + s * 8, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    }
+
     // --- gx: D + bias -> scratch, in this thread's own read-back order: [gate * 4 + k4][row][4 floats] ---
     float* gx_mine = p.gx_scr + ((((size_t)tile * CLUSTER + rank) * 4 + cq) * 16 * BM + rit) * 4;
     if (!fold0) {
-    mbar_wait(d_full, 0);
+    mbar_wait(d_full, gbase & 1);
     tc_fence_after();
     if (tr) LSTM_TRACE(2);
 #pragma unroll
@@ -342,7 +376,7 @@ lstm_cluster_kernel(const __grid_constant__ Params p) {
 
     for (int t = 0; t < p.T; ++t) {
       const bool first_folded = fold0 && t == 0;   // the accumulator holds gx: form gx + bias (kept for the later steps) and add hw0
-      mbar_wait(d_full, (fold0 ? t : t + 1) & 1);
+      mbar_wait(d_full, (gbase + (fold0 ? t : t + 1)) & 1);
       tc_fence_after();
       if (tr) LSTM_TRACE(4 + 5 * t);
       // ---- gate math of 16 units, four at a time ----
