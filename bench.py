@@ -562,7 +562,7 @@ def run_native(args, rank, local_rank, world):
             "peak_kind": f"{'STREAM copy' if tighter == 'hbm' else 'bf16 dense sustained'}, {peak_kind}",
             "algorithmic_bytes_per_step": R * alg_bytes, "useful_flops_per_step": 2.0 * R * total_macs,
             "t_hbm_ms": t_hbm_ms, "t_tensor_ms": t_tensor_ms, "ms_per_step": step_ms,
-            # dram__bytes_read + write summed over the launches of one pass, ncu --set full (profiles/r02a_full.md), c2 only
+            # dram__bytes_read + write summed over the launches of one pass, ncu --set full (profiles/r02p_full.md), c2 only
             "traffic": TRAFFIC_C2 if (args.config == "c2" and prec == air.AIR_PREC_TC_SPLIT) else None,
             "traffic_unit": "bytes per step (all launches)",
             "dominant_stage": dom, "stage_ms": {k: round(v, 4) for k, v in acc.items()},
@@ -662,9 +662,10 @@ def run_native(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE c2 pass (profiles/r02a_full.md, ncu --set full):
-# enc1 43.6 + enc L2 ~5 + lstm 16.0 + heads 13.6 + where_read 44.0 + glimpse row kernel 24.2 + paint/ELBO 158.0 MB
-TRAFFIC_C2 = 304.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE c2 pass (profiles/r02p_full.md, ncu --set full):
+# enc1 43.6 + encoder layer 2 4.5 + lstm 6.5 + heads 13.4 + where_read 42.4 + glimpse row kernel 24.3 + paint/ELBO 156.0
+# + scalars 0.1 MB (the canvases' last 33 MB are still dirty in L2 when the pass ends)
+TRAFFIC_C2 = 290.8e6
 
 
 def kernel_train_loop(air, cfg, prec, B, T, dev, sets, params, prior, world, dist, barrier, n_train):
