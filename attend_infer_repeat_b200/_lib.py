@@ -136,6 +136,7 @@ SYMBOLS = {
     "air_lstm_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P]),
     "air_stn_read": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "air_stn_paint": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "air_glimpse_viz": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
     "air_bernoulli_to_modified_geometric": (C.c_int32, [_P, _P, C.c_int64, C.c_int32, _P]),
     "air_geometric_prior": (C.c_int32, [C.c_double, C.c_int32, C.c_int32, _P, _P]),
     "air_tabular_kl": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int32, C.c_double, _P]),

@@ -2698,6 +2698,16 @@ int32_t air_stn_paint(const float* glimpse, const float* where, float* out, int3
   return AIR_OK;
 }
 
+int32_t air_glimpse_viz(const float* glimpse, const float* presence, float* out, int64_t rows, int32_t G, void* stream) {
+  if (!glimpse || !presence || !out || rows < 0 || G < 1) return fail(AIR_ERR_ARG, "air_glimpse_viz: bad argument");
+  if (rows == 0) return AIR_OK;
+  const long long n = (long long)rows * G;
+  const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
+  air::glimpse_viz_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(glimpse, presence, out, (long long)rows, G);
+  AIR_CUDA(cudaGetLastError());
+  return AIR_OK;
+}
+
 int32_t air_bernoulli_to_modified_geometric(const float* probs, float* pmf, int64_t n, int32_t T, void* stream) {
   if (!probs || !pmf || n < 0 || T < 1 || T > AIR_MAX_STEPS)
     return fail(AIR_ERR_ARG, "air_bernoulli_to_modified_geometric: bad argument (T must be in [1, AIR_MAX_STEPS])");

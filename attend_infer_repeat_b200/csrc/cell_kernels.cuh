@@ -1141,6 +1141,17 @@ stn_paint_kernel(const float* __restrict__ glimpse, const float* __restrict__ wh
   }
 }
 
+// model.py:90: the visualisation tensor presence * sigmoid(glimpse), [rows = T * B][G].  The paint kernel writes it when asked
+// (ElboArgs.glimpse_viz); this is the same arithmetic as a stand-alone pass for callers that fetch it only now and then --
+// the reference's graph computes it only when `air.glimpse` is fetched, which its training loop never does.
+__global__ void __launch_bounds__(256)
+glimpse_viz_kernel(const float* __restrict__ glimpse, const float* __restrict__ presence, float* __restrict__ out,
+                   long long rows, int G) {
+  const long long n = rows * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fmul_rn(presence[i / G], sigmoid_lean(glimpse[i]));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // batch means of the per-sample terms (model.py:103,151,184,212,247-248,322; ops.py:12-29).  One CTA,
 // fixed summation order (deterministic).

@@ -114,6 +114,18 @@ def stn_paint(glimpse, where, canvas_hw):
     return out
 
 
+def glimpse_viz(glimpse, presence):
+    """model.py:90: presence * sigmoid(glimpse) for decoded glimpses [T,B,G] (or [T,B,h,w]) and presence [T,B,1]."""
+    glimpse, presence = _cuda_f32(glimpse, "glimpse"), _cuda_f32(presence, "presence")
+    rows = presence.numel()
+    G = glimpse.numel() // max(rows, 1)
+    out = torch.empty_like(glimpse)
+    with torch.cuda.device(glimpse.device):
+        check(_lib.lib().air_glimpse_viz(ptr(glimpse), ptr(presence), ptr(out), rows, G, current_stream_ptr()),
+              "air_glimpse_viz")
+    return out
+
+
 def bernoulli_to_modified_geometric(presence_prob):
     """prior.py:62-68: [..., T] Bernoulli success probabilities -> [..., T+1] pmf over the number of steps."""
     p = _cuda_f32(presence_prob, "presence_prob")

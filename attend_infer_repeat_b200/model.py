@@ -78,8 +78,10 @@ class AIRModel:
                             debug=self.debug,
                             output_std=self.output_std, output_multiplier=self.output_multiplier,
                             **kwargs)
+        # `glimpse` (model.py:90, presence * sigmoid(decoded glimpse)) is a visualisation attribute: the reference's graph
+        # evaluates it only when it is fetched, so it is computed on first access here (air_glimpse_viz), not by every pass
         self.engine = self.cell.engine(self.batch_size, self.max_steps, materialise_canvas=self._materialise_canvas,
-                                       materialise_viz=self._materialise_canvas)
+                                       materialise_viz=False)
         self.forward()
 
     @property
@@ -125,8 +127,10 @@ class AIRModel:
 
         # attributes named by AIRCell.output_names (model.py:86-87) and the post-processing of model.py:89-104
         for name in self.cell.output_names:
-            setattr(self, name, o[name])
+            if name != "glimpse":
+                setattr(self, name, o[name])
         self.decoded_glimpse = o["glimpse"]
+        self.__dict__.pop("glimpse", None)       # lazy: see __getattr__
         self.final_state = (o["final_h"], o["final_c"])
         if o["glimpse_viz"] is not None:
             self.glimpse = o["glimpse_viz"].view(T, B, *self.glimpse_size)
@@ -154,6 +158,10 @@ class AIRModel:
 
     def __getattr__(self, name):
         # (only reached when normal lookup fails)
+        if name == "glimpse" and self.__dict__.get("decoded_glimpse") is not None:
+            g = F.glimpse_viz(self.decoded_glimpse, self.presence).view(self.max_steps, self.batch_size, *self.glimpse_size)
+            self.__dict__["glimpse"] = g
+            return g
         if name in AIRModel._LAZY_LOSS_ATTRS and self.__dict__.get("_loss_outputs") is not None:
             self._materialise_losses()
             if name in self.__dict__:
@@ -264,8 +272,7 @@ class AIRModel:
                                where_shift_prior=where_shift_prior, num_steps_prior=num_steps_prior,
                                use_reinforce=use_reinforce)
         # the training engine (same arithmetic mode as the model, activations kept) replaces the inference engine
-        self.engine = self.cell.engine(self.batch_size, self.max_steps, materialise_canvas=True,
-                                       materialise_viz=self._materialise_canvas)
+        self.engine = self.cell.engine(self.batch_size, self.max_steps, materialise_canvas=True, materialise_viz=False)
         if self.baseline_module is not None and hasattr(self.baseline_module, "attach") and use_reinforce:
             self.baseline_module.attach(self.engine)     # BaselineMLP on the engine (before the training workspace is sized)
         self.engine.train_enable(True)

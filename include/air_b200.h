@@ -384,6 +384,11 @@ int32_t air_stn_read(const float* img, const float* where, float* crop, int32_t 
 /* inverse SpatialTransformer (modules.py:100-102; cell.py:59,159): out[B,H,W] gathered from glimpse[B,h,w] */
 int32_t air_stn_paint(const float* glimpse, const float* where, float* out, int32_t B, int32_t H,
                       int32_t W, int32_t h, int32_t w, void* stream);
+
+/* model.py:90  `self.glimpse = presence * sigmoid(glimpse)`: the visualisation tensor, [rows = T * B][G] from the decoded
+ * glimpses and the presence column.  air_forward writes it into outs->glimpse_viz when that pointer is given; this entry
+ * computes it on request (the reference's graph evaluates it only when the attribute is fetched). */
+int32_t air_glimpse_viz(const float* glimpse, const float* presence, float* out, int64_t rows, int32_t G, void* stream);
 /* prior.py:62-68: probs[n,T] -> pmf[n,T+1] (float64 island inside) */
 int32_t air_bernoulli_to_modified_geometric(const float* probs, float* pmf, int64_t n, int32_t T,
                                             void* stream);

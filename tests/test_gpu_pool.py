@@ -70,3 +70,29 @@ def test_pool_host_stream_equals_synchronous_calls_in_order(n_batches):
     for (s0, l0), (s1, l1) in zip(ref, got):
         assert torch.equal(s0, s1) and torch.equal(l0, l1)
     pool.close()
+
+
+def test_glimpse_viz_on_request_equals_the_fused_output_and_the_oracle():
+    """model.py:90 `presence * sigmoid(glimpse)`: air_glimpse_viz on request is bit-identical to what the paint kernel writes
+    when outs->glimpse_viz is given, and AIRModel.glimpse (lazy) matches the oracle."""
+    import attend_infer_repeat_b200.functional as F
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    B, T = 96, 3
+    cfg = U.cell_cfg(ocfg, air.AIR_PREC_TC_SPLIT)
+    params = O.flatten_params(ocfg, O.init_params(ocfg, 0)).to(DEV)
+    pr = U.prior_struct(O.PriorConfig(), 20000)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    d = (torch.rand(B, 50, 50, device=DEV, generator=g), torch.randn(T, B, 4, device=DEV, generator=g),
+         torch.randn(T, B, cfg.na, device=DEV, generator=g), torch.rand(T, B, 1, device=DEV, generator=g))
+    eng = air.Engine(cfg, B, T, device=DEV)                               # materialise_viz=True
+    out = eng.forward(params, *d, pr)
+    viz = F.glimpse_viz(out["glimpse"], out["presence"])
+    assert torch.equal(viz, out["glimpse_viz"])
+    assert float(viz.abs().max()) > 0
+    lean = air.Engine(cfg, B, T, device=DEV, materialise_viz=False)
+    out2 = lean.forward(params, *d, pr)
+    assert out2["glimpse_viz"] is None
+    for k in ("canvas", "glimpse", "loss_per_sample", "scalars"):
+        assert torch.equal(out[k], out2[k]), k
+    eng.close()
+    lean.close()
