@@ -239,12 +239,25 @@ __device__ __forceinline__ void presence_step(const PresenceArgs& pa, size_t i, 
 }
 __device__ __forceinline__ void presence_scan(const PresenceArgs& pa, int b, int T, int B) {
   float pres = pa.presence_in ? pa.presence_in[b] : 1.0f;
-  for (int t = 0; t < T; ++t) {
-    const size_t i = (size_t)t * B + b;
-    float p;
-    presence_step(pa, i, pres, p);
-    pa.presence_prob[i] = p;
-    pa.presence[i] = pres;
+  // every logit / uniform draw of the canvas is loaded before the first store: the stores below may alias them as far as the
+  // compiler knows, and the scan would otherwise be T dependent memory round trips instead of one
+  float lg[AIR_MAX_STEPS], uu[AIR_MAX_STEPS];
+#pragma unroll
+  for (int t = 0; t < AIR_MAX_STEPS; ++t) {
+    lg[t] = t < T ? __ldg(pa.logit + (size_t)t * B + b) : 0.f;
+    uu[t] = (t < T && pa.discrete) ? __ldg(pa.u_pres + (size_t)t * B + b) : 0.f;
+  }
+#pragma unroll
+  for (int t = 0; t < AIR_MAX_STEPS; ++t) {
+    if (t < T) {
+      const size_t i = (size_t)t * B + b;
+      float p = sigmoid_f(lg[t] + pa.step_bias);
+      if (pa.explore_eps >= 0.f) p = __fadd_rn(pa.explore_eps / 2.0f, __fmul_rn(1.0f - pa.explore_eps, p));
+      if (pa.discrete) pres *= (uu[t] < p) ? 1.0f : 0.0f;
+      else pres = p;
+      pa.presence_prob[i] = p;
+      pa.presence[i] = pres;
+    }
   }
 }
 
