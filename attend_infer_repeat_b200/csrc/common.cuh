@@ -28,6 +28,19 @@ __device__ __forceinline__ float softplus_f(float x) {
   return logf(ex + 1.0f);
 }
 
+// the same three branches with MUFU.EX2 / MUFU.LG2 (ex2.approx, lg2.approx): absolute error <= 4e-7 -- the 16 accurate
+// expf + logf pairs per thread were two thirds of the row kernel's what-head epilogue (14 k clocks in which the tensor
+// core waits for the sampled code)
+__device__ __forceinline__ float softplus_lean(float x) {
+  const float thr = -13.942385f;
+  if (x > -thr) return x;
+  float ex, lg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * 1.4426950408889634f));
+  if (x < thr) return ex;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ex + 1.0f));
+  return lg * 0.6931471805599453f;
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // visualisation-only sigmoid (glimpse_viz, model.py:90): ex2.approx + fast division, ~2^-21 relative

@@ -163,6 +163,16 @@ __device__ __noinline__ void tile_flush(float* stage, int lane, float* __restric
       const float4 t = *reinterpret_cast<const float4*>(stage + stage_idx(r, c4));
       if (row_w + r < n_rows) *reinterpret_cast<float4*>(out + (size_t)(row_w + r) * ld + col0 + 4 * c4) = t;
     }
+  } else if (((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0) && ((n_cols & 1) == 0)) {
+    // even row pitch (the what head: na = 50 floats = 200 bytes): 8-byte stores, four rows per instruction
+    const int c2 = lane & 7;
+#pragma unroll 4
+    for (int i = 0; i < 8; ++i) {
+      const int r = (lane >> 3) + 4 * i;
+      const float2 t = *reinterpret_cast<const float2*>(stage + stage_idx(r, c2 >> 1) + 2 * (c2 & 1));
+      if (row_w + r < n_rows && col0 + 2 * c2 < n_cols)
+        *reinterpret_cast<float2*>(out + (size_t)(row_w + r) * ld + col0 + 2 * c2) = t;
+    }
   } else {
     const int cc = lane & 15;
 #pragma unroll 4
@@ -416,6 +426,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_kernel(const __grid_consta
         float e[16];
         // the noise of this thread's latents (coalesced through the staging tile), fetched ahead of the wait
         if (mine) {
+          // this thread's two bias lines (location and raw scale), pulled into L1 behind the accumulator wait
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(K.bias + c0));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(K.bias + p.na_off + c0));
           if (!p.prefetch_eps) tile_fetch(stage, lane, p.eps_what, na, row_w, c0, na, p.M);
           else tile_fetch_wait();
           stage_get(stage, lane, e);
@@ -434,7 +447,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_kernel(const __grid_consta
             tmem_ld_wait(vs);
             bias_group(vs, K.bias + p.na_off + c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vs[j] = softplus_f(vs[j] + p.what_offset);
+            for (int j = 0; j < 16; ++j) vs[j] = softplus_lean(vs[j] + p.what_offset);
+            if (threadIdx.x == 64) ROW_TRACE(MAXU + ti, 2);
             stage_put(stage, lane, vs);
             tile_flush(stage, lane, p.what_scale, na, row_w, c0, na, p.M);
 #pragma unroll
