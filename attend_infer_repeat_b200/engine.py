@@ -511,15 +511,15 @@ class EnginePool:
 
     Consecutive batches are enqueued round-robin, so kernels of DIFFERENT batches may run side by side: the tensor-core
     kernels of one pass hold 96-128 of the 148 SMs with one CTA each and leave the SIMT pipes idle, the per-canvas
-    kernels (where_read, paint) do the opposite, and every kernel has a tail in which SMs drain.  With three batches in
-    flight the B200 spends that slack on the neighbouring batch (measured at B = 4096: 0.295 -> 0.237 ms per batch;
-    more than three streams add nothing).  The results of a batch are in the ``out`` dict of the engine that ran it;
+    kernels (where_read, paint) do the opposite, and every kernel has a tail in which SMs drain.  With several batches in
+    flight the B200 spends that slack on the neighbouring batches (measured at B = 4096: 0.268 ms per batch alone, 0.246
+    with two, 0.217 with three, 0.206 with four, 0.205 with six).  The results of a batch are in the ``out`` dict of the engine that ran it;
     they are valid on that engine's stream -- call ``join()`` (or ``torch.cuda.current_stream().wait_stream(stream)``)
     before consuming them elsewhere.  Input tensors must stay alive until the batch has run (they are used on a stream
     other than the one they were allocated on).
     """
 
-    def __init__(self, cfg: CellConfig, B: int, T: int, n_streams: int = 3, device=None, **engine_kwargs):
+    def __init__(self, cfg: CellConfig, B: int, T: int, n_streams: int = 4, device=None, **engine_kwargs):
         assert n_streams >= 1
         self.engines = [Engine(cfg, B, T, device=device, **engine_kwargs) for _ in range(n_streams)]
         self.device = self.engines[0].device

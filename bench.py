@@ -737,7 +737,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="canvases per GPU (default: the configuration's)")
     ap.add_argument("--precision", default="tc", choices=["fp32", "tc"])
     ap.add_argument("--input-sets", type=int, default=4)
-    ap.add_argument("--streams", type=int, default=3,
+    ap.add_argument("--streams", type=int, default=4,
                     help="forward / IWAE configs: independent batches in flight (EnginePool); 1 = one pass at a time")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
