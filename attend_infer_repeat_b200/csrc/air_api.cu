@@ -607,6 +607,28 @@ int32_t launch_row_path(air_handle* h, int which, const float* eps_where, const 
     }
     p.prefetch_eps = (seen_what && !out_before) ? 1 : 0;
   }
+  // glimpse VAE launch: the decoder's output tasks are the last users of the staging tiles, so they may store through the
+  // TMA engine (the map is cached per output pointer)
+  static const bool no_out_tma = getenv("AIR_ROW_NO_OUT_TMA") != nullptr;
+  if (which == 1 && !no_out_tma) {
+    bool out_last = true, seen_out = false;
+    for (const Task& t : sch.tasks) {
+      if (t.type == T_OUT && t.out_kind == OUT_GLOBAL) seen_out = true;
+      else if (seen_out && t.type != T_LOAD_HL && t.type != T_ELU) out_last = false;   // T_ELU does not touch the tiles
+    }
+    if (out_last && seen_out) {
+      const auto key = std::make_tuple((const void*)o->glimpse, (int)h->G, (long long)p.M, 777);
+      auto it = h->tmap_cache2.find(key);
+      if (it == h->tmap_cache2.end()) {
+        CUtensorMap tm;
+        if (air::row::make_row_out_tmap(&tm, o->glimpse, h->G, p.M)) it = h->tmap_cache2.emplace(key, tm).first;
+      }
+      if (it != h->tmap_cache2.end()) {
+        p.tm_out = it->second;
+        p.out_tma = 1;
+      }
+    }
+  }
   // debug: AIR_ROW_TRACE=<prefix> dumps the per-unit / per-task SM-clock stamps of every launch to <prefix>.<seq>.bin
   static const char* trace_prefix = getenv("AIR_ROW_TRACE");
   if (trace_prefix) {

@@ -81,6 +81,7 @@ struct Task {
 
 struct Params {
   CUtensorMap tm[MAXTM];
+  CUtensorMap tm_out;   // fp32 [M rows][ldo columns] output of the OUT_GLOBAL tasks, box 16 columns x 32 rows, no swizzle
   Unit unit[MAXU];
   Task task[MAXTASK];
   int n_units, n_tasks, n_tm;
@@ -100,6 +101,8 @@ struct Params {
   float* what_scale;
   int na, na_off;
   float what_offset;
+  int out_tma;           // the OUT_GLOBAL tasks store through tm_out (TMA tensor store from the warp's staging tile); legal iff
+                         // every other user of the staging tiles runs before the first such task (host checks)
   int prefetch_eps;      // the what head's noise may be staged at kernel start (no T_OUT precedes the T_WHAT task)
   int* range_flag;
   long long* trace;      // debug (AIR_ROW_TRACE): [CTA][MAXU + MAXTASK][4] SM-clock stamps, or null
@@ -183,6 +186,25 @@ __device__ __noinline__ void tile_flush(float* stage, int lane, float* __restric
     }
   }
   __syncwarp();
+}
+// One 16-column group of 32 rows through the TMA engine: the warp parks the values in its staging tile as plain [32][16] rows
+// and one lane issues a 2-D tensor store (rows / columns outside the tensor are clipped by the map).  The epilogue warps issue
+// no global store themselves -- measured with the staged STG path, the stores were 3 k of an output task's 4.4 k clocks.
+__device__ __forceinline__ void tma_store_group(const CUtensorMap* tm, float* stage, int lane, const float (&v)[16], int col0,
+                                                int row0) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the tile
+  __syncwarp();
+  float4* st4 = reinterpret_cast<float4*>(stage + lane * 16);
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) st4[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(col0), "r"(row0),
+                 "r"(smem_u32(stage))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
 }
 // the same as an asynchronous copy (cp.async, 4 bytes per lane and row pair; zero-filled outside): no register, no stall;
 // tile_fetch_wait() before the tile is read
@@ -545,6 +567,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s_m[rit * 8 + j] = v[j];
               }
+            } else if (p.out_tma) {
+              tma_store_group(&p.tm_out, stage, lane, v, K.s0 + cA, row_w);
             } else {
               stage_put(stage, lane, v);
               tile_flush(stage, lane, K.out, K.ldo, row_w, K.s0 + cA, K.s0 + K.n_valid, p.M);
@@ -556,8 +580,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_kernel(const __grid_consta
             tc_fence_before();
             mbar_arrive(&d_free[d]);
             bias_group(v, K.bias + cB);
-            stage_put(stage, lane, v);
-            tile_flush(stage, lane, K.out, K.ldo, row_w, K.s0 + cB, K.s0 + K.n_valid, p.M);
+            if (p.out_tma) {
+              tma_store_group(&p.tm_out, stage, lane, v, K.s0 + cB, row_w);
+            } else {
+              stage_put(stage, lane, v);
+              tile_flush(stage, lane, K.out, K.ldo, row_w, K.s0 + cB, K.s0 + K.n_valid, p.M);
+            }
           } else {
             tc_fence_before();
             mbar_arrive(&d_free[d]);
@@ -567,6 +595,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 1) row_kernel(const __grid_consta
       if (threadIdx.x == 64) ROW_TRACE(MAXU + ti, 3);
     }
     if ((ovf & 0x80008000u) && p.range_flag) atomicOr(p.range_flag, 1);
+    // the staging tiles must outlive the TMA engine's reads of them
+    if (p.out_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -853,6 +883,18 @@ inline std::string simulate(const Schedule& s) {
 inline int row_box_rows(int n_alloc) { return 2 * n_alloc < 128 ? 2 * n_alloc : 128; }
 inline bool make_row_weight_tmap(CUtensorMap* tm, const __half* base, int kpad, int n_alloc) {
   return make_tmap(tm, base, kpad, 2 * (int64_t)n_alloc, row_box_rows(n_alloc));
+}
+
+// fp32 [rows][ld] output tensor, box 16 columns x 32 rows (one warp's staging tile), no swizzle
+inline bool make_row_out_tmap(CUtensorMap* tm, float* base, int ld, long long rows) {
+  air::tc::EncodeTiledFn fn = air::tc::get_encode_fn();
+  if (!fn || (ld % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {16, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline cudaError_t launch_row(const Params& p, cudaStream_t st) {
