@@ -100,6 +100,7 @@ SYMBOLS = {
     "air_forward_host_u8": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P, _P,
                                         _P]),
     "air_cache_weights": (C.c_int32, [_P, C.c_int32]),
+    "air_set_launch_overlap": (C.c_int32, [_P, C.c_int32]),
     "air_params_updated": (C.c_int32, [_P]),
     "air_train_enable": (C.c_int32, [_P, C.c_int32]),
     "air_train_workspace_bytes": (C.c_int64, [_P]),

@@ -145,6 +145,7 @@ struct air_handle {
   air::tc::PrepEntry* prep_table = nullptr;
   int prep_tiles = 0;
   int* range_flag = nullptr;
+  bool launch_overlap = true;      // programmatic dependent launch between the kernels of a pass (air_set_launch_overlap)
   float* hw0 = nullptr;            // h0 @ W_h of the cluster LSTM (lstm_h0w_kernel), rebuilt with the weight arena
   std::map<std::pair<const void*, int>, CUtensorMap> tmap_cache;
   // training (air_train_enable / air_backward; either engine): saved activations + gradient scratch, one cudaMalloc
@@ -670,6 +671,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
   const int thr = 256;
   const bool tc = h->use_tc;
   const air::HlOut no_hl{nullptr, 0, 0, 0};
+  const air::PdlScope pdl_scope(h->launch_overlap);
   int32_t rc;
   // training mode (air_train_enable, fp32 engine): every activation the backward pass needs is kept
   const bool train = h->train && prior != nullptr && T_run == c.T && !h_in && !canvas_in;
@@ -2070,6 +2072,11 @@ int32_t air_cache_weights(air_handle* h, int32_t on) {
   h->weights_ready = nullptr;
   return AIR_OK;
 }
+int32_t air_set_launch_overlap(air_handle* h, int32_t on) {
+  if (!h) return fail(AIR_ERR_ARG, "air_set_launch_overlap: NULL handle");
+  h->launch_overlap = on != 0;
+  return AIR_OK;
+}
 int32_t air_params_updated(air_handle* h) {
   if (!h) return fail(AIR_ERR_ARG, "air_params_updated: NULL handle");
   h->weights_ready = nullptr;
@@ -2273,6 +2280,7 @@ int32_t air_forward(air_handle* h, const float* params, const float* img, const 
 int32_t air_forward_host(air_handle* h, const float* params, const float* img_host, const float* eps_where_host,
                          const float* eps_what_host, const float* u_pres_host, const air_prior* prior,
                          const air_outputs* outs, float* scalars_host, float* loss_per_sample_host, void* stream) {
+  const air::PdlScope pdl_scope(h ? h->launch_overlap : true);
   if (!h || !params || !img_host || !eps_where_host || !eps_what_host || !u_pres_host)
     return fail(AIR_ERR_ARG, "air_forward_host: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -2298,6 +2306,7 @@ int32_t air_forward_host_u8(air_handle* h, const float* params, const uint8_t* i
                             const float* eps_where_host, const float* eps_what_host, const float* u_pres_host,
                             const air_prior* prior, const air_outputs* outs, float* scalars_host,
                             float* loss_per_sample_host, void* stream) {
+  const air::PdlScope pdl_scope(h ? h->launch_overlap : true);
   if (!h || !params || !img_u8_host || !eps_where_host || !eps_what_host || !u_pres_host)
     return fail(AIR_ERR_ARG, "air_forward_host_u8: NULL argument");
   int32_t rc = check_outs(outs, prior != nullptr);
@@ -2352,6 +2361,7 @@ int32_t air_draw_noise(air_handle* h, uint64_t seed, float* eps_where, float* ep
 int32_t air_forward_host_u8_rng(air_handle* h, const float* params, const uint8_t* img_u8_host, uint64_t seed,
                                 const air_prior* prior, const air_outputs* outs, float* scalars_host,
                                 float* loss_per_sample_host, void* stream) {
+  const air::PdlScope pdl_scope(h ? h->launch_overlap : true);
   if (!h || !params || !img_u8_host) return fail(AIR_ERR_ARG, "air_forward_host_u8_rng: NULL argument");
   int32_t rc = check_outs(outs, prior != nullptr);
   if (rc != AIR_OK) return rc;
@@ -2415,6 +2425,7 @@ int32_t air_feed_host_u8(air_handle* h, int32_t slot, const uint8_t* img_u8_host
 
 int32_t air_forward_fed_u8_rng(air_handle* h, const float* params, int32_t slot, uint64_t seed, const air_prior* prior,
                                const air_outputs* outs, float* scalars_host, float* loss_per_sample_host, void* stream) {
+  const air::PdlScope pdl_scope(h ? h->launch_overlap : true);
   if (!h || !params || slot < 0 || slot > 1) return fail(AIR_ERR_ARG, "air_forward_fed_u8_rng: bad argument");
   if (!h->feed_stream || !h->feed_pending[slot])
     return fail(AIR_ERR_ARG, "air_forward_fed_u8_rng: nothing was fed into this slot (call air_feed_host_u8 first)");
@@ -2454,6 +2465,7 @@ int32_t air_forward_dataset_u8(air_handle* h, const float* params, const uint8_t
                                const int32_t* idx, const float* eps_where, const float* eps_what, const float* u_pres,
                                const float* baseline, const air_prior* prior, const air_outputs* outs, float* img_out,
                                void* stream) {
+  const air::PdlScope pdl_scope(h ? h->launch_overlap : true);
   if (!h || !params || !dataset_u8 || !idx || !eps_where || !eps_what || n_dataset < 1)
     return fail(AIR_ERR_ARG, "air_forward_dataset_u8: bad argument");
   if (h->cfg.discrete_steps && !u_pres) return fail(AIR_ERR_ARG, "air_forward_dataset_u8: u_pres is required");

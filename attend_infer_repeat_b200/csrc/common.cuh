@@ -102,6 +102,19 @@ inline bool pdl_enabled() {
   static const bool on = getenv("AIR_NO_PDL") == nullptr;
   return on;
 }
+// Per-thread switch consulted by launch_k, set for the duration of a call by the entry points that act on a handle
+// (air_set_launch_overlap).  Programmatic dependent launch lets the next kernel's CTAs take their SMs before the previous
+// kernel has finished: a gain for ONE stream (prologues overlap tails), a loss when several handles share the device --
+// an early tensor-kernel CTA then holds a whole SM while it only waits, and a neighbouring batch's kernel cannot use it.
+inline bool& pdl_thread_flag() {
+  static thread_local bool on = true;
+  return on;
+}
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_thread_flag()) { pdl_thread_flag() = on; }
+  ~PdlScope() { pdl_thread_flag() = prev; }
+};
 
 #ifdef __CUDACC__
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: the opt-in is remembered per (device, kernel),
@@ -137,7 +150,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() && pdl_thread_flag()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

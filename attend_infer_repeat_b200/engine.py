@@ -300,6 +300,11 @@ class Engine:
         params_updated() after writing to the buffer)."""
         check(self.lib.air_cache_weights(self._handle, int(on)), "air_cache_weights")
 
+    def set_launch_overlap(self, on: bool = True):
+        """Programmatic dependent launch between the kernels of a pass: on for a handle that has the device to itself, off
+        when several handles' passes are in flight (EnginePool does this)."""
+        check(self.lib.air_set_launch_overlap(self._handle, int(on)), "air_set_launch_overlap")
+
     def params_updated(self):
         check(self.lib.air_params_updated(self._handle), "air_params_updated")
 
@@ -525,6 +530,8 @@ class EnginePool:
         self.device = self.engines[0].device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         self._i = 0
+        for e in self.engines:      # with neighbours on the device, an early-launched CTA that only waits wastes its SM
+            e.set_launch_overlap(n_streams == 1)
 
     def __len__(self):
         return len(self.engines)

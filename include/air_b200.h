@@ -264,6 +264,13 @@ int32_t air_gather_u8(const uint8_t* dataset_u8, const int32_t* idx, float* img_
  * made with the SAME params pointer; the caller must then call air_params_updated(h) after changing the buffer's contents
  * (a TF graph has the same contract between a variable assignment and the ops that read it). */
 int32_t air_cache_weights(air_handle* h, int32_t on);
+
+/* Programmatic dependent launch between the kernels of a forward pass (default on): the next kernel's CTAs are scheduled while
+ * the previous kernel drains, which shortens ONE pass.  Turn it off for handles that share the device with other handles'
+ * passes (several batches in flight, EnginePool): an early tensor-kernel CTA holds a whole SM while it only waits for its
+ * predecessor, and a neighbouring batch's kernel cannot use that SM (measured at B = 4096, four batches in flight: 0.2155 ->
+ * 0.2036 ms per batch without it; one batch alone: 0.2670 -> 0.2716). */
+int32_t air_set_launch_overlap(air_handle* h, int32_t on);
 int32_t air_params_updated(air_handle* h);
 
 /* Importance-weighted bound (BASELINE.json configs[4]; an EXTENSION: the reference has no IWAE).  The K particles of a

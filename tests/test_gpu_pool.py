@@ -96,3 +96,29 @@ def test_glimpse_viz_on_request_equals_the_fused_output_and_the_oracle():
         assert torch.equal(out[k], out2[k]), k
     eng.close()
     lean.close()
+
+
+def test_launch_overlap_switch_changes_scheduling_only():
+    """air_set_launch_overlap (programmatic dependent launch on / off): bit-identical outputs either way; the pool turns it off
+    for its engines when more than one batch is in flight and leaves it on for a pool of one."""
+    ocfg = U.oracle_cfg(**U.SCRIPT)
+    B, T = 128, 3
+    cfg = U.cell_cfg(ocfg, air.AIR_PREC_TC_SPLIT)
+    params = O.flatten_params(ocfg, O.init_params(ocfg, 0)).to(DEV)
+    pr = U.prior_struct(O.PriorConfig(), 20000)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    d = (torch.rand(B, 50, 50, device=DEV, generator=g), torch.randn(T, B, 4, device=DEV, generator=g),
+         torch.randn(T, B, cfg.na, device=DEV, generator=g), torch.rand(T, B, 1, device=DEV, generator=g))
+    eng = air.Engine(cfg, B, T, device=DEV)
+    keys = ("canvas", "glimpse", "what", "where", "presence", "loss_per_sample", "scalars")
+    a = {k: v.clone() for k, v in eng.forward(params, *d, pr).items() if k in keys}
+    eng.set_launch_overlap(False)
+    b = {k: v.clone() for k, v in eng.forward(params, *d, pr).items() if k in keys}
+    eng.set_launch_overlap(True)
+    c = {k: v.clone() for k, v in eng.forward(params, *d, pr).items() if k in keys}
+    torch.cuda.synchronize()
+    for k in keys:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+    eng.close()
+    with pytest.raises(Exception):
+        air._lib.check(air._lib.lib().air_set_launch_overlap(None, 1), "air_set_launch_overlap")
