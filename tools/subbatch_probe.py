@@ -18,6 +18,7 @@ for S in ((1, 2, 3, 4, 6, 8) if full else (1, 2, 4)):
     engs = [air.Engine(cfg, B, T, device=dev) for _ in range(S)]
     for e in engs:
         e.cache_weights(True)
+        e.set_launch_overlap(S == 1 or os.environ.get("PROBE_KEEP_PDL") is not None)   # what EnginePool does
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     data = [(torch.rand(B, 50, 50, device=dev), torch.randn(T, B, 4, device=dev), torch.randn(T, B, cfg.na, device=dev),
              torch.rand(T, B, 1, device=dev)) for _ in range(S)]
