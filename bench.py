@@ -201,6 +201,9 @@ def workload_config(args, n):
             "outputs": "all 10 AIRCell outputs materialised [T,B,.] fp32 + per-sample ELBO terms (the model-level visualisation "
                        "tensor presence * sigmoid(glimpse), model.py:90, is computed on request as in the reference's graph)",
             "parallelism": f"dp{n}", "precision": args.precision,
+            "arithmetic": ("fp32-equivalent: every GEMM operand carried as an fp16 hi/lo pair, three tcgen05 MMAs per product, fp32 "
+                           "accumulation in tensor memory; the per-canvas stages in fp32" if args.precision == "tc" else
+                           "fp32 FMA on CUDA cores"),
             "streams": (args.streams if conf["mode"] != "train" else 1),
             "batches_in_flight": (f"{args.streams} independent batches of {args.batch} canvases, one per CUDA stream / handle "
                                   "(EnginePool); every step is one full pass over one batch"
