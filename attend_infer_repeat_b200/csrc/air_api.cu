@@ -948,13 +948,24 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     AIR_CUDA(cudaMalloc(&rtr, sizeof(long long) * 8 * (size_t)B));
     AIR_CUDA(cudaMemsetAsync(rtr, 0, sizeof(long long) * 8 * (size_t)B, st));
   }
-  AIR_CUDA(air::launch_k(air::where_read_kernel, dim3(B), dim3(read_threads),
-                         air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st,
-                         row_heads ? (const float*)nullptr : (const float*)h->m, eps_where, img, o->where, o->where_loc, o->where_scale,
-                         (tc && !train) ? nullptr : h->crop.f32,
-                         tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl, T_run, B, c.H, c.W, c.h, c.w,
-                         c.max_crop_size, c.scale_bias, c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0,
-                         c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0, pa, rtr));
+  {
+    const float* m_arg = row_heads ? (const float*)nullptr : (const float*)h->m;
+    float* crop_arg = (tc && !train) ? nullptr : h->crop.f32;
+    const air::HlOut hl_arg = tc ? (chain ? h->crop.hlt_out() : h->crop.hl_out()) : no_hl;
+    const double sw = c.w > 1 ? 2.0 / (double)(c.w - 1) : 0.0, sh = c.h > 1 ? 2.0 / (double)(c.h - 1) : 0.0;
+    static const bool no_fixed = getenv("AIR_READ_NO_FIXED") != nullptr;
+    // the quoted configuration (three steps, 50x50 image, 20x20 glimpse, 128 threads) has its own instantiation
+    if (!no_fixed && T_run == 3 && c.H == 50 && c.W == 50 && c.h == 20 && c.w == 20 && read_threads == 128)
+      AIR_CUDA(air::launch_k(air::where_read_kernel<3, 50, 50, 20, 20, 128>, dim3(B), dim3(read_threads),
+                             air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st, m_arg, eps_where, img, o->where,
+                             o->where_loc, o->where_scale, crop_arg, hl_arg, T_run, B, c.H, c.W, c.h, c.w,
+                             c.max_crop_size, c.scale_bias, sw, sh, pa, rtr));
+    else
+      AIR_CUDA(air::launch_k(air::where_read_kernel<0, 0, 0, 0, 0, 0>, dim3(B), dim3(read_threads),
+                             air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st, m_arg, eps_where, img, o->where,
+                             o->where_loc, o->where_scale, crop_arg, hl_arg, T_run, B, c.H, c.W, c.h, c.w,
+                             c.max_crop_size, c.scale_bias, sw, sh, pa, rtr));
+  }
   if (read_trace) {
     std::vector<long long> host((size_t)B * 8);
     AIR_CUDA(cudaMemcpyAsync(host.data(), rtr, sizeof(long long) * host.size(), cudaMemcpyDeviceToHost, st));
@@ -1827,7 +1838,8 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
     return fail(AIR_ERR_ARG, "air_create: image / glimpse tile does not fit in shared memory");
   }
   if (smem_read > 48 * 1024) {
-    cudaFuncSetAttribute(air::where_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
+    cudaFuncSetAttribute(air::where_read_kernel<0, 0, 0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
+    cudaFuncSetAttribute(air::where_read_kernel<3, 50, 50, 20, 20, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
     cudaFuncSetAttribute(air::stn_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
   }
 

@@ -261,11 +261,16 @@ __device__ __forceinline__ void presence_scan(const PresenceArgs& pa, int b, int
   }
 }
 
+// FT .. FNT > 0 fix the step count, the shapes and the thread count at compile time (the quoted configuration: every divisor and
+// trip count folds); 0 = taken from the arguments
+template <int FT, int FH, int FW, int Fh, int Fw, int FNT>
 __global__ void __launch_bounds__(WHERE_READ_THREADS, 2048 / WHERE_READ_THREADS)
 where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_where, const float* __restrict__ img,
                   float* __restrict__ where, float* __restrict__ where_loc, float* __restrict__ where_scale,
-                  float* __restrict__ crop, HlOut crop_hl, int T, int B, int H, int W, int h, int w, float max_crop,
+                  float* __restrict__ crop, HlOut crop_hl, int T_, int B, int H_, int W_, int h_, int w_, float max_crop,
                   float scale_bias, double step_w, double step_h, PresenceArgs pa, long long* trace) {
+  const int T = FT ? FT : T_, H = FH ? FH : H_, W = FW ? FW : W_, h = Fh ? Fh : h_, w = Fw ? Fw : w_;
+  const int NTC = FNT ? FNT : (int)blockDim.x;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_where[AIR_MAX_STEPS][4];
@@ -310,10 +315,10 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   }
   if (pa.logit && threadIdx.x == 64) presence_scan(pa, b, T, B);   // StepsPredictor + Bernoulli draw (cell.py:137-151)
   if (!bulk)
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_img[i] = src[i];
+    for (int i = threadIdx.x; i < P; i += NTC) s_img[i] = src[i];
   __syncthreads();
   READ_STAMP(1);
-  for (int i = threadIdx.x; i < T * (w + h); i += blockDim.x) {
+  for (int i = threadIdx.x; i < T * (w + h); i += NTC) {
     const int t = i / (w + h), j = i - t * (w + h);
     if (j < w) s_tx[t * w + j] = make_tap(fwd_coord_s(s_where[t][0], s_where[t][1], j, step_w, W), W, 1);
     else       s_ty[t * h + (j - w)] = make_tap(fwd_coord_s(s_where[t][2], s_where[t][3], j - w, step_h, H), H, W);
@@ -322,7 +327,7 @@ where_read_kernel(const float* __restrict__ m, const float* __restrict__ eps_whe
   READ_STAMP(2);
   if (bulk) mbar_wait(&bar, 0);
   READ_STAMP(3);
-  const int NT = blockDim.x;
+  const int NT = NTC;
   if (!crop && crop_hl.p && crop_hl.nsl > 0 && (G & 7) == 0) {
     // tensor-core engine, fused-chain operand layout ([row tile of 128][K slice of 16][128 rows][16 fp16]): 16-byte
     // stores of 8 consecutive glimpse pixels into the hi plane and into the lo plane.  The gather runs with lane <->
@@ -740,14 +745,47 @@ __host__ __device__ inline bool paint_pairs(const ElboArgs& a) {
          ((reinterpret_cast<uintptr_t>(a.canvas_in) & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.img) & 7) == 0);
 }
 
+// Shape policy of the paint kernel.  PaintRt reads the shape and the host-computed loop shapes from the arguments; PaintFx
+// makes them compile-time constants for one (canvas, glimpse, threads) combination -- every index product, trip count and
+// divisor then folds, the short loops unroll -- and is selected at launch when the shapes match (the quoted configuration).
+struct PaintRt {
+  static constexpr bool fixed = false;
+  __device__ static int H(const ElboArgs& a) { return a.H; }
+  __device__ static int W(const ElboArgs& a) { return a.W; }
+  __device__ static int h(const ElboArgs& a) { return a.h; }
+  __device__ static int w(const ElboArgs& a) { return a.w; }
+  __device__ static int NT(const ElboArgs&) { return (int)blockDim.x; }
+  __device__ static int col_cp(const ElboArgs& a) { return a.col_cp; }
+  __device__ static int col_rg(const ElboArgs& a) { return a.col_rg; }
+  __device__ static int col_ni(const ElboArgs& a) { return a.col_ni; }
+  __device__ static int row_tprb(const ElboArgs& a) { return a.row_tprb; }
+  __device__ static int row_rpp(const ElboArgs& a) { return a.row_rpp; }
+};
+template <int FH, int FW, int Fh, int Fw, int FNT>
+struct PaintFx {   // column pairs assumed (FW even, aligned pointers: checked at launch)
+  static constexpr bool fixed = true;
+  static constexpr int CP = FW < FNT ? FW : FNT, RG = FNT / CP, NI = (Fh + RG - 1) / RG;
+  static constexpr int TPRB = (FW / 2) < FNT ? (FW / 2) : FNT, RPP = FNT / TPRB;
+  __device__ static constexpr int H(const ElboArgs&) { return FH; }
+  __device__ static constexpr int W(const ElboArgs&) { return FW; }
+  __device__ static constexpr int h(const ElboArgs&) { return Fh; }
+  __device__ static constexpr int w(const ElboArgs&) { return Fw; }
+  __device__ static constexpr int NT(const ElboArgs&) { return FNT; }
+  __device__ static constexpr int col_cp(const ElboArgs&) { return CP; }
+  __device__ static constexpr int col_rg(const ElboArgs&) { return RG; }
+  __device__ static constexpr int col_ni(const ElboArgs&) { return NI; }
+  __device__ static constexpr int row_tprb(const ElboArgs&) { return TPRB; }
+  __device__ static constexpr int row_rpp(const ElboArgs&) { return RPP; }
+};
+
 // column pass: s_col[t][i][c] for every glimpse row i and canvas column c (zero outside the footprint / absent steps)
-template <int T>
+template <int T, class D>
 __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __restrict__ s_gl,
                                               const Tap* __restrict__ s_tx, const float* __restrict__ s_pres,
                                               float* __restrict__ s_col) {
-  const int W = a.W, h = a.h, w = a.w;
-  const int CP = a.col_cp;                      // columns resident in one sweep
-  const int RG = a.col_rg;                      // glimpse rows per sweep
+  const int W = D::W(a), h = D::h(a), w = D::w(a);
+  const int CP = D::col_cp(a);                  // columns resident in one sweep
+  const int RG = D::col_rg(a);                  // glimpse rows per sweep
   int cslot, islot;
   small_divmod((int)threadIdx.x, CP, islot, cslot);
   if (islot >= RG) return;
@@ -765,7 +803,7 @@ __device__ __forceinline__ void paint_columns(const ElboArgs& a, const float* __
       const float* gf = g + islot * w + tx.i_f;
       const float* gc = g + islot * w + tx.i_c;
       float* d = dst + islot * W;
-      const int n_i = a.col_ni, gstep = RG * w, dstep = RG * W;
+      const int n_i = D::col_ni(a), gstep = RG * w, dstep = RG * W;
 #pragma unroll 4
       for (int k = 0; k < n_i; ++k) {
         if (islot + k * RG < h) d[k * dstep] = fmaf(wc, gc[k * gstep], __fmul_rn(wf, gf[k * gstep]));
@@ -789,11 +827,11 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
 }
 // FAST: the hot configuration (canvases written, reconstruction term wanted, no initial canvas) with those three facts as
 // compile-time constants -- no predicates, no dead pointer arithmetic in the loop
-template <int T, int CPT, bool FAST>
+template <int T, int CPT, bool FAST, class D>
 __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap* __restrict__ s_ty) {
-  const int H = a.H, W = a.W;
-  const int TPRB = a.row_tprb;                  // threads per row (W / CPT) resident in one pass
-  const int RPP = a.row_rpp;                    // rows per pass
+  const int H = D::H(a), W = D::W(a);
+  const int TPRB = D::row_tprb(a);              // threads per row (W / CPT) resident in one pass
+  const int RPP = D::row_rpp(a);                // rows per pass
   int cslot, rslot;
   small_divmod((int)threadIdx.x, TPRB, rslot, cslot);
   const float mult = a.output_multiplier;
@@ -957,13 +995,14 @@ __device__ __forceinline__ float paint_rows_direct(const ElboArgs& a, int b, con
   return rec;
 }
 
-template <int T>
+template <int T, class D>
 __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ float s_pres[AIR_MAX_STEPS], s_red[32];
   __shared__ float4 s_inv[AIR_MAX_STEPS];
-  const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
+  const int B = a.B, H = D::H(a), W = D::W(a), h = D::h(a), w = D::w(a);
+  const int NT = D::NT(a);
   const int G = h * w;
   float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
   Tap* s_tx = reinterpret_cast<Tap*>(smem_raw + (sizeof(float) * (size_t)T * G + 15) / 16 * 16);         // [T][W]
@@ -978,7 +1017,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   // The first n_prior_ctas CTAs of the grid compute the prior terms (8 lanes per canvas) while the others paint: the
   // latency-bound float64 / log chains hide behind the paint CTAs instead of costing a launch.
   if ((int)blockIdx.x < a.n_prior_ctas) {
-    prior_terms_group<T>(a, (int)((blockIdx.x * blockDim.x + threadIdx.x) / PriorGroup<T>::L), 0);
+    prior_terms_group<T>(a, (int)((blockIdx.x * NT + threadIdx.x) / PriorGroup<T>::L), 0);
     PAINT_STAMP(6);
     return;
   }
@@ -993,7 +1032,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
       bulk_g2s(s_gl + (size_t)t * G, a.glimpse + ((size_t)t * B + b) * G, (uint32_t)G * 4u, &bar);
   }
   if (!bulk)
-    for (int i = threadIdx.x; i < T * G; i += blockDim.x) {
+    for (int i = threadIdx.x; i < T * G; i += NT) {
       const int t = i / G, g = i - t * G;
       s_gl[i] = a.glimpse[((size_t)t * B + b) * G + g];
     }
@@ -1022,7 +1061,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float4 iv = s_inv[t];
-    for (int j = threadIdx.x; j < W + H; j += blockDim.x) {
+    for (int j = threadIdx.x; j < W + H; j += NT) {
       if (j < W) s_tx[t * W + j] = make_tap(inv_coord_s(iv.x, iv.z, j, a.step_W, w), w, 1);
       else if (!a.separable) s_ty[t * H + (j - W)] = make_tap(inv_coord_s(iv.y, iv.w, j - W, a.step_H, h), h, w);
       else {
@@ -1039,13 +1078,13 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   PAINT_STAMP(2);
   if (bulk) mbar_wait(&bar, 0);
   PAINT_STAMP(3);
-  if (a.separable) paint_columns<T>(a, s_gl, s_tx, s_pres, s_col);
+  if (a.separable) paint_columns<T, D>(a, s_gl, s_tx, s_pres, s_col);
 
   // optional visualisation output: presence * sigmoid(glimpse)   (model.py:90)
   if (a.glimpse_viz) {
     if (((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.glimpse_viz) & 15) == 0) && T * (G >> 2) < 2048) {
       const int G4 = G >> 2;                       // 16-byte pieces, all T glimpses in one flat loop
-      for (int i = threadIdx.x; i < T * G4; i += blockDim.x) {
+      for (int i = threadIdx.x; i < T * G4; i += NT) {
         int t, g;
         small_divmod(i, G4, t, g);
         const float pres_t = s_pres[t];
@@ -1059,7 +1098,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
       for (int t = 0; t < T; ++t) {
         float* dst = a.glimpse_viz + ((size_t)t * B + b) * G;
         const float pres_t = s_pres[t];
-        for (int g = threadIdx.x; g < G; g += blockDim.x) dst[g] = __fmul_rn(pres_t, sigmoid_lean(s_gl[t * G + g]));
+        for (int g = threadIdx.x; g < G; g += NT) dst[g] = __fmul_rn(pres_t, sigmoid_lean(s_gl[t * G + g]));
       }
     }
   }
@@ -1069,8 +1108,8 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   PAINT_STAMP(4);
   float rec;
   const bool fast = a.do_elbo && a.canvas && !a.canvas_in;
-  if (a.separable && pair && fast) rec = paint_rows<T, 2, true>(a, b, s_ty);
-  else if (a.separable) rec = pair ? paint_rows<T, 2, false>(a, b, s_ty) : paint_rows<T, 1, false>(a, b, s_ty);
+  if (a.separable && pair && fast) rec = paint_rows<T, 2, true, D>(a, b, s_ty);
+  else if (a.separable) rec = pair ? paint_rows<T, 2, false, D>(a, b, s_ty) : paint_rows<T, 1, false, D>(a, b, s_ty);
   else rec = pair ? paint_rows_direct<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows_direct<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
   PAINT_STAMP(5);
   if (!a.do_elbo) return;
@@ -1088,10 +1127,21 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
 
 template <int T>
 inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStream_t st) {
-  cudaError_t e = ensure_dynamic_smem(paint_elbo_kernel<T>, smem);
-  if (e != cudaSuccess) return e;
   static const int nt = getenv("AIR_PAINT_THREADS") ? atoi(getenv("AIR_PAINT_THREADS")) : 256;
-  return launch_k(paint_elbo_kernel<T>, dim3(a.B + a.n_prior_ctas), dim3(nt), smem, st, a);
+  static const bool no_fixed = getenv("AIR_PAINT_NO_FIXED") != nullptr;
+  // the configuration the metric is quoted on (50x50 canvas, 20x20 glimpse, three steps, 256 threads, separable, column
+  // pairs): shapes and loop shapes as compile-time constants
+  using Fx = PaintFx<50, 50, 20, 20, 256>;
+  if constexpr (T == 3) {
+    if (!no_fixed && nt == 256 && a.H == 50 && a.W == 50 && a.h == 20 && a.w == 20 && a.separable && paint_pairs(a)) {
+      cudaError_t e = ensure_dynamic_smem(paint_elbo_kernel<T, Fx>, smem);
+      if (e != cudaSuccess) return e;
+      return launch_k(paint_elbo_kernel<T, Fx>, dim3(a.B + a.n_prior_ctas), dim3(nt), smem, st, a);
+    }
+  }
+  cudaError_t e = ensure_dynamic_smem(paint_elbo_kernel<T, PaintRt>, smem);
+  if (e != cudaSuccess) return e;
+  return launch_k(paint_elbo_kernel<T, PaintRt>, dim3(a.B + a.n_prior_ctas), dim3(nt), smem, st, a);
 }
 // host-side constants of ElboArgs (float64 maths on the host, exactly what the device code computed per tap before)
 inline void fill_elbo_consts(ElboArgs& a) {
