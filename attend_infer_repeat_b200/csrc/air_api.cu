@@ -960,6 +960,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
                              air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st, m_arg, eps_where, img, o->where,
                              o->where_loc, o->where_scale, crop_arg, hl_arg, T_run, B, c.H, c.W, c.h, c.w,
                              c.max_crop_size, c.scale_bias, sw, sh, pa, rtr));
+    else if (!no_fixed && T_run == 5 && c.H == 100 && c.W == 100 && c.h == 28 && c.w == 28 && read_threads == 128)   // configs[3]
+      AIR_CUDA(air::launch_k(air::where_read_kernel<5, 100, 100, 28, 28, 128>, dim3(B), dim3(read_threads),
+                             air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st, m_arg, eps_where, img, o->where,
+                             o->where_loc, o->where_scale, crop_arg, hl_arg, T_run, B, c.H, c.W, c.h, c.w,
+                             c.max_crop_size, c.scale_bias, sw, sh, pa, rtr));
     else
       AIR_CUDA(air::launch_k(air::where_read_kernel<0, 0, 0, 0, 0, 0>, dim3(B), dim3(read_threads),
                              air::where_read_smem(T_run, c.H, c.W, c.h, c.w), st, m_arg, eps_where, img, o->where,
@@ -1840,6 +1845,7 @@ int32_t air_create(const air_config* cfg, air_handle** out) {
   if (smem_read > 48 * 1024) {
     cudaFuncSetAttribute(air::where_read_kernel<0, 0, 0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
     cudaFuncSetAttribute(air::where_read_kernel<3, 50, 50, 20, 20, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
+    cudaFuncSetAttribute(air::where_read_kernel<5, 100, 100, 28, 28, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
     cudaFuncSetAttribute(air::stn_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_read);
   }
 

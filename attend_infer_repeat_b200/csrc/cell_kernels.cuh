@@ -914,13 +914,13 @@ __device__ __forceinline__ float paint_rows(const ElboArgs& a, int b, const Tap*
 
 // direct form of the row pass (round 1): four taps per pixel from the staged glimpse; s_tx [T][W], s_ty [T][H] with indices
 // pre-multiplied by the glimpse pitch w
-template <int T, int CPT>
+template <int T, int CPT, class D>
 __device__ __forceinline__ float paint_rows_direct(const ElboArgs& a, int b, const float* __restrict__ s_gl,
                                             const Tap* __restrict__ s_tx, const Tap* __restrict__ s_ty,
                                             const float* __restrict__ s_pres) {
-  const int B = a.B, H = a.H, W = a.W;
-  const int P = H * W, G = a.h * a.w;
-  const int NT = blockDim.x;
+  const int B = a.B, H = D::H(a), W = D::W(a);
+  const int P = H * W, G = D::h(a) * D::w(a);
+  const int NT = D::NT(a);
   const int TPR = W / CPT;                      // threads per row
   const int TPRB = TPR < NT ? TPR : NT;         // ... resident in one pass
   const int RPP = NT / TPRB;                    // rows per pass
@@ -1110,7 +1110,7 @@ __global__ void __launch_bounds__(256, PAINT_MIN_CTAS) paint_elbo_kernel(ElboArg
   const bool fast = a.do_elbo && a.canvas && !a.canvas_in;
   if (a.separable && pair && fast) rec = paint_rows<T, 2, true, D>(a, b, s_ty);
   else if (a.separable) rec = pair ? paint_rows<T, 2, false, D>(a, b, s_ty) : paint_rows<T, 1, false, D>(a, b, s_ty);
-  else rec = pair ? paint_rows_direct<T, 2>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows_direct<T, 1>(a, b, s_gl, s_tx, s_ty, s_pres);
+  else rec = pair ? paint_rows_direct<T, 2, D>(a, b, s_gl, s_tx, s_ty, s_pres) : paint_rows_direct<T, 1, D>(a, b, s_gl, s_tx, s_ty, s_pres);
   PAINT_STAMP(5);
   if (!a.do_elbo) return;
   rec = block_sum(rec, s_red);
@@ -1132,6 +1132,14 @@ inline cudaError_t launch_paint_elbo_t(const ElboArgs& a, size_t smem, cudaStrea
   // the configuration the metric is quoted on (50x50 canvas, 20x20 glimpse, three steps, 256 threads, separable, column
   // pairs): shapes and loop shapes as compile-time constants
   using Fx = PaintFx<50, 50, 20, 20, 256>;
+  if constexpr (T == 5) {   // BASELINE configs[3]: 100x100 canvas, 28x28 glimpse, five steps (direct form)
+    using Fx4 = PaintFx<100, 100, 28, 28, 256>;
+    if (!no_fixed && nt == 256 && a.H == 100 && a.W == 100 && a.h == 28 && a.w == 28 && !a.separable && paint_pairs(a)) {
+      cudaError_t e = ensure_dynamic_smem(paint_elbo_kernel<T, Fx4>, smem);
+      if (e != cudaSuccess) return e;
+      return launch_k(paint_elbo_kernel<T, Fx4>, dim3(a.B + a.n_prior_ctas), dim3(nt), smem, st, a);
+    }
+  }
   if constexpr (T == 3) {
     if (!no_fixed && nt == 256 && a.H == 50 && a.W == 50 && a.h == 20 && a.w == 20 && a.separable && paint_pairs(a)) {
       cudaError_t e = ensure_dynamic_smem(paint_elbo_kernel<T, Fx>, smem);
