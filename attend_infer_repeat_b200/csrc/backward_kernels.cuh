@@ -123,7 +123,8 @@ __device__ __forceinline__ float btap_weight(const BTap& t, int idx) {
   return wgt;
 }
 
-template <int T>
+// FH .. Fw > 0: canvas / glimpse shape as compile-time constants (the quoted configuration), 0: from the arguments
+template <int T, int FH, int FW, int Fh, int Fw>
 __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float4 s_inv[AIR_MAX_STEPS];
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
   __shared__ float s_red[8][4 * T];
   __shared__ float s_redp[8][T];
   __shared__ int s_rect[T][4];   // canvas rectangle inside glimpse t's footprint: c_lo, c_hi, r_lo, r_hi
-  const int B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
+  const int B = a.B, H = FH ? FH : a.H, W = FW ? FW : a.W, h = Fh ? Fh : a.h, w = Fw ? Fw : a.w;
   const int P = H * W, G = h * w;
   const int b = blockIdx.x;
   float* s_gl = reinterpret_cast<float*>(smem_raw);                                                      // [T][G]
@@ -316,9 +317,17 @@ __global__ void __launch_bounds__(256) paint_bwd_kernel(BwdArgs a) {
 template <int T>
 inline cudaError_t launch_paint_bwd_t(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = paint_bwd_smem(a.T, a.H, a.W, a.h, a.w);
-  cudaError_t e = ensure_dynamic_smem(paint_bwd_kernel<T>, smem);
+  static const bool no_fixed = getenv("AIR_BWD_NO_FIXED") != nullptr;
+  if constexpr (T == 3) {
+    if (!no_fixed && a.H == 50 && a.W == 50 && a.h == 20 && a.w == 20) {
+      cudaError_t e = ensure_dynamic_smem(paint_bwd_kernel<T, 50, 50, 20, 20>, smem);
+      if (e != cudaSuccess) return e;
+      return launch_k(paint_bwd_kernel<T, 50, 50, 20, 20>, dim3(a.B), dim3(256), smem, st, a);
+    }
+  }
+  cudaError_t e = ensure_dynamic_smem(paint_bwd_kernel<T, 0, 0, 0, 0>, smem);
   if (e != cudaSuccess) return e;
-  return launch_k(paint_bwd_kernel<T>, dim3(a.B), dim3(256), smem, st, a);
+  return launch_k(paint_bwd_kernel<T, 0, 0, 0, 0>, dim3(a.B), dim3(256), smem, st, a);
 }
 inline cudaError_t launch_paint_bwd(const BwdArgs& a, cudaStream_t st) {
   switch (a.T) {
@@ -341,10 +350,11 @@ inline cudaError_t launch_paint_bwd(const BwdArgs& a, cudaStream_t st) {
 __host__ __device__ inline size_t read_bwd_smem(int T, int H, int W, int h, int w) {
   return (sizeof(float) * (size_t)H * W + 15) / 16 * 16 + sizeof(BTap) * (size_t)T * (w + h);
 }
+template <int FT, int FH, int FW, int Fh, int Fw>
 __global__ void __launch_bounds__(256) read_bwd_kernel(BwdArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float s_red[8][4];
-  const int T = a.T, B = a.B, H = a.H, W = a.W, h = a.h, w = a.w;
+  const int T = FT ? FT : a.T, B = a.B, H = FH ? FH : a.H, W = FW ? FW : a.W, h = Fh ? Fh : a.h, w = Fw ? Fw : a.w;
   const int P = H * W, G = h * w;
   const int b = blockIdx.x;
   float* s_img = reinterpret_cast<float*>(smem_raw);
@@ -402,9 +412,15 @@ __global__ void __launch_bounds__(256) read_bwd_kernel(BwdArgs a) {
 }
 inline cudaError_t launch_read_bwd(const BwdArgs& a, cudaStream_t st) {
   const size_t smem = read_bwd_smem(a.T, a.H, a.W, a.h, a.w);
-  cudaError_t e = ensure_dynamic_smem(read_bwd_kernel, smem);
+  static const bool no_fixed = getenv("AIR_BWD_NO_FIXED") != nullptr;
+  if (!no_fixed && a.T == 3 && a.H == 50 && a.W == 50 && a.h == 20 && a.w == 20) {
+    cudaError_t e = ensure_dynamic_smem(read_bwd_kernel<3, 50, 50, 20, 20>, smem);
+    if (e != cudaSuccess) return e;
+    return launch_k(read_bwd_kernel<3, 50, 50, 20, 20>, dim3(a.B), dim3(256), smem, st, a);
+  }
+  cudaError_t e = ensure_dynamic_smem(read_bwd_kernel<0, 0, 0, 0, 0>, smem);
   if (e != cudaSuccess) return e;
-  return launch_k(read_bwd_kernel, dim3(a.B), dim3(256), smem, st, a);
+  return launch_k(read_bwd_kernel<0, 0, 0, 0, 0>, dim3(a.B), dim3(256), smem, st, a);
 }
 
 // d Normal||Normal KL / d (mu_a, s_a)   [upstream _kl_normal_normal]
