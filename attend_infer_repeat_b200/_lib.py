@@ -102,6 +102,7 @@ SYMBOLS = {
     "air_cache_weights": (C.c_int32, [_P, C.c_int32]),
     "air_set_launch_overlap": (C.c_int32, [_P, C.c_int32]),
     "air_params_updated": (C.c_int32, [_P]),
+    "air_prior_table_device": (C.c_int32, [_P, C.POINTER(air_prior), _P]),
     "air_train_enable": (C.c_int32, [_P, C.c_int32]),
     "air_train_workspace_bytes": (C.c_int64, [_P]),
     "air_backward": (C.c_int32, [_P, _P, _P, _P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), C.c_float, C.c_float,
@@ -126,6 +127,7 @@ SYMBOLS = {
     "air_baseline_input_width": (C.c_int32, [_P]),
     "air_baseline_forward": (C.c_int32, [_P, _P, _P, C.POINTER(air_outputs), _P, _P]),
     "air_baseline_backward": (C.c_int32, [_P, _P, _P, _P, _P]),
+    "air_baseline_backward_async": (C.c_int32, [_P, _P, _P, _P, _P]),
     "air_elbo_scalars": (C.c_int32, [_P, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_elbo_scalars_raw": (C.c_int32, [C.c_int32, _P, C.POINTER(air_prior), C.POINTER(air_outputs), _P]),
     "air_prior_terms": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(air_prior),

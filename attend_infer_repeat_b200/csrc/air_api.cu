@@ -152,6 +152,9 @@ struct air_handle {
   // inference: the prepared fp16-split weight arena is reused while the caller vouches that `params` is unchanged
   bool cache_weights = false;
   const float* weights_ready = nullptr;
+  const float* hw0_ready = nullptr;   // parameters for which hw0 (lstm_h0w_kernel) is current
+  double* prior_dev = nullptr;        // air_prior_table_device: geometric_prior table in device memory ([AIR_MAX_STEPS + 1])
+  bool prior_dev_on = false;
   bool train = false;
   bool fwd_saved = false;          // the last forward on this handle ran in training mode with a prior (backward is valid)
   char* tws = nullptr;
@@ -690,12 +693,15 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     AIR_CUDA(air::launch_k(air::tc::prep_weights_kernel, dim3(h->prep_tiles), dim3(256), 0, st, params, h->arena,
                            h->prep_table, (int)h->tcw.size(), h->range_flag, h->bias_arena));
     ++h->launches;
-    if (h->lstm_ok && h->hw0) {
-      AIR_CUDA(air::launch_k(air::lstm::lstm_h0w_kernel, dim3((4 * nh + 255) / 256), dim3(256), 0, st,
-                             params + h->lstm_h.w_off, params + h->lstm_h0, h->hw0, nh));
-      ++h->launches;
-    }
     h->weights_ready = params;
+  }
+  // h0 @ W_h of the cluster LSTM (only passes that broadcast the trainable initial state read it: not the training forward,
+  // which keeps per-canvas rows, and not air_cell_step with explicit state)
+  if (tc && h->lstm_ok && h->hw0 && !train && !h_in && !(h->cache_weights && h->hw0_ready == params)) {
+    AIR_CUDA(air::launch_k(air::lstm::lstm_h0w_kernel, dim3((4 * nh + 31) / 32), dim3(256), 0, st,
+                           params + h->lstm_h.w_off, params + h->lstm_h0, h->hw0, nh));
+    ++h->launches;
+    h->hw0_ready = params;
   }
   const bool enc1 = enc1_active(h);
   if (tc && !enc1) {
@@ -1088,6 +1094,7 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     for (int k = 0; k <= T_run; ++k)
       a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
                                                   : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
+    a.steps_prior_dev = h->prior_dev_on ? h->prior_dev : nullptr;
   }
   a.lp_const = (float)(0.5 * 1.8378770664093453 /* log(2 pi) */ + std::log((double)c.output_std));
   a.prior_part = h->prior_part;
@@ -1150,6 +1157,7 @@ void carve_workspace(air_handle* h, Carver& cv) {
   const size_t TB = (size_t)c.T * c.B, B = c.B;
   const bool tc = h->use_tc;
   const int B_alloc = round_up(c.B, air::tc::BM), TB_alloc = round_up((int)TB, air::tc::BM);
+  h->prior_dev = cv.take<double>(AIR_MAX_STEPS + 1);
   auto f32 = [&](Buf& b, size_t rows, int width) {
     b.f32 = cv.take<float>(rows * width);
     b.ld = width;
@@ -1638,6 +1646,7 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   for (int k = 0; k <= T; ++k)
     a.steps_prior[k] = prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
                                                 : (double)air::geom_prior_f32((float)prior->steps_success_prob, k);
+  a.steps_prior_dev = h->prior_dev_on ? h->prior_dev : nullptr;
 
   // 1. reconstruction term -> d glimpse, d where (inverse transformer)            cell.py:159-164, model.py:319-321
   AIR_CUDA(air::launch_paint_bwd(a, st));
@@ -2088,6 +2097,7 @@ int32_t air_cache_weights(air_handle* h, int32_t on) {
   if (!h) return fail(AIR_ERR_ARG, "air_cache_weights: NULL handle");
   h->cache_weights = on != 0;
   h->weights_ready = nullptr;
+  h->hw0_ready = nullptr;
   return AIR_OK;
 }
 int32_t air_set_launch_overlap(air_handle* h, int32_t on) {
@@ -2095,9 +2105,32 @@ int32_t air_set_launch_overlap(air_handle* h, int32_t on) {
   h->launch_overlap = on != 0;
   return AIR_OK;
 }
+namespace {
+struct PriorTable { double v[AIR_MAX_STEPS + 1]; };
+__global__ void prior_table_kernel(PriorTable t, double* dst) {
+  if (threadIdx.x <= AIR_MAX_STEPS) dst[threadIdx.x] = t.v[threadIdx.x];
+}
+}   // namespace
+int32_t air_prior_table_device(air_handle* h, const air_prior* prior, void* stream) {
+  if (!h) return fail(AIR_ERR_ARG, "air_prior_table_device: NULL handle");
+  if (!prior) {
+    h->prior_dev_on = false;
+    return AIR_OK;
+  }
+  PriorTable t;
+  for (int k = 0; k <= AIR_MAX_STEPS; ++k)
+    t.v[k] = k <= h->cfg.T ? (prior->steps_prob_is_f64 ? air::geom_prior_f64(prior->steps_success_prob, k)
+                                                      : (double)air::geom_prior_f32((float)prior->steps_success_prob, k))
+                           : 1.0;
+  prior_table_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, h->prior_dev);
+  AIR_CUDA(cudaGetLastError());
+  h->prior_dev_on = true;
+  return AIR_OK;
+}
 int32_t air_params_updated(air_handle* h) {
   if (!h) return fail(AIR_ERR_ARG, "air_params_updated: NULL handle");
   h->weights_ready = nullptr;
+  h->hw0_ready = nullptr;
   return AIR_OK;
 }
 
@@ -2255,7 +2288,9 @@ int32_t air_baseline_forward(air_handle* h, const float* bparams, const float* i
   return AIR_OK;
 }
 
-int32_t air_baseline_backward(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad, void* stream) {
+namespace {
+int32_t baseline_backward_impl(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad, void* stream,
+                               bool join) {
   if (!h || !bparams || !d_baseline || !bgrad) return fail(AIR_ERR_ARG, "air_baseline_backward: NULL argument");
   if (!h->bl.attached) return fail(AIR_ERR_ARG, "air_baseline_backward: air_baseline_attach first");
   cudaStream_t st = (cudaStream_t)stream;
@@ -2281,7 +2316,18 @@ int32_t air_baseline_backward(air_handle* h, const float* bparams, const float* 
       ld_cur = l.K;
     }
   }
-  return join_side_streams(h, st);
+  return join ? join_side_streams(h, st) : AIR_OK;
+}
+}   // namespace
+int32_t air_baseline_backward(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad, void* stream) {
+  return baseline_backward_impl(h, bparams, d_baseline, bgrad, stream, true);
+}
+// The weight-gradient GEMMs stay on the handle's side streams without being joined: they overlap the air_backward that
+// follows on the same stream, whose final join covers them (the big one, [B, 3177]^T [B, 256], is 50 MB of operand traffic
+// that nothing on the main gradient path waits for).
+int32_t air_baseline_backward_async(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad,
+                                    void* stream) {
+  return baseline_backward_impl(h, bparams, d_baseline, bgrad, stream, false);
 }
 
 int32_t air_forward(air_handle* h, const float* params, const float* img, const float* eps_where,

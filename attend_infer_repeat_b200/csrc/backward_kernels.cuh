@@ -92,6 +92,7 @@ struct BwdArgs {
   double step_W, step_H, step_w, step_h;   // np.linspace steps (host, float64) as in the forward
   air_prior prior;
   double steps_prior[AIR_MAX_STEPS + 1];
+  const double* steps_prior_dev;    // non-null: the table is read from device memory (air_prior_table_device)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(128) latent_bwd_kernel(BwdArgs a) {
 #pragma unroll
   for (int k = 0; k <= T; ++k) {
     double g = 0.0;
-    if (q[k] > 0.0) g = (double)coef * (double)pr.steps_weight * (log(q[k] / a.steps_prior[k]) + 1.0);
+    if (q[k] > 0.0) g = (double)coef * (double)pr.steps_weight * (log(q[k] / (a.steps_prior_dev ? a.steps_prior_dev[k] : a.steps_prior[k])) + 1.0);
     if (k >= 1 && pr.analytic) {
       dsw_run += (double)coef * ((double)klw[k - 1] + (double)klwh[k - 1]);
       g += dsw_run;

@@ -489,6 +489,8 @@ struct ElboArgs {
   air_prior prior;
   double steps_prior[AIR_MAX_STEPS + 1];   // geometric_prior(success_prob, T) (prior.py:26-32): the same table for
                                            // every canvas, computed once on the host (air_api.cu:steps_prior_table)
+  const double* steps_prior_dev;           // non-null: the table is read from device memory instead (air_prior_table_device:
+                                           // an annealed prior under a replayed CUDA graph, whose kernel arguments are frozen)
 };
 
 // prior.py:26-32 geometric_prior in float64 [upstream Geometric(probs=1-s).prob(k) = exp(k*log1p(-probs) + log(probs))]
@@ -589,7 +591,7 @@ __device__ __forceinline__ void prior_terms_group(const ElboArgs& a, int b_in, i
   float q = 0.f, kl = 0.f;
   if (k <= T) {
     q = (float)(pi / sum);
-    kl = tabular_kl_entry(q, a.steps_prior[k], 0.0);
+    kl = tabular_kl_entry(q, a.steps_prior_dev ? a.steps_prior_dev[k] : a.steps_prior[k], 0.0);
     if (valid) a.num_steps_posterior[(size_t)b * (T + 1) + k] = q;
   }
   float kl_n = 0.f;   // fp32 sum over n in index order (model.py:149)

@@ -525,12 +525,24 @@ __global__ void __launch_bounds__(256)
 lstm_h0w_kernel(const float* __restrict__ w_h, const float* __restrict__ h0, float* __restrict__ hw0, int nh) {
   griddep_launch();
   griddep_wait();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= 4 * nh) return;
+  // block = 32 outputs x 8 slices of k: eight independent partial sums per output, loads of a warp contiguous in n
+  __shared__ float part[8][33];
+  const int nl = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + nl;
   float acc = 0.f;
-  for (int k = 0; k < nh; ++k) acc = fmaf(h0[k], w_h[(size_t)k * 4 * nh + n], acc);
-  const int upc = nh >> 2, gate = n / nh, unit = n % nh;
-  hw0[(unit / upc) * nh + gate * upc + unit % upc] = acc;
+  if (n < 4 * nh) {
+#pragma unroll 8
+    for (int k = ks; k < nh; k += 8) acc = fmaf(h0[k], w_h[(size_t)k * 4 * nh + n], acc);
+  }
+  part[ks][nl] = acc;
+  __syncthreads();
+  if (ks == 0 && n < 4 * nh) {
+    float sum = part[0][nl];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) sum += part[j][nl];
+    const int upc = nh >> 2, gate = n / nh, unit = n % nh;
+    hw0[(unit / upc) * nh + gate * upc + unit % upc] = sum;
+  }
 }
 
 inline cudaError_t launch_lstm(const Params& p, cudaStream_t st) {

@@ -308,6 +308,14 @@ class Engine:
     def params_updated(self):
         check(self.lib.air_params_updated(self._handle), "air_params_updated")
 
+    def prior_table_device(self, prior: Optional[air_prior]):
+        """Replayed CUDA graphs: write geometric_prior(prior.steps_success_prob, T) into the handle's device table (a one-warp
+        kernel on the current stream) and make forward() / backward() read it from there, so that a captured step follows the
+        annealed prior (model.py:133-142).  None switches back to the table in the kernel arguments."""
+        with torch.cuda.device(self.device):
+            check(self.lib.air_prior_table_device(self._handle, C.byref(prior) if prior is not None else None,
+                                                  current_stream_ptr()), "air_prior_table_device")
+
     # -- training step (SURVEY 8f row 1) -----------------------------------------------------------------
     def train_enable(self, on: bool = True):
         """Keep the activations of every following forward() for backward() (either engine: on an AIR_PREC_TC_SPLIT
@@ -349,11 +357,13 @@ class Engine:
                                                 current_stream_ptr()), "air_baseline_forward")
         return out
 
-    def baseline_backward(self, bparams, d_baseline, bgrad) -> torch.Tensor:
-        """d baseline_loss / d baseline parameters for the last baseline_forward(), into bgrad (flat)."""
+    def baseline_backward(self, bparams, d_baseline, bgrad, defer_join: bool = False) -> torch.Tensor:
+        """d baseline_loss / d baseline parameters for the last baseline_forward(), into bgrad (flat).  ``defer_join``: the
+        weight-gradient GEMMs stay on the side streams and bgrad is complete only after the next backward() on this engine
+        (air_baseline_backward_async)."""
+        fn = self.lib.air_baseline_backward_async if defer_join else self.lib.air_baseline_backward
         with torch.cuda.device(self.device):
-            check(self.lib.air_baseline_backward(self._handle, ptr(bparams), ptr(d_baseline), ptr(bgrad),
-                                                 current_stream_ptr()), "air_baseline_backward")
+            check(fn(self._handle, ptr(bparams), ptr(d_baseline), ptr(bgrad), current_stream_ptr()), "air_baseline_backward")
         return bgrad
 
     def rmsprop_step(self, params, grad, mg, ms, mom, learning_rate, decay=0.9, momentum=0.9, epsilon=1e-10,

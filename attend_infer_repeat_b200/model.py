@@ -123,6 +123,8 @@ class AIRModel:
         eps_where, eps_what, u_pres = (n.contiguous() for n in noise)
         self._last_noise = (eps_where, eps_what, u_pres)
         self._prior_struct = self._current_prior()
+        if self.__dict__.get("_prior_on_device") and not torch.cuda.is_current_stream_capturing():
+            self.engine.prior_table_device(self._prior_struct)   # graph mode: kernels read the step prior from device memory
         o = self.engine.forward(self.cell.params, self.obs, eps_where, eps_what, u_pres, self._prior_struct)
 
         # attributes named by AIRCell.output_names (model.py:86-87) and the post-processing of model.py:89-104
@@ -236,7 +238,7 @@ class AIRModel:
                    where_shift_prior=None,
                    num_steps_prior=None, use_prior=True,
                    use_reinforce=True, baseline=None, decay_rate=None,
-                   optimizer=None, opt_kwargs=dict(momentum=.9, centered=True)):
+                   optimizer=None, opt_kwargs=dict(momentum=.9, centered=True), cuda_graph=None):
         """Creates the train step and the global_step (model.py:261-376).
 
         The returned ``train_op(obs=None, nums=None, noise=None)`` is the sess.run(train_step) of the reference: forward +
@@ -245,7 +247,15 @@ class AIRModel:
         parameter buffer (air_rmsprop_step, TF semantics).  The engine is switched to training mode, in which every
         activation the backward pass needs is kept.  A baseline module (BaselineMLP) is trained by its own RMSProp at 10x the
         learning rate on .5 * mean((stop_gradient(iw) - baseline)^2) (model.py:253-259,362-367); decay_rate switches on
-        the NVIL normalisation of the importance weight by its moving moments (model.py:232-239)."""
+        the NVIL normalisation of the importance weight by its moving moments (model.py:232-239).
+
+        ``cuda_graph`` (default: on for one process, ``AIR_TRAIN_GRAPH=0`` turns it off; opt-in under torch.distributed, where
+        ``release_graphs()`` has to precede ``dist.destroy_process_group()``): like the reference, which builds its graph once and
+        re-runs it, the step is enqueued eagerly twice and then captured as ONE CUDA graph (forward, BaselineMLP, both
+        backward passes, the gradient all-reduces, both optimiser updates: ~110 launches on three streams) that every
+        later ``train_op`` call replays.  Inputs are copied into the graph's static buffers; the annealed step prior is
+        re-computed on the host every call and handed over through device memory (``Engine.prior_table_device``).  The
+        NVIL variant (``decay_rate``) reads batch moments on the host every step and stays eager."""
         if num_steps_prior is None:
             raise ValueError("num_steps_prior is required (model.py:292 dereferences it)")
         if optimizer is not None:
@@ -278,6 +288,19 @@ class AIRModel:
         self.engine.train_enable(True)
         n = self.engine.n_params
         dev = self.obs.device
+        if cuda_graph is None:
+            import os
+            import torch.distributed as dist
+            sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            # under sharding the captured graph holds NCCL kernels, and NCCL cannot tear a communicator down while such a
+            # graph is alive: release_graphs() must then precede dist.destroy_process_group() -- a contract the caller has
+            # to know about, so it is opt-in there (cuda_graph=True or AIR_TRAIN_GRAPH=1)
+            cuda_graph = os.environ.get("AIR_TRAIN_GRAPH", "0" if sharded else "1") != "0"
+        self._graph_ok = bool(cuda_graph) and decay_rate is None and self.obs.is_cuda
+        self._graphs, self._eager_steps, self._g_obs, self._g_noise = {}, 0, None, None
+        self.graph_launches_per_step, self.graph_replays = 0, 0
+        self._prior_on_device = False
+        self.engine.prior_table_device(None)
         self._grad = torch.zeros(n, device=dev)
         self._slots = dict(mg=torch.zeros(n, device=dev), ms=torch.ones(n, device=dev), mom=torch.zeros(n, device=dev))
         self.forward()
@@ -289,6 +312,87 @@ class AIRModel:
         return self._train_step, lambda: self.global_step
 
     def _run_train_step(self, obs=None, nums=None, noise=None):
+        if self._graph_ok and self._eager_steps >= 2:
+            return self._replay_train_step(obs, nums, noise)
+        self._eager_steps += 1
+        out = self._enqueue_train_step(obs, nums, noise)
+        # UPDATE_OPS (model.py:357-360): the moving moments of the importance weight absorb this batch AFTER the gradient
+        # was taken with their previous values (TF leaves the order of the read and the assign unspecified)
+        if self.decay_rate is not None and self._train_cfg["use_reinforce"]:
+            sc = out["scalars"].double().cpu()
+            from ._lib import SCALAR_INDEX as SI
+            m_iw, m_iw2 = float(sc[SI["mean_iw"]]), float(sc[SI["mean_iw2"]])
+            m_b, m_b2 = float(sc[SI["mean_baseline"]]), float(sc[SI["mean_baseline2"]])
+            # tf.nn.moments over the [B,B] broadcast of iw_j - baseline_i: mean = E iw - E b, var = Var iw + Var b
+            mean, var = m_iw - m_b, max(m_iw2 - m_iw * m_iw, 0.0) + max(m_b2 - m_b * m_b, 0.0)
+            d = float(self.decay_rate)
+            self.imp_weight_moving_mean -= (1.0 - d) * (self.imp_weight_moving_mean - mean)
+            self.imp_weight_moving_var -= (1.0 - d) * (self.imp_weight_moving_var - var)
+        self.global_step += 1
+        return out
+
+    def release_graphs(self):
+        """Destroy the captured training-step graphs (the next train_op captures again).  With torch.distributed initialised
+        this MUST be called before dist.destroy_process_group(): the graphs hold NCCL kernels of the default group."""
+        if self.__dict__.get("_graphs"):
+            torch.cuda.synchronize()
+            self._graphs.clear()
+
+    def __del__(self):
+        try:
+            self.release_graphs()
+        except Exception:
+            pass
+
+    def _replay_train_step(self, obs=None, nums=None, noise=None):
+        """The captured step: copy the inputs into the graph's buffers, hand over this iteration's step prior, replay."""
+        if self._g_obs is None:
+            self._g_obs = self.obs.clone()
+        if obs is not None:
+            assert tuple(obs.shape) == tuple(self._g_obs.shape)
+            self._g_obs.copy_(obs)
+        self.obs = self._g_obs
+        if nums is not None:
+            self.nums = nums
+        if noise is not None:
+            if self._g_noise is None:
+                self._g_noise = tuple(torch.empty(n.shape, device=self._g_obs.device, dtype=torch.float32) for n in noise)
+            for d, n in zip(self._g_noise, noise):
+                d.copy_(n)
+        pr = self._current_prior()                 # host arithmetic: the annealed success probability of THIS iteration
+        self._prior_on_device = True
+        self.engine.prior_table_device(pr)
+        key = (noise is None, bool(self.use_prior), float(self.learning_rate), float(self.l2_weight))
+        ent = self._graphs.get(key)
+        if ent is None:
+            g = torch.cuda.CUDAGraph()
+            keep_nums, self.nums = self.nums, None     # (the count of ground-truth objects is not part of the step)
+            launches0 = self.engine.launch_count
+            try:
+                # thread_local: NCCL's watchdog thread polls its events while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    out = self._enqueue_train_step(None, None, self._g_noise if noise is not None else None)
+            finally:
+                self.nums = keep_nums
+            ent = self._graphs[key] = (g, out, self._last_noise, self.__dict__.get("baseline"))
+            self.graph_launches_per_step = self.engine.launch_count - launches0   # kernel nodes of one replay (library's own)
+        g, out, self._last_noise, baseline = ent
+        g.replay()
+        self.graph_replays += 1
+        # what forward() / _expose_losses leave behind on the Python side
+        self._prior_struct = pr
+        self.__dict__.pop("glimpse", None)
+        for k in AIRModel._LAZY_LOSS_ATTRS:
+            self.__dict__.pop(k, None)
+        self._loss_outputs = out
+        if baseline is not None:
+            self.baseline = baseline
+        if self.nums is not None:
+            self.gt_num_steps = self.nums.sum(0).reshape(-1)
+        self.global_step += 1
+        return out
+
+    def _enqueue_train_step(self, obs=None, nums=None, noise=None):
         import torch.distributed as dist
         from . import sharding
         out = self.forward(obs, nums, noise)
@@ -303,23 +407,25 @@ class AIRModel:
                                      nvil_shift=pr.nvil_shift, nvil_scale=pr.nvil_scale)
         eps_where, eps_what, _ = self._last_noise
         o = self._opt
-        # The baseline's own gradient (model.py:253-259) needs only this step's forward results: it goes FIRST, so that under
-        # sharding its all-reduce hides behind the main backward pass, and the main gradient's all-reduce behind the baseline's
-        # optimiser step -- every collective is issued on NCCL's stream (async_op) and joined where its result is consumed.
-        base_work = None
+        # The baseline's own gradient (model.py:253-259) needs only this step's forward results: it goes FIRST and its
+        # weight-gradient GEMMs (the [B,3177]^T [B,256] product above all) are left on the engine's side streams, where they
+        # overlap the cell's backward pass; air_backward's final join covers them.
+        g_base = None
         if has_baseline:
             bm = self.baseline_module
             # the (global) importance-weight mean sits in the scalar block: read on the device by the gradient kernel
             tmean = out["scalars"][SCALAR_INDEX["mean_iw"]:SCALAR_INDEX["mean_iw"] + 1]
-            g_base = bm.backward(self.reinforce_imp_weight, self.baseline, tmean, 1.0 / (world * B))
-            if world > 1:
-                base_work = dist.all_reduce(g_base, async_op=True)
+            g_base = bm.backward(self.reinforce_imp_weight, self.baseline, tmean, 1.0 / (world * B),
+                                 defer_join=getattr(bm, "_engine", None) is eng)
         # baseline_mean = NaN: air_backward reads scalars[mean_baseline] on the device (no host synchronisation in the step)
         eng.backward(self.cell.params, self.obs, eps_where, eps_what, pr, self._grad,
                      baseline_mean=float("nan") if has_baseline else 0.0,
                      inv_batch=1.0 / (world * B), l2_weight=float(self.l2_weight) / world)
-        grad_work = None
+        # under sharding: both collectives are issued on NCCL's stream (async_op) and joined where their results are consumed
+        base_work = grad_work = None
         if world > 1:
+            if g_base is not None:
+                base_work = dist.all_reduce(g_base, async_op=True)
             grad_work = dist.all_reduce(self._grad, async_op=True)   # the ONE data-path collective of the cell's parameters
         # the baseline's train step at 10x the learning rate (model.py:362-367, _make_baseline_train_step :253-259)
         if has_baseline:
@@ -331,19 +437,6 @@ class AIRModel:
             grad_work.wait()
         eng.rmsprop_step(self.cell.params, self._grad, self._slots["mg"], self._slots["ms"], self._slots["mom"],
                          float(self.learning_rate), o["decay"], o["momentum"], o["epsilon"])
-        # UPDATE_OPS (model.py:357-360): the moving moments of the importance weight absorb this batch AFTER the gradient
-        # was taken with their previous values (TF leaves the order of the read and the assign unspecified)
-        if self.decay_rate is not None and self._train_cfg["use_reinforce"]:
-            sc = out["scalars"].double().cpu()
-            from ._lib import SCALAR_INDEX as SI
-            m_iw, m_iw2 = float(sc[SI["mean_iw"]]), float(sc[SI["mean_iw2"]])
-            m_b, m_b2 = float(sc[SI["mean_baseline"]]), float(sc[SI["mean_baseline2"]])
-            # tf.nn.moments over the [B,B] broadcast of iw_j - baseline_i: mean = E iw - E b, var = Var iw + Var b
-            mean, var = m_iw - m_b, max(m_iw2 - m_iw * m_iw, 0.0) + max(m_b2 - m_b * m_b, 0.0)
-            d = float(self.decay_rate)
-            self.imp_weight_moving_mean -= (1.0 - d) * (self.imp_weight_moving_mean - mean)
-            self.imp_weight_moving_var -= (1.0 - d) * (self.imp_weight_moving_var - var)
-        self.global_step += 1
         return out
 
     def toggle_prior(self):

@@ -166,7 +166,7 @@ class BaselineMLP:
         self._engine = engine
         return self
 
-    def backward(self, target, baseline, target_mean=None, inv_batch=None):
+    def backward(self, target, baseline, target_mean=None, inv_batch=None, defer_join=False):
         """Gradient of baseline_loss = .5 * mean((stop_gradient(target) - baseline)^2) (model.py:253-259; target [B],
         baseline [B,1] -> [B,B] broadcast) with respect to the baseline's parameters, for the LAST
         call; left in ``self.grad`` (flat).  ``target_mean`` / ``inv_batch`` are the global-batch values under sharding."""
@@ -178,8 +178,10 @@ class BaselineMLP:
         else:
             tm = float(target.mean()) if target_mean is None else float(target_mean)
             d_out = F.baseline_grad(target, baseline, tm, ib)
+        self._d_out = d_out     # (kept alive: with defer_join the side streams still read it after this call returns)
         if getattr(self, "_engine", None) is not None:
-            return self._engine.baseline_backward(self.params, d_out, self.grad)
+            # defer_join: self.grad is complete after the engine's next backward() (Engine.baseline_backward)
+            return self._engine.baseline_backward(self.params, d_out, self.grad, defer_join=defer_join)
         self.grad.zero_()
         self.mlp.backward(d_out, self.grad_views)
         return self.grad

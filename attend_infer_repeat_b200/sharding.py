@@ -54,7 +54,7 @@ def combine_scalars(scalars: torch.Tensor, n_local: int, steps_weight: float = 1
     wire = torch.float32 if dev.type == "cuda" else torch.float64          # NCCL path: fp32 on the wire (16 floats)
     buf = torch.zeros(AIR_N_SCALARS, dtype=wire, device=dev)
     buf[mean_idx] = (scalars[mean_idx].double() * float(n_local)).to(wire)
-    buf[AIR_N_SCALARS - 1] = float(n_local)
+    buf[AIR_N_SCALARS - 1:].fill_(float(n_local))     # (fill_, not item assignment: no host-to-device copy, capturable)
     dist.all_reduce(buf, group=group)
     m = buf / buf[AIR_N_SCALARS - 1]                                       # global means at the mean slots
     I = SCALAR_INDEX

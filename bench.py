@@ -594,7 +594,7 @@ def run_native(args, rank, local_rank, world):
                                transform_var_bias=.5, step_bias=.75, output_multiplier=.5, precision=prec, seed=0)
         pr = dict(loc=0., scale=1.)
         nsp = dict(anneal='exp', init=1. - 1e-15, final=1e-7, steps_div=1e4, steps=1e5, hold_init=1e3, analytic=True)
-        train_op, _ = model.train_step(1e-5, 0., pr, pr, pr, nsp)
+        train_op, _ = model.train_step(1e-5, 0., pr, pr, pr, nsp, cuda_graph=not args.no_train_graph)
         model.global_step = 20000
         torch.cuda.manual_seed(1234 + rank)
 
@@ -605,14 +605,16 @@ def run_native(args, rank, local_rank, world):
         for i in range(max(args.warmup, 3)):
             step(i)
         barrier()
-        launches0 = model.engine.launch_count
+        launches0, replays0 = model.engine.launch_count, model.graph_replays
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
         t_wall0 = time.time()
         ms = timed(step, args.steps)
         t_wall1 = time.time()
-        launches = model.engine.launch_count - launches0
+        # (a replayed step launches its kernels as graph nodes: the library's launch counter does not see them)
+        launches = (model.engine.launch_count - launches0) + (model.graph_replays - replays0) * model.graph_launches_per_step
+        extra["cuda_graph"] = {"replays": model.graph_replays - replays0, "kernel_nodes_per_step": model.graph_launches_per_step}
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
         value = world * B * T * args.steps / (ms * 1e-3)
         elbo = -float(model.engine.scalar("loss"))
@@ -664,6 +666,8 @@ def run_native(args, rank, local_rank, world):
         if world == 1:
             line["cpu_baseline"], line["elbo_delta_vs_oracle"] = cpu_baseline(args, dev, prec)
         emit(line)
+    if mode == "train":
+        model.release_graphs()      # (the captured step holds NCCL kernels: before the process group goes away)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -746,6 +750,8 @@ def main():
     ap.add_argument("--streams", type=int, default=4,
                     help="forward / IWAE configs: independent batches in flight (EnginePool); 1 = one pass at a time")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-train-graph", action="store_true",
+                    help="c3: enqueue every training step eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = CONFIGS[args.config]["batch"]

@@ -273,6 +273,14 @@ int32_t air_cache_weights(air_handle* h, int32_t on);
 int32_t air_set_launch_overlap(air_handle* h, int32_t on);
 int32_t air_params_updated(air_handle* h);
 
+/* Replayed CUDA graphs (the training step of AIRModel.train_step, model.py:261-376, captured once and replayed): kernel
+ * arguments are frozen at capture, but the annealed prior on the number of steps (model.py:133-142, a new success
+ * probability every iteration) is not.  With a non-NULL `prior` this call writes geometric_prior(success_prob, T)
+ * (prior.py:26-32; float64 or float32 island as `steps_prob_is_f64` says) into the handle's device table from a one-warp
+ * kernel on `stream`, and every later air_forward / air_backward on the handle reads the table from there instead of from
+ * its own `prior` argument (whose other fields are used as before).  prior == NULL switches back. */
+int32_t air_prior_table_device(air_handle* h, const air_prior* prior, void* stream);
+
 /* Importance-weighted bound (BASELINE.json configs[4]; an EXTENSION: the reference has no IWAE).  The K particles of a
  * canvas are K consecutive rows (row = canvas * K + particle: same image, own noise) of an ordinary air_forward over
  * R = n_canvases * K rows with a prior; this call turns that pass's outputs into
@@ -348,6 +356,11 @@ int32_t air_baseline_input_width(const air_handle* h);
 int32_t air_baseline_forward(air_handle* h, const float* bparams, const float* img, const air_outputs* outs, float* baseline,
                              void* stream);
 int32_t air_baseline_backward(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad, void* stream);
+/* Same, but the weight-gradient GEMMs are left running on the handle's side streams: `bgrad` is complete only after the NEXT
+ * air_backward on the same handle and stream has returned (its final join covers them).  The training step of
+ * model.py:362-367 uses it so that the baseline's gradient overlaps the cell's backward pass. */
+int32_t air_baseline_backward_async(air_handle* h, const float* bparams, const float* d_baseline, float* bgrad,
+                                    void* stream);
 
 /* Re-form the batch means in outs->scalars from the per-sample vectors an earlier air_forward left in
  * `outs`, now with a baseline[B] (BaselineMLP is evaluated on the cell outputs, so it can only be

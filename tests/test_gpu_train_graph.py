@@ -1,0 +1,94 @@
+"""AIRModel.train_step(cuda_graph=True): the training step captured once and replayed (the reference builds its TF graph once
+and re-runs it, model.py:261-376) must do what the eagerly enqueued step does -- including the ANNEALED prior on the number of
+steps (model.py:133-142), which changes every iteration and reaches the replayed kernels through device memory
+(air_prior_table_device)."""
+from functools import partial
+
+import pytest
+import torch
+
+import attend_infer_repeat_b200 as air
+from oracle import air_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(B, T, seed=3, precision=None):
+    img, nums = O.synthetic_multi_mnist(B, 50, 50, seed=seed)
+    kw = {} if precision is None else dict(precision=precision)
+    return air.AIRonMNIST(img.cuda(), nums.cuda(), max_steps=T, explore_eps=1e-3, inpt_encoder_hidden=[256, 256],
+                          glimpse_encoder_hidden=[256, 256], glimpse_decoder_hidden=[256, 256],
+                          transform_estimator_hidden=[256, 256], steps_pred_hidden=[128, 64], baseline_hidden=[256, 128],
+                          transform_var_bias=.5, step_bias=.75, output_multiplier=.5, seed=0, **kw)
+
+
+def _run(graph, steps, B, T, monkeypatch, precision=None, given_noise=True):
+    model = _model(B, T, precision=precision)
+    pr = dict(loc=0., scale=1.)
+    # a prior that moves visibly every iteration: a frozen table would show up in kl_num_steps at once
+    nsp = dict(anneal='exp', init=.9, final=1e-3, steps_div=2., steps=40., hold_init=0., analytic=True)
+    train_op, global_step = model.train_step(1e-4, 0., pr, pr, pr, nsp, cuda_graph=graph)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    torch.cuda.manual_seed(5)
+    batches = [O.synthetic_multi_mnist(B, 50, 50, seed=20 + i)[0].cuda() for i in range(3)]
+    log = []
+    for i in range(steps):
+        noise = model.cell.draw_noise(B, T, generator=gen) if given_noise else None
+        train_op(batches[i % 3], None, noise)
+        log.append((float(model.kl_num_steps), float(model.loss.value), float(model.baseline_loss),
+                    float(model.steps_prior_success_prob)))
+    assert global_step() == steps
+    graphs = len(model.__dict__.get("_graphs", {}))
+    return log, model.params.clone(), model.baseline_module.params.clone(), graphs
+
+
+@pytest.mark.parametrize("precision", [None, air.AIR_PREC_TC_SPLIT])
+def test_replayed_train_step_equals_the_eager_one(monkeypatch, precision):
+    B, T, steps = 64, 3, 8
+    eager, p_e, b_e, n_e = _run(False, steps, B, T, monkeypatch, precision)
+    graph, p_g, b_g, n_g = _run(True, steps, B, T, monkeypatch, precision)
+    assert n_e == 0 and n_g == 1
+    probs = [r[3] for r in graph]
+    assert probs == [r[3] for r in eager] and len(set(probs)) == steps          # the prior did move
+    # (split-K weight gradients combine with fp32 atomics: two runs agree to rounding at first -- step 2 is the first replay --
+    # and then drift apart slowly as centered RMSProp amplifies it; a frozen prior table would be off by > 1e-2 in the KL term)
+    for i, (a, b) in enumerate(zip(eager, graph)):
+        tol = 2e-5 if i < 4 else 1e-3
+        for x, y in zip(a, b):
+            assert abs(x - y) <= tol * max(abs(x), abs(y), 1.0), (i, a, b)
+    kl = [r[0] for r in graph]
+    assert max(kl) - min(kl) > 1e-2                     # ... and the KL term followed it
+    # centered RMSProp normalises the gradient: a rounding-level difference may move a parameter by up to lr per step
+    assert float((p_e - p_g).abs().max()) <= steps * 1e-4 and float((p_e - p_g).abs().mean()) < 2e-6
+    assert float((b_e - b_g).abs().max()) <= steps * 1e-3 and float((b_e - b_g).abs().mean()) < 2e-5
+
+
+def test_replayed_train_step_draws_fresh_noise(monkeypatch):
+    """noise=None: the draws are part of the captured graph and must differ from replay to replay."""
+    B, T = 32, 3
+    model = _model(B, T)
+    pr = dict(loc=0., scale=1.)
+    train_op, _ = model.train_step(1e-4, 0., pr, pr, pr, dict(init=.5, analytic=True), cuda_graph=True)
+    seen = []
+    for i in range(6):
+        train_op()
+        seen.append(model._last_noise[1].clone())
+    assert len(model._graphs) == 1
+    for i in range(1, 6):
+        assert not torch.equal(seen[i], seen[i - 1])
+    assert torch.isfinite(model.params).all()
+
+
+def test_toggle_prior_recaptures(monkeypatch):
+    B, T = 32, 3
+    model = _model(B, T)
+    pr = dict(loc=0., scale=1.)
+    train_op, _ = model.train_step(1e-4, 0., pr, pr, pr, dict(init=.5, analytic=True), cuda_graph=True)
+    for i in range(4):
+        train_op()
+    with_prior = float(model.loss.value) - float(model.rec_loss)
+    model.toggle_prior()
+    for i in range(2):
+        train_op()
+    assert len(model._graphs) == 2
+    assert abs(float(model.loss.value) - float(model.rec_loss)) < 1e-6 * abs(float(model.rec_loss)) and with_prior > 0
