@@ -1684,14 +1684,24 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
                          st)) != AIR_OK)
     return rc;
   // 8. LSTM through time                                                          cell.py:126-127
+  // (tensor-core gradient GEMMs: the gate kernel also writes dgates_t as the bf16 hi/lo planes the recurrent product reads)
+  const int g_np = 4 * nh, g_ma = round_up(B, 128);
+  const bool gate_planes = h->tc_bwd && B >= 64 && g_np % 64 == 0 && (size_t)g_ma * g_np <= h->hl_dy_halves;
   for (int t = T - 1; t >= 0; --t) {
     const size_t off = (size_t)t * B;
     AIR_CUDA(air::launch_k(air::lstm_bwd_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
                            (const float*)(h->gates_all + off * 4 * nh), (const float*)(h->c_all + off * nh),
                            (const float*)(h->c_all + (off + B) * nh), (const float*)(h->g_h + off * nh),
                            (const float*)(t == T - 1 ? nullptr : h->g_hrec), h->g_c, h->g_gates + off * 4 * nh, B, nh,
-                           c.forget_bias, t == T - 1 ? 1 : 0, h->g_gx));
+                           c.forget_bias, t == T - 1 ? 1 : 0, h->g_gx, gate_planes ? h->hl_dy2[0] : (__half*)nullptr,
+                           (size_t)g_ma * g_np, g_np, h->t_range_flag));
     ++h->launches;
+    if (gate_planes) {
+      h->dy_ready = h->g_gates + off * 4 * nh;
+      h->dy_ready_m = B;
+      h->dy_ready_n = g_np;
+      h->dy_ready_buf = 0;
+    }
     // d h_{t-1} = dgates_t @ W_h^T  (t = 0: gradient of the trainable initial state)
     if ((rc = layer_input_grad(h, params, h->lstm_h, h->g_gates + off * 4 * nh, 4 * nh, h->g_hrec, nh, B, false, nullptr,
                                0, st)) != AIR_OK)
@@ -2259,7 +2269,7 @@ int32_t air_baseline_forward(air_handle* h, const float* bparams, const float* i
   air_handle::Baseline& bl = h->bl;
   const int B = c.B;
   const size_t n = (size_t)B * bl.n_in;
-  AIR_CUDA(air::launch_k(air::baseline_gather_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, img,
+  AIR_CUDA(air::launch_k(air::baseline_gather_kernel, dim3((unsigned)B), dim3(256), 0, st, img,
                          (const float*)o->what, (const float*)o->where, (const float*)o->presence, (const float*)o->final_h,
                          (const float*)o->final_c, bl.x.f32, bl.x.hl, bl.x.plane(), bl.x.kpad, B, c.T, h->P, c.na, c.nh, bl.n_in));
   ++h->launches;

@@ -11,6 +11,7 @@
 // plus the centered RMSProp update (tf.train.RMSPropOptimizer(centered=True, momentum=.9), model.py:265,355-360).
 // Per-canvas kernels: one CTA (or warp) per canvas, the tile staged in shared memory, warp-shuffle reductions.
 #pragma once
+#include <cuda_bf16.h>
 #include "cell_kernels.cuh"
 
 namespace air {
@@ -612,7 +613,8 @@ __global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const
                                           const float* __restrict__ c_new, const float* __restrict__ dh_heads,
                                           const float* __restrict__ dh_rec, float* __restrict__ dc,
                                           float* __restrict__ dgates, int B, int nh, float forget_bias, int first,
-                                          float* __restrict__ dgx) {
+                                          float* __restrict__ dgx, __half* __restrict__ hl_dst, size_t hl_plane,
+                                          int hl_ld, int* range_flag) {
   griddep_launch();
   griddep_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -633,6 +635,20 @@ __global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const
   dg[2 * nh + u] = d_f;
   dg[3 * nh + u] = d_o;
   dc[idx] = dcv * sf;
+  if (hl_dst) {   // the row-major bf16 hi/lo planes of dgates_t: the A operand of d h_{t-1} = dgates_t @ W_h^T, which follows
+    __half* d = hl_dst + b * (size_t)hl_ld + u;
+    const float v[4] = {d_i, d_j, d_f, d_o};
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v[q]);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v[q] - __bfloat162float(hi));
+      reinterpret_cast<__nv_bfloat16*>(d)[(size_t)q * nh] = hi;
+      reinterpret_cast<__nv_bfloat16*>(d + hl_plane)[(size_t)q * nh] = lo;
+      bad |= !(fabsf(v[q]) <= 3.0e38f);
+    }
+    if (bad && range_flag) atomicOr(range_flag, 1);
+  }
   if (dgx) {   // the LSTM's input half sees the same encoder output at every step: d gx = sum_t dgates_t, accumulated here
     float* sx = dgx + b * 4 * (size_t)nh;
     sx[u] = (first ? 0.f : sx[u]) + d_i;
@@ -653,38 +669,42 @@ __global__ void l2_grad_kernel(const float* __restrict__ w, float* __restrict__ 
 // BaselineMLP input rows (modules.py:131-141): x[b] = concat[img[b] (P), what[:, b] (T * na), where[:, b] (T * 4),
 // presence[:, b] (T), h[b] (nh), c[b] (nh)] -- the time-major cell outputs transposed to batch-major exactly as
 // tf.transpose(t, (1, 0, 2)) + reshape does.  One pass: fp32 rows and (tensor-core engine) the fp16 hi/lo operand planes.
-__global__ void baseline_gather_kernel(const float* __restrict__ img, const float* __restrict__ what,
-                                       const float* __restrict__ where, const float* __restrict__ presence,
-                                       const float* __restrict__ hfin, const float* __restrict__ cfin, float* __restrict__ x,
-                                       __half* __restrict__ hl, size_t plane, int ld_hl, int B, int T, int P, int na, int nh,
-                                       int n_in) {
+__global__ void __launch_bounds__(256)
+baseline_gather_kernel(const float* __restrict__ img, const float* __restrict__ what, const float* __restrict__ where,
+                       const float* __restrict__ presence, const float* __restrict__ hfin, const float* __restrict__ cfin,
+                       float* __restrict__ x, __half* __restrict__ hl, size_t plane, int ld_hl, int B, int T, int P, int na,
+                       int nh, int n_in) {
   griddep_launch();
   griddep_wait();
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * n_in) return;
-  const int b = (int)(idx / n_in);
-  int k = (int)(idx % n_in);
-  const int col = k;
-  float v;
-  if (k < P) {
-    v = img[(size_t)b * P + k];
-  } else if ((k -= P) < T * na) {
-    v = what[((size_t)(k / na) * B + b) * na + k % na];
-  } else if ((k -= T * na) < T * 4) {
-    v = where[((size_t)(k / 4) * B + b) * 4 + k % 4];
-  } else if ((k -= T * 4) < T) {
-    v = presence[(size_t)k * B + b];
-  } else if ((k -= T) < nh) {
-    v = hfin[(size_t)b * nh + k];
-  } else {
-    v = cfin[(size_t)b * nh + (k - nh)];
-  }
-  x[idx] = v;
-  if (hl) {
-    __half hi, lo;
-    split_f16(v, hi, lo);
-    hl[(size_t)b * ld_hl + col] = hi;
-    hl[plane + (size_t)b * ld_hl + col] = lo;
+  // one CTA per canvas, two neighbouring columns per thread (32-bit index arithmetic, 4-byte stores into the planes)
+  const int b = blockIdx.x;
+  auto fetch = [&](int k) -> float {
+    if (k < P) return img[(size_t)b * P + k];
+    if ((k -= P) < T * na) return what[((size_t)(k / na) * B + b) * na + k % na];
+    if ((k -= T * na) < T * 4) return where[((size_t)(k >> 2) * B + b) * 4 + (k & 3)];
+    if ((k -= T * 4) < T) return presence[(size_t)k * B + b];
+    if ((k -= T) < nh) return hfin[(size_t)b * nh + k];
+    return cfin[(size_t)b * nh + (k - nh)];
+  };
+  float* xr = x + (size_t)b * n_in;
+  __half* hr = hl ? hl + (size_t)b * ld_hl : nullptr;
+  for (int k = 2 * threadIdx.x; k < n_in; k += 2 * blockDim.x) {
+    const bool two = k + 1 < n_in;
+    const float v0 = fetch(k), v1 = two ? fetch(k + 1) : 0.f;
+    xr[k] = v0;
+    if (two) xr[k + 1] = v1;
+    if (hr) {
+      __half h0, l0, h1, l1;
+      split_f16(v0, h0, l0);
+      split_f16(v1, h1, l1);
+      if (two) {
+        *reinterpret_cast<__half2*>(hr + k) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(hr + plane + k) = __halves2half2(l0, l1);
+      } else {
+        hr[k] = h0;
+        hr[plane + k] = l0;
+      }
+    }
   }
 }
 

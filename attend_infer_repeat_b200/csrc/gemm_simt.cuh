@@ -193,6 +193,9 @@ inline cudaError_t launch_gemm_simt(bool ta, bool tb, const float* A, int lda, c
 #define AIR_GEMM_LAUNCH(BM, BN, TM, TN, TA_, TB_)                                                                   \
   return launch_k(gemm_simt_kernel<BM, BN, 16, TM, TN, TA_, TB_>, dim3((N + BN - 1) / BN, (M + BM - 1) / BM, nz),  \
                   dim3((BM / TM) * (BN / TN)), 0, st, A, lda, B, ldb, C, ldc, M, N, K, k_chunk, acc, elu_y, ldy)
+  if (N > 32 && M > 32 && !ta && tb && (long long)((N + 63) / 64) * ((M + 127) / 128) * nz < 148) {
+    AIR_GEMM_LAUNCH(32, 64, 4, 4, false, true);   // input gradients of small layers: 32-row tiles fill the machine
+  }
   if (N > 32) {
     if (!ta && tb) { AIR_GEMM_LAUNCH(128, 64, 8, 4, false, true); }
     if (ta && !tb) { AIR_GEMM_LAUNCH(128, 64, 8, 4, true, false); }

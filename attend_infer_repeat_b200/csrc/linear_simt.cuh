@@ -159,7 +159,14 @@ inline cudaError_t launch_linear_simt(const float* A, int lda, const float* Wt, 
                                       const float* addend, int ldadd, float* C, int ldc, int M, int N, int K,
                                       int act, cudaStream_t st) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  if (N > 32) {
+  if (N > 32 && M > 32 && (long long)((N + 63) / 64) * ((M + 127) / 128) < 148) {
+    // too few 128-row tiles to fill the machine (the BaselineMLP's [4096, 256] x [256, 128] layer: 64 CTAs): 32-row tiles.
+    // The order of the k accumulation per output does not depend on the tile, so the results are the same bit for bit.
+    constexpr int BM = 32, BN = 64, BK = 16, TM = 4, TN = 4;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    return launch_k(linear_simt_kernel<BM, BN, BK, TM, TN>, grid, dim3((BM / TM) * (BN / TN)), 0, st, A, lda, Wt, ldw,
+                    bias, addend, ldadd, C, ldc, M, N, K, act);
+  } else if (N > 32) {
     constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     return launch_k(linear_simt_kernel<BM, BN, BK, TM, TN>, grid, dim3((BM / TM) * (BN / TN)), 0, st, A, lda, Wt, ldw,

@@ -458,21 +458,23 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int ld_src, __h
 // exact whatever the buffer held before.  One 32 x 32 tile per CTA through shared memory.
 // as_bf16: the planes hold bf16 hi / lo (x = hi + lo to 16 significant bits, fp32 exponent range) -- per-sample gradients
 // span too many decades for fp16 (1 / s_x factors of the inverse transformer).
-constexpr int ST_M = 32;    // batch rows per CTA of split_transpose_kernel
+constexpr int ST_M = 64;    // batch rows per CTA of split_transpose_kernel
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, float scale, __half* __restrict__ dst,
                        size_t plane, int ld_dst, int* range_flag, int as_bf16, __half* __restrict__ rm, size_t plane_rm,
                        int ld_rm, float* __restrict__ colsum) {
   // optional by-products of the same read (gradient tensors dY): `rm` = the row-major bf16 planes [2][..][ld_rm] with
   // columns [C, ld_rm) zero-filled (A operand of dX = dY @ W^T; the grid must then cover ld_rm columns), `colsum` += the
-  // column sums (bias gradient, fp32 atomics)
-  __shared__ float tile[32][33];
+  // column sums (bias gradient, fp32 atomics).
+  // A 64 (rows) x 32 (columns) tile per CTA: every thread stores PAIRS of neighbouring rows (4 bytes, 128 per warp) into the
+  // transposed planes (ld_dst and `plane` are even, m0 is a multiple of 64).
+  __shared__ float tile[ST_M][33];
   griddep_launch();
   griddep_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32, m0 = blockIdx.y * ST_M;
 #pragma unroll
-  for (int i = 0; i < 32; i += 8) {
+  for (int i = 0; i < ST_M; i += 8) {
     const int m = m0 + ty + i, c = c0 + tx;
     const float x = (m < M && c < C) ? src[(size_t)m * ld + c] * scale : 0.f;
     tile[ty + i][tx] = x;
@@ -488,28 +490,30 @@ split_transpose_kernel(const float* __restrict__ src, int ld, int M, int C, floa
   if (colsum && ty == 0 && c0 + tx < C) {
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sum += tile[i][tx];
+    for (int i = 0; i < ST_M; ++i) sum += tile[i][tx];
     atomicAdd(colsum + c0 + tx, sum);
   }
   bool overflow = false;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
-    const int c = c0 + ty + i, m = m0 + tx;
+    const int c = c0 + ty + i, m = m0 + 2 * tx;
     if (c < C && m < ld_dst) {
-      const float x = tile[tx][ty + i];
+      const float x0 = tile[2 * tx][ty + i], x1 = tile[2 * tx + 1][ty + i];
       __half* d = dst + (size_t)c * ld_dst + m;
       if (as_bf16) {
-        const __nv_bfloat16 bh = __float2bfloat16_rn(x);
-        const __nv_bfloat16 bl = __float2bfloat16_rn(x - __bfloat162float(bh));
-        overflow |= !(fabsf(x) <= 3.0e38f);
-        reinterpret_cast<__nv_bfloat16*>(d)[0] = bh;
-        reinterpret_cast<__nv_bfloat16*>(d)[plane] = bl;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+        overflow |= !(fabsf(x0) <= 3.0e38f) || !(fabsf(x1) <= 3.0e38f);
+        *reinterpret_cast<__nv_bfloat162*>(d) = __halves2bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162*>(d + plane) = __halves2bfloat162(l0, l1);
       } else {
-        __half hi, lo;
-        split_f16(x, hi, lo);
-        overflow |= __hisinf(hi) || __hisnan(hi);
-        d[0] = hi;
-        d[plane] = lo;
+        __half hi0, lo0, hi1, lo1;
+        split_f16(x0, hi0, lo0);
+        split_f16(x1, hi1, lo1);
+        overflow |= __hisinf(hi0) || __hisnan(hi0) || __hisinf(hi1) || __hisnan(hi1);
+        *reinterpret_cast<__half2*>(d) = __halves2half2(hi0, hi1);
+        *reinterpret_cast<__half2*>(d + plane) = __halves2half2(lo0, lo1);
       }
     }
   }

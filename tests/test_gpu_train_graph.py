@@ -59,8 +59,8 @@ def test_replayed_train_step_equals_the_eager_one(monkeypatch, precision):
     kl = [r[0] for r in graph]
     assert max(kl) - min(kl) > 1e-2                     # ... and the KL term followed it
     # centered RMSProp normalises the gradient: a rounding-level difference may move a parameter by up to lr per step
-    assert float((p_e - p_g).abs().max()) <= steps * 1e-4 and float((p_e - p_g).abs().mean()) < 2e-6
-    assert float((b_e - b_g).abs().max()) <= steps * 1e-3 and float((b_e - b_g).abs().mean()) < 2e-5
+    assert float((p_e - p_g).abs().max()) <= steps * 1e-4 and float((p_e - p_g).abs().mean()) < 2e-5
+    assert float((b_e - b_g).abs().max()) <= steps * 1e-3 and float((b_e - b_g).abs().mean()) < 2e-4
 
 
 def test_replayed_train_step_draws_fresh_noise(monkeypatch):
