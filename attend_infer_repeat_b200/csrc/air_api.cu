@@ -695,9 +695,9 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     ++h->launches;
     h->weights_ready = params;
   }
-  // h0 @ W_h of the cluster LSTM (only passes that broadcast the trainable initial state read it: not the training forward,
-  // which keeps per-canvas rows, and not air_cell_step with explicit state)
-  if (tc && h->lstm_ok && h->hw0 && !train && !h_in && !(h->cache_weights && h->hw0_ready == params)) {
+  // h0 @ W_h of the cluster LSTM (only passes that broadcast the trainable initial state read it: not air_cell_step with
+  // explicit state)
+  if (tc && h->lstm_ok && h->hw0 && !h_in && !(h->cache_weights && h->hw0_ready == params)) {
     AIR_CUDA(air::launch_k(air::lstm::lstm_h0w_kernel, dim3((4 * nh + 31) / 32), dim3(256), 0, st,
                            params + h->lstm_h.w_off, params + h->lstm_h0, h->hw0, nh));
     ++h->launches;
@@ -823,7 +823,11 @@ int32_t forward_impl(air_handle* h, const float* params, const float* img, const
     }
     lp.hs_last_only = train ? 0 : 1;
     lp.n_enc = h->n_enc;
-    const bool rows = h_in || train;   // explicit per-canvas state (air_cell_step) or the tiled copy kept for the backward
+    // explicit per-canvas state (air_cell_step): rows.  The training forward broadcasts (h0, c0) like inference and folds
+    // step 1's recurrent product into the constant hw0; the tiled copies the backward pass reads (hprev slice 0, c_all
+    // slice 0) are written by lstm_init_state_kernel, which the LSTM kernel no longer depends on.
+    static const bool train_rows = getenv("AIR_LSTM_TRAIN_ROWS") != nullptr;   // (the previous behaviour, for comparison)
+    const bool rows = h_in || (train && train_rows);
     lp.h_init = rows ? h->h_init.f32 : params + h->lstm_h0;   // cell.py:103: (h0, c0) [1,nh] tiled to the batch
     lp.h_init_ld = rows ? nh : 0;
     static const bool no_fold = getenv("AIR_LSTM_NO_FOLD") != nullptr;
@@ -1689,7 +1693,9 @@ int32_t backward_impl(air_handle* h, const float* params, const float* img, cons
   const bool gate_planes = h->tc_bwd && B >= 64 && g_np % 64 == 0 && (size_t)g_ma * g_np <= h->hl_dy_halves;
   for (int t = T - 1; t >= 0; --t) {
     const size_t off = (size_t)t * B;
-    AIR_CUDA(air::launch_k(air::lstm_bwd_pointwise_kernel, dim3((B * nh + thr - 1) / thr), dim3(thr), 0, st,
+    const bool pair = nh % 2 == 0;
+    AIR_CUDA(air::launch_k(pair ? air::lstm_bwd_pointwise_kernel<2> : air::lstm_bwd_pointwise_kernel<1>,
+                           dim3((B * (pair ? nh / 2 : nh) + thr - 1) / thr), dim3(thr), 0, st,
                            (const float*)(h->gates_all + off * 4 * nh), (const float*)(h->c_all + off * nh),
                            (const float*)(h->c_all + (off + B) * nh), (const float*)(h->g_h + off * nh),
                            (const float*)(t == T - 1 ? nullptr : h->g_hrec), h->g_c, h->g_gates + off * 4 * nh, B, nh,

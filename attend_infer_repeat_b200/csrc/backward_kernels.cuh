@@ -609,52 +609,95 @@ inline cudaError_t launch_latent_bwd(const BwdArgs& a, cudaStream_t st) {
 //   dh_rec [B,nh] (from step t+1 through W_h, null at the last step), dc [B,nh] in: d L / d c_t from step t+1, out: for t-1
 //   -> dgates [B,4nh]
 // ---------------------------------------------------------------------------------------------------
-__global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
-                                          const float* __restrict__ c_new, const float* __restrict__ dh_heads,
-                                          const float* __restrict__ dh_rec, float* __restrict__ dc,
-                                          float* __restrict__ dgates, int B, int nh, float forget_bias, int first,
-                                          float* __restrict__ dgx, __half* __restrict__ hl_dst, size_t hl_plane,
-                                          int hl_ld, int* range_flag) {
+// U = units per thread (2 when nh is even: 8-byte loads / stores of the fp32 rows, 4-byte stores into the bf16 planes)
+template <int U>
+__global__ void __launch_bounds__(256)
+lstm_bwd_pointwise_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                          const float* __restrict__ dh_heads, const float* __restrict__ dh_rec, float* __restrict__ dc,
+                          float* __restrict__ dgates, int B, int nh, float forget_bias, int first, float* __restrict__ dgx,
+                          __half* __restrict__ hl_dst, size_t hl_plane, int hl_ld, int* range_flag) {
   griddep_launch();
   griddep_wait();
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * nh) return;
-  const size_t b = idx / nh;
-  const int u = (int)(idx % nh);
-  const float* g = gates + b * 4 * (size_t)nh;
-  const float si = sigmoid_f(g[u]), tj = tanhf(g[nh + u]), sf = sigmoid_f(g[2 * nh + u] + forget_bias),
-              so = sigmoid_f(g[3 * nh + u]);
-  const float tc = tanhf(c_new[idx]);
-  const float dh = dh_heads[idx] + (dh_rec ? dh_rec[idx] : 0.f);
-  const float dcv = (first ? 0.f : dc[idx]) + dh * so * (1.0f - tc * tc);
-  float* dg = dgates + b * 4 * (size_t)nh;
-  const float d_i = dcv * tj * si * (1.0f - si), d_j = dcv * si * (1.0f - tj * tj);
-  const float d_f = dcv * c_prev[idx] * sf * (1.0f - sf), d_o = dh * tc * so * (1.0f - so);
-  dg[u] = d_i;
-  dg[nh + u] = d_j;
-  dg[2 * nh + u] = d_f;
-  dg[3 * nh + u] = d_o;
-  dc[idx] = dcv * sf;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int upr = nh / U;                     // threads per canvas row
+  if (tid >= (size_t)B * upr) return;
+  const size_t b = tid / upr;
+  const int u = (int)(tid % upr) * U;
+  const size_t idx = b * nh + u;
+  const float* g = gates + b * 4 * (size_t)nh + u;
+  float gi[U], gj[U], gf[U], go[U], cp[U], cn[U], dhh[U], dhr[U], dcc[U];
+  auto ld = [&](const float* p, float* out) {
+    if (U == 2) {
+      const float2 v = *reinterpret_cast<const float2*>(p);
+      out[0] = v.x;
+      out[U - 1] = v.y;
+    } else {
+      out[0] = p[0];
+    }
+  };
+  auto st = [&](float* p, const float* v) {
+    if (U == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[U - 1]);
+    else p[0] = v[0];
+  };
+  ld(g, gi); ld(g + nh, gj); ld(g + 2 * nh, gf); ld(g + 3 * nh, go);
+  ld(c_prev + idx, cp); ld(c_new + idx, cn); ld(dh_heads + idx, dhh);
+#pragma unroll
+  for (int q = 0; q < U; ++q) dhr[q] = dcc[q] = 0.f;
+  if (dh_rec) ld(dh_rec + idx, dhr);
+  if (!first) ld(dc + idx, dcc);
+  float d_i[U], d_j[U], d_f[U], d_o[U], dc_out[U];
+#pragma unroll
+  for (int q = 0; q < U; ++q) {
+    const float si = sigmoid_f(gi[q]), tj = tanhf(gj[q]), sf = sigmoid_f(gf[q] + forget_bias), so = sigmoid_f(go[q]);
+    const float tc = tanhf(cn[q]);
+    const float dh = dhh[q] + dhr[q];
+    const float dcv = dcc[q] + dh * so * (1.0f - tc * tc);
+    d_i[q] = dcv * tj * si * (1.0f - si);
+    d_j[q] = dcv * si * (1.0f - tj * tj);
+    d_f[q] = dcv * cp[q] * sf * (1.0f - sf);
+    d_o[q] = dh * tc * so * (1.0f - so);
+    dc_out[q] = dcv * sf;
+  }
+  float* dg = dgates + b * 4 * (size_t)nh + u;
+  st(dg, d_i); st(dg + nh, d_j); st(dg + 2 * nh, d_f); st(dg + 3 * nh, d_o);
+  st(dc + idx, dc_out);
   if (hl_dst) {   // the row-major bf16 hi/lo planes of dgates_t: the A operand of d h_{t-1} = dgates_t @ W_h^T, which follows
-    __half* d = hl_dst + b * (size_t)hl_ld + u;
-    const float v[4] = {d_i, d_j, d_f, d_o};
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(hl_dst) + b * (size_t)hl_ld + u;
+    const float* v[4] = {d_i, d_j, d_f, d_o};
     bool bad = false;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v[q]);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(v[q] - __bfloat162float(hi));
-      reinterpret_cast<__nv_bfloat16*>(d)[(size_t)q * nh] = hi;
-      reinterpret_cast<__nv_bfloat16*>(d + hl_plane)[(size_t)q * nh] = lo;
-      bad |= !(fabsf(v[q]) <= 3.0e38f);
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat16 hi[U], lo[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        hi[q] = __float2bfloat16_rn(v[k][q]);
+        lo[q] = __float2bfloat16_rn(v[k][q] - __bfloat162float(hi[q]));
+        bad |= !(fabsf(v[k][q]) <= 3.0e38f);
+      }
+      __nv_bfloat16* dk = d + (size_t)k * nh;
+      if (U == 2) {
+        *reinterpret_cast<__nv_bfloat162*>(dk) = __halves2bfloat162(hi[0], hi[U - 1]);
+        *reinterpret_cast<__nv_bfloat162*>(dk + hl_plane) = __halves2bfloat162(lo[0], lo[U - 1]);
+      } else {
+        dk[0] = hi[0];
+        dk[hl_plane] = lo[0];
+      }
     }
     if (bad && range_flag) atomicOr(range_flag, 1);
   }
   if (dgx) {   // the LSTM's input half sees the same encoder output at every step: d gx = sum_t dgates_t, accumulated here
-    float* sx = dgx + b * 4 * (size_t)nh;
-    sx[u] = (first ? 0.f : sx[u]) + d_i;
-    sx[nh + u] = (first ? 0.f : sx[nh + u]) + d_j;
-    sx[2 * nh + u] = (first ? 0.f : sx[2 * nh + u]) + d_f;
-    sx[3 * nh + u] = (first ? 0.f : sx[3 * nh + u]) + d_o;
+    float* sx = dgx + b * 4 * (size_t)nh + u;
+    const float* v[4] = {d_i, d_j, d_f, d_o};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float acc[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) acc[q] = 0.f;
+      if (!first) ld(sx + (size_t)k * nh, acc);
+#pragma unroll
+      for (int q = 0; q < U; ++q) acc[q] += v[k][q];
+      st(sx + (size_t)k * nh, acc);
+    }
   }
 }
 
