@@ -320,6 +320,11 @@ def run_native(args, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # several ranks on one host: each binds to its GPU's local CPUs BEFORE any pinned buffer exists (NUMA-local feed)
+    bound_cpus = None
+    if world > 1 and os.environ.get("AIR_NO_CPU_BIND") is None:
+        from attend_infer_repeat_b200.sharding import bind_host_to_device
+        bound_cpus = bind_host_to_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -675,6 +680,8 @@ def run_native(args, rank, local_rank, world):
                 "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": None, "elbo_delta_vs_oracle": None, "elbo": elbo}
         line.update(extra)
+        line["host_binding"] = (f"rank bound to the {len(bound_cpus)} NVML-local CPUs of its GPU (sched_setaffinity)"
+                                if bound_cpus else "none")
         if world == 1:
             line["cpu_baseline"], line["elbo_delta_vs_oracle"] = cpu_baseline(args, dev, prec)
         emit(line)

@@ -185,3 +185,13 @@ def test_rect_stn_bbox_matches_the_reference_formula():
     assert rect_stn_bbox(50, 50, (1., 0., 1., 0.)) == [-.5, -.5, 50., 50.]           # identity: the whole image
     b = rect_stn_bbox(50, 40, (.5, .2, .25, -.4))
     assert b == [40 * (1 - .25 - .4) / 2 - .5, 50 * (1 - .5 + .2) / 2 - .5, 40 * .25, 50 * .5]
+
+
+def test_bind_host_to_device_never_raises_without_a_gpu():
+    """sharding.bind_host_to_device: no NVML / no GPU here -> None, and the process keeps its CPU set."""
+    import os
+    from attend_infer_repeat_b200.sharding import bind_host_to_device
+    before = os.sched_getaffinity(0)
+    got = bind_host_to_device(0)
+    assert got is None or set(got) <= before
+    assert os.sched_getaffinity(0) == (before if got is None else set(got))
