@@ -150,4 +150,9 @@ def main(argv=None):
 
 
 if __name__ == "__main__":
-    main()
+    _model = main()
+    # a captured training step holds NCCL kernels under torchrun: the graphs go before the process group does
+    _model.release_graphs()
+    import torch.distributed as _dist
+    if _dist.is_available() and _dist.is_initialized():
+        _dist.destroy_process_group()
